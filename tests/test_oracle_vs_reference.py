@@ -1,0 +1,118 @@
+"""The in-repo oracle must be bit-identical to the imported reference (build container only).
+
+Skipped where /root/reference is not mounted (the GPU box): there the committed golden
+vectors (tests/test_oracle_golden.py) pin the oracle instead.
+"""
+import pytest
+import torch
+
+from oracle import ref_loader
+from oracle import ssd_oracle as O
+from ssdbox import configs, synth
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_loader.load()
+
+
+def _priors(name):
+    cfg, c = configs.get(name)
+    return O.prior_boxes(cfg.MODEL, c["layer_dims"]), cfg, c
+
+
+@pytest.mark.parametrize("name", list(configs.CONFIGS))
+def test_priors_bit_exact(ref, name):
+    pri, cfg, c = _priors(name)
+    rp = ref.PriorBoxSSD(cfg)
+    assert rp.num_priors == O.num_priors_per_cell(cfg.MODEL)
+    assert torch.equal(rp.forward(c["layer_dims"]), pri)
+    assert pri.size(0) == c["num_priors"]
+
+
+def test_box_algebra_bit_exact(ref):
+    pri, _, _ = _priors("ssd300_voc")
+    bu = ref.box_utils
+    t = synth.gen_targets(1, 21, 16, 5)[0]
+    assert torch.equal(bu.point_form(pri), O.point_form(pri))
+    assert torch.equal(bu.jaccard(t[:, :4], bu.point_form(pri)), O.iou_matrix(t[:, :4], O.point_form(pri)))
+    m = t[torch.randint(0, t.size(0), (pri.size(0),)), :4]
+    assert torch.equal(bu.encode(m, pri, [0.1, 0.2]), O.encode_boxes(m, pri, [0.1, 0.2]))
+    loc = synth.gen_loc(1, pri.size(0), 3)[0]
+    assert torch.equal(bu.decode(loc, pri, [0.1, 0.2]), O.decode_boxes(loc, pri, [0.1, 0.2]))
+    x = synth.gen_train_logits(2, 500, 21, 1).view(-1, 21)
+    assert torch.equal(bu.log_sum_exp(x), O.log_sum_exp(x))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_match_bit_exact(ref, seed):
+    pri, _, _ = _priors("ssd300_voc")
+    tg = synth.gen_targets(4, 21, 16, seed)
+    P = pri.size(0)
+    loc_t = torch.zeros(4, P, 4)
+    conf_t = torch.zeros(4, P, dtype=torch.int64)
+    for b, t in enumerate(tg):
+        ref.box_utils.match(0.5, t[:, :4], pri, [0.1, 0.2], t[:, 4], loc_t, conf_t, b)
+        m = O.match_image(0.5, t[:, :4], pri, [0.1, 0.2], t[:, 4])
+        assert torch.equal(conf_t[b], m["conf"])
+        assert torch.equal(loc_t[b], m["loc"])
+
+
+def test_match_duplicate_truths_last_wins(ref):
+    pri, _, _ = _priors("ssd300_voc")
+    t = torch.tensor([[0.1, 0.1, 0.4, 0.5, 3.0], [0.1, 0.1, 0.4, 0.5, 7.0]])
+    P = pri.size(0)
+    loc_t = torch.zeros(1, P, 4)
+    conf_t = torch.zeros(1, P, dtype=torch.int64)
+    ref.box_utils.match(0.5, t[:, :4], pri, [0.1, 0.2], t[:, 4], loc_t, conf_t, 0)
+    m = O.match_image(0.5, t[:, :4], pri, [0.1, 0.2], t[:, 4])
+    assert torch.equal(conf_t[0], m["conf"])
+    assert int(m["conf"][m["best_prior"][0]]) == 8
+
+
+@pytest.mark.parametrize("name,B,seed", [("ssd300_voc", 4, 0), ("ssd300_voc", 3, 1),
+                                         ("fssd300_coco", 2, 2), ("refinedet320_voc", 3, 3)])
+def test_multibox_loss_bit_exact(ref, name, B, seed):
+    pri, cfg, c = _priors(name)
+    C = cfg.MODEL.NUM_CLASSES
+    P = pri.size(0)
+    tg = synth.gen_targets(B, C, c["gt_max"], seed)
+    loc = synth.gen_loc(B, P, seed)
+    conf = synth.gen_train_logits(B, P, C, seed)
+    rl, rc = ref.multibox_loss(C, (loc, conf, pri), tg)
+    # stable=False reproduces the literal reference sort; stable=True is the canonical order.
+    for stable in (False, True):
+        ol, oc = O.multibox_loss(loc, conf, pri, tg, C, stable=stable)
+        assert float(rl) == float(ol)
+        assert float(rc) == float(oc)
+
+
+@pytest.mark.parametrize("bias,seed", [(10.0, 0), (10.0, 1), (6.0, 2)])
+def test_detect_bit_exact(ref, bias, seed):
+    pri, cfg, c = _priors("ssd300_voc")
+    B, P, C = 2, pri.size(0), 21
+    loc = synth.gen_loc(B, P, seed)
+    sc = synth.gen_detect_scores(B, P, C, seed, bkg_bias=bias)
+    r = ref.detect(C, loc, sc, pri)
+    for stable in (False, True):
+        o = O.detect(loc, sc, pri, C, stable=stable)
+        assert torch.equal(r, o)
+    # conf flattened to [B*P, C] (rfb_net.py:222-226) is accepted too
+    assert torch.equal(r, O.detect(loc, sc.view(-1, C), pri, C))
+
+
+def test_nms_bit_exact(ref):
+    g = torch.Generator().manual_seed(7)
+    for n, k in [(1, 200), (5, 200), (50, 10), (300, 200), (700, 200)]:
+        xy = torch.rand(n, 2, generator=g) * 0.6
+        wh = torch.rand(n, 2, generator=g) * 0.3 + 0.02
+        boxes = torch.cat([xy, xy + wh], 1)
+        scores = torch.rand(n, generator=g)
+        rk, rc = ref.nms(boxes, scores, 0.45, k)
+        ok, oc = O.greedy_nms(boxes, scores, 0.45, k)
+        assert rc == oc and torch.equal(rk, ok)
+    rk, rc = ref.nms(torch.zeros(0, 4), torch.zeros(0), 0.45, 200)
+    ok, oc = O.greedy_nms(torch.zeros(0, 4), torch.zeros(0), 0.45, 200)
+    assert rc == oc == 0
