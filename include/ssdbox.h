@@ -1,0 +1,234 @@
+/*
+ * ssdbox.h -- C ABI of libssdbox.so: the SSD-series box hot path on B200 (sm_100a).
+ *
+ * The reference (arleyzhang/object-detection-pytorch) is pure Python and has no FFI of its
+ * own; each entry point below names the reference function (file:line under the reference
+ * root) whose arithmetic it replaces.  INTEGRATION.md shows the ctypes binding a maintainer
+ * adds to lib/layers/ to route the reference's PriorBoxSSD / MultiBoxLoss / DetectOut
+ * through these calls.
+ *
+ * Conventions
+ *   - every pointer is a BORROWED DEVICE pointer (row-major, contiguous, fp32 unless typed
+ *     otherwise) that the caller keeps alive until the stream work has completed; the only
+ *     host pointers are the small *_cfg structs and ssdbox_last_error's buffer;
+ *   - all work is enqueued on `stream` (a cudaStream_t); no call synchronises, allocates
+ *     device memory or touches the default stream, so every call is CUDA-graph capturable;
+ *   - scratch memory is caller-provided: ask ssdbox_workspace_bytes(), pass `ws`/`ws_bytes`
+ *     (256-byte aligned).  The library keeps no mutable global state besides a cache of
+ *     per-device attributes; calls are re-entrant and thread-safe;
+ *   - every function returns SSDBOX_OK (0) or a negative SSDBOX_E* code, never throws across
+ *     the ABI; ssdbox_last_error() returns the calling thread's last message;
+ *   - there is NO CPU fallback: without a CUDA device the compute calls return SSDBOX_ECUDA.
+ *
+ * Ground truth layout (lib/datasets/det_dataset.py:63-85 collate -> train.py:128-130):
+ *   gt          [gt_offsets[B], 5]  rows = (x1, y1, x2, y2, label0based) normalised xyxy
+ *   gt_offsets  int32 [B+1]         image b owns rows gt_offsets[b] .. gt_offsets[b+1]-1
+ * An image with zero rows is all background (multibox_loss_v1.py:70-71 skips such images).
+ */
+#ifndef SSDBOX_H_
+#define SSDBOX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSDBOX_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SSDBOX_API __attribute__((visibility("default")))
+#else
+#define SSDBOX_API
+#endif
+
+typedef void* ssdbox_stream_t; /* cudaStream_t */
+
+enum {
+  SSDBOX_OK = 0,
+  SSDBOX_EINVAL = -1,     /* bad argument value (null pointer, negative size, nms_thresh<=0 ...) */
+  SSDBOX_ESHAPE = -2,     /* unsupported shape (too many classes / truths / top_k ...)           */
+  SSDBOX_EALIGN = -3,     /* pointer not aligned as required (boxes: 16 B)                       */
+  SSDBOX_EWORKSPACE = -4, /* ws_bytes smaller than ssdbox_workspace_bytes()                      */
+  SSDBOX_ECUDA = -5       /* CUDA runtime / launch error, message in ssdbox_last_error()         */
+};
+
+enum {
+  SSDBOX_OP_MATCH = 1,
+  SSDBOX_OP_LOSS_FWD = 2,
+  SSDBOX_OP_DETECT = 3,
+  SSDBOX_OP_NMS = 4,
+  SSDBOX_OP_LSE = 5,
+  SSDBOX_OP_MINE = 6
+};
+
+SSDBOX_API int ssdbox_abi_version(void);
+/* copies the calling thread's last error message (NUL terminated) into buf; returns its length */
+SSDBOX_API int ssdbox_last_error(char* buf, size_t n);
+/* bytes of scratch `op` needs for these sizes (P = priors, C = classes, gmax = max truths per
+ * image, top_k as in DetectOut / nms, n = candidate count for SSDBOX_OP_NMS passed as P) */
+SSDBOX_API size_t ssdbox_workspace_bytes(int op, int B, int P, int C, int gmax, int top_k);
+
+/* ------------------------------------------------------------------------------------------
+ * Prior generation -- PriorBoxSSD.forward / _create_prior (lib/layers/functions/prior_box.py:
+ * 92-111, 122-143).  fp64 arithmetic, rounded once to fp32, optional clamp to [0,1].
+ * ---------------------------------------------------------------------------------------- */
+#define SSDBOX_MAX_LAYERS 16
+#define SSDBOX_MAX_MIN_SIZES 4
+#define SSDBOX_MAX_RATIOS 6
+
+typedef struct {
+  int32_t num_layers;
+  int32_t clip;                 /* cfg.MODEL.CLIP  */
+  int32_t flip;                 /* cfg.MODEL.FLIP  */
+  int32_t has_max;              /* len(cfg.MODEL.MAX_SIZES) != 0 */
+  double image_h, image_w;      /* cfg.MODEL.IMAGE_SIZE = (h, w) */
+  int32_t feat_h[SSDBOX_MAX_LAYERS], feat_w[SSDBOX_MAX_LAYERS]; /* layer_dims */
+  double step[SSDBOX_MAX_LAYERS];                                /* cfg.MODEL.STEPS */
+  int32_t num_min[SSDBOX_MAX_LAYERS];
+  double min_size[SSDBOX_MAX_LAYERS][SSDBOX_MAX_MIN_SIZES];      /* cfg.MODEL.MIN_SIZES */
+  double max_size[SSDBOX_MAX_LAYERS];                            /* cfg.MODEL.MAX_SIZES */
+  int32_t num_ratio[SSDBOX_MAX_LAYERS];
+  double ratio[SSDBOX_MAX_LAYERS][SSDBOX_MAX_RATIOS];            /* cfg.MODEL.ASPECT_RATIOS */
+} ssdbox_prior_cfg;
+
+/* number of priors the configuration produces (host-side arithmetic only), <0 on error */
+SSDBOX_API int64_t ssdbox_priorbox_count(const ssdbox_prior_cfg* cfg);
+/* out: [count,4] (cx,cy,w,h) */
+SSDBOX_API int ssdbox_priorbox(const ssdbox_prior_cfg* cfg, float* out, int64_t out_rows, ssdbox_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Box algebra -- lib/layers/box_utils.py
+ * ---------------------------------------------------------------------------------------- */
+/* point_form :6-15   (cx,cy,w,h) -> (x1,y1,x2,y2) */
+SSDBOX_API int ssdbox_point_form(const float* boxes, int64_t n, float* out, ssdbox_stream_t stream);
+/* intent of center_size :18-27   (x1,y1,x2,y2) -> (cx,cy,w,h) */
+SSDBOX_API int ssdbox_center_form(const float* boxes, int64_t n, float* out, ssdbox_stream_t stream);
+/* jaccard :51-70   a[G,4] xyxy, b[P,4] xyxy -> out[G,P] */
+SSDBOX_API int ssdbox_jaccard(const float* a, int32_t G, const float* b, int32_t P, float* out, ssdbox_stream_t stream);
+/* encode :201-222  matched[n,4] xyxy, priors[n,4] centre form -> out[n,4] */
+SSDBOX_API int ssdbox_encode(const float* matched, const float* priors, int64_t n, float var0, float var1,
+                  float* out, ssdbox_stream_t stream);
+/* decode :226-244  loc[n,4]; priors[prior_rows,4] reused cyclically (row i uses prior i % prior_rows)
+ * so a whole [B,P,4] batch decodes in one call; out[n,4] xyxy.  out_center (nullable) receives
+ * the centre form of the decoded box (RefineDet refined anchors). */
+SSDBOX_API int ssdbox_decode(const float* loc, const float* priors, int64_t n, int64_t prior_rows, float var0,
+                  float var1, float* out, float* out_center, ssdbox_stream_t stream);
+/* log_sum_exp :265-273  x[rows,C] -> out[rows]; uses ONE global max over all of x like the
+ * reference (two passes).  ws: SSDBOX_OP_LSE. */
+SSDBOX_API int ssdbox_log_sum_exp(const float* x, int64_t rows, int32_t C, float* out, void* ws, size_t ws_bytes,
+                       ssdbox_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * match -- box_utils.py:92-133 for a whole batch (the python loop of multibox_loss.py:69-74).
+ *   priors            [P,4] centre form (prior_batch_stride = 0) or per-image [B,P,4]
+ *                     (prior_batch_stride = 4*P floats; RefineDet refined anchors)
+ *   anchors_xyxy      nullable; when given ([B,P,4] or [P,4], same stride rule) it replaces
+ *                     point_form(priors) in the IoU (RefineDet: IoU against the decoded ARM boxes)
+ *   loc_t  [B,P,4]    encoded regression targets           (nullable)
+ *   conf_t [B,P]      int64 class targets, 0 = background  (nullable)
+ *   match_idx [B,P]   int32 index of the matched truth within its image (nullable)
+ *   overlap [B,P]     best-truth IoU, 2.0 for forced best priors (nullable)
+ * IoU, argmax (first index on ties), the sequential "last truth wins" forced assignment and the
+ * threshold compare are bit-exact with the reference; encode uses logf (1e-5 relative).
+ * ws: SSDBOX_OP_MATCH.
+ * ---------------------------------------------------------------------------------------- */
+SSDBOX_API int ssdbox_match_encode(const float* gt, const int32_t* gt_offsets, int32_t gmax, const float* priors,
+                        int64_t prior_batch_stride, const float* anchors_xyxy, int32_t B, int32_t P,
+                        float threshold, float var0, float var1, int32_t binarize_labels,
+                        float* loc_t, int64_t* conf_t, int32_t* match_idx, float* overlap, void* ws,
+                        size_t ws_bytes, ssdbox_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Hard-negative selection in isolation -- multibox_loss.py:97-103.
+ *   keys [B,P]  mining loss (fp32), pos [B,P] uint8 (conf_t > 0), pool [B,P] uint8 nullable
+ *   neg  [B,P]  uint8 out: rank(key zeroed at positives, descending, ties by ascending prior
+ *               index) < min(negpos_ratio * num_pos, P-1)
+ * Bit-exact with the reference's double sort on identical keys (canonical tie order).
+ * ws: SSDBOX_OP_MINE.
+ * ---------------------------------------------------------------------------------------- */
+SSDBOX_API int ssdbox_hard_negative_mine(const float* keys, const uint8_t* pos, const uint8_t* pool, int32_t B,
+                              int32_t P, int32_t negpos_ratio, uint8_t* neg, void* ws, size_t ws_bytes,
+                              ssdbox_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * MultiBoxLoss -- lib/layers/modules/multibox_loss.py:48-117 (+ autograd, train.py:143-144).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, P, C;
+  int32_t gmax;               /* max truths per image (>= every gt_offsets difference) */
+  float threshold;            /* overlap_thresh (0.5)  */
+  int32_t negpos_ratio;       /* neg_pos (3)           */
+  float var0, var1;           /* cfg.MODEL.VARIANCE    */
+  int32_t binarize_labels;    /* RefineDet ARM: every truth label becomes class 1 */
+  int32_t finalize;           /* 1: losses = sums / N on device; 0: leave sums for an all-reduce */
+  int64_t prior_batch_stride; /* 0 or 4*P (see ssdbox_match_encode) */
+} ssdbox_loss_cfg;
+
+/* forward.
+ *   loc [B,P,4], conf [B,P,C] raw logits, priors, anchors_xyxy (nullable), gt/gt_offsets
+ *   pool  [B,P] uint8 nullable  RefineDet: anchors with pool==0 are neither positive nor mined
+ *   sums  double[3]  out: { sum smooth-L1 over positives, sum CE over pos U neg, N = #positives }
+ *   losses float[2]  out: { loss_l, loss_c } = sums[0..1] / N when cfg->finalize (0 if N == 0)
+ *   sel   [B,P] int16 out (kept for backward): -1 = row not in pos U neg, else its class target
+ *   tidx  [B,P] int16 out (kept for backward): matched truth index within the image
+ *   dbg_conf_t int64 [B,P], dbg_loc_t [B,P,4], dbg_neg uint8 [B,P], dbg_keys [B,P]: nullable
+ *         materialisations of the reference's intermediates (tests / drop-in users of loc_t).
+ * ws: SSDBOX_OP_LOSS_FWD. */
+SSDBOX_API int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float* loc, const float* conf,
+                             const float* priors, const float* anchors_xyxy, const uint8_t* pool,
+                             const float* gt, const int32_t* gt_offsets, double* sums, float* losses,
+                             int16_t* sel, int16_t* tidx, int64_t* dbg_conf_t, float* dbg_loc_t,
+                             uint8_t* dbg_neg, float* dbg_keys, void* ws, size_t ws_bytes,
+                             ssdbox_stream_t stream);
+/* losses = sums[0..1] / sums[2]  (after the caller all-reduced `sums` across ranks) */
+SSDBOX_API int ssdbox_multibox_loss_finalize(const double* sums, float* losses, ssdbox_stream_t stream);
+/* backward: grad_loc [B,P,4], grad_conf [B,P,C] (both fully written);
+ * grad_out float[2] device = upstream gradients of (loss_l, loss_c); sums[2] = N (global). */
+SSDBOX_API int ssdbox_multibox_loss_bwd(const ssdbox_loss_cfg* cfg, const float* loc, const float* conf,
+                             const float* priors, const float* gt, const int32_t* gt_offsets,
+                             const int16_t* sel, const int16_t* tidx, const double* sums,
+                             const float* grad_out, float* grad_loc, float* grad_conf,
+                             ssdbox_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * nms -- box_utils.py:279-343.  boxes[n,4] xyxy, scores[n]; keep int64[n] zero padded (indices
+ * into boxes, visiting order), count int32[1] (device).  Canonical tie order: equal scores are
+ * visited higher index first.  Requires 1 <= top_k <= 1024.  ws: SSDBOX_OP_NMS (P = n).
+ * ---------------------------------------------------------------------------------------- */
+SSDBOX_API int ssdbox_nms(const float* boxes, const float* scores, int32_t n, float overlap, int32_t top_k,
+               int64_t* keep, int32_t* count, void* ws, size_t ws_bytes, ssdbox_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * DetectOut.forward -- lib/layers/functions/detection.py:25-64.
+ *   loc [B,P,4]; scores [B,P,C] (== [B*P,C], rfb_net.py:222-226) softmax probabilities
+ *   priors [P,4] (or per image, prior_batch_stride = 4*P)
+ *   score_keep [B,P] uint8 nullable: RefineDet, scores of anchors with 0 are treated as 0
+ *   out [B,C,top_k,5] fully written: rows (score,x1,y1,x2,y2) in NMS order, zero padded,
+ *       class-0 plane zero;  counts int32 [B,C] nullable
+ * Errors like detection.py:19-20: nms_thresh <= 0 -> SSDBOX_EINVAL.  ws: SSDBOX_OP_DETECT.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, P, C;
+  int32_t top_k;              /* 1..1024 */
+  float conf_thresh, nms_thresh;
+  float var0, var1;
+  int64_t prior_batch_stride;
+} ssdbox_detect_cfg;
+
+SSDBOX_API int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, const float* scores,
+                  const float* priors, const uint8_t* score_keep, float* out, int32_t* counts, void* ws,
+                  size_t ws_bytes, ssdbox_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * RefineDet glue (not in the reference snapshot; arXiv 1711.06897).
+ *   arm_conf [n,2] logits -> keep[n] uint8 = softmax(arm_conf)[:,1] > theta
+ * (refined anchors come from ssdbox_decode with out_center).
+ * ---------------------------------------------------------------------------------------- */
+SSDBOX_API int ssdbox_arm_filter(const float* arm_conf, int64_t n, float theta, uint8_t* keep, ssdbox_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSDBOX_H_ */

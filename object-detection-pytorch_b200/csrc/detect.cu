@@ -1,0 +1,421 @@
+// DetectOut.forward (lib/layers/functions/detection.py:25-64) and nms (box_utils.py:279-343).
+//
+// Detect = 4 launches on the caller's stream:
+//   init_kernel            candidate counters := 0
+//   detect_stream_kernel   THE HBM-bound kernel: scores [B*P, C] streamed once through the TMA
+//                          bulk-copy ring; one thread per prior row tests every class against
+//                          conf_thresh, warps aggregate the hits of a class with one ballot and
+//                          one atomicAdd and append (ordered score << 32 | prior) to the
+//                          (image, class) candidate list.  The transposed [C,P] view of
+//                          detection.py:38-39 is never materialised; decode runs only on candidates.
+//   detect_segment_kernel  one CTA per (image, class): bitonic sort of the candidates by
+//                          (score desc, prior desc) = the reference's visiting order, top_k cut,
+//                          decode of the survivors, 200x200 suppression bit-matrix built with warp
+//                          ballots in shared memory, one-warp greedy sweep, zero-padded output rows.
+//   detect_overflow_kernel only for (image, class) lists that exceeded the candidate capacity
+//                          (dense scores): exact radix-select of the top_k scores of the class
+//                          column straight from `scores`, then the same sort + NMS tail.
+#include "ops.h"
+#include "ring.cuh"
+#include "select.cuh"
+#include "ssdbox_dev.cuh"
+
+namespace ssdbox {
+
+// ------------------------------------------------------------------------------------------------
+// candidate pass
+// ------------------------------------------------------------------------------------------------
+struct DetStreamArgs {
+  RingPlan ring;            // scores [B*P, C]
+  const uint8_t* keep;      // [B*P] nullable
+  uint32_t* cnt;            // [B*C]
+  unsigned long long* cand; // [B*C, cap]
+  int P;
+  int cap;
+  float thr;
+};
+
+template <int CT>
+__global__ void __launch_bounds__(kRingThreads, 1) detect_stream_kernel(DetStreamArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_ring[];
+  RingCtx rc = ring_setup(a.ring, smem_ring);
+  const int C = CT > 0 ? CT : a.ring.C;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == kRingConsumerWarps) {
+    ring_produce(a.ring, rc);
+    return;
+  }
+  const int wg = warp >> 2;
+  const int r = tid & 127;
+  const int R = a.ring.R, NS = a.ring.NS;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  for (int it = wg; it < rc.n_local; it += 2) {
+    int s = it % NS, n = it / NS;
+    long long row = (rc.t0 + it) * R + r;
+    bool valid = (r < R) && (row < a.ring.rows);
+    uint32_t b = 0, p = 0;
+    bool kept = true;
+    if (valid) {
+      b = (uint32_t)row / (uint32_t)a.P;
+      p = (uint32_t)row - b * (uint32_t)a.P;
+      if (a.keep) kept = a.keep[row] != 0;
+    }
+    uint32_t vmask = __ballot_sync(SSDBOX_FULL_MASK, valid);
+    // the warp's rows are consecutive: uniform image iff first and last valid row agree
+    uint32_t b_first = __shfl_sync(SSDBOX_FULL_MASK, b, 0);
+    uint32_t b_last = __shfl_sync(SSDBOX_FULL_MASK, b, vmask ? 31 - __clz(vmask) : 0);
+    const bool uniform = b_first == b_last;
+    mbar_wait(&rc.full[s], (uint32_t)(n & 1));
+    if (vmask) {
+      const float* rp = rc.stages + (size_t)s * rc.stage_floats + (size_t)r * C;
+#pragma unroll 4
+      for (int c = 1; c < C; ++c) {
+        float v = valid ? rp[c] : 0.0f;
+        if (!kept) v = 0.0f;
+        bool hit = valid && v > a.thr;                       // detection.py:48 strict >
+        uint32_t hm = __ballot_sync(SSDBOX_FULL_MASK, hit);
+        if (hm == 0u) continue;
+        uint32_t slot = 0;
+        if (uniform) {
+          int leader = __ffs(hm) - 1;
+          uint32_t base = 0;
+          if (lane == leader) base = atomicAdd(&a.cnt[(size_t)b_first * C + c], (uint32_t)__popc(hm));
+          base = __shfl_sync(SSDBOX_FULL_MASK, base, leader);
+          slot = base + (uint32_t)__popc(hm & lt_mask);
+        } else if (hit) {
+          slot = atomicAdd(&a.cnt[(size_t)b * C + c], 1u);
+        }
+        if (hit && slot < (uint32_t)a.cap)
+          a.cand[((size_t)b * C + c) * a.cap + slot] = ((unsigned long long)f2ord(v) << 32) | p;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&rc.empty[s]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// NMS on candidates already sorted in visiting order (keys descending)
+// ------------------------------------------------------------------------------------------------
+struct NmsSmem {
+  float4* box;      // [top_k]
+  float* area;      // [top_k]
+  uint32_t* mask;   // [top_k * W]
+  uint16_t* keep;   // [top_k]
+  int* cnt;         // [1]
+};
+
+static inline size_t nms_smem_bytes(int top_k) {
+  int W = (top_k + 31) / 32;
+  return (size_t)top_k * 16 + (size_t)top_k * 4 + (size_t)top_k * W * 4 + align_up((size_t)top_k * 2, 16) + 16;
+}
+
+__device__ __forceinline__ NmsSmem carve_nms(unsigned char* base, int top_k) {
+  NmsSmem s;
+  int W = (top_k + 31) / 32;
+  s.box = reinterpret_cast<float4*>(base);
+  s.area = reinterpret_cast<float*>(base + (size_t)top_k * 16);
+  s.mask = reinterpret_cast<uint32_t*>(base + (size_t)top_k * 20);
+  s.keep = reinterpret_cast<uint16_t*>(base + (size_t)top_k * 20 + (size_t)top_k * W * 4);
+  s.cnt = reinterpret_cast<int*>(base + (size_t)top_k * 20 + (size_t)top_k * W * 4 + (((size_t)top_k * 2 + 15) / 16) * 16);
+  return s;
+}
+
+// s.box / s.area hold the m sorted boxes.  Greedy sweep of box_utils.py:311-342:
+// box j (later in the order) is dropped by a kept box i iff !(IoU(j | i) <= thr).
+__device__ __forceinline__ int nms_sweep(const NmsSmem& s, int m, float thr) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const int W = (m + 31) / 32;
+  for (int item = warp; item < m * W; item += nwarp) {
+    int i = item / W, wd = item - i * W;
+    int j = wd * 32 + lane;
+    bool bit = false;
+    if (wd * 32 + 31 > i) {
+      if (j > i && j < m) {
+        float4 bi = s.box[i], bj = s.box[j];
+        Box I, J;
+        I.x1 = bi.x; I.y1 = bi.y; I.x2 = bi.z; I.y2 = bi.w;
+        J.x1 = bj.x; J.y1 = bj.y; J.x2 = bj.z; J.y2 = bj.w;
+        bit = !(iou_nms(I, s.area[i], J, s.area[j]) <= thr);     // :342 keeps IoU <= overlap
+      }
+    }
+    uint32_t word = __ballot_sync(SSDBOX_FULL_MASK, bit);
+    if (lane == 0) s.mask[item] = word;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t removed = 0u;   // lane l owns bits 32l .. 32l+31
+    int cnt = 0;
+    for (int i = 0; i < m; ++i) {
+      uint32_t w = __shfl_sync(SSDBOX_FULL_MASK, removed, i >> 5);
+      if (!((w >> (i & 31)) & 1u)) {
+        if (lane == 0) s.keep[cnt] = (uint16_t)i;
+        ++cnt;
+        if (lane < W) removed |= s.mask[i * W + lane];
+      }
+    }
+    if (lane == 0) *s.cnt = cnt;
+  }
+  __syncthreads();
+  return *s.cnt;
+}
+
+struct DetSegArgs {
+  int B, P, C, top_k, cap;
+  float nms_thr, conf_thr, var0, var1;
+  long long prior_stride;
+  const float* loc;
+  const float* scores;
+  const float* priors;
+  const uint8_t* keep;
+  const uint32_t* cnt;
+  const unsigned long long* cand;
+  uint32_t* scratch;   // [kOverflowSlots, P]
+  float* out;
+  int32_t* counts;
+};
+
+// keys[0..n) hold the candidates (unsorted; n <= npad, npad power of two, padding = 0):
+// sort -> top_k -> decode -> NMS -> write the [top_k,5] rows of this (image, class).
+__device__ void segment_finish(const DetSegArgs& a, int b, int seg, unsigned long long* keys, int n, int npad,
+                               const NmsSmem& ns) {
+  const int tid = threadIdx.x;
+  bitonic_sort_desc(keys, npad);
+  const int m = n < a.top_k ? n : a.top_k;
+  const float* pri = a.priors + (size_t)b * (size_t)a.prior_stride;
+  for (int i = tid; i < m; i += blockDim.x) {
+    uint32_t p = (uint32_t)(keys[i] & 0xffffffffull);
+    Box bx = decode_box(*reinterpret_cast<const float4*>(a.loc + ((size_t)b * a.P + p) * 4),
+                        *reinterpret_cast<const float4*>(pri + (size_t)p * 4), a.var0, a.var1);   // detection.py:43
+    ns.box[i] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
+    ns.area[i] = box_area(bx);                                                                    // box_utils.py:298
+  }
+  __syncthreads();
+  const int count = nms_sweep(ns, m, a.nms_thr);
+  float* o = a.out + (size_t)seg * a.top_k * 5;
+  for (int e = tid; e < a.top_k * 5; e += blockDim.x) {
+    int k = e / 5, f = e - k * 5;
+    float v = 0.0f;
+    if (k < count) {
+      int i = ns.keep[k];
+      if (f == 0) v = ord2f((uint32_t)(keys[i] >> 32));
+      else {
+        float4 bx = ns.box[i];
+        v = f == 1 ? bx.x : (f == 2 ? bx.y : (f == 3 ? bx.z : bx.w));
+      }
+    }
+    o[e] = v;                                                    // detection.py:57-59
+  }
+  if (tid == 0 && a.counts) a.counts[seg] = count;
+}
+
+constexpr int kSegThreads = 256;
+
+__global__ void __launch_bounds__(kSegThreads) detect_segment_kernel(DetSegArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_seg[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_seg);
+  NmsSmem ns = carve_nms(smem_seg + (size_t)a.cap * 8, a.top_k);
+  const int seg = blockIdx.x, tid = threadIdx.x;
+  const int b = seg / a.C, c = seg - b * a.C;
+  const uint32_t total = c == 0 ? 0u : a.cnt[seg];
+  if (total > (uint32_t)a.cap) return;   // detect_overflow_kernel owns this segment
+  if (total == 0u) {                     // background plane / no candidate: zeros (detection.py:37,50-51)
+    float* o = a.out + (size_t)seg * a.top_k * 5;
+    for (int e = tid; e < a.top_k * 5; e += kSegThreads) o[e] = 0.0f;
+    if (tid == 0 && a.counts) a.counts[seg] = 0;
+    return;
+  }
+  const int n = (int)total;
+  int npad = 32;
+  while (npad < n) npad <<= 1;
+  const unsigned long long* src = a.cand + (size_t)seg * a.cap;
+  for (int i = tid; i < npad; i += kSegThreads) keys[i] = i < n ? src[i] : 0ull;
+  __syncthreads();
+  segment_finish(a, b, seg, keys, n, npad, ns);
+}
+
+constexpr int kOvfThreads = 1024;
+
+__global__ void __launch_bounds__(kOvfThreads, 1) detect_overflow_kernel(DetSegArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_ovf[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_ovf);          // [1024]
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_ovf + 8192);                      // 2048
+  int* s_iscr = reinterpret_cast<int*>(smem_ovf + 16384);                               // 64
+  int* s_res = s_iscr + 64;                                                             // 8: res[0..1], [4] = counter
+  NmsSmem ns = carve_nms(smem_ovf + 16384 + 288, a.top_k);
+  uint32_t* uk = a.scratch + (size_t)blockIdx.x * a.P;
+  const int tid = threadIdx.x;
+  const int nseg = a.B * a.C;
+  for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+    const int b = seg / a.C, c = seg - b * a.C;
+    if (c == 0 || a.cnt[seg] <= (uint32_t)a.cap) continue;   // uniform across the CTA
+    // ordered scores of the class column; 0 = not a candidate
+    for (int p = tid; p < a.P; p += kOvfThreads) {
+      size_t row = (size_t)b * a.P + p;
+      float v = a.scores[row * a.C + c];
+      if (a.keep && !a.keep[row]) v = 0.0f;
+      uk[p] = v > a.conf_thr ? f2ord(v) : 0u;
+    }
+    if (tid == 0) s_res[4] = 0;
+    __syncthreads();
+    uint32_t Tu = cta_select_threshold<true>(uk, a.P, a.top_k, nullptr, s_hist, s_iscr, s_res);
+    __syncthreads();
+    for (int p = tid; p < a.P; p += kOvfThreads) {
+      uint32_t u = uk[p];
+      if (u != 0u && u >= Tu) {
+        int slot = atomicAdd(&s_res[4], 1);
+        if (slot < 1024) keys[slot] = ((unsigned long long)u << 32) | (uint32_t)p;
+      }
+    }
+    __syncthreads();
+    int n = s_res[4];
+    if (n > 1024) n = 1024;
+    int npad = 32;
+    while (npad < n) npad <<= 1;
+    for (int i = n + tid; i < npad; i += kOvfThreads) keys[i] = 0ull;
+    __syncthreads();
+    segment_finish(a, b, seg, keys, n, npad, ns);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone nms(boxes, scores, overlap, top_k), box_utils.py:279-343 -- one CTA
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kOvfThreads, 1)
+nms_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, int n, float thr, int top_k,
+           int64_t* __restrict__ keep, int32_t* __restrict__ count, uint32_t* uk) {
+  extern __shared__ __align__(16) unsigned char smem_nms[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_nms);
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_nms + 8192);
+  int* s_iscr = reinterpret_cast<int*>(smem_nms + 16384);
+  int* s_res = s_iscr + 64;
+  NmsSmem ns = carve_nms(smem_nms + 16384 + 288, top_k);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n; i += kOvfThreads) {
+    uk[i] = f2ord(scores[i]);
+    keep[i] = 0;                                           // :291 zero-initialised keep
+  }
+  if (tid == 0) s_res[4] = 0;
+  __syncthreads();
+  const int K = n < top_k ? n : top_k;                     // :301 idx[-top_k:]
+  uint32_t Tu = cta_select_threshold<true>(uk, n, K, nullptr, s_hist, s_iscr, s_res);
+  __syncthreads();
+  for (int i = tid; i < n; i += kOvfThreads) {
+    uint32_t u = uk[i];
+    if (u != 0u && u >= Tu) {
+      int slot = atomicAdd(&s_res[4], 1);
+      if (slot < 1024) keys[slot] = ((unsigned long long)u << 32) | (uint32_t)i;
+    }
+  }
+  __syncthreads();
+  int m = s_res[4];
+  if (m > 1024) m = 1024;
+  int npad = 32;
+  while (npad < m) npad <<= 1;
+  for (int i = m + tid; i < npad; i += kOvfThreads) keys[i] = 0ull;
+  __syncthreads();
+  bitonic_sort_desc(keys, npad);
+  for (int i = tid; i < m; i += kOvfThreads) {
+    uint32_t idx = (uint32_t)(keys[i] & 0xffffffffull);
+    const float* bp = boxes + (size_t)idx * 4;
+    Box bx;
+    bx.x1 = bp[0]; bx.y1 = bp[1]; bx.x2 = bp[2]; bx.y2 = bp[3];
+    ns.box[i] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
+    ns.area[i] = box_area(bx);
+  }
+  __syncthreads();
+  const int cnt = nms_sweep(ns, m, thr);
+  for (int k = tid; k < cnt; k += kOvfThreads) keep[k] = (int64_t)(keys[ns.keep[k]] & 0xffffffffull);
+  if (tid == 0) *count = cnt;
+}
+
+}  // namespace ssdbox
+
+using namespace ssdbox;
+
+extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, const float* scores, const float* priors,
+                             const uint8_t* score_keep, float* out, int32_t* counts, void* ws, size_t ws_bytes,
+                             ssdbox_stream_t stream) {
+  SSDBOX_REQUIRE(cfg, SSDBOX_EINVAL, "detect: null cfg");
+  SSDBOX_REQUIRE(cfg->nms_thresh > 0.0f, SSDBOX_EINVAL, "nms_threshold must be non negative.");  // detection.py:19-20
+  const int B = cfg->B, P = cfg->P, C = cfg->C, top_k = cfg->top_k;
+  SSDBOX_REQUIRE(B >= 0 && P >= 0 && C >= 1, SSDBOX_EINVAL, "detect: negative size");
+  SSDBOX_REQUIRE(top_k >= 1 && top_k <= kTopKLimit, SSDBOX_ESHAPE, "detect: top_k %d outside 1..%d", top_k, kTopKLimit);
+  SSDBOX_REQUIRE((long long)B * P < (1ll << 31) && (long long)B * C < (1ll << 31), SSDBOX_ESHAPE, "detect: B*P and B*C must be < 2^31");
+  SSDBOX_REQUIRE(cfg->prior_batch_stride == 0 || cfg->prior_batch_stride == (int64_t)P * 4, SSDBOX_EINVAL,
+                 "detect: prior_batch_stride must be 0 or 4*P");
+  if (B == 0) return SSDBOX_OK;
+  SSDBOX_REQUIRE(out && ws, SSDBOX_EINVAL, "detect: null pointer");
+  SSDBOX_REQUIRE(P == 0 || (loc && scores && priors), SSDBOX_EINVAL, "detect: null pointer");
+  SSDBOX_REQUIRE(aligned16(loc) && aligned16(priors), SSDBOX_EALIGN, "detect: box pointers must be 16-byte aligned");
+  SSDBOX_REQUIRE(ws_bytes >= detect_ws_bytes(B, P, C, top_k), SSDBOX_EWORKSPACE, "detect: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DevInfo dev;
+  int rc = get_dev_info(&dev);
+  if (rc) return rc;
+  const int cap = detect_cand_cap(top_k);
+  Carver cv(ws);
+  uint32_t* cnt = cv.take<uint32_t>((size_t)B * C);
+  unsigned long long* cand = cv.take<unsigned long long>((size_t)B * C * cap);
+  uint32_t* scratch = cv.take<uint32_t>((size_t)kOverflowSlots * P);
+
+  rc = launch_init(nullptr, 0, cnt, (size_t)B * C, nullptr, 0, nullptr, 0, st);
+  if (rc) return rc;
+
+  if (P > 0) {
+    DetStreamArgs sa{};
+    rc = plan_ring(&sa.ring, scores, (long long)B * P, C, dev.sm_count, dev.max_smem_optin);
+    if (rc) return rc;
+    sa.keep = score_keep;
+    sa.cnt = cnt;
+    sa.cand = cand;
+    sa.P = P;
+    sa.cap = cap;
+    sa.thr = cfg->conf_thresh;
+    void (*kern)(DetStreamArgs) = detect_stream_kernel<0>;
+    if (C == 81) kern = detect_stream_kernel<81>;
+    else if (C == 21) kern = detect_stream_kernel<21>;
+    SSDBOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa.ring.smem_bytes));
+    kern<<<sa.ring.grid, kRingThreads, sa.ring.smem_bytes, st>>>(sa);
+    SSDBOX_LAUNCH_OK("detect_stream_kernel");
+  }
+
+  DetSegArgs g{};
+  g.B = B; g.P = P; g.C = C; g.top_k = top_k; g.cap = cap;
+  g.nms_thr = cfg->nms_thresh; g.conf_thr = cfg->conf_thresh; g.var0 = cfg->var0; g.var1 = cfg->var1;
+  g.prior_stride = (long long)cfg->prior_batch_stride;
+  g.loc = loc; g.scores = scores; g.priors = priors; g.keep = score_keep;
+  g.cnt = cnt; g.cand = cand; g.scratch = scratch; g.out = out; g.counts = counts;
+  size_t seg_smem = (size_t)cap * 8 + nms_smem_bytes(top_k);
+  SSDBOX_CUDA(cudaFuncSetAttribute(detect_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem));
+  detect_segment_kernel<<<B * C, kSegThreads, seg_smem, st>>>(g);
+  SSDBOX_LAUNCH_OK("detect_segment_kernel");
+
+  size_t ovf_smem = 16384 + 288 + nms_smem_bytes(top_k);
+  SSDBOX_CUDA(cudaFuncSetAttribute(detect_overflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ovf_smem));
+  int ovf_grid = dev.sm_count < kOverflowSlots ? dev.sm_count : kOverflowSlots;
+  if (ovf_grid > B * C) ovf_grid = B * C;
+  detect_overflow_kernel<<<ovf_grid, kOvfThreads, ovf_smem, st>>>(g);
+  SSDBOX_LAUNCH_OK("detect_overflow_kernel");
+  return SSDBOX_OK;
+}
+
+extern "C" int ssdbox_nms(const float* boxes, const float* scores, int32_t n, float overlap, int32_t top_k,
+                          int64_t* keep, int32_t* count, void* ws, size_t ws_bytes, ssdbox_stream_t stream) {
+  SSDBOX_REQUIRE(n >= 0, SSDBOX_EINVAL, "nms: negative n");
+  SSDBOX_REQUIRE(top_k >= 1 && top_k <= kTopKLimit, SSDBOX_ESHAPE, "nms: top_k %d outside 1..%d", top_k, kTopKLimit);
+  SSDBOX_REQUIRE(count, SSDBOX_EINVAL, "nms: null count");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n == 0) {                                            // box_utils.py:292-293
+    SSDBOX_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), st));
+    return SSDBOX_OK;
+  }
+  SSDBOX_REQUIRE(boxes && scores && keep && ws, SSDBOX_EINVAL, "nms: null pointer");
+  SSDBOX_REQUIRE(ws_bytes >= nms_ws_bytes(n, top_k), SSDBOX_EWORKSPACE, "nms: workspace too small");
+  size_t smem = 16384 + 288 + nms_smem_bytes(top_k);
+  SSDBOX_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nms_kernel<<<1, kOvfThreads, smem, st>>>(boxes, scores, n, overlap, top_k, keep, count, static_cast<uint32_t*>(ws));
+  SSDBOX_LAUNCH_OK("nms_kernel");
+  return SSDBOX_OK;
+}

@@ -1,0 +1,541 @@
+// MultiBoxLoss forward / backward: lib/layers/modules/multibox_loss.py:48-117 (+ autograd).
+//
+// Forward = 4 launches on the caller's stream (CUDA-graph capturable, no host sync):
+//   init_kernel        per-truth best-prior keys := (0, prior 0); tickets / histograms := 0
+//   match_kernel       (match.cu) class target + matched truth per prior, IoU matrix never stored
+//   loss_stream_kernel THE HBM-bound kernel: conf [B*P, C] streamed once through a ring of
+//                      TMA bulk-copy (cp.async.bulk + mbarrier) stages; one thread per prior row
+//                      computes log-sum-exp, key = lse - x[target] and bumps the image's level-1
+//                      mining histogram (top 11 bits of the order-preserving key)
+//   mine_reduce_kernel one CTA per image: radix-select of the num_neg-th largest mining key
+//                      (level 1 comes from the streamed histogram, levels 2/3 touch only the
+//                      winning bin), canonical tie order, fixed-order fp64 reduction of
+//                      smooth-L1 / CE, last CTA folds the per-image partials (deterministic).
+// The final CE over pos U neg needs no second pass over conf: CE(row) = lse - x[target] is the
+// very key the stream kernel wrote.  Backward zero-fills grad_conf and touches conf only on the
+// selected rows.
+#include "ops.h"
+#include "ring.cuh"
+#include "select.cuh"
+#include "ssdbox_dev.cuh"
+
+namespace ssdbox {
+
+// ------------------------------------------------------------------------------------------------
+// streaming pass
+// ------------------------------------------------------------------------------------------------
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct StreamArgs {
+  RingPlan ring;       // conf [B*P, C]
+  const int16_t* lab;
+  const uint8_t* pool;
+  float* keys;
+  uint32_t* hist;
+  int P;
+};
+
+template <int CT>
+__device__ __forceinline__ float row_key(const float* __restrict__ rp, int C, int lb) {
+  float m, s;
+  if (CT > 0) {
+    float v[CT > 0 ? CT : 1];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) v[c] = rp[c];
+    float m4[4] = {v[0], v[0], v[0], v[0]};
+#pragma unroll
+    for (int c = 1; c < CT; ++c) m4[c & 3] = fmaxf(m4[c & 3], v[c]);
+    m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+    float nml = -m * kLog2e;
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < CT; ++c) s4[c & 3] += ex2_approx(fmaf(v[c], kLog2e, nml));
+    s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  } else {
+    m = rp[0];
+    for (int c = 1; c < C; ++c) m = fmaxf(m, rp[c]);
+    float nml = -m * kLog2e;
+    s = 0.f;
+    for (int c = 0; c < C; ++c) s += ex2_approx(fmaf(rp[c], kLog2e, nml));
+  }
+  float lse = logf(s) + m;        // box_utils.py:273 log(sum(exp(x - max))) + max (row max here)
+  return lse - rp[lb];            // multibox_loss.py:94  lse - gather(conf_t)
+}
+
+template <int CT>
+__global__ void __launch_bounds__(kRingThreads, 1) loss_stream_kernel(StreamArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_ring[];
+  RingCtx rc = ring_setup(a.ring, smem_ring);
+  const int C = CT > 0 ? CT : a.ring.C;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == kRingConsumerWarps) {
+    ring_produce(a.ring, rc);
+    return;
+  }
+  const int wg = warp >> 2;
+  const int r = tid & 127;
+  const int R = a.ring.R, NS = a.ring.NS;
+  for (int it = wg; it < rc.n_local; it += 2) {
+    int s = it % NS, n = it / NS;
+    long long row = (rc.t0 + it) * R + r;
+    bool valid = (r < R) && (row < a.ring.rows);
+    int lb = 0;
+    int inpool = 1;
+    if (valid) {
+      lb = a.lab[row];
+      if (a.pool) inpool = a.pool[row];
+    }
+    mbar_wait(&rc.full[s], (uint32_t)(n & 1));
+    float key = 0.f;
+    if (valid) key = row_key<CT>(rc.stages + (size_t)s * rc.stage_floats + (size_t)r * C, C, lb);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&rc.empty[s]);
+    if (valid) {
+      a.keys[row] = key;
+      if (inpool) {
+        float mk = lb > 0 ? 0.0f : key;                    // multibox_loss.py:97 positives -> 0
+        uint32_t b = (uint32_t)row / (uint32_t)a.P;
+        atomicAdd(&a.hist[(size_t)b * kHistBins + (f2ord(mk) >> 21)], 1u);
+      }
+    }
+  }
+}
+
+static int launch_stream(StreamArgs a, const float* conf, long long rows, int C, int sm_count, int max_smem,
+                         cudaStream_t st) {
+  if (rows == 0) return SSDBOX_OK;
+  int rc = plan_ring(&a.ring, conf, rows, C, sm_count, max_smem);
+  if (rc) return rc;
+  void (*kern)(StreamArgs) = loss_stream_kernel<0>;
+  if (C == 81) kern = loss_stream_kernel<81>;
+  else if (C == 21) kern = loss_stream_kernel<21>;
+  else if (C == 2) kern = loss_stream_kernel<2>;
+  SSDBOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.ring.smem_bytes));
+  kern<<<a.ring.grid, kRingThreads, a.ring.smem_bytes, st>>>(a);
+  SSDBOX_LAUNCH_OK("loss_stream_kernel");
+  return SSDBOX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-image selection of the K largest ordered keys (descending, ties by ascending index)
+// ------------------------------------------------------------------------------------------------
+constexpr int kMineThreads = 1024;
+
+struct MineArgs {
+  int B, P, C;
+  int negpos_ratio;
+  float var0, var1;
+  int finalize;
+  long long prior_stride;
+  const float* loc;
+  const float* priors;
+  const float* gt;
+  const int32_t* gt_offsets;
+  const uint8_t* pool;
+  const float* keys;
+  const int16_t* lab;
+  const int16_t* tidx;
+  const uint32_t* hist;
+  uint32_t* ukey_global;   // used when the ordered keys do not fit in shared memory
+  int uk_in_smem;
+  double* partial;
+  uint32_t* ticket;
+  double* sums;
+  float* losses;
+  int16_t* sel;
+  uint8_t* dbg_neg;
+  float* dbg_keys;
+};
+
+__global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_mine[];
+  unsigned char* smem_raw = smem_mine;
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw);             // 2048
+  double* s_dscr = reinterpret_cast<double*>(smem_raw + 8192);          // 40
+  int* s_iscr = reinterpret_cast<int*>(smem_raw + 8192 + 320);          // 64
+  int* s_res = s_iscr + 64;                                             // 8
+  uint32_t* uk = a.uk_in_smem ? reinterpret_cast<uint32_t*>(smem_raw + 8192 + 320 + 288)
+                              : a.ukey_global + (size_t)blockIdx.x * a.P;
+  __shared__ int s_last;
+
+  const int b = blockIdx.x, tid = threadIdx.x, P = a.P;
+  const size_t off = (size_t)b * P;
+  const int g0 = a.gt_offsets[b];
+  const float* pri = a.priors + (size_t)b * (size_t)a.prior_stride;
+  const uint32_t ord_zero = f2ord(0.0f);
+
+  // pass A: positives (count, CE, smooth-L1) and the ordered mining keys
+  int npos = 0;
+  double ce = 0.0, l1 = 0.0;
+  for (int p = tid; p < P; p += kMineThreads) {
+    size_t i = off + p;
+    int lb = a.lab[i];
+    int inpool = a.pool ? a.pool[i] : 1;
+    float key = a.keys[i];
+    if (a.dbg_keys) a.dbg_keys[i] = key;
+    uint32_t u;
+    if (!inpool) {
+      u = 0u;
+    } else if (lb > 0) {
+      ++npos;
+      ce += (double)key;
+      const float* row = a.gt + (size_t)(g0 + a.tidx[i]) * 5;
+      Box m;
+      m.x1 = row[0]; m.y1 = row[1]; m.x2 = row[2]; m.y2 = row[3];
+      float4 t = encode_box(m, *reinterpret_cast<const float4*>(pri + (size_t)p * 4), a.var0, a.var1);
+      float4 l = *reinterpret_cast<const float4*>(a.loc + i * 4);
+      l1 += (double)(smooth_l1(l.x, t.x) + smooth_l1(l.y, t.y) + smooth_l1(l.z, t.z) + smooth_l1(l.w, t.w));
+      u = ord_zero;
+    } else {
+      u = f2ord(key);
+    }
+    uk[p] = u;
+  }
+  int npos_blk = (int)(block_sum((double)npos, s_dscr) + 0.5);
+  ce = block_sum(ce, s_dscr);
+  l1 = block_sum(l1, s_dscr);
+
+  // multibox_loss.py:101-102  num_neg = clamp(ratio * num_pos, max = P - 1)
+  long long kk = (long long)a.negpos_ratio * npos_blk;
+  if (kk > P - 1) kk = P - 1;
+  const int K = (int)kk;
+  uint32_t Tu = 0xffffffffu;
+  if (K > 0) Tu = cta_select_threshold<false>(uk, P, K, a.hist + (size_t)b * kHistBins, s_hist, s_iscr, s_res);
+  __syncthreads();
+
+  // final pass: neg = rank < num_neg (:103); CE over pos U neg (:106-110)
+  double ce_neg = 0.0;
+  for (int p = tid; p < P; p += kMineThreads) {
+    size_t i = off + p;
+    uint32_t u = uk[p];
+    int lb = a.lab[i];
+    bool inpool = u != 0u;
+    bool is_pos = inpool && lb > 0;
+    bool negsel = K > 0 && inpool && u >= Tu;
+    a.sel[i] = is_pos ? (int16_t)lb : (negsel ? (int16_t)0 : (int16_t)-1);
+    if (negsel && !is_pos) ce_neg += (double)a.keys[i];
+    if (a.dbg_neg) a.dbg_neg[i] = negsel ? 1 : 0;
+  }
+  ce_neg = block_sum(ce_neg, s_dscr);
+
+  if (tid == 0) {
+    a.partial[(size_t)b * 3 + 0] = l1;
+    a.partial[(size_t)b * 3 + 1] = ce + ce_neg;
+    a.partial[(size_t)b * 3 + 2] = (double)npos_blk;
+    __threadfence();
+    unsigned t = atomicAdd(a.ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last CTA: fold the per-image partials in image order (bit-reproducible run to run)
+  if (tid == 0) {
+    double sl = 0.0, sc = 0.0, sn = 0.0;
+    for (int i = 0; i < a.B; ++i) {
+      sl += __ldcg(&a.partial[(size_t)i * 3 + 0]);
+      sc += __ldcg(&a.partial[(size_t)i * 3 + 1]);
+      sn += __ldcg(&a.partial[(size_t)i * 3 + 2]);
+    }
+    a.sums[0] = sl;
+    a.sums[1] = sc;
+    a.sums[2] = sn;
+    if (a.finalize && a.losses) {     // multibox_loss.py:114-116 (N == 0 -> 0 instead of inf/nan)
+      a.losses[0] = sn > 0.0 ? (float)(sl / sn) : 0.0f;
+      a.losses[1] = sn > 0.0 ? (float)(sc / sn) : 0.0f;
+    }
+  }
+}
+
+__global__ void finalize_kernel(const double* __restrict__ sums, float* __restrict__ losses) {
+  double n = sums[2];
+  losses[0] = n > 0.0 ? (float)(sums[0] / n) : 0.0f;
+  losses[1] = n > 0.0 ? (float)(sums[1] / n) : 0.0f;
+}
+
+// stand-alone mining on caller-supplied keys (multibox_loss.py:97-103 in isolation)
+__global__ void __launch_bounds__(kMineThreads, 1)
+mine_only_kernel(const float* __restrict__ keys, const uint8_t* __restrict__ pos, const uint8_t* __restrict__ pool, int P,
+                 int ratio, uint8_t* __restrict__ neg, uint32_t* ukey_global, int uk_in_smem) {
+  extern __shared__ __align__(16) unsigned char smem_mine[];
+  unsigned char* smem_raw = smem_mine;
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw);
+  double* s_dscr = reinterpret_cast<double*>(smem_raw + 8192);
+  int* s_iscr = reinterpret_cast<int*>(smem_raw + 8192 + 320);
+  int* s_res = s_iscr + 64;
+  uint32_t* uk = uk_in_smem ? reinterpret_cast<uint32_t*>(smem_raw + 8192 + 320 + 288)
+                            : ukey_global + (size_t)blockIdx.x * P;
+  const int tid = threadIdx.x;
+  const size_t off = (size_t)blockIdx.x * P;
+  int npos = 0;
+  for (int p = tid; p < P; p += kMineThreads) {
+    int inpool = pool ? pool[off + p] : 1;
+    int ps = pos[off + p] != 0;
+    uint32_t u = 0u;
+    if (inpool) {
+      if (ps) { ++npos; u = f2ord(0.0f); } else u = f2ord(keys[off + p]);
+    }
+    uk[p] = u;
+  }
+  int npos_blk = (int)(block_sum((double)npos, s_dscr) + 0.5);
+  long long kk = (long long)ratio * npos_blk;
+  if (kk > P - 1) kk = P - 1;
+  const int K = (int)kk;
+  uint32_t Tu = 0xffffffffu;
+  if (K > 0) Tu = cta_select_threshold<false>(uk, P, K, nullptr, s_hist, s_iscr, s_res);
+  __syncthreads();
+  for (int p = tid; p < P; p += kMineThreads) {
+    uint32_t u = uk[p];
+    neg[off + p] = (K > 0 && u != 0u && u >= Tu) ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: d(loss_l)/d(loc) and d(loss_c)/d(conf)   (autograd of multibox_loss.py:87-116)
+// ------------------------------------------------------------------------------------------------
+constexpr int kBwdThreads = 256;
+constexpr int kBwdRows = 128;
+
+struct BwdArgs {
+  int B, P, C;
+  float var0, var1;
+  long long prior_stride;
+  const float* loc;
+  const float* conf;
+  const float* priors;
+  const float* gt;
+  const int32_t* gt_offsets;
+  const int16_t* sel;
+  const int16_t* tidx;
+  const double* sums;
+  const float* grad_out;
+  float* grad_loc;
+  float* grad_conf;
+  int conf_aligned;
+};
+
+__global__ void __launch_bounds__(kBwdThreads) loss_bwd_kernel(BwdArgs a) {
+  __shared__ int s_sel[kBwdRows];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long rows = (long long)a.B * a.P;
+  const long long tiles = (rows + kBwdRows - 1) / kBwdRows;
+  const double n = a.sums[2];
+  const float scale_l = n > 0.0 ? (float)((double)a.grad_out[0] / n) : 0.0f;
+  const float scale_c = n > 0.0 ? (float)((double)a.grad_out[1] / n) : 0.0f;
+  const int C = a.C;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    long long r0 = tile * kBwdRows;
+    int nrows = rows - r0 < kBwdRows ? (int)(rows - r0) : kBwdRows;
+    if (tid < kBwdRows) {
+      int lb = -1;
+      if (tid < nrows) {
+        long long row = r0 + tid;
+        lb = a.sel[row];
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lb > 0) {
+          int b = (int)(row / a.P);
+          int p = (int)(row - (long long)b * a.P);
+          const float* tr = a.gt + (size_t)(a.gt_offsets[b] + a.tidx[row]) * 5;
+          Box m;
+          m.x1 = tr[0]; m.y1 = tr[1]; m.x2 = tr[2]; m.y2 = tr[3];
+          float4 t = encode_box(m, *reinterpret_cast<const float4*>(a.priors + (size_t)b * (size_t)a.prior_stride + (size_t)p * 4),
+                                a.var0, a.var1);
+          float4 l = *reinterpret_cast<const float4*>(a.loc + row * 4);
+          float dx = l.x - t.x, dy = l.y - t.y, dz = l.z - t.z, dw = l.w - t.w;
+          g.x = scale_l * fminf(fmaxf(dx, -1.f), 1.f);     // smooth-L1': d for |d|<1, sign(d) otherwise
+          g.y = scale_l * fminf(fmaxf(dy, -1.f), 1.f);
+          g.z = scale_l * fminf(fmaxf(dz, -1.f), 1.f);
+          g.w = scale_l * fminf(fmaxf(dw, -1.f), 1.f);
+        }
+        *reinterpret_cast<float4*>(a.grad_loc + row * 4) = g;
+      }
+      s_sel[tid] = lb;
+    }
+    // zero-fill this tile of grad_conf (the overwhelming majority of rows is not selected)
+    float* gc = a.grad_conf + r0 * C;
+    long long nf = (long long)nrows * C;
+    if (a.conf_aligned) {
+      long long n4 = nf >> 2;
+      float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (long long i = tid; i < n4; i += kBwdThreads) __stcs(reinterpret_cast<float4*>(gc) + i, z);
+      for (long long i = (n4 << 2) + tid; i < nf; i += kBwdThreads) gc[i] = 0.f;
+    } else {
+      for (long long i = tid; i < nf; i += kBwdThreads) gc[i] = 0.f;
+    }
+    __syncthreads();
+    // selected rows: (softmax - onehot) * grad / N, one warp per row
+    for (int rr = warp; rr < nrows; rr += kBwdThreads / 32) {
+      int lb = s_sel[rr];
+      if (lb < 0) continue;
+      const float* x = a.conf + (r0 + rr) * C;
+      float m = -INFINITY;
+      for (int c = lane; c < C; c += 32) m = fmaxf(m, x[c]);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(SSDBOX_FULL_MASK, m, d));
+      float s = 0.f;
+      for (int c = lane; c < C; c += 32) s += expf(x[c] - m);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(SSDBOX_FULL_MASK, s, d);
+      float inv = 1.0f / s;
+      float* g = gc + (long long)rr * C;
+      for (int c = lane; c < C; c += 32) g[c] = scale_c * (expf(x[c] - m) * inv - (c == lb ? 1.0f : 0.0f));
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace ssdbox
+
+using namespace ssdbox;
+
+static int check_loss_cfg(const ssdbox_loss_cfg* c) {
+  SSDBOX_REQUIRE(c, SSDBOX_EINVAL, "loss: null cfg");
+  SSDBOX_REQUIRE(c->B >= 0 && c->P >= 0 && c->C >= 1 && c->gmax >= 0 && c->negpos_ratio >= 0, SSDBOX_EINVAL,
+                 "loss: negative size");
+  SSDBOX_REQUIRE(c->gmax <= kGmaxLimit, SSDBOX_ESHAPE, "loss: gmax %d > %d", c->gmax, kGmaxLimit);
+  SSDBOX_REQUIRE(c->C <= kClassLimit, SSDBOX_ESHAPE, "loss: %d classes > %d", c->C, kClassLimit);
+  SSDBOX_REQUIRE(c->B <= 65535, SSDBOX_ESHAPE, "loss: batch %d > 65535", c->B);
+  SSDBOX_REQUIRE((long long)c->B * c->P < (1ll << 31), SSDBOX_ESHAPE, "loss: B*P must be < 2^31");
+  SSDBOX_REQUIRE(c->prior_batch_stride == 0 || c->prior_batch_stride == (int64_t)c->P * 4, SSDBOX_EINVAL,
+                 "loss: prior_batch_stride must be 0 or 4*P");
+  return SSDBOX_OK;
+}
+
+extern "C" int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float* loc, const float* conf,
+                                        const float* priors, const float* anchors_xyxy, const uint8_t* pool,
+                                        const float* gt, const int32_t* gt_offsets, double* sums, float* losses,
+                                        int16_t* sel, int16_t* tidx, int64_t* dbg_conf_t, float* dbg_loc_t,
+                                        uint8_t* dbg_neg, float* dbg_keys, void* ws, size_t ws_bytes,
+                                        ssdbox_stream_t stream) {
+  int rc = check_loss_cfg(cfg);
+  if (rc) return rc;
+  const int B = cfg->B, P = cfg->P, C = cfg->C;
+  SSDBOX_REQUIRE(sums && ws && gt_offsets, SSDBOX_EINVAL, "loss: null pointer");
+  SSDBOX_REQUIRE(!cfg->finalize || losses, SSDBOX_EINVAL, "loss: finalize needs `losses`");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B == 0 || P == 0) {
+    SSDBOX_CUDA(cudaMemsetAsync(sums, 0, 3 * sizeof(double), st));
+    if (losses) SSDBOX_CUDA(cudaMemsetAsync(losses, 0, 2 * sizeof(float), st));
+    return SSDBOX_OK;
+  }
+  SSDBOX_REQUIRE(loc && conf && priors && sel && tidx && (gt || cfg->gmax == 0), SSDBOX_EINVAL, "loss: null pointer");
+  SSDBOX_REQUIRE(aligned16(loc) && aligned16(priors) && (!anchors_xyxy || aligned16(anchors_xyxy)) &&
+                     (!dbg_loc_t || aligned16(dbg_loc_t)),
+                 SSDBOX_EALIGN, "loss: box pointers must be 16-byte aligned");
+  SSDBOX_REQUIRE((reinterpret_cast<uintptr_t>(conf) & 3u) == 0, SSDBOX_EALIGN, "loss: conf must be 4-byte aligned");
+  SSDBOX_REQUIRE(ws_bytes >= loss_ws_bytes(B, P, C, cfg->gmax), SSDBOX_EWORKSPACE, "loss: workspace too small");
+  DevInfo dev;
+  rc = get_dev_info(&dev);
+  if (rc) return rc;
+
+  Carver c(ws);
+  LossWs w;
+  carve_match_core(c, B, cfg->gmax, &w.m);
+  w.m.lab = c.take<int16_t>((size_t)B * P);
+  w.m.tidx = tidx;
+  w.keys = c.take<float>((size_t)B * P);
+  w.ukey = c.take<uint32_t>((size_t)B * P);
+  w.hist = c.take<uint32_t>((size_t)B * kHistBins);
+  w.partial = c.take<double>((size_t)B * 3);
+  w.ticket = c.take<uint32_t>(1);
+
+  rc = launch_init(w.m.gt_best, (size_t)(B + 1) * gt_pad(cfg->gmax), w.m.done, (size_t)B + 1, w.hist,
+                   (size_t)B * kHistBins, w.ticket, 1, st);
+  if (rc) return rc;
+  MatchArgs ma{gt, gt_offsets, cfg->gmax, priors, (long long)cfg->prior_batch_stride, anchors_xyxy, B, P,
+               cfg->threshold, cfg->binarize_labels};
+  rc = launch_match(ma, w.m, w.m.lab, tidx, nullptr, st);
+  if (rc) return rc;
+
+  StreamArgs sa{};
+  sa.lab = w.m.lab;
+  sa.pool = pool;
+  sa.keys = w.keys;
+  sa.hist = w.hist;
+  sa.P = P;
+  rc = launch_stream(sa, conf, (long long)B * P, C, dev.sm_count, dev.max_smem_optin, st);
+  if (rc) return rc;
+
+  MineArgs m{};
+  m.B = B; m.P = P; m.C = C;
+  m.negpos_ratio = cfg->negpos_ratio;
+  m.var0 = cfg->var0; m.var1 = cfg->var1;
+  m.finalize = cfg->finalize;
+  m.prior_stride = (long long)cfg->prior_batch_stride;
+  m.loc = loc; m.priors = priors; m.gt = gt; m.gt_offsets = gt_offsets; m.pool = pool;
+  m.keys = w.keys; m.lab = w.m.lab; m.tidx = tidx; m.hist = w.hist;
+  m.ukey_global = w.ukey;
+  size_t fixed = 8192 + 320 + 288;
+  m.uk_in_smem = (fixed + (size_t)P * 4 <= (size_t)dev.max_smem_optin - 1024) ? 1 : 0;
+  m.partial = w.partial; m.ticket = w.ticket; m.sums = sums; m.losses = losses; m.sel = sel;
+  m.dbg_neg = dbg_neg; m.dbg_keys = dbg_keys;
+  size_t smem = fixed + (m.uk_in_smem ? (size_t)P * 4 : 0);
+  SSDBOX_CUDA(cudaFuncSetAttribute(mine_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mine_reduce_kernel<<<B, kMineThreads, smem, st>>>(m);
+  SSDBOX_LAUNCH_OK("mine_reduce_kernel");
+
+  if (dbg_conf_t || dbg_loc_t) {
+    // encode against the centre-form priors (for RefineDet: the refined anchors' centre form)
+    rc = launch_materialize(ma, cfg->var0, cfg->var1, w.m.lab, tidx, dbg_loc_t, dbg_conf_t, nullptr, st);
+    if (rc) return rc;
+  }
+  return SSDBOX_OK;
+}
+
+extern "C" int ssdbox_multibox_loss_finalize(const double* sums, float* losses, ssdbox_stream_t stream) {
+  SSDBOX_REQUIRE(sums && losses, SSDBOX_EINVAL, "finalize: null pointer");
+  finalize_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(sums, losses);
+  SSDBOX_LAUNCH_OK("finalize_kernel");
+  return SSDBOX_OK;
+}
+
+extern "C" int ssdbox_multibox_loss_bwd(const ssdbox_loss_cfg* cfg, const float* loc, const float* conf,
+                                        const float* priors, const float* gt, const int32_t* gt_offsets,
+                                        const int16_t* sel, const int16_t* tidx, const double* sums,
+                                        const float* grad_out, float* grad_loc, float* grad_conf,
+                                        ssdbox_stream_t stream) {
+  int rc = check_loss_cfg(cfg);
+  if (rc) return rc;
+  if (cfg->B == 0 || cfg->P == 0) return SSDBOX_OK;
+  SSDBOX_REQUIRE(loc && conf && priors && gt_offsets && sel && tidx && sums && grad_out && grad_loc && grad_conf,
+                 SSDBOX_EINVAL, "loss_bwd: null pointer");
+  SSDBOX_REQUIRE(aligned16(loc) && aligned16(priors) && aligned16(grad_loc), SSDBOX_EALIGN,
+                 "loss_bwd: box pointers must be 16-byte aligned");
+  DevInfo dev;
+  rc = get_dev_info(&dev);
+  if (rc) return rc;
+  BwdArgs a{};
+  a.B = cfg->B; a.P = cfg->P; a.C = cfg->C;
+  a.var0 = cfg->var0; a.var1 = cfg->var1;
+  a.prior_stride = (long long)cfg->prior_batch_stride;
+  a.loc = loc; a.conf = conf; a.priors = priors; a.gt = gt; a.gt_offsets = gt_offsets;
+  a.sel = sel; a.tidx = tidx; a.sums = sums; a.grad_out = grad_out;
+  a.grad_loc = grad_loc; a.grad_conf = grad_conf;
+  a.conf_aligned = aligned16(grad_conf) ? 1 : 0;
+  long long tiles = ((long long)a.B * a.P + kBwdRows - 1) / kBwdRows;
+  long long grid = (long long)dev.sm_count * 8;
+  if (grid > tiles) grid = tiles;
+  loss_bwd_kernel<<<(int)grid, kBwdThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  SSDBOX_LAUNCH_OK("loss_bwd_kernel");
+  return SSDBOX_OK;
+}
+
+extern "C" int ssdbox_hard_negative_mine(const float* keys, const uint8_t* pos, const uint8_t* pool, int32_t B,
+                                         int32_t P, int32_t negpos_ratio, uint8_t* neg, void* ws, size_t ws_bytes,
+                                         ssdbox_stream_t stream) {
+  SSDBOX_REQUIRE(B >= 0 && P >= 0 && negpos_ratio >= 0, SSDBOX_EINVAL, "mine: negative size");
+  if (B == 0 || P == 0) return SSDBOX_OK;
+  SSDBOX_REQUIRE(keys && pos && neg && ws, SSDBOX_EINVAL, "mine: null pointer");
+  SSDBOX_REQUIRE(ws_bytes >= mine_ws_bytes(B, P), SSDBOX_EWORKSPACE, "mine: workspace too small");
+  DevInfo dev;
+  int rc = get_dev_info(&dev);
+  if (rc) return rc;
+  size_t fixed = 8192 + 320 + 288;
+  int in_smem = (fixed + (size_t)P * 4 <= (size_t)dev.max_smem_optin - 1024) ? 1 : 0;
+  size_t smem = fixed + (in_smem ? (size_t)P * 4 : 0);
+  SSDBOX_CUDA(cudaFuncSetAttribute(mine_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mine_only_kernel<<<B, kMineThreads, smem, static_cast<cudaStream_t>(stream)>>>(keys, pos, pool, P, negpos_ratio, neg,
+                                                                                static_cast<uint32_t*>(ws), in_smem);
+  SSDBOX_LAUNCH_OK("mine_only_kernel");
+  return SSDBOX_OK;
+}

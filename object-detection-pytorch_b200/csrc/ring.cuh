@@ -1,0 +1,115 @@
+// The row-tile ring shared by the two HBM-bound streaming kernels (MultiBoxLoss key pass and
+// Detect candidate pass): a [rows, C] fp32 matrix is cut into tiles of R rows; each CTA owns a
+// contiguous run of tiles and pulls them through NS shared-memory stages with 1-D TMA bulk
+// copies (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) issued by one producer lane.
+// Two consumer groups of 4 warps alternate stages; one thread owns one row of a stage (row stride
+// C floats: conflict-free for odd C).  full[s] (count 1 + tx bytes) / empty[s] (count 4 warps).
+#pragma once
+#include "common.h"
+#include "ssdbox_dev.cuh"
+
+namespace ssdbox {
+
+constexpr int kRingConsumerWarps = 8;
+constexpr int kRingThreads = (kRingConsumerWarps + 1) * 32;
+constexpr int kRingMaxStages = 8;
+constexpr int kRingHeaderBytes = 128;
+
+struct RingPlan {
+  const float* src;
+  long long rows;
+  long long tiles;
+  int C;
+  int R;
+  int NS;
+  int tiles_per_cta;
+  int bulk_ok;
+  int grid;
+  size_t smem_bytes;
+};
+
+// host: choose R / NS / grid for `rows` x C given the device limits
+static inline int plan_ring(RingPlan* p, const float* src, long long rows, int C, int sm_count, int max_smem) {
+  size_t budget = (size_t)max_smem - 1024 - kRingHeaderBytes;
+  int R = 128;
+  while (R >= 32 && (size_t)2 * R * C * 4 > budget) R >>= 1;
+  if (R < 32) return fail(SSDBOX_ESHAPE, "%d classes do not fit the shared-memory ring", C);
+  size_t stage_bytes = (size_t)R * C * 4;
+  int NS = (int)(budget / stage_bytes);
+  if (NS > kRingMaxStages) NS = kRingMaxStages;
+  p->src = src;
+  p->rows = rows;
+  p->C = C;
+  p->R = R;
+  p->NS = NS;
+  p->tiles = (rows + R - 1) / R;
+  int grid = (int)(p->tiles < sm_count ? p->tiles : sm_count);
+  if (grid < 1) grid = 1;
+  p->tiles_per_cta = (int)((p->tiles + grid - 1) / grid);
+  if (p->tiles_per_cta < 1) p->tiles_per_cta = 1;
+  p->grid = (int)((p->tiles + p->tiles_per_cta - 1) / p->tiles_per_cta);
+  if (p->grid < 1) p->grid = 1;
+  p->bulk_ok = aligned16(src) ? 1 : 0;
+  p->smem_bytes = kRingHeaderBytes + (size_t)NS * stage_bytes;
+  return SSDBOX_OK;
+}
+
+struct RingCtx {
+  uint64_t* full;
+  uint64_t* empty;
+  float* stages;
+  size_t stage_floats;
+  long long t0;
+  int n_local;
+};
+
+__device__ __forceinline__ RingCtx ring_setup(const RingPlan& p, unsigned char* smem_raw) {
+  RingCtx r;
+  r.full = reinterpret_cast<uint64_t*>(smem_raw);
+  r.empty = r.full + kRingMaxStages;
+  r.stages = reinterpret_cast<float*>(smem_raw + kRingHeaderBytes);
+  r.stage_floats = (size_t)p.R * p.C;
+  r.t0 = (long long)blockIdx.x * p.tiles_per_cta;
+  long long t1 = r.t0 + p.tiles_per_cta;
+  if (t1 > p.tiles) t1 = p.tiles;
+  r.n_local = t1 > r.t0 ? (int)(t1 - r.t0) : 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.NS; ++s) {
+      mbar_init(&r.full[s], 1);
+      mbar_init(&r.empty[s], kRingConsumerWarps / 2);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  return r;
+}
+
+// whole producer warp calls this and then exits
+__device__ __forceinline__ void ring_produce(const RingPlan& p, const RingCtx& r) {
+  const int lane = threadIdx.x & 31;
+  uint64_t policy = l2_evict_first_policy();
+  for (int it = 0; it < r.n_local; ++it) {
+    int s = it % p.NS, n = it / p.NS;
+    if (lane == 0) mbar_wait(&r.empty[s], (uint32_t)((n & 1) ^ 1));
+    __syncwarp();
+    long long r0 = (r.t0 + it) * p.R;
+    long long left = p.rows - r0;
+    int nrows = left < p.R ? (int)left : p.R;
+    uint32_t bytes = (uint32_t)nrows * (uint32_t)p.C * 4u;
+    const float* src = p.src + r0 * p.C;
+    float* dst = r.stages + (size_t)s * r.stage_floats;
+    if (p.bulk_ok && (bytes & 15u) == 0u) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&r.full[s], bytes);
+        bulk_g2s(dst, src, bytes, &r.full[s], policy);
+      }
+    } else {  // unaligned base or ragged tail: plain loads through the generic proxy
+      int nf = nrows * p.C;
+      for (int i = lane; i < nf; i += 32) dst[i] = src[i];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&r.full[s]);
+    }
+  }
+}
+
+}  // namespace ssdbox

@@ -1,0 +1,174 @@
+"""ctypes binding of libssdbox.so (include/ssdbox.h) + small torch glue.
+
+The library is the product; this file only turns torch tensors into (pointer, size, stream)
+arguments.  There is deliberately NO CPU fallback: a non-CUDA tensor raises, and a missing
+library raises at import of the first op.
+"""
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libssdbox.so")
+
+OK, EINVAL, ESHAPE, EALIGN, EWORKSPACE, ECUDA = 0, -1, -2, -3, -4, -5
+OP_MATCH, OP_LOSS_FWD, OP_DETECT, OP_NMS, OP_LSE, OP_MINE = 1, 2, 3, 4, 5, 6
+MAX_LAYERS, MAX_MIN_SIZES, MAX_RATIOS = 16, 4, 6
+
+# every symbol include/ssdbox.h declares (tests check the library exports exactly these)
+SYMBOLS = [
+    "ssdbox_abi_version", "ssdbox_last_error", "ssdbox_workspace_bytes", "ssdbox_priorbox_count",
+    "ssdbox_priorbox", "ssdbox_point_form", "ssdbox_center_form", "ssdbox_jaccard", "ssdbox_encode",
+    "ssdbox_decode", "ssdbox_log_sum_exp", "ssdbox_match_encode", "ssdbox_hard_negative_mine",
+    "ssdbox_multibox_loss_fwd", "ssdbox_multibox_loss_finalize", "ssdbox_multibox_loss_bwd",
+    "ssdbox_nms", "ssdbox_detect", "ssdbox_arm_filter",
+]
+
+
+class PriorCfg(C.Structure):
+    _fields_ = [
+        ("num_layers", C.c_int32), ("clip", C.c_int32), ("flip", C.c_int32), ("has_max", C.c_int32),
+        ("image_h", C.c_double), ("image_w", C.c_double),
+        ("feat_h", C.c_int32 * MAX_LAYERS), ("feat_w", C.c_int32 * MAX_LAYERS),
+        ("step", C.c_double * MAX_LAYERS),
+        ("num_min", C.c_int32 * MAX_LAYERS),
+        ("min_size", (C.c_double * MAX_MIN_SIZES) * MAX_LAYERS),
+        ("max_size", C.c_double * MAX_LAYERS),
+        ("num_ratio", C.c_int32 * MAX_LAYERS),
+        ("ratio", (C.c_double * MAX_RATIOS) * MAX_LAYERS),
+    ]
+
+
+class LossCfg(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("P", C.c_int32), ("C", C.c_int32), ("gmax", C.c_int32),
+        ("threshold", C.c_float), ("negpos_ratio", C.c_int32), ("var0", C.c_float), ("var1", C.c_float),
+        ("binarize_labels", C.c_int32), ("finalize", C.c_int32), ("prior_batch_stride", C.c_int64),
+    ]
+
+
+class DetectCfg(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("P", C.c_int32), ("C", C.c_int32), ("top_k", C.c_int32),
+        ("conf_thresh", C.c_float), ("nms_thresh", C.c_float), ("var0", C.c_float), ("var1", C.c_float),
+        ("prior_batch_stride", C.c_int64),
+    ]
+
+
+_lib = None
+_lock = threading.Lock()
+P_ = C.c_void_p
+
+
+def _declare(lib):
+    i32, i64, f32, sz = C.c_int32, C.c_int64, C.c_float, C.c_size_t
+    lib.ssdbox_abi_version.restype = C.c_int
+    lib.ssdbox_abi_version.argtypes = []
+    lib.ssdbox_last_error.restype = C.c_int
+    lib.ssdbox_last_error.argtypes = [C.c_char_p, sz]
+    lib.ssdbox_workspace_bytes.restype = sz
+    lib.ssdbox_workspace_bytes.argtypes = [C.c_int] * 6
+    lib.ssdbox_priorbox_count.restype = i64
+    lib.ssdbox_priorbox_count.argtypes = [C.POINTER(PriorCfg)]
+    sigs = {
+        "ssdbox_priorbox": [C.POINTER(PriorCfg), P_, i64, P_],
+        "ssdbox_point_form": [P_, i64, P_, P_],
+        "ssdbox_center_form": [P_, i64, P_, P_],
+        "ssdbox_jaccard": [P_, i32, P_, i32, P_, P_],
+        "ssdbox_encode": [P_, P_, i64, f32, f32, P_, P_],
+        "ssdbox_decode": [P_, P_, i64, i64, f32, f32, P_, P_, P_],
+        "ssdbox_log_sum_exp": [P_, i64, i32, P_, P_, sz, P_],
+        "ssdbox_match_encode": [P_, P_, i32, P_, i64, P_, i32, i32, f32, f32, f32, i32, P_, P_, P_, P_, P_, sz, P_],
+        "ssdbox_hard_negative_mine": [P_, P_, P_, i32, i32, i32, P_, P_, sz, P_],
+        "ssdbox_multibox_loss_fwd": [C.POINTER(LossCfg)] + [P_] * 15 + [P_, sz, P_],
+        "ssdbox_multibox_loss_finalize": [P_, P_, P_],
+        "ssdbox_multibox_loss_bwd": [C.POINTER(LossCfg)] + [P_] * 11 + [P_],
+        "ssdbox_nms": [P_, P_, i32, f32, i32, P_, P_, P_, sz, P_],
+        "ssdbox_detect": [C.POINTER(DetectCfg), P_, P_, P_, P_, P_, P_, P_, sz, P_],
+        "ssdbox_arm_filter": [P_, i64, f32, P_, P_],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = args
+
+
+def lib():
+    """The loaded library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.isfile(LIB_PATH):
+                    raise RuntimeError(
+                        "ssdbox: %s is missing -- build it with `python object-detection-pytorch_b200/build.py` "
+                        "(there is no CPU / eager fallback)" % LIB_PATH)
+                l = C.CDLL(LIB_PATH)
+                _declare(l)
+                _lib = l
+    return _lib
+
+
+def last_error():
+    buf = C.create_string_buffer(512)
+    lib().ssdbox_last_error(buf, 512)
+    return buf.value.decode("utf-8", "replace")
+
+
+def check(rc):
+    if rc == OK:
+        return
+    msg = last_error()
+    if rc == EINVAL:
+        raise ValueError(msg)
+    raise RuntimeError("ssdbox error %d: %s" % (rc, msg))
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t, dtype=None, name="tensor", allow_none=False):
+    """Device pointer of a contiguous CUDA tensor (validated like torch would)."""
+    if t is None:
+        if allow_none:
+            return None
+        raise ValueError("ssdbox: %s is None" % name)
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("ssdbox: %s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("ssdbox: %s lives on %s -- the box path has no CPU implementation; move it to a CUDA device"
+                           % (name, t.device))
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("ssdbox: %s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("ssdbox: %s must be contiguous" % name)
+    return C.c_void_p(t.data_ptr()) if t.numel() else C.c_void_p(0)
+
+
+def as_f32(t, device=None):
+    """contiguous fp32 CUDA view/copy of t (host tensors are uploaded)."""
+    if device is not None and t.device != device:
+        t = t.to(device, non_blocking=True)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class Workspace(object):
+    """Grow-only per-owner scratch buffer (pointer stays stable once large enough: graph-safe)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes, device):
+        nbytes = int(nbytes)
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        return C.c_void_p(self.buf.data_ptr()), self.buf.numel()
+
+
+def workspace_bytes(op, B=0, P=0, Cn=0, gmax=0, top_k=0):
+    return int(lib().ssdbox_workspace_bytes(op, int(B), int(P), int(Cn), int(gmax), int(top_k)))

@@ -1,0 +1,50 @@
+"""DetectOut -- drop-in for lib/layers/functions/detection.py:6-64.  Same constructor; call it
+as `detector(loc_data, conf_data, prior_data)` (the reference relies on the legacy
+Function.__call__ -> forward dispatch, evaluate_utils.py:60).  Returns the [B, C, top_k, 5]
+tensor of (score, x1, y1, x2, y2) rows in NMS order, zero padded, on the input's device."""
+import ctypes as C
+
+import torch
+
+from . import _abi
+
+
+class DetectOut(object):
+    def __init__(self, num_classes, bkg_label, top_k, conf_thresh, nms_thresh, variance):
+        self.num_classes = num_classes
+        self.background_label = bkg_label
+        self.top_k = top_k
+        self.nms_thresh = nms_thresh
+        if nms_thresh <= 0:                                   # detection.py:19-20
+            raise ValueError('nms_threshold must be non negative.')
+        self.conf_thresh = conf_thresh
+        self.variance = variance
+        self._ws = _abi.Workspace()
+        self.last_counts = None
+
+    def forward(self, loc_data, conf_data, prior_data, score_keep=None, out=None):
+        if not loc_data.is_cuda:
+            raise RuntimeError("ssdbox: DetectOut runs on CUDA tensors only (no CPU path)")
+        dev = loc_data.device
+        num = loc_data.size(0)
+        pri = _abi.as_f32(prior_data, dev)
+        per_image = pri.dim() == 3
+        P = pri.size(-2)
+        loc = _abi.as_f32(loc_data).view(num, P, 4)
+        scores = _abi.as_f32(conf_data, dev).view(num, P, self.num_classes)      # detection.py:38
+        if out is None:
+            out = torch.empty(num, self.num_classes, self.top_k, 5, dtype=torch.float32, device=dev)
+        counts = torch.empty(num, self.num_classes, dtype=torch.int32, device=dev)
+        cfg = _abi.DetectCfg(num, P, self.num_classes, int(self.top_k), float(self.conf_thresh),
+                             float(self.nms_thresh), float(self.variance[0]), float(self.variance[1]),
+                             4 * P if per_image else 0)
+        ws, n = self._ws.get(_abi.workspace_bytes(_abi.OP_DETECT, num, P, self.num_classes, 0, self.top_k), dev)
+        keep = score_keep.to(dev).to(torch.uint8).contiguous() if score_keep is not None else None
+        _abi.check(_abi.lib().ssdbox_detect(
+            C.byref(cfg), _abi.ptr(loc, torch.float32, "loc_data"), _abi.ptr(scores, torch.float32, "conf_data"),
+            _abi.ptr(pri, torch.float32, "prior_data"), _abi.ptr(keep, torch.uint8, "score_keep", True),
+            _abi.ptr(out, torch.float32, "out"), _abi.ptr(counts), ws, n, _abi.stream_ptr(dev)))
+        self.last_counts = counts
+        return out
+
+    __call__ = forward

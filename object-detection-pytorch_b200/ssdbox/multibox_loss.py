@@ -1,0 +1,179 @@
+"""MultiBoxLoss -- drop-in for lib/layers/modules/multibox_loss.py:10-117 (and the
+empty-target variant multibox_loss_v1.py:70-71).  Same constructor and
+forward(predictions, targets) -> (loss_l, loss_c); both outputs are differentiable w.r.t.
+loc_data / conf_data (train.py:142-144).  All arithmetic runs in libssdbox.so."""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _abi
+
+
+def pack_targets(targets, device):
+    """list of B tensors [G_b,5] (or the 1-element sentinel of multibox_loss_v1.py:70) ->
+    (gt [sum G,5] f32 on device, offsets int32 [B+1] on device, gmax).  Only shapes are read on
+    the host (no device sync)."""
+    offs = [0]
+    rows = []
+    gmax = 0
+    for t in targets:
+        g = int(t.size(0)) if (t.dim() == 2 and t.size(-1) == 5) else 0
+        offs.append(offs[-1] + g)
+        gmax = max(gmax, g)
+        if g:
+            rows.append(t if t.device == device else t.to(device, non_blocking=True))
+    if rows:
+        gt = torch.cat(rows, 0).to(torch.float32).contiguous()
+    else:
+        gt = torch.zeros(1, 5, dtype=torch.float32, device=device)
+    offsets = torch.tensor(offs, dtype=torch.int32).to(device, non_blocking=True)
+    return gt, offsets, gmax
+
+
+class _State(object):
+    """Per-module reusable buffers (stable pointers: the forward can be captured in a CUDA graph)."""
+
+    def __init__(self):
+        self.ws = _abi.Workspace()
+        self.key = None
+        self.sel = self.tidx = self.sums = self.losses = None
+
+    def ensure(self, B, P, device):
+        key = (B, P, device)
+        if self.key != key:
+            self.sel = torch.empty(B, P, dtype=torch.int16, device=device)
+            self.tidx = torch.empty(B, P, dtype=torch.int16, device=device)
+            self.sums = torch.zeros(3, dtype=torch.float64, device=device)
+            self.losses = torch.zeros(2, dtype=torch.float32, device=device)
+            self.key = key
+
+
+def loss_forward_raw(state, loc, conf, priors, gt, offsets, gmax, num_classes, threshold, negpos_ratio,
+                     variance, anchors_xyxy=None, pool=None, binarize=False, finalize=True, debug=None):
+    """One call of ssdbox_multibox_loss_fwd on validated CUDA tensors.  Fills state.{sums,losses,sel,tidx}."""
+    B, P = loc.size(0), loc.size(1)
+    dev = loc.device
+    state.ensure(B, P, dev)
+    per_image = priors.dim() == 3
+    cfg = _abi.LossCfg(B, P, int(num_classes), int(gmax), float(threshold), int(negpos_ratio),
+                       float(variance[0]), float(variance[1]), 1 if binarize else 0, 1 if finalize else 0,
+                       4 * P if per_image else 0)
+    ws, n = state.ws.get(_abi.workspace_bytes(_abi.OP_LOSS_FWD, B, P, num_classes, gmax), dev)
+    dbg = debug or {}
+    _abi.check(_abi.lib().ssdbox_multibox_loss_fwd(
+        C.byref(cfg), _abi.ptr(loc, torch.float32, "loc_data"), _abi.ptr(conf, torch.float32, "conf_data"),
+        _abi.ptr(priors, torch.float32, "priors"), _abi.ptr(anchors_xyxy, torch.float32, "anchors", True),
+        _abi.ptr(pool, torch.uint8, "pool", True), _abi.ptr(gt, torch.float32, "gt"),
+        _abi.ptr(offsets, torch.int32, "gt_offsets"), _abi.ptr(state.sums), _abi.ptr(state.losses),
+        _abi.ptr(state.sel), _abi.ptr(state.tidx), _abi.ptr(dbg.get("conf_t"), torch.int64, "conf_t", True),
+        _abi.ptr(dbg.get("loc_t"), torch.float32, "loc_t", True), _abi.ptr(dbg.get("neg"), torch.uint8, "neg", True),
+        _abi.ptr(dbg.get("keys"), torch.float32, "keys", True), ws, n, _abi.stream_ptr(dev)))
+    return cfg
+
+
+class _MultiBoxLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, loc, conf, priors, gt, offsets, anchors_xyxy, pool, mod, gmax):
+        st = mod._state
+        process_group = mod.process_group
+        distributed = mod._is_distributed()
+        cfg = loss_forward_raw(st, loc, conf, priors, gt, offsets, gmax, mod.num_classes, mod.threshold,
+                               mod.negpos_ratio, mod.variance, anchors_xyxy, pool, mod.binarize_labels,
+                               finalize=not distributed, debug=mod._debug)
+        if distributed:
+            # the only collective of the path: {sum smooth-L1, sum CE, N_pos} summed over ranks
+            import torch.distributed as dist
+            dist.all_reduce(st.sums, op=dist.ReduceOp.SUM, group=process_group)
+            _abi.check(_abi.lib().ssdbox_multibox_loss_finalize(_abi.ptr(st.sums), _abi.ptr(st.losses),
+                                                                _abi.stream_ptr(loc.device)))
+        ctx.cfg = cfg
+        ctx.save_for_backward(loc, conf, priors, gt, offsets, st.sel.clone(), st.tidx.clone(), st.sums.clone())
+        out = st.losses.clone()
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, g_l, g_c):
+        loc, conf, priors, gt, offsets, sel, tidx, sums = ctx.saved_tensors
+        dev = loc.device
+        gout = torch.stack([g_l.reshape(()).to(torch.float32), g_c.reshape(()).to(torch.float32)]).contiguous()
+        grad_loc = torch.empty_like(loc)
+        grad_conf = torch.empty_like(conf)
+        _abi.check(_abi.lib().ssdbox_multibox_loss_bwd(
+            C.byref(ctx.cfg), _abi.ptr(loc), _abi.ptr(conf), _abi.ptr(priors), _abi.ptr(gt), _abi.ptr(offsets),
+            _abi.ptr(sel), _abi.ptr(tidx), _abi.ptr(sums), _abi.ptr(gout), _abi.ptr(grad_loc), _abi.ptr(grad_conf),
+            _abi.stream_ptr(dev)))
+        return grad_loc, grad_conf, None, None, None, None, None, None, None
+
+
+class MultiBoxLoss(nn.Module):
+    """SSD weighted loss (multibox_loss.py:10-46).  Arguments as in the reference; as there,
+    prior_for_matching / bkg_label / neg_mining / neg_overlap / encode_target are stored but
+    unused.  `variance` replaces the reference's read of the global cfg (multibox_loss.py:46);
+    `distributed=True` (or an initialised default process group with world size > 1) all-reduces
+    the loss numerators and the positive count across ranks (images are sharded by rank)."""
+
+    def __init__(self, num_classes, overlap_thresh, prior_for_matching, bkg_label, neg_mining, neg_pos,
+                 neg_overlap, encode_target, use_gpu=True, variance=(0.1, 0.2), distributed=None,
+                 process_group=None):
+        super(MultiBoxLoss, self).__init__()
+        self.use_gpu = use_gpu
+        self.num_classes = num_classes
+        self.threshold = overlap_thresh
+        self.background_label = bkg_label
+        self.encode_target = encode_target
+        self.use_prior_for_matching = prior_for_matching
+        self.do_neg_mining = neg_mining
+        self.negpos_ratio = neg_pos
+        self.neg_overlap = neg_overlap
+        self.variance = list(variance)
+        self.binarize_labels = False
+        self.distributed = distributed
+        self.process_group = process_group
+        self._state = _State()
+        self._debug = None
+
+    def _is_distributed(self):
+        if self.distributed is False:
+            return False
+        import torch.distributed as dist
+        ok = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1
+        if self.distributed and not ok:
+            raise RuntimeError("ssdbox: distributed=True but no process group with world size > 1 is initialised")
+        return ok
+
+    def forward(self, predictions, targets):
+        loc_data, conf_data, priors = predictions
+        if not loc_data.is_cuda:
+            raise RuntimeError("ssdbox: MultiBoxLoss runs on CUDA tensors only (no CPU path)")
+        dev = loc_data.device
+        loc = _abi.as_f32(loc_data)
+        conf = _abi.as_f32(conf_data).view(loc.size(0), loc.size(1), -1)
+        if conf.size(2) != self.num_classes:
+            raise ValueError("conf_data has %d classes, MultiBoxLoss was built for %d" % (conf.size(2), self.num_classes))
+        pri = _abi.as_f32(priors, dev)[:loc.size(1), :].contiguous()        # multibox_loss.py:62
+        gt, offsets, gmax = pack_targets(targets, dev)
+        return self.forward_packed(loc, conf, pri, gt, offsets, gmax)
+
+    def forward_packed(self, loc, conf, priors, gt, offsets, gmax, anchors_xyxy=None, pool=None):
+        """Same as forward with the targets already in the C-ABI layout (no host work: capturable)."""
+        return _MultiBoxLossFn.apply(loc, conf, priors, gt, offsets, anchors_xyxy, pool, self, int(gmax))
+
+    def intermediates(self, predictions, targets):
+        """Runs the forward and also materialises the reference's intermediates
+        (conf_t, loc_t, neg mask, mining keys) -- used by the parity tests."""
+        loc_data, conf_data, priors = predictions
+        dev = loc_data.device
+        B, P = loc_data.size(0), loc_data.size(1)
+        self._debug = dict(conf_t=torch.empty(B, P, dtype=torch.int64, device=dev),
+                           loc_t=torch.empty(B, P, 4, dtype=torch.float32, device=dev),
+                           neg=torch.empty(B, P, dtype=torch.uint8, device=dev),
+                           keys=torch.empty(B, P, dtype=torch.float32, device=dev))
+        try:
+            ll, lc = self.forward(predictions, targets)
+            d = dict(self._debug)
+        finally:
+            self._debug = None
+        d.update(loss_l=ll, loss_c=lc, sums=self._state.sums.clone(), sel=self._state.sel.clone(),
+                 tidx=self._state.tidx.clone())
+        return d
