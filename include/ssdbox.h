@@ -228,6 +228,18 @@ SSDBOX_API int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
  * ---------------------------------------------------------------------------------------- */
 SSDBOX_API int ssdbox_arm_filter(const float* arm_conf, int64_t n, float theta, uint8_t* keep, ssdbox_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Opt-in per-kernel timing for bench.py / profiling (the only process-global state; off by
+ * default).  While enabled every launch of the library is bracketed by CUDA events on the
+ * caller's stream (do NOT enable during CUDA-graph capture).  ssdbox_timers_read synchronises
+ * the pending events and returns the accumulated device time and launch count of one kernel:
+ *   0 init, 1 match, 2 loss_stream, 3 mine_reduce, 4 loss_bwd, 5 detect_stream,
+ *   6 detect_segment, 7 detect_overflow, 8 materialize
+ * ---------------------------------------------------------------------------------------- */
+#define SSDBOX_KERNEL_COUNT 9
+SSDBOX_API int ssdbox_timers_enable(int on);
+SSDBOX_API int ssdbox_timers_read(int kernel_id, double* total_ms, int64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

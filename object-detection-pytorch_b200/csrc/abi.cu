@@ -1,6 +1,7 @@
 // Error reporting, device-attribute cache, ABI version, workspace sizing.
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "common.h"
 #include "sizes.h"
@@ -49,7 +50,80 @@ int get_dev_info(DevInfo* out) {
   return SSDBOX_OK;
 }
 
+// ---- opt-in kernel timers ---------------------------------------------------------------------
+struct TimerSlot {
+  std::vector<cudaEvent_t> start, stop;   // pending pairs
+  double total_ms = 0.0;
+  long long launches = 0;
+};
+static std::mutex g_timer_mu;
+static bool g_timer_on = false;
+static TimerSlot g_timers[KID_COUNT];
+
+void timer_begin(int kid, cudaStream_t st) {
+  if (!g_timer_on) return;
+  std::lock_guard<std::mutex> lk(g_timer_mu);
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  g_timers[kid].start.push_back(e);
+}
+
+void timer_end(int kid, cudaStream_t st) {
+  if (!g_timer_on) return;
+  std::lock_guard<std::mutex> lk(g_timer_mu);
+  if (g_timers[kid].start.size() == g_timers[kid].stop.size()) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) {
+    cudaEventDestroy(g_timers[kid].start.back());
+    g_timers[kid].start.pop_back();
+    return;
+  }
+  cudaEventRecord(e, st);
+  g_timers[kid].stop.push_back(e);
+}
+
+static void timer_collect() {
+  for (int k = 0; k < KID_COUNT; ++k) {
+    TimerSlot& t = g_timers[k];
+    for (size_t i = 0; i < t.stop.size(); ++i) {
+      float ms = 0.f;
+      if (cudaEventSynchronize(t.stop[i]) == cudaSuccess && cudaEventElapsedTime(&ms, t.start[i], t.stop[i]) == cudaSuccess) {
+        t.total_ms += ms;
+        t.launches += 1;
+      }
+      cudaEventDestroy(t.start[i]);
+      cudaEventDestroy(t.stop[i]);
+    }
+    t.start.clear();
+    t.stop.clear();
+  }
+}
+
 }  // namespace ssdbox
+
+extern "C" int ssdbox_timers_enable(int on) {
+  std::lock_guard<std::mutex> lk(ssdbox::g_timer_mu);
+  ssdbox::timer_collect();
+  if (on) {
+    for (int k = 0; k < ssdbox::KID_COUNT; ++k) {
+      ssdbox::g_timers[k].total_ms = 0.0;
+      ssdbox::g_timers[k].launches = 0;
+    }
+  }
+  ssdbox::g_timer_on = on != 0;
+  return SSDBOX_OK;
+}
+
+extern "C" int ssdbox_timers_read(int kernel_id, double* total_ms, int64_t* launches) {
+  if (kernel_id < 0 || kernel_id >= ssdbox::KID_COUNT || !total_ms || !launches)
+    return ssdbox::fail(SSDBOX_EINVAL, "timers_read: bad argument");
+  std::lock_guard<std::mutex> lk(ssdbox::g_timer_mu);
+  ssdbox::timer_collect();
+  *total_ms = ssdbox::g_timers[kernel_id].total_ms;
+  *launches = ssdbox::g_timers[kernel_id].launches;
+  return SSDBOX_OK;
+}
 
 extern "C" int ssdbox_abi_version(void) { return SSDBOX_ABI_VERSION; }
 

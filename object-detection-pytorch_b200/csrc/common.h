@@ -26,6 +26,20 @@ int get_dev_info(DevInfo* out);
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// ---- opt-in per-kernel timing (bench / profiling only; off by default) -------------------------
+enum KernelId {
+  KID_INIT = 0, KID_MATCH, KID_LOSS_STREAM, KID_MINE, KID_LOSS_BWD, KID_DET_STREAM, KID_DET_SEGMENT,
+  KID_DET_OVERFLOW, KID_MATERIALIZE, KID_COUNT
+};
+void timer_begin(int kid, cudaStream_t st);
+void timer_end(int kid, cudaStream_t st);
+struct TimerScope {
+  int kid;
+  cudaStream_t st;
+  TimerScope(int k, cudaStream_t s) : kid(k), st(s) { timer_begin(k, s); }
+  ~TimerScope() { timer_end(kid, st); }
+};
+
 // carve consecutive 256-byte aligned regions out of the caller's workspace
 struct Carver {
   char* base;

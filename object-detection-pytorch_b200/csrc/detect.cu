@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) detect_stream_kernel(DetStrea
   const int R = a.ring.R, NS = a.ring.NS;
   const uint32_t lt_mask = (1u << lane) - 1u;
   for (int it = wg; it < rc.n_local; it += 2) {
-    int s = it % NS, n = it / NS;
+    const int s = it % NS, j = it % (2 * NS), ph = it / (2 * NS);
     long long row = (rc.t0 + it) * R + r;
     bool valid = (r < R) && (row < a.ring.rows);
     uint32_t b = 0, p = 0;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) detect_stream_kernel(DetStrea
     uint32_t b_first = __shfl_sync(SSDBOX_FULL_MASK, b, 0);
     uint32_t b_last = __shfl_sync(SSDBOX_FULL_MASK, b, vmask ? 31 - __clz(vmask) : 0);
     const bool uniform = b_first == b_last;
-    mbar_wait(&rc.full[s], (uint32_t)(n & 1));
+    mbar_wait(&rc.full[j], (uint32_t)(ph & 1));
     if (vmask) {
       const float* rp = rc.stages + (size_t)s * rc.stage_floats + (size_t)r * C;
 #pragma unroll 4
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) detect_stream_kernel(DetStrea
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&rc.empty[s]);
+    if (lane == 0) mbar_arrive(&rc.empty[j]);
   }
 }
 
@@ -377,7 +377,10 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
     if (C == 81) kern = detect_stream_kernel<81>;
     else if (C == 21) kern = detect_stream_kernel<21>;
     SSDBOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa.ring.smem_bytes));
+{
+    TimerScope ts__(KID_DET_STREAM, st);
     kern<<<sa.ring.grid, kRingThreads, sa.ring.smem_bytes, st>>>(sa);
+  }
     SSDBOX_LAUNCH_OK("detect_stream_kernel");
   }
 
@@ -389,14 +392,20 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
   g.cnt = cnt; g.cand = cand; g.scratch = scratch; g.out = out; g.counts = counts;
   size_t seg_smem = (size_t)cap * 8 + nms_smem_bytes(top_k);
   SSDBOX_CUDA(cudaFuncSetAttribute(detect_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem));
-  detect_segment_kernel<<<B * C, kSegThreads, seg_smem, st>>>(g);
+{
+    TimerScope ts__(KID_DET_SEGMENT, st);
+    detect_segment_kernel<<<B * C, kSegThreads, seg_smem, st>>>(g);
+  }
   SSDBOX_LAUNCH_OK("detect_segment_kernel");
 
   size_t ovf_smem = 16384 + 288 + nms_smem_bytes(top_k);
   SSDBOX_CUDA(cudaFuncSetAttribute(detect_overflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ovf_smem));
   int ovf_grid = dev.sm_count < kOverflowSlots ? dev.sm_count : kOverflowSlots;
   if (ovf_grid > B * C) ovf_grid = B * C;
-  detect_overflow_kernel<<<ovf_grid, kOvfThreads, ovf_smem, st>>>(g);
+{
+    TimerScope ts__(KID_DET_OVERFLOW, st);
+    detect_overflow_kernel<<<ovf_grid, kOvfThreads, ovf_smem, st>>>(g);
+  }
   SSDBOX_LAUNCH_OK("detect_overflow_kernel");
   return SSDBOX_OK;
 }

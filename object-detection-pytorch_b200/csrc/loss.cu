@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) loss_stream_kernel(StreamArgs
   const int r = tid & 127;
   const int R = a.ring.R, NS = a.ring.NS;
   for (int it = wg; it < rc.n_local; it += 2) {
-    int s = it % NS, n = it / NS;
+    const int s = it % NS, j = it % (2 * NS), ph = it / (2 * NS);
     long long row = (rc.t0 + it) * R + r;
     bool valid = (r < R) && (row < a.ring.rows);
     int lb = 0;
@@ -85,11 +85,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) loss_stream_kernel(StreamArgs
       lb = a.lab[row];
       if (a.pool) inpool = a.pool[row];
     }
-    mbar_wait(&rc.full[s], (uint32_t)(n & 1));
+    mbar_wait(&rc.full[j], (uint32_t)(ph & 1));
     float key = 0.f;
     if (valid) key = row_key<CT>(rc.stages + (size_t)s * rc.stage_floats + (size_t)r * C, C, lb);
     __syncwarp();
-    if (lane == 0) mbar_arrive(&rc.empty[s]);
+    if (lane == 0) mbar_arrive(&rc.empty[j]);
     if (valid) {
       a.keys[row] = key;
       if (inpool) {
@@ -111,7 +111,10 @@ static int launch_stream(StreamArgs a, const float* conf, long long rows, int C,
   else if (C == 21) kern = loss_stream_kernel<21>;
   else if (C == 2) kern = loss_stream_kernel<2>;
   SSDBOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.ring.smem_bytes));
-  kern<<<a.ring.grid, kRingThreads, a.ring.smem_bytes, st>>>(a);
+{
+    TimerScope ts__(KID_LOSS_STREAM, st);
+    kern<<<a.ring.grid, kRingThreads, a.ring.smem_bytes, st>>>(a);
+  }
   SSDBOX_LAUNCH_OK("loss_stream_kernel");
   return SSDBOX_OK;
 }
@@ -471,7 +474,10 @@ extern "C" int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float*
   m.dbg_neg = dbg_neg; m.dbg_keys = dbg_keys;
   size_t smem = fixed + (m.uk_in_smem ? (size_t)P * 4 : 0);
   SSDBOX_CUDA(cudaFuncSetAttribute(mine_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mine_reduce_kernel<<<B, kMineThreads, smem, st>>>(m);
+{
+    TimerScope ts__(KID_MINE, st);
+    mine_reduce_kernel<<<B, kMineThreads, smem, st>>>(m);
+  }
   SSDBOX_LAUNCH_OK("mine_reduce_kernel");
 
   if (dbg_conf_t || dbg_loc_t) {
@@ -515,7 +521,11 @@ extern "C" int ssdbox_multibox_loss_bwd(const ssdbox_loss_cfg* cfg, const float*
   long long tiles = ((long long)a.B * a.P + kBwdRows - 1) / kBwdRows;
   long long grid = (long long)dev.sm_count * 8;
   if (grid > tiles) grid = tiles;
-  loss_bwd_kernel<<<(int)grid, kBwdThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    TimerScope ts__(KID_LOSS_BWD, st);
+    loss_bwd_kernel<<<(int)grid, kBwdThreads, 0, st>>>(a);
+  }
   SSDBOX_LAUNCH_OK("loss_bwd_kernel");
   return SSDBOX_OK;
 }

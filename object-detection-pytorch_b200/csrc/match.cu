@@ -36,7 +36,10 @@ int launch_init(unsigned long long* best, size_t nbest, uint32_t* z0, size_t n0,
   if (m == 0) return SSDBOX_OK;
   int blocks = (int)((m + 255) / 256);
   if (blocks > 592) blocks = 592;
-  init_kernel<<<blocks, 256, 0, st>>>(best, nbest, z0, n0, z1, n1, z2, n2);
+{
+    TimerScope ts__(KID_INIT, st);
+    init_kernel<<<blocks, 256, 0, st>>>(best, nbest, z0, n0, z1, n1, z2, n2);
+  }
   SSDBOX_LAUNCH_OK("init_kernel");
   return SSDBOX_OK;
 }
@@ -184,7 +187,10 @@ int launch_match(const MatchArgs& a, const MatchWs& w, int16_t* lab, int16_t* ti
     SSDBOX_CUDA(cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   dim3 grid((a.P + kMatchTile - 1) / kMatchTile, a.B);
-  match_kernel<<<grid, kMatchThreads, smem, st>>>(a, w.gt_best, w.done, lab, tidx, overlap, gpad);
+{
+    TimerScope ts__(KID_MATCH, st);
+    match_kernel<<<grid, kMatchThreads, smem, st>>>(a, w.gt_best, w.done, lab, tidx, overlap, gpad);
+  }
   SSDBOX_LAUNCH_OK("match_kernel");
   return SSDBOX_OK;
 }
@@ -221,7 +227,10 @@ int launch_materialize(const MatchArgs& a, float var0, float var1, const int16_t
   if (n == 0) return SSDBOX_OK;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  materialize_kernel<<<blocks, 256, 0, st>>>(a, var0, var1, lab, tidx, loc_t, conf_t, match_idx);
+{
+    TimerScope ts__(KID_MATERIALIZE, st);
+    materialize_kernel<<<blocks, 256, 0, st>>>(a, var0, var1, lab, tidx, loc_t, conf_t, match_idx);
+  }
   SSDBOX_LAUNCH_OK("materialize_kernel");
   return SSDBOX_OK;
 }

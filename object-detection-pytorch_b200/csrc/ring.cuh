@@ -3,7 +3,14 @@
 // contiguous run of tiles and pulls them through NS shared-memory stages with 1-D TMA bulk
 // copies (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) issued by one producer lane.
 // Two consumer groups of 4 warps alternate stages; one thread owns one row of a stage (row stride
-// C floats: conflict-free for odd C).  full[s] (count 1 + tx bytes) / empty[s] (count 4 warps).
+// C floats: conflict-free for odd C).
+//
+// Barriers: iteration `it` of a CTA uses stage it % NS but barrier pair j = it % (2*NS)
+// (full[j]: count 1 + tx bytes, empty[j]: count 4 warps), phase it / (2*NS).  With 2*NS pairs
+// every barrier is always consumed by the same consumer group (2*NS is even), so each waiter
+// follows its barrier phase by phase and the 1-bit parity can never alias (with one pair per
+// stage and NS odd, a group would skip every other phase of a stage and could pass a wait two
+// phases early).
 #pragma once
 #include "common.h"
 #include "ssdbox_dev.cuh"
@@ -13,7 +20,7 @@ namespace ssdbox {
 constexpr int kRingConsumerWarps = 8;
 constexpr int kRingThreads = (kRingConsumerWarps + 1) * 32;
 constexpr int kRingMaxStages = 8;
-constexpr int kRingHeaderBytes = 128;
+constexpr int kRingHeaderBytes = 256;   // 2 * kRingMaxStages pairs of 8-byte mbarriers
 
 struct RingPlan {
   const float* src;
@@ -66,7 +73,7 @@ struct RingCtx {
 __device__ __forceinline__ RingCtx ring_setup(const RingPlan& p, unsigned char* smem_raw) {
   RingCtx r;
   r.full = reinterpret_cast<uint64_t*>(smem_raw);
-  r.empty = r.full + kRingMaxStages;
+  r.empty = r.full + 2 * kRingMaxStages;
   r.stages = reinterpret_cast<float*>(smem_raw + kRingHeaderBytes);
   r.stage_floats = (size_t)p.R * p.C;
   r.t0 = (long long)blockIdx.x * p.tiles_per_cta;
@@ -74,9 +81,9 @@ __device__ __forceinline__ RingCtx ring_setup(const RingPlan& p, unsigned char* 
   if (t1 > p.tiles) t1 = p.tiles;
   r.n_local = t1 > r.t0 ? (int)(t1 - r.t0) : 0;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.NS; ++s) {
-      mbar_init(&r.full[s], 1);
-      mbar_init(&r.empty[s], kRingConsumerWarps / 2);
+    for (int j = 0; j < 2 * p.NS; ++j) {
+      mbar_init(&r.full[j], 1);
+      mbar_init(&r.empty[j], kRingConsumerWarps / 2);
     }
     fence_mbar_init();
   }
@@ -89,8 +96,12 @@ __device__ __forceinline__ void ring_produce(const RingPlan& p, const RingCtx& r
   const int lane = threadIdx.x & 31;
   uint64_t policy = l2_evict_first_policy();
   for (int it = 0; it < r.n_local; ++it) {
-    int s = it % p.NS, n = it / p.NS;
-    if (lane == 0) mbar_wait(&r.empty[s], (uint32_t)((n & 1) ^ 1));
+    const int s = it % p.NS;
+    const int j = it % (2 * p.NS);
+    if (it >= p.NS && lane == 0) {   // stage s was last used by iteration it - NS: wait for its release
+      int prev = it - p.NS;
+      mbar_wait(&r.empty[prev % (2 * p.NS)], (uint32_t)((prev / (2 * p.NS)) & 1));
+    }
     __syncwarp();
     long long r0 = (r.t0 + it) * p.R;
     long long left = p.rows - r0;
@@ -100,14 +111,14 @@ __device__ __forceinline__ void ring_produce(const RingPlan& p, const RingCtx& r
     float* dst = r.stages + (size_t)s * r.stage_floats;
     if (p.bulk_ok && (bytes & 15u) == 0u) {
       if (lane == 0) {
-        mbar_arrive_expect_tx(&r.full[s], bytes);
-        bulk_g2s(dst, src, bytes, &r.full[s], policy);
+        mbar_arrive_expect_tx(&r.full[j], bytes);
+        bulk_g2s(dst, src, bytes, &r.full[j], policy);
       }
     } else {  // unaligned base or ragged tail: plain loads through the generic proxy
       int nf = nrows * p.C;
       for (int i = lane; i < nf; i += 32) dst[i] = src[i];
       __syncwarp();
-      if (lane == 0) mbar_arrive(&r.full[s]);
+      if (lane == 0) mbar_arrive(&r.full[j]);
     }
   }
 }

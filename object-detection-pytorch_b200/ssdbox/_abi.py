@@ -23,8 +23,11 @@ SYMBOLS = [
     "ssdbox_priorbox", "ssdbox_point_form", "ssdbox_center_form", "ssdbox_jaccard", "ssdbox_encode",
     "ssdbox_decode", "ssdbox_log_sum_exp", "ssdbox_match_encode", "ssdbox_hard_negative_mine",
     "ssdbox_multibox_loss_fwd", "ssdbox_multibox_loss_finalize", "ssdbox_multibox_loss_bwd",
-    "ssdbox_nms", "ssdbox_detect", "ssdbox_arm_filter",
+    "ssdbox_nms", "ssdbox_detect", "ssdbox_arm_filter", "ssdbox_timers_enable", "ssdbox_timers_read",
 ]
+
+KERNEL_NAMES = ["init", "match", "loss_stream", "mine_reduce", "loss_bwd", "detect_stream", "detect_segment",
+                "detect_overflow", "materialize"]
 
 
 class PriorCfg(C.Structure):
@@ -89,6 +92,8 @@ def _declare(lib):
         "ssdbox_detect": [C.POINTER(DetectCfg), P_, P_, P_, P_, P_, P_, P_, sz, P_],
         "ssdbox_arm_filter": [P_, i64, f32, P_, P_],
     }
+    sigs["ssdbox_timers_enable"] = [C.c_int]
+    sigs["ssdbox_timers_read"] = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     for name, args in sigs.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int
@@ -172,3 +177,17 @@ class Workspace(object):
 
 def workspace_bytes(op, B=0, P=0, Cn=0, gmax=0, top_k=0):
     return int(lib().ssdbox_workspace_bytes(op, int(B), int(P), int(Cn), int(gmax), int(top_k)))
+
+
+def timers_enable(on):
+    check(lib().ssdbox_timers_enable(1 if on else 0))
+
+
+def timers_read():
+    """{kernel name: (total device ms, launches)} accumulated since timers_enable(True)."""
+    out = {}
+    for i, name in enumerate(KERNEL_NAMES):
+        ms, n = C.c_double(0), C.c_int64(0)
+        check(lib().ssdbox_timers_read(i, C.byref(ms), C.byref(n)))
+        out[name] = (ms.value, n.value)
+    return out
