@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""bench.py -- SSD512-COCO box hot path on B200: match + MultiBoxLoss forward AND Detect/NMS.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ssdbox|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input of BASELINE.json
+configs[1] (SSD512 VGG16 COCO: P=24564 priors, C=81 classes, B=64 images PER GPU):
+    T  match + MultiBoxLoss forward  (init, match, loss_stream, mine_reduce kernels)
+    D  DetectOut: threshold, top-200, NMS (init, detect_stream, detect_segment, detect_overflow)
+`value` = images/s with inputs resident in HBM (whole job: N * B / max-over-ranks step time; every
+image passes through both T and D), timed with CUDA events around K CUDA-graph replays.
+`e2e` = same metric through the public modules (MultiBoxLoss.forward / DetectOut.__call__) with
+pinned HOST inputs: H2D of loc/conf/targets/scores and D2H of the losses and the detection tensor
+inside the timed region.  `--impl reference` times the reference algorithm's CPU path (the oracle
+port: /root/reference itself is Python and not present on the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "object-detection-pytorch_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = "SSD512 COCO images/s: match+MultiBoxLoss & Detect/NMS, 1/2/4/8 B200"
+WORKLOAD = "ssd512_coco"
+VAR = [0.1, 0.2]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ssdbox", choices=["ssdbox", "reference"])
+    ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: the config's batch)")
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--dense", action="store_true", help="detect scores with background bias 4 (worst case)")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# bytes model (SURVEY.md section 8d / BASELINE.md section 3), per image
+# ----------------------------------------------------------------------------------------------
+def bytes_T(P, C, G, B):
+    return P * (4 * C + 16) + 20 * G + 16.0 * P / B
+
+
+def bytes_D(P, C, top_k):
+    return P * (4 * C + 16) + 20 * C * top_k
+
+
+def load_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic():
+    """dram bytes per launch of the dominant kernels from the committed ncu capture (or None)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU side (oracle port of the reference algorithm) -- the only place bench.py executes oracle/
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_pass(name, C, P, priors_cpu, bt, bd, seed, dense):
+    """times ONE pass: T on `bt` images + D on `bd` images; returns (t_T, t_D) seconds."""
+    from oracle import ssd_oracle as O
+    from ssdbox import configs, synth
+    _, c = configs.get(name)
+    tg = synth.gen_targets(bt, C, c["gt_max"], seed)
+    loc = synth.gen_loc(max(bt, bd), P, seed)
+    conf = synth.gen_train_logits(bt, P, C, seed)
+    sc = synth.gen_detect_scores(bd, P, C, seed, bkg_bias=4.0 if dense else 10.0)
+    t0 = time.perf_counter()
+    O.multibox_loss(loc[:bt], conf, priors_cpu, tg, C)
+    t1 = time.perf_counter()
+    O.detect(loc[:bd], sc, priors_cpu, C)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm on the host cores (oracle port, all threads)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import warnings
+    warnings.filterwarnings("ignore")
+    from oracle import ssd_oracle as O
+    from ssdbox import configs
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg, c = configs.get(args.workload)
+    C = cfg.MODEL.NUM_CLASSES
+    pri = O.prior_boxes(cfg.MODEL, c["layer_dims"])
+    P = pri.size(0)
+    bt, bd = 4, 2
+    for i in range(args.warmup):
+        cpu_reference_pass(args.workload, C, P, pri, bt, bd, i, args.dense)
+    tt = td = 0.0
+    t_start = time.perf_counter()
+    for i in range(args.steps):
+        a, b = cpu_reference_pass(args.workload, C, P, pri, bt, bd, 100 + i, args.dense)
+        tt += a
+        td += b
+    wall = time.perf_counter() - t_start
+    per_img = tt / (args.steps * bt) + td / (args.steps * bd)
+    value = 1.0 / per_img
+    sample = "per step: match+MultiBoxLoss fwd on %d images + Detect on %d images (sparse scores), torch CPU, %d threads" % (bt, bd, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (tt + td) / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: P=%d C=%d, CPU sample of the B=%d step" % (args.workload, P, C, c["batch"]),
+                   "inputs": "synthetic seeded (ssdbox.synth), same generator as the GPU arm"},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "phases": {"train_fwd_images_per_s": args.steps * bt / tt, "detect_images_per_s": args.steps * bd / td},
+        "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import ssdbox
+    from ssdbox import _abi, configs, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the box path has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    cfg, c = configs.get(args.workload)
+    C = cfg.MODEL.NUM_CLASSES
+    B = args.batch or c["batch"]
+    top_k = 200
+    priors = ssdbox.PriorBoxSSD(cfg).forward(c["layer_dims"], keep_on_device=True)
+    P = priors.size(0)
+
+    # ---- synthetic inputs: drawn on the CPU (seeded per rank), kept in pinned memory for e2e ----
+    seed = 1000 * rank
+    tg = synth.gen_targets(B, C, c["gt_max"], seed)
+    gt_h, offs_h = synth.pack_targets(tg)
+    gmax = max(int(t.size(0)) for t in tg)
+    g_avg = float(gt_h.size(0)) / B
+    loc_h = synth.gen_loc(B, P, seed).pin_memory()
+    conf_h = synth.gen_train_logits(B, P, C, seed).pin_memory()
+    sc_h = synth.gen_detect_scores(B, P, C, seed, bkg_bias=4.0 if args.dense else 10.0).pin_memory()
+    gt_h, offs_h = gt_h.pin_memory(), offs_h.pin_memory()
+    loc, conf, sc = loc_h.to(dev), conf_h.to(dev), sc_h.to(dev)
+    gt, offs = gt_h.to(dev), offs_h.to(dev)
+
+    crit = ssdbox.MultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, distributed=(world > 1))
+    det = ssdbox.DetectOut(C, 0, top_k, 0.01, 0.45, VAR)
+    det_out = torch.empty(B, C, top_k, 5, dtype=torch.float32, device=dev)
+
+    def step():
+        with torch.no_grad():
+            ll, lc = crit.forward_packed(loc, conf, priors, gt, offs, gmax)
+            out = det.forward(loc, sc, priors, out=det_out)
+        return ll, lc, out
+
+    # eager warm-up (lazy init, workspace allocation), also the functional sanity of the step
+    for _ in range(2):
+        ll, lc, out = step()
+    torch.cuda.synchronize()
+    sanity = {"loss_l": float(ll), "loss_c": float(lc), "detections": int((out[..., 0] > 0).sum())}
+
+    # ---- per-kernel device times (eager, CUDA events inside the library on the launch stream) ---
+    _abi.timers_enable(True)
+    n_prof = max(3, min(args.steps, 20))
+    for _ in range(n_prof):
+        step()
+    torch.cuda.synchronize()
+    kt = _abi.timers_read()
+    _abi.timers_enable(False)
+    kernels_us = {k: (1e3 * v[0] / v[1]) for k, v in kt.items() if v[1]}
+
+    # ---- the timed region: K replays of the captured step (or eager launches) -------------------
+    use_graph = not args.no_graph
+    graph = None
+    if use_graph:
+        try:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                step()
+            torch.cuda.current_stream().wait_stream(s)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+        except Exception as e:  # e.g. NCCL capture unsupported
+            sys.stderr.write("bench: CUDA-graph capture failed (%r); timing eager launches\n" % (e,))
+            graph = None
+            torch.cuda.synchronize()
+
+    def run_once():
+        if graph is not None:
+            graph.replay()
+        else:
+            step()
+
+    for _ in range(max(args.warmup, 3)):
+        run_once()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        run_once()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    elapsed_ms = e0.elapsed_time(e1)
+    # keep the GPU busy a little longer so the clock sampler sees load even for short K
+    if rank == 0:
+        t_end = time.perf_counter() + 0.6
+        while time.perf_counter() < t_end:
+            run_once()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = n_gpus * B / (ms_per_step * 1e-3)
+
+    # ---- e2e: public modules, pinned host inputs, H2D + D2H inside the timed region -------------
+    loc_d, conf_d, sc_d = torch.empty_like(loc), torch.empty_like(conf), torch.empty_like(sc)
+    out_h = torch.empty(B, C, top_k, 5, dtype=torch.float32).pin_memory()
+    loss_h = torch.empty(2, dtype=torch.float32).pin_memory()
+    tg_h = [t.pin_memory() for t in tg]
+
+    def e2e_step():
+        with torch.no_grad():
+            loc_d.copy_(loc_h, non_blocking=True)
+            conf_d.copy_(conf_h, non_blocking=True)
+            tgd = [t.to(dev, non_blocking=True) for t in tg_h]
+            ll, lc = crit((loc_d, conf_d, priors), tgd)
+            loss_h.copy_(torch.stack([ll, lc]), non_blocking=True)
+            sc_d.copy_(sc_h, non_blocking=True)
+            o = det(loc_d, sc_d, priors)
+            out_h.copy_(o, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_step()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = loc_h.numel() * 4 + conf_h.numel() * 4 + sc_h.numel() * 4 + gt_h.numel() * 4
+    d2h = out_h.numel() * 4 + 8
+    e2e = {"value": n_gpus * B / e2e_s, "unit": "images/s", "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
+           "api": "ssdbox.MultiBoxLoss.forward + ssdbox.DetectOut.__call__ from pinned host tensors"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel + per-phase fractions ----------------------------------
+    peak, peak_src = load_peak()
+    traffic = load_traffic()
+    t_us = sum(kernels_us.get(k, 0.0) for k in ("init", "match", "loss_stream", "mine_reduce"))
+    d_us = sum(kernels_us.get(k, 0.0) for k in ("init", "detect_stream", "detect_segment", "detect_overflow"))
+    dom = max(("loss_stream", "detect_stream"), key=lambda k: kernels_us.get(k, 0.0))
+    dom_us = kernels_us[dom]
+    dom_bytes = float(B) * P * 4 * C       # the compulsory read of conf / scores [B,P,C] fp32
+    achieved = dom_bytes / (dom_us * 1e-6) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic.get(dom), "avg_launch_us": dom_us,
+                "algorithmic_bytes_per_launch": dom_bytes, "peak_source": peak_src}
+    other = "detect_stream" if dom == "loss_stream" else "loss_stream"
+    phases = {
+        "step_bytes_model": "T: P*(4C+16)+20G+16P/B per image; D: P*(4C+16)+20*C*top_k per image (SURVEY.md 8d)",
+        "train_fwd": {"kernel_us_sum": t_us, "bytes_per_image": bytes_T(P, C, g_avg, B),
+                      "hbm_frac_of_kernel_sum": bytes_T(P, C, g_avg, B) * B / (t_us * 1e-6) / 1e9 / peak if t_us else None},
+        "detect": {"kernel_us_sum": d_us, "bytes_per_image": bytes_D(P, C, top_k),
+                   "hbm_frac_of_kernel_sum": bytes_D(P, C, top_k) * B / (d_us * 1e-6) / 1e9 / peak if d_us else None},
+        "step_hbm_frac": (bytes_T(P, C, g_avg, B) + bytes_D(P, C, top_k)) * B / (ms_per_step * 1e-3) / 1e9 / peak,
+        other + "_kernel": {"avg_launch_us": kernels_us.get(other), "achieved_GBps": dom_bytes / (kernels_us[other] * 1e-6) / 1e9 if other in kernels_us else None,
+                            "traffic": traffic.get(other)},
+        "kernels_us": kernels_us,
+    }
+
+    # ---- CPU baseline: the oracle port on this box's host cores (bounded sample) ----------------
+    cpu_baseline = None
+    if not args.no_cpu_baseline and n_gpus == 1:
+        import warnings
+        warnings.filterwarnings("ignore")
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        pri_cpu = priors.cpu()
+        bt, bd, reps = 4, 2, 3
+        cpu_reference_pass(args.workload, C, P, pri_cpu, bt, bd, 7, args.dense)
+        tt = td = 0.0
+        for i in range(reps):
+            a, b = cpu_reference_pass(args.workload, C, P, pri_cpu, bt, bd, 50 + i, args.dense)
+            tt += a
+            td += b
+        per_img = tt / (reps * bt) + td / (reps * bd)
+        cpu_baseline = {"value": 1.0 / per_img, "unit": "images/s", "cores": cores, "kind": "port",
+                        "sample": "%d reps of (match+MultiBoxLoss fwd on %d images + Detect on %d images) of the same workload, torch CPU oracle, %d threads"
+                                  % (reps, bt, bd, cores),
+                        "train_fwd_images_per_s": reps * bt / tt, "detect_images_per_s": reps * bd / td}
+
+    launches_per_step = 8
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": n_gpus, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: SSD512 VGG16 COCO box path, P=%d priors, C=%d classes, B=%d images per GPU, "
+                               "step = match+MultiBoxLoss fwd + DetectOut(top_k=200, conf 0.01, nms 0.45)" % (args.workload, P, C, B),
+                   "global_batch": n_gpus * B, "detect_scores": "dense (bkg bias 4)" if args.dense else "sparse/realistic (bkg bias 10)",
+                   "l2": "inputs larger than L2 (conf and scores are %.0f MB each vs 126 MB L2)" % (conf.numel() * 4 / 1e6),
+                   "launch": "CUDA graph replay" if graph is not None else "eager launches",
+                   "parallelism": "images sharded by rank; one all-reduce of {sum_l, sum_c, N_pos} per step" if n_gpus > 1 else "single GPU"},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "phases": phases, "sanity": sanity,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -50,11 +50,22 @@ class _State(object):
 
 
 def loss_forward_raw(state, loc, conf, priors, gt, offsets, gmax, num_classes, threshold, negpos_ratio,
-                     variance, anchors_xyxy=None, pool=None, binarize=False, finalize=True, debug=None):
-    """One call of ssdbox_multibox_loss_fwd on validated CUDA tensors.  Fills state.{sums,losses,sel,tidx}."""
+                     variance, anchors_xyxy=None, pool=None, binarize=False, finalize=True, debug=None,
+                     fresh=False):
+    """One call of ssdbox_multibox_loss_fwd on validated CUDA tensors.  Returns
+    (cfg, sums[3] f64, losses[2] f32, sel[B,P] i16, tidx[B,P] i16).  With fresh=False the outputs are
+    the module's persistent buffers (overwritten by the next call); fresh=True allocates new ones
+    (what autograd saves for backward)."""
     B, P = loc.size(0), loc.size(1)
     dev = loc.device
-    state.ensure(B, P, dev)
+    if fresh:
+        sel = torch.empty(B, P, dtype=torch.int16, device=dev)
+        tidx = torch.empty(B, P, dtype=torch.int16, device=dev)
+        sums = torch.empty(3, dtype=torch.float64, device=dev)
+        losses = torch.empty(2, dtype=torch.float32, device=dev)
+    else:
+        state.ensure(B, P, dev)
+        sel, tidx, sums, losses = state.sel, state.tidx, state.sums, state.losses
     per_image = priors.dim() == 3
     cfg = _abi.LossCfg(B, P, int(num_classes), int(gmax), float(threshold), int(negpos_ratio),
                        float(variance[0]), float(variance[1]), 1 if binarize else 0, 1 if finalize else 0,
@@ -65,31 +76,35 @@ def loss_forward_raw(state, loc, conf, priors, gt, offsets, gmax, num_classes, t
         C.byref(cfg), _abi.ptr(loc, torch.float32, "loc_data"), _abi.ptr(conf, torch.float32, "conf_data"),
         _abi.ptr(priors, torch.float32, "priors"), _abi.ptr(anchors_xyxy, torch.float32, "anchors", True),
         _abi.ptr(pool, torch.uint8, "pool", True), _abi.ptr(gt, torch.float32, "gt"),
-        _abi.ptr(offsets, torch.int32, "gt_offsets"), _abi.ptr(state.sums), _abi.ptr(state.losses),
-        _abi.ptr(state.sel), _abi.ptr(state.tidx), _abi.ptr(dbg.get("conf_t"), torch.int64, "conf_t", True),
+        _abi.ptr(offsets, torch.int32, "gt_offsets"), _abi.ptr(sums), _abi.ptr(losses),
+        _abi.ptr(sel), _abi.ptr(tidx), _abi.ptr(dbg.get("conf_t"), torch.int64, "conf_t", True),
         _abi.ptr(dbg.get("loc_t"), torch.float32, "loc_t", True), _abi.ptr(dbg.get("neg"), torch.uint8, "neg", True),
         _abi.ptr(dbg.get("keys"), torch.float32, "keys", True), ws, n, _abi.stream_ptr(dev)))
-    return cfg
+    return cfg, sums, losses, sel, tidx
 
 
 class _MultiBoxLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, loc, conf, priors, gt, offsets, anchors_xyxy, pool, mod, gmax):
         st = mod._state
-        process_group = mod.process_group
         distributed = mod._is_distributed()
-        cfg = loss_forward_raw(st, loc, conf, priors, gt, offsets, gmax, mod.num_classes, mod.threshold,
-                               mod.negpos_ratio, mod.variance, anchors_xyxy, pool, mod.binarize_labels,
-                               finalize=not distributed, debug=mod._debug)
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        cfg, sums, losses, sel, tidx = loss_forward_raw(
+            st, loc, conf, priors, gt, offsets, gmax, mod.num_classes, mod.threshold, mod.negpos_ratio,
+            mod.variance, anchors_xyxy, pool, mod.binarize_labels, finalize=not distributed, debug=mod._debug,
+            fresh=need_grad)
         if distributed:
             # the only collective of the path: {sum smooth-L1, sum CE, N_pos} summed over ranks
             import torch.distributed as dist
-            dist.all_reduce(st.sums, op=dist.ReduceOp.SUM, group=process_group)
-            _abi.check(_abi.lib().ssdbox_multibox_loss_finalize(_abi.ptr(st.sums), _abi.ptr(st.losses),
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=mod.process_group)
+            _abi.check(_abi.lib().ssdbox_multibox_loss_finalize(_abi.ptr(sums), _abi.ptr(losses),
                                                                 _abi.stream_ptr(loc.device)))
-        ctx.cfg = cfg
-        ctx.save_for_backward(loc, conf, priors, gt, offsets, st.sel.clone(), st.tidx.clone(), st.sums.clone())
-        out = st.losses.clone()
+        mod._last = (sums, sel, tidx)
+        if need_grad:
+            ctx.cfg = cfg
+            ctx.save_for_backward(loc, conf, priors, gt, offsets, sel, tidx, sums)
+            return losses[0], losses[1]
+        out = losses.clone()
         return out[0], out[1]
 
     @staticmethod
@@ -132,6 +147,7 @@ class MultiBoxLoss(nn.Module):
         self.process_group = process_group
         self._state = _State()
         self._debug = None
+        self._last = None
 
     def _is_distributed(self):
         if self.distributed is False:
@@ -174,6 +190,6 @@ class MultiBoxLoss(nn.Module):
             d = dict(self._debug)
         finally:
             self._debug = None
-        d.update(loss_l=ll, loss_c=lc, sums=self._state.sums.clone(), sel=self._state.sel.clone(),
-                 tidx=self._state.tidx.clone())
+        sums, sel, tidx = self._last
+        d.update(loss_l=ll, loss_c=lc, sums=sums.clone(), sel=sel.clone(), tidx=tidx.clone())
         return d
