@@ -266,6 +266,22 @@ def main():
     _abi.timers_enable(False)
     kernels_us = {k: (1e3 * v[0] / v[1]) for k, v in kt.items() if v[1]}
 
+    # forward + backward through the autograd module (reported beside the headline, not part of it)
+    loc_g = loc.clone().requires_grad_(True)
+    conf_g = conf.clone().requires_grad_(True)
+    for i in range(4):
+        if i == 1:
+            _abi.timers_enable(True)
+        a_, b_ = crit.forward_packed(loc_g, conf_g, priors, gt, offs, gmax)
+        (a_ + b_).backward()
+        loc_g.grad = None
+        conf_g.grad = None
+    torch.cuda.synchronize()
+    kb = _abi.timers_read()
+    _abi.timers_enable(False)
+    bwd_us = 1e3 * kb["loss_bwd"][0] / max(kb["loss_bwd"][1], 1)
+    del loc_g, conf_g
+
     # ---- the timed region: K replays of the captured step (or eager launches) -------------------
     use_graph = not args.no_graph
     graph = None
@@ -380,6 +396,9 @@ def main():
         "step_bytes_model": "T: P*(4C+16)+20G+16P/B per image; D: P*(4C+16)+20*C*top_k per image (SURVEY.md 8d)",
         "train_fwd": {"kernel_us_sum": t_us, "bytes_per_image": bytes_T(P, C, g_avg, B),
                       "hbm_frac_of_kernel_sum": bytes_T(P, C, g_avg, B) * B / (t_us * 1e-6) / 1e9 / peak if t_us else None},
+        "train_bwd": {"kernel_us_sum": bwd_us, "note": "zero_fill + sparse-row kernels; grad_conf/grad_loc fully written",
+                      "bytes_written_per_image": P * (4 * C + 16),
+                      "hbm_frac": P * (4 * C + 16) * B / (bwd_us * 1e-6) / 1e9 / peak if bwd_us else None},
         "detect": {"kernel_us_sum": d_us, "bytes_per_image": bytes_D(P, C, top_k),
                    "hbm_frac_of_kernel_sum": bytes_D(P, C, top_k) * B / (d_us * 1e-6) / 1e9 / peak if d_us else None},
         "step_hbm_frac": (bytes_T(P, C, g_avg, B) + bytes_D(P, C, top_k)) * B / (ms_per_step * 1e-3) / 1e9 / peak,

@@ -35,6 +35,29 @@ struct DetStreamArgs {
   float thr;
 };
 
+// One element above the threshold (rare: ~5e-4 of the elements with a trained detector).
+// e = index of the element inside the tile (row-major [rows, C]).
+template <int CT>
+__device__ __forceinline__ void emit_candidate(const DetStreamArgs& a, int C, long long r0, int e, float v) {
+  int r = CT > 0 ? e / CT : e / C;
+  int c = e - r * C;
+  if (c == 0) return;                                    // background plane is never scored (detection.py:47)
+  long long row = r0 + r;
+  if (a.keep && !a.keep[row]) v = 0.0f;                  // RefineDet: filtered anchors score 0
+  if (!(v > a.thr)) return;                              // detection.py:48 strict >
+  uint32_t b = (uint32_t)row / (uint32_t)a.P;
+  uint32_t p = (uint32_t)row - b * (uint32_t)a.P;
+  uint32_t* ctr = &a.cnt[(size_t)b * C + c];
+  // dense scores: once a list has overflowed its extra candidates are never read (the overflow
+  // kernel re-selects from the score column), so skip the atomic; a stale read only costs an atomic
+  if (__ldcg(ctr) > (uint32_t)a.cap) return;
+  uint32_t slot = atomicAdd(ctr, 1u);
+  if (slot < (uint32_t)a.cap)
+    a.cand[((size_t)b * C + c) * a.cap + slot] = ((unsigned long long)f2ord(v) << 32) | p;
+}
+
+// The tile is scanned as a flat float4 stream (no per-row structure): 4 elements cost one LDS.128,
+// three FMNMX and one compare; the (row, class) decomposition happens only for the rare hits.
 template <int CT>
 __global__ void __launch_bounds__(kRingThreads, 1) detect_stream_kernel(DetStreamArgs a) {
   extern __shared__ __align__(128) unsigned char smem_ring[];
@@ -46,48 +69,51 @@ __global__ void __launch_bounds__(kRingThreads, 1) detect_stream_kernel(DetStrea
     return;
   }
   const int wg = warp >> 2;
-  const int r = tid & 127;
+  const int t = tid & 127;
   const int R = a.ring.R, NS = a.ring.NS;
-  const uint32_t lt_mask = (1u << lane) - 1u;
+  const float thr = a.thr;
   for (int it = wg; it < rc.n_local; it += 2) {
     const int s = it % NS, j = it % (2 * NS), ph = it / (2 * NS);
-    long long row = (rc.t0 + it) * R + r;
-    bool valid = (r < R) && (row < a.ring.rows);
-    uint32_t b = 0, p = 0;
-    bool kept = true;
-    if (valid) {
-      b = (uint32_t)row / (uint32_t)a.P;
-      p = (uint32_t)row - b * (uint32_t)a.P;
-      if (a.keep) kept = a.keep[row] != 0;
-    }
-    uint32_t vmask = __ballot_sync(SSDBOX_FULL_MASK, valid);
-    // the warp's rows are consecutive: uniform image iff first and last valid row agree
-    uint32_t b_first = __shfl_sync(SSDBOX_FULL_MASK, b, 0);
-    uint32_t b_last = __shfl_sync(SSDBOX_FULL_MASK, b, vmask ? 31 - __clz(vmask) : 0);
-    const bool uniform = b_first == b_last;
+    const long long r0 = (rc.t0 + it) * R;
+    const long long left = a.ring.rows - r0;
+    const int nrows = left < R ? (int)left : R;
+    const int nf = nrows * C;
+    const int n4 = nf >> 2;
+    const float* st = rc.stages + (size_t)s * rc.stage_floats;
+    const float4* st4 = reinterpret_cast<const float4*>(st);
     mbar_wait(&rc.full[j], (uint32_t)(ph & 1));
-    if (vmask) {
-      const float* rp = rc.stages + (size_t)s * rc.stage_floats + (size_t)r * C;
-#pragma unroll 4
-      for (int c = 1; c < C; ++c) {
-        float v = valid ? rp[c] : 0.0f;
-        if (!kept) v = 0.0f;
-        bool hit = valid && v > a.thr;                       // detection.py:48 strict >
-        uint32_t hm = __ballot_sync(SSDBOX_FULL_MASK, hit);
-        if (hm == 0u) continue;
-        uint32_t slot = 0;
-        if (uniform) {
-          int leader = __ffs(hm) - 1;
-          uint32_t base = 0;
-          if (lane == leader) base = atomicAdd(&a.cnt[(size_t)b_first * C + c], (uint32_t)__popc(hm));
-          base = __shfl_sync(SSDBOX_FULL_MASK, base, leader);
-          slot = base + (uint32_t)__popc(hm & lt_mask);
-        } else if (hit) {
-          slot = atomicAdd(&a.cnt[(size_t)b * C + c], 1u);
+    int i = t;
+    for (; i + 3 * 128 < n4; i += 4 * 128) {             // 4 independent 16-byte loads in flight
+      float4 v0 = st4[i], v1 = st4[i + 128], v2 = st4[i + 256], v3 = st4[i + 384];
+      float m0 = fmaxf(fmaxf(v0.x, v0.y), fmaxf(v0.z, v0.w));
+      float m1 = fmaxf(fmaxf(v1.x, v1.y), fmaxf(v1.z, v1.w));
+      float m2 = fmaxf(fmaxf(v2.x, v2.y), fmaxf(v2.z, v2.w));
+      float m3 = fmaxf(fmaxf(v3.x, v3.y), fmaxf(v3.z, v3.w));
+      if (fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) > thr) {
+        const float4 vv[4] = {v0, v1, v2, v3};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          int e = (i + q * 128) * 4;
+          if (vv[q].x > thr) emit_candidate<CT>(a, C, r0, e, vv[q].x);
+          if (vv[q].y > thr) emit_candidate<CT>(a, C, r0, e + 1, vv[q].y);
+          if (vv[q].z > thr) emit_candidate<CT>(a, C, r0, e + 2, vv[q].z);
+          if (vv[q].w > thr) emit_candidate<CT>(a, C, r0, e + 3, vv[q].w);
         }
-        if (hit && slot < (uint32_t)a.cap)
-          a.cand[((size_t)b * C + c) * a.cap + slot] = ((unsigned long long)f2ord(v) << 32) | p;
       }
+    }
+    for (; i < n4; i += 128) {
+      float4 v = st4[i];
+      if (fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) > thr) {
+        int e = i * 4;
+        if (v.x > thr) emit_candidate<CT>(a, C, r0, e, v.x);
+        if (v.y > thr) emit_candidate<CT>(a, C, r0, e + 1, v.y);
+        if (v.z > thr) emit_candidate<CT>(a, C, r0, e + 2, v.z);
+        if (v.w > thr) emit_candidate<CT>(a, C, r0, e + 3, v.w);
+      }
+    }
+    for (int e = (n4 << 2) + t; e < nf; e += 128) {      // ragged tail of the last tile
+      float v = st[e];
+      if (v > thr) emit_candidate<CT>(a, C, r0, e, v);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&rc.empty[j]);
@@ -170,6 +196,8 @@ struct DetSegArgs {
   const uint8_t* keep;
   const uint32_t* cnt;
   const unsigned long long* cand;
+  uint32_t* ovf_count; // [1] number of (image, class) lists that overflowed
+  int32_t* ovf_list;   // [B*C] their segment ids
   uint32_t* scratch;   // [kOverflowSlots, P]
   float* out;
   int32_t* counts;
@@ -218,7 +246,10 @@ __global__ void __launch_bounds__(kSegThreads) detect_segment_kernel(DetSegArgs 
   const int seg = blockIdx.x, tid = threadIdx.x;
   const int b = seg / a.C, c = seg - b * a.C;
   const uint32_t total = c == 0 ? 0u : a.cnt[seg];
-  if (total > (uint32_t)a.cap) return;   // detect_overflow_kernel owns this segment
+  if (total > (uint32_t)a.cap) {         // detect_overflow_kernel owns this segment
+    if (tid == 0) a.ovf_list[atomicAdd(a.ovf_count, 1u)] = seg;
+    return;
+  }
   if (total == 0u) {                     // background plane / no candidate: zeros (detection.py:37,50-51)
     float* o = a.out + (size_t)seg * a.top_k * 5;
     for (int e = tid; e < a.top_k * 5; e += kSegThreads) o[e] = 0.0f;
@@ -245,10 +276,10 @@ __global__ void __launch_bounds__(kOvfThreads, 1) detect_overflow_kernel(DetSegA
   NmsSmem ns = carve_nms(smem_ovf + 16384 + 288, a.top_k);
   uint32_t* uk = a.scratch + (size_t)blockIdx.x * a.P;
   const int tid = threadIdx.x;
-  const int nseg = a.B * a.C;
-  for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+  const int novf = (int)*a.ovf_count;      // written by detect_segment_kernel (previous launch)
+  for (int w = blockIdx.x; w < novf; w += gridDim.x) {
+    const int seg = a.ovf_list[w];
     const int b = seg / a.C, c = seg - b * a.C;
-    if (c == 0 || a.cnt[seg] <= (uint32_t)a.cap) continue;   // uniform across the CTA
     // ordered scores of the class column; 0 = not a candidate
     for (int p = tid; p < a.P; p += kOvfThreads) {
       size_t row = (size_t)b * a.P + p;
@@ -356,11 +387,12 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
   if (rc) return rc;
   const int cap = detect_cand_cap(top_k);
   Carver cv(ws);
-  uint32_t* cnt = cv.take<uint32_t>((size_t)B * C);
+  uint32_t* cnt = cv.take<uint32_t>((size_t)B * C + 1);   // [B*C] counters + overflow count
+  int32_t* ovf_list = cv.take<int32_t>((size_t)B * C);
   unsigned long long* cand = cv.take<unsigned long long>((size_t)B * C * cap);
   uint32_t* scratch = cv.take<uint32_t>((size_t)kOverflowSlots * P);
 
-  rc = launch_init(nullptr, 0, cnt, (size_t)B * C, nullptr, 0, nullptr, 0, st);
+  rc = launch_init(nullptr, 0, cnt, (size_t)B * C + 1, nullptr, 0, nullptr, 0, st);
   if (rc) return rc;
 
   if (P > 0) {
@@ -389,7 +421,7 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
   g.nms_thr = cfg->nms_thresh; g.conf_thr = cfg->conf_thresh; g.var0 = cfg->var0; g.var1 = cfg->var1;
   g.prior_stride = (long long)cfg->prior_batch_stride;
   g.loc = loc; g.scores = scores; g.priors = priors; g.keep = score_keep;
-  g.cnt = cnt; g.cand = cand; g.scratch = scratch; g.out = out; g.counts = counts;
+  g.cnt = cnt; g.cand = cand; g.ovf_count = cnt + (size_t)B * C; g.ovf_list = ovf_list; g.scratch = scratch; g.out = out; g.counts = counts;
   size_t seg_smem = (size_t)cap * 8 + nms_smem_bytes(top_k);
   SSDBOX_CUDA(cudaFuncSetAttribute(detect_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem));
 {

@@ -123,6 +123,7 @@ static int launch_stream(StreamArgs a, const float* conf, long long rows, int C,
 // per-image selection of the K largest ordered keys (descending, ties by ascending index)
 // ------------------------------------------------------------------------------------------------
 constexpr int kMineThreads = 1024;
+constexpr int kMineFixedSmem = 8192 + 320 + 288;   // level histogram + reduction scratch
 
 struct MineArgs {
   int B, P, C;
@@ -157,8 +158,10 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
   double* s_dscr = reinterpret_cast<double*>(smem_raw + 8192);          // 40
   int* s_iscr = reinterpret_cast<int*>(smem_raw + 8192 + 320);          // 64
   int* s_res = s_iscr + 64;                                             // 8
-  uint32_t* uk = a.uk_in_smem ? reinterpret_cast<uint32_t*>(smem_raw + 8192 + 320 + 288)
+  // smem mode: ordered keys + class targets of the whole image stay on chip between the passes
+  uint32_t* uk = a.uk_in_smem ? reinterpret_cast<uint32_t*>(smem_raw + kMineFixedSmem)
                               : a.ukey_global + (size_t)blockIdx.x * a.P;
+  int16_t* s_lab = reinterpret_cast<int16_t*>(smem_raw + kMineFixedSmem + (size_t)a.P * 4);
   __shared__ int s_last;
 
   const int b = blockIdx.x, tid = threadIdx.x, P = a.P;
@@ -166,33 +169,49 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
   const int g0 = a.gt_offsets[b];
   const float* pri = a.priors + (size_t)b * (size_t)a.prior_stride;
   const uint32_t ord_zero = f2ord(0.0f);
+  const bool in_smem = a.uk_in_smem != 0;
 
-  // pass A: positives (count, CE, smooth-L1) and the ordered mining keys
+  // pass A: positives (count, CE, smooth-L1) and the ordered mining keys; loads batched 4 deep
   int npos = 0;
   double ce = 0.0, l1 = 0.0;
-  for (int p = tid; p < P; p += kMineThreads) {
-    size_t i = off + p;
-    int lb = a.lab[i];
-    int inpool = a.pool ? a.pool[i] : 1;
-    float key = a.keys[i];
-    if (a.dbg_keys) a.dbg_keys[i] = key;
-    uint32_t u;
-    if (!inpool) {
-      u = 0u;
-    } else if (lb > 0) {
-      ++npos;
-      ce += (double)key;
-      const float* row = a.gt + (size_t)(g0 + a.tidx[i]) * 5;
-      Box m;
-      m.x1 = row[0]; m.y1 = row[1]; m.x2 = row[2]; m.y2 = row[3];
-      float4 t = encode_box(m, *reinterpret_cast<const float4*>(pri + (size_t)p * 4), a.var0, a.var1);
-      float4 l = *reinterpret_cast<const float4*>(a.loc + i * 4);
-      l1 += (double)(smooth_l1(l.x, t.x) + smooth_l1(l.y, t.y) + smooth_l1(l.z, t.z) + smooth_l1(l.w, t.w));
-      u = ord_zero;
-    } else {
-      u = f2ord(key);
+  for (int p0 = tid; p0 < P; p0 += 4 * kMineThreads) {
+    float key[4];
+    int lb[4], inp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int p = p0 + u * kMineThreads;
+      key[u] = 0.f; lb[u] = 0; inp[u] = 0;
+      if (p < P) {
+        key[u] = a.keys[off + p];
+        lb[u] = a.lab[off + p];
+        inp[u] = a.pool ? a.pool[off + p] : 1;
+      }
     }
-    uk[p] = u;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int p = p0 + u * kMineThreads;
+      if (p >= P) continue;
+      size_t i = off + p;
+      if (a.dbg_keys) a.dbg_keys[i] = key[u];
+      uint32_t uo;
+      if (!inp[u]) {
+        uo = 0u;
+      } else if (lb[u] > 0) {
+        ++npos;
+        ce += (double)key[u];
+        const float* row = a.gt + (size_t)(g0 + a.tidx[i]) * 5;
+        Box m;
+        m.x1 = row[0]; m.y1 = row[1]; m.x2 = row[2]; m.y2 = row[3];
+        float4 t = encode_box(m, *reinterpret_cast<const float4*>(pri + (size_t)p * 4), a.var0, a.var1);
+        float4 l = *reinterpret_cast<const float4*>(a.loc + i * 4);
+        l1 += (double)(smooth_l1(l.x, t.x) + smooth_l1(l.y, t.y) + smooth_l1(l.z, t.z) + smooth_l1(l.w, t.w));
+        uo = ord_zero;
+      } else {
+        uo = f2ord(key[u]);
+      }
+      uk[p] = uo;
+      if (in_smem) s_lab[p] = (int16_t)lb[u];
+    }
   }
   int npos_blk = (int)(block_sum((double)npos, s_dscr) + 0.5);
   ce = block_sum(ce, s_dscr);
@@ -206,17 +225,18 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
   if (K > 0) Tu = cta_select_threshold<false>(uk, P, K, a.hist + (size_t)b * kHistBins, s_hist, s_iscr, s_res);
   __syncthreads();
 
-  // final pass: neg = rank < num_neg (:103); CE over pos U neg (:106-110)
+  // final pass: neg = rank < num_neg (:103); CE over pos U neg (:106-110).  The CE of a selected
+  // negative is its mining key, recovered exactly from the ordered key (no second read of keys).
   double ce_neg = 0.0;
   for (int p = tid; p < P; p += kMineThreads) {
     size_t i = off + p;
     uint32_t u = uk[p];
-    int lb = a.lab[i];
+    int lb = in_smem ? (int)s_lab[p] : (int)a.lab[i];
     bool inpool = u != 0u;
     bool is_pos = inpool && lb > 0;
     bool negsel = K > 0 && inpool && u >= Tu;
     a.sel[i] = is_pos ? (int16_t)lb : (negsel ? (int16_t)0 : (int16_t)-1);
-    if (negsel && !is_pos) ce_neg += (double)a.keys[i];
+    if (negsel && !is_pos) ce_neg += (double)ord2f(u);
     if (a.dbg_neg) a.dbg_neg[i] = negsel ? 1 : 0;
   }
   ce_neg = block_sum(ce_neg, s_dscr);
@@ -297,7 +317,6 @@ mine_only_kernel(const float* __restrict__ keys, const uint8_t* __restrict__ pos
 // backward: d(loss_l)/d(loc) and d(loss_c)/d(conf)   (autograd of multibox_loss.py:87-116)
 // ------------------------------------------------------------------------------------------------
 constexpr int kBwdThreads = 256;
-constexpr int kBwdRows = 128;
 
 struct BwdArgs {
   int B, P, C;
@@ -317,73 +336,79 @@ struct BwdArgs {
   int conf_aligned;
 };
 
+// (1) grad_conf := 0 at full store bandwidth (only ~4*num_pos rows per image are ever non-zero)
+__global__ void __launch_bounds__(kBwdThreads) zero_fill_kernel(float* __restrict__ dst, size_t n, int aligned) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (aligned) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    const size_t n4 = n >> 2;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    size_t i = tid;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+      __stcs(d4 + i, z);
+      __stcs(d4 + i + stride, z);
+      __stcs(d4 + i + 2 * stride, z);
+      __stcs(d4 + i + 3 * stride, z);
+    }
+    for (; i < n4; i += stride) __stcs(d4 + i, z);
+    for (size_t k = (n4 << 2) + tid; k < n; k += stride) dst[k] = 0.f;
+  } else {
+    for (size_t k = tid; k < n; k += stride) dst[k] = 0.f;
+  }
+}
+
+// (2) one warp per 32 consecutive rows: grad_loc for every row (coalesced float4), then
+// (softmax - onehot) * grad / N for the selected rows of the group.
 __global__ void __launch_bounds__(kBwdThreads) loss_bwd_kernel(BwdArgs a) {
-  __shared__ int s_sel[kBwdRows];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lane = threadIdx.x & 31;
   const long long rows = (long long)a.B * a.P;
-  const long long tiles = (rows + kBwdRows - 1) / kBwdRows;
+  const long long warp_global = ((long long)blockIdx.x * kBwdThreads + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * kBwdThreads) >> 5;
   const double n = a.sums[2];
   const float scale_l = n > 0.0 ? (float)((double)a.grad_out[0] / n) : 0.0f;
   const float scale_c = n > 0.0 ? (float)((double)a.grad_out[1] / n) : 0.0f;
   const int C = a.C;
-  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    long long r0 = tile * kBwdRows;
-    int nrows = rows - r0 < kBwdRows ? (int)(rows - r0) : kBwdRows;
-    if (tid < kBwdRows) {
-      int lb = -1;
-      if (tid < nrows) {
-        long long row = r0 + tid;
-        lb = a.sel[row];
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lb > 0) {
-          int b = (int)(row / a.P);
-          int p = (int)(row - (long long)b * a.P);
-          const float* tr = a.gt + (size_t)(a.gt_offsets[b] + a.tidx[row]) * 5;
-          Box m;
-          m.x1 = tr[0]; m.y1 = tr[1]; m.x2 = tr[2]; m.y2 = tr[3];
-          float4 t = encode_box(m, *reinterpret_cast<const float4*>(a.priors + (size_t)b * (size_t)a.prior_stride + (size_t)p * 4),
-                                a.var0, a.var1);
-          float4 l = *reinterpret_cast<const float4*>(a.loc + row * 4);
-          float dx = l.x - t.x, dy = l.y - t.y, dz = l.z - t.z, dw = l.w - t.w;
-          g.x = scale_l * fminf(fmaxf(dx, -1.f), 1.f);     // smooth-L1': d for |d|<1, sign(d) otherwise
-          g.y = scale_l * fminf(fmaxf(dy, -1.f), 1.f);
-          g.z = scale_l * fminf(fmaxf(dz, -1.f), 1.f);
-          g.w = scale_l * fminf(fmaxf(dw, -1.f), 1.f);
-        }
-        *reinterpret_cast<float4*>(a.grad_loc + row * 4) = g;
+  for (long long grp = warp_global; grp * 32 < rows; grp += nwarps) {
+    const long long row = grp * 32 + lane;
+    int lb = -1;
+    if (row < rows) {
+      lb = a.sel[row];
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lb > 0) {
+        int b = (int)(row / a.P);
+        int p = (int)(row - (long long)b * a.P);
+        const float* tr = a.gt + (size_t)(a.gt_offsets[b] + a.tidx[row]) * 5;
+        Box m;
+        m.x1 = tr[0]; m.y1 = tr[1]; m.x2 = tr[2]; m.y2 = tr[3];
+        float4 t = encode_box(m, *reinterpret_cast<const float4*>(a.priors + (size_t)b * (size_t)a.prior_stride + (size_t)p * 4),
+                              a.var0, a.var1);
+        float4 l = *reinterpret_cast<const float4*>(a.loc + row * 4);
+        g.x = scale_l * fminf(fmaxf(l.x - t.x, -1.f), 1.f);     // smooth-L1': d for |d|<1, sign(d) otherwise
+        g.y = scale_l * fminf(fmaxf(l.y - t.y, -1.f), 1.f);
+        g.z = scale_l * fminf(fmaxf(l.z - t.z, -1.f), 1.f);
+        g.w = scale_l * fminf(fmaxf(l.w - t.w, -1.f), 1.f);
       }
-      s_sel[tid] = lb;
+      *reinterpret_cast<float4*>(a.grad_loc + row * 4) = g;
     }
-    // zero-fill this tile of grad_conf (the overwhelming majority of rows is not selected)
-    float* gc = a.grad_conf + r0 * C;
-    long long nf = (long long)nrows * C;
-    if (a.conf_aligned) {
-      long long n4 = nf >> 2;
-      float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (long long i = tid; i < n4; i += kBwdThreads) __stcs(reinterpret_cast<float4*>(gc) + i, z);
-      for (long long i = (n4 << 2) + tid; i < nf; i += kBwdThreads) gc[i] = 0.f;
-    } else {
-      for (long long i = tid; i < nf; i += kBwdThreads) gc[i] = 0.f;
-    }
-    __syncthreads();
-    // selected rows: (softmax - onehot) * grad / N, one warp per row
-    for (int rr = warp; rr < nrows; rr += kBwdThreads / 32) {
-      int lb = s_sel[rr];
-      if (lb < 0) continue;
-      const float* x = a.conf + (r0 + rr) * C;
+    uint32_t selmask = __ballot_sync(SSDBOX_FULL_MASK, lb >= 0);
+    while (selmask) {
+      int src = __ffs(selmask) - 1;
+      selmask &= selmask - 1;
+      int tl = __shfl_sync(SSDBOX_FULL_MASK, lb, src);
+      const float* x = a.conf + (grp * 32 + src) * C;
+      float* g = a.grad_conf + (grp * 32 + src) * C;
       float m = -INFINITY;
       for (int c = lane; c < C; c += 32) m = fmaxf(m, x[c]);
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(SSDBOX_FULL_MASK, m, d));
-      float s = 0.f;
-      for (int c = lane; c < C; c += 32) s += expf(x[c] - m);
+      float sum = 0.f;
+      for (int c = lane; c < C; c += 32) sum += expf(x[c] - m);
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(SSDBOX_FULL_MASK, s, d);
-      float inv = 1.0f / s;
-      float* g = gc + (long long)rr * C;
-      for (int c = lane; c < C; c += 32) g[c] = scale_c * (expf(x[c] - m) * inv - (c == lb ? 1.0f : 0.0f));
+      for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(SSDBOX_FULL_MASK, sum, d);
+      float inv = 1.0f / sum;
+      for (int c = lane; c < C; c += 32) g[c] = scale_c * (expf(x[c] - m) * inv - (c == tl ? 1.0f : 0.0f));
     }
-    __syncthreads();
   }
 }
 
@@ -468,11 +493,11 @@ extern "C" int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float*
   m.loc = loc; m.priors = priors; m.gt = gt; m.gt_offsets = gt_offsets; m.pool = pool;
   m.keys = w.keys; m.lab = w.m.lab; m.tidx = tidx; m.hist = w.hist;
   m.ukey_global = w.ukey;
-  size_t fixed = 8192 + 320 + 288;
-  m.uk_in_smem = (fixed + (size_t)P * 4 <= (size_t)dev.max_smem_optin - 1024) ? 1 : 0;
+  size_t fixed = kMineFixedSmem;
+  m.uk_in_smem = (fixed + (size_t)P * 6 + 16 <= (size_t)dev.max_smem_optin - 1024) ? 1 : 0;
   m.partial = w.partial; m.ticket = w.ticket; m.sums = sums; m.losses = losses; m.sel = sel;
   m.dbg_neg = dbg_neg; m.dbg_keys = dbg_keys;
-  size_t smem = fixed + (m.uk_in_smem ? (size_t)P * 4 : 0);
+  size_t smem = fixed + (m.uk_in_smem ? (size_t)P * 6 + 16 : 0);
   SSDBOX_CUDA(cudaFuncSetAttribute(mine_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 {
     TimerScope ts__(KID_MINE, st);
@@ -518,13 +543,15 @@ extern "C" int ssdbox_multibox_loss_bwd(const ssdbox_loss_cfg* cfg, const float*
   a.sel = sel; a.tidx = tidx; a.sums = sums; a.grad_out = grad_out;
   a.grad_loc = grad_loc; a.grad_conf = grad_conf;
   a.conf_aligned = aligned16(grad_conf) ? 1 : 0;
-  long long tiles = ((long long)a.B * a.P + kBwdRows - 1) / kBwdRows;
-  long long grid = (long long)dev.sm_count * 8;
-  if (grid > tiles) grid = tiles;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long rows = (long long)a.B * a.P;
   {
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     TimerScope ts__(KID_LOSS_BWD, st);
-    loss_bwd_kernel<<<(int)grid, kBwdThreads, 0, st>>>(a);
+    zero_fill_kernel<<<dev.sm_count * 16, kBwdThreads, 0, st>>>(grad_conf, (size_t)rows * a.C, a.conf_aligned);
+    long long groups = (rows + 31) / 32;
+    long long blocks = (groups + (kBwdThreads / 32) - 1) / (kBwdThreads / 32);
+    if (blocks > (long long)dev.sm_count * 32) blocks = (long long)dev.sm_count * 32;
+    loss_bwd_kernel<<<(int)blocks, kBwdThreads, 0, st>>>(a);
   }
   SSDBOX_LAUNCH_OK("loss_bwd_kernel");
   return SSDBOX_OK;

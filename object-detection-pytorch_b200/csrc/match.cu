@@ -75,15 +75,18 @@ match_kernel(MatchArgs a, unsigned long long* __restrict__ gt_best, uint32_t* __
   const float* pri = a.priors + (size_t)b * (size_t)a.prior_stride;
   const float* anc = a.anchors_xyxy ? a.anchors_xyxy + (size_t)b * (size_t)a.prior_stride : nullptr;
 
+  // each thread owns 4 CONSECUTIVE priors (the anchors of one feature-map cell for SSD heads), so a
+  // warp covers 128 consecutive priors = a short run of neighbouring cells with a tight bounding box
   Box box[kMatchPPT];
   float area[kMatchPPT];
   float bt_ov[kMatchPPT];
   int bt_idx[kMatchPPT];
   int pidx[kMatchPPT];
   bool valid[kMatchPPT];
+  float wx1 = INFINITY, wy1 = INFINITY, wx2 = -INFINITY, wy2 = -INFINITY;
 #pragma unroll
   for (int k = 0; k < kMatchPPT; ++k) {
-    int p = blockIdx.x * kMatchTile + k * kMatchThreads + tid;
+    int p = blockIdx.x * kMatchTile + tid * kMatchPPT + k;
     pidx[k] = p;
     valid[k] = p < a.P;
     if (valid[k]) {
@@ -93,16 +96,28 @@ match_kernel(MatchArgs a, unsigned long long* __restrict__ gt_best, uint32_t* __
       } else {
         box[k] = point_form(*reinterpret_cast<const float4*>(pri + (size_t)p * 4));
       }
+      wx1 = fminf(wx1, box[k].x1); wy1 = fminf(wy1, box[k].y1);
+      wx2 = fmaxf(wx2, box[k].x2); wy2 = fmaxf(wy2, box[k].y2);
     } else {
       box[k].x1 = box[k].y1 = box[k].x2 = box[k].y2 = 0.0f;
     }
     area[k] = box_area(box[k]);
-    bt_ov[k] = -1.0f;
+    bt_ov[k] = 0.0f;     // max over truths of IoU >= 0; all-zero column -> truth 0 (first index)
     bt_idx[k] = 0;
+  }
+  // warp-wide bounding box of the 128 priors: a truth that does not overlap it has IoU == 0 with
+  // every prior of the warp and can change neither running maximum (both updates are strict >)
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    wx1 = fminf(wx1, __shfl_xor_sync(SSDBOX_FULL_MASK, wx1, d));
+    wy1 = fminf(wy1, __shfl_xor_sync(SSDBOX_FULL_MASK, wy1, d));
+    wx2 = fmaxf(wx2, __shfl_xor_sync(SSDBOX_FULL_MASK, wx2, d));
+    wy2 = fmaxf(wy2, __shfl_xor_sync(SSDBOX_FULL_MASK, wy2, d));
   }
 
   for (int g = 0; g < G; ++g) {
     float4 tv = s_box[g];
+    if (!(tv.x < wx2 && tv.z > wx1 && tv.y < wy2 && tv.w > wy1)) continue;   // warp-uniform
     Box t;
     t.x1 = tv.x; t.y1 = tv.y; t.x2 = tv.z; t.y2 = tv.w;
     float ta = s_area[g];
