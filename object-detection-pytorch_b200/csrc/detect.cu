@@ -35,18 +35,8 @@ struct DetStreamArgs {
   float thr;
 };
 
-// One element above the threshold (rare: ~5e-4 of the elements with a trained detector).
-// e = index of the element inside the tile (row-major [rows, C]).
-template <int CT>
-__device__ __forceinline__ void emit_candidate(const DetStreamArgs& a, int C, long long r0, int e, float v) {
-  int r = CT > 0 ? e / CT : e / C;
-  int c = e - r * C;
-  if (c == 0) return;                                    // background plane is never scored (detection.py:47)
-  long long row = r0 + r;
-  if (a.keep && !a.keep[row]) v = 0.0f;                  // RefineDet: filtered anchors score 0
-  if (!(v > a.thr)) return;                              // detection.py:48 strict >
-  uint32_t b = (uint32_t)row / (uint32_t)a.P;
-  uint32_t p = (uint32_t)row - b * (uint32_t)a.P;
+// One (row, class) score above the threshold (rare: ~5e-4 of the elements with a trained detector).
+__device__ __forceinline__ void emit_candidate(const DetStreamArgs& a, int C, uint32_t b, uint32_t p, int c, float v) {
   uint32_t* ctr = &a.cnt[(size_t)b * C + c];
   // dense scores: once a list has overflowed its extra candidates are never read (the overflow
   // kernel re-selects from the score column), so skip the atomic; a stale read only costs an atomic
@@ -56,8 +46,9 @@ __device__ __forceinline__ void emit_candidate(const DetStreamArgs& a, int C, lo
     a.cand[((size_t)b * C + c) * a.cap + slot] = ((unsigned long long)f2ord(v) << 32) | p;
 }
 
-// The tile is scanned as a flat float4 stream (no per-row structure): 4 elements cost one LDS.128,
-// three FMNMX and one compare; the (row, class) decomposition happens only for the rare hits.
+// Consumer: one thread per prior row computes the maximum over the foreground classes (conflict-
+// free LDS, 4 independent FMNMX chains); rows with a hit (a few per cent) are then re-scanned by
+// the whole warp, lane = class, so the per-hit work never serialises a warp over 80 classes.
 template <int CT>
 __global__ void __launch_bounds__(kRingThreads, 1) detect_stream_kernel(DetStreamArgs a) {
   extern __shared__ __align__(128) unsigned char smem_ring[];
@@ -69,51 +60,43 @@ __global__ void __launch_bounds__(kRingThreads, 1) detect_stream_kernel(DetStrea
     return;
   }
   const int wg = warp >> 2;
-  const int t = tid & 127;
+  const int r = tid & 127;
   const int R = a.ring.R, NS = a.ring.NS;
   const float thr = a.thr;
   for (int it = wg; it < rc.n_local; it += 2) {
     const int s = it % NS, j = it % (2 * NS), ph = it / (2 * NS);
-    const long long r0 = (rc.t0 + it) * R;
-    const long long left = a.ring.rows - r0;
-    const int nrows = left < R ? (int)left : R;
-    const int nf = nrows * C;
-    const int n4 = nf >> 2;
+    const long long row = (rc.t0 + it) * R + r;
+    const bool valid = (r < R) && (row < a.ring.rows);
+    bool kept = true;
+    if (valid && a.keep) kept = a.keep[row] != 0;          // RefineDet: filtered anchors score 0
     const float* st = rc.stages + (size_t)s * rc.stage_floats;
-    const float4* st4 = reinterpret_cast<const float4*>(st);
+    const float* rp = st + (size_t)r * C;
     mbar_wait(&rc.full[j], (uint32_t)(ph & 1));
-    int i = t;
-    for (; i + 3 * 128 < n4; i += 4 * 128) {             // 4 independent 16-byte loads in flight
-      float4 v0 = st4[i], v1 = st4[i + 128], v2 = st4[i + 256], v3 = st4[i + 384];
-      float m0 = fmaxf(fmaxf(v0.x, v0.y), fmaxf(v0.z, v0.w));
-      float m1 = fmaxf(fmaxf(v1.x, v1.y), fmaxf(v1.z, v1.w));
-      float m2 = fmaxf(fmaxf(v2.x, v2.y), fmaxf(v2.z, v2.w));
-      float m3 = fmaxf(fmaxf(v3.x, v3.y), fmaxf(v3.z, v3.w));
-      if (fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) > thr) {
-        const float4 vv[4] = {v0, v1, v2, v3};
+    float m = -INFINITY;
+    if (valid) {
+      if (CT > 1) {
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          int e = (i + q * 128) * 4;
-          if (vv[q].x > thr) emit_candidate<CT>(a, C, r0, e, vv[q].x);
-          if (vv[q].y > thr) emit_candidate<CT>(a, C, r0, e + 1, vv[q].y);
-          if (vv[q].z > thr) emit_candidate<CT>(a, C, r0, e + 2, vv[q].z);
-          if (vv[q].w > thr) emit_candidate<CT>(a, C, r0, e + 3, vv[q].w);
-        }
+        for (int c = 1; c < CT; ++c) m4[c & 3] = fmaxf(m4[c & 3], rp[c]);
+        m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      } else {
+        for (int c = 1; c < C; ++c) m = fmaxf(m, rp[c]);
       }
+      if (!kept) m = 0.0f;
     }
-    for (; i < n4; i += 128) {
-      float4 v = st4[i];
-      if (fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) > thr) {
-        int e = i * 4;
-        if (v.x > thr) emit_candidate<CT>(a, C, r0, e, v.x);
-        if (v.y > thr) emit_candidate<CT>(a, C, r0, e + 1, v.y);
-        if (v.z > thr) emit_candidate<CT>(a, C, r0, e + 2, v.z);
-        if (v.w > thr) emit_candidate<CT>(a, C, r0, e + 3, v.w);
+    uint32_t hits = __ballot_sync(SSDBOX_FULL_MASK, valid && m > thr);     // detection.py:48 strict >
+    while (hits) {
+      const int src = __ffs(hits) - 1;
+      hits &= hits - 1;
+      const long long hrow = row - lane + src;             // rows of a warp are consecutive
+      const bool hkept = __shfl_sync(SSDBOX_FULL_MASK, kept ? 1 : 0, src) != 0;
+      const uint32_t b = (uint32_t)hrow / (uint32_t)a.P;
+      const uint32_t p = (uint32_t)hrow - b * (uint32_t)a.P;
+      const float* hp = st + (size_t)(r - lane + src) * C;
+      for (int c = 1 + lane; c < C; c += 32) {
+        float v = hkept ? hp[c] : 0.0f;
+        if (v > thr) emit_candidate(a, C, b, p, c, v);
       }
-    }
-    for (int e = (n4 << 2) + t; e < nf; e += 128) {      // ragged tail of the last tile
-      float v = st[e];
-      if (v > thr) emit_candidate<CT>(a, C, r0, e, v);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&rc.empty[j]);
