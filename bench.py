@@ -6,7 +6,7 @@
 One "step" = one pass of the hot path over one batch of synthetic input of BASELINE.json
 configs[1] (SSD512 VGG16 COCO: P=24564 priors, C=81 classes, B=64 images PER GPU):
     T  match + MultiBoxLoss forward  (init, match, loss_stream, mine_reduce kernels)
-    D  DetectOut: threshold, top-200, NMS (init, detect_stream, detect_segment, detect_overflow)
+    D  DetectOut: threshold, top-200, NMS (init, detect_stream, detect_segment small/big, detect_overflow)
 `value` = images/s with inputs resident in HBM (whole job: N * B / max-over-ranks step time; every
 image passes through both T and D), timed with CUDA events around K CUDA-graph replays.
 `e2e` = same metric through the public modules (MultiBoxLoss.forward / DetectOut.__call__) with
@@ -383,7 +383,7 @@ def main():
     peak, peak_src = load_peak()
     traffic = load_traffic()
     t_us = sum(kernels_us.get(k, 0.0) for k in ("init", "match", "loss_stream", "mine_reduce"))
-    d_us = sum(kernels_us.get(k, 0.0) for k in ("init", "detect_stream", "detect_segment", "detect_overflow"))
+    d_us = sum(kernels_us.get(k, 0.0) for k in ("init", "detect_stream", "detect_segment", "detect_segment_big", "detect_overflow"))
     dom = max(("loss_stream", "detect_stream"), key=lambda k: kernels_us.get(k, 0.0))
     dom_us = kernels_us[dom]
     dom_bytes = float(B) * P * 4 * C       # the compulsory read of conf / scores [B,P,C] fp32
@@ -428,7 +428,7 @@ def main():
                                   % (reps, bt, bd, cores),
                         "train_fwd_images_per_s": reps * bt / tt, "detect_images_per_s": reps * bd / td}
 
-    launches_per_step = 8
+    launches_per_step = 9
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

@@ -234,9 +234,9 @@ SSDBOX_API int ssdbox_arm_filter(const float* arm_conf, int64_t n, float theta, 
  * caller's stream (do NOT enable during CUDA-graph capture).  ssdbox_timers_read synchronises
  * the pending events and returns the accumulated device time and launch count of one kernel:
  *   0 init, 1 match, 2 loss_stream, 3 mine_reduce, 4 loss_bwd, 5 detect_stream,
- *   6 detect_segment, 7 detect_overflow, 8 materialize
+ *   6 detect_segment (warp path), 7 detect_overflow, 8 materialize, 9 detect_segment_big
  * ---------------------------------------------------------------------------------------- */
-#define SSDBOX_KERNEL_COUNT 9
+#define SSDBOX_KERNEL_COUNT 10
 SSDBOX_API int ssdbox_timers_enable(int on);
 SSDBOX_API int ssdbox_timers_read(int kernel_id, double* total_ms, int64_t* launches);
 

@@ -29,7 +29,7 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 // ---- opt-in per-kernel timing (bench / profiling only; off by default) -------------------------
 enum KernelId {
   KID_INIT = 0, KID_MATCH, KID_LOSS_STREAM, KID_MINE, KID_LOSS_BWD, KID_DET_STREAM, KID_DET_SEGMENT,
-  KID_DET_OVERFLOW, KID_MATERIALIZE, KID_COUNT
+  KID_DET_OVERFLOW, KID_MATERIALIZE, KID_DET_SEGMENT_BIG, KID_COUNT
 };
 void timer_begin(int kid, cudaStream_t st);
 void timer_end(int kid, cudaStream_t st);

@@ -181,6 +181,8 @@ struct DetSegArgs {
   const unsigned long long* cand;
   uint32_t* ovf_count; // [1] number of (image, class) lists that overflowed
   int32_t* ovf_list;   // [B*C] their segment ids
+  uint32_t* big_count; // [1] number of lists with 32 < n <= cap
+  int32_t* big_list;   // [B*C]
   uint32_t* scratch;   // [kOverflowSlots, P]
   float* out;
   int32_t* counts;
@@ -220,32 +222,113 @@ __device__ void segment_finish(const DetSegArgs& a, int b, int seg, unsigned lon
   if (tid == 0 && a.counts) a.counts[seg] = count;
 }
 
+// ------------------------------------------------------------------------------------------------
+// (image, class) segments.  Small segments (<= 32 candidates: the normal case with a trained
+// detector, ~12 on average at SSD512-COCO) are finished by ONE WARP entirely in registers:
+// shuffle bitonic sort, decode, suppression bits via broadcast + ballot sweep.  Larger ones are
+// queued for the CTA-wide kernel (<= capacity) or the overflow kernel (> capacity).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSmallThreads = 128;
+
+__device__ __forceinline__ void warp_zero_rows(float* o, int nfloat, int lane) {
+  if ((reinterpret_cast<uintptr_t>(o) & 15u) == 0 && (nfloat & 3) == 0) {
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = lane; e < (nfloat >> 2); e += 32) reinterpret_cast<float4*>(o)[e] = z;
+  } else {
+    for (int e = lane; e < nfloat; e += 32) o[e] = 0.0f;
+  }
+}
+
+__global__ void __launch_bounds__(kSmallThreads) detect_segment_small_kernel(DetSegArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int seg = blockIdx.x * (kSmallThreads / 32) + (threadIdx.x >> 5);
+  if (seg >= a.B * a.C) return;
+  const int b = seg / a.C, c = seg - b * a.C;
+  const uint32_t total = c == 0 ? 0u : a.cnt[seg];
+  if (total > 32u) {                       // queue for the CTA-wide kernels
+    if (lane == 0) {
+      if (total > (uint32_t)a.cap) a.ovf_list[atomicAdd(a.ovf_count, 1u)] = seg;
+      else a.big_list[atomicAdd(a.big_count, 1u)] = seg;
+    }
+    return;
+  }
+  float* o = a.out + (size_t)seg * a.top_k * 5;
+  warp_zero_rows(o, a.top_k * 5, lane);    // background plane / no candidate: zeros (detection.py:37,50-51)
+  if (total == 0u) {
+    if (lane == 0 && a.counts) a.counts[seg] = 0;
+    return;
+  }
+  const int n = (int)total;
+  unsigned long long key = lane < n ? a.cand[(size_t)seg * a.cap + lane] : 0ull;
+  // bitonic sort, descending (= visiting order: score desc, higher prior first); padding sinks
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      unsigned long long other = __shfl_xor_sync(SSDBOX_FULL_MASK, key, j);
+      bool desc = (lane & k) == 0;
+      bool lower = (lane & j) == 0;
+      bool keep_max = lower == desc;
+      key = keep_max ? (key > other ? key : other) : (key < other ? key : other);
+    }
+  }
+  const int m = n < a.top_k ? n : a.top_k;           // box_utils.py:301 idx[-top_k:]
+  Box me;
+  me.x1 = me.y1 = me.x2 = me.y2 = 0.f;
+  if (lane < m) {
+    uint32_t p = (uint32_t)(key & 0xffffffffull);
+    me = decode_box(*reinterpret_cast<const float4*>(a.loc + ((size_t)b * a.P + p) * 4),
+                    *reinterpret_cast<const float4*>(a.priors + (size_t)b * (size_t)a.prior_stride + (size_t)p * 4),
+                    a.var0, a.var1);
+  }
+  const float my_area = box_area(me);
+  uint32_t supp_by = 0u;                              // bit i: box i (earlier in the order) suppresses me
+  for (int i = 0; i + 1 < m; ++i) {
+    Box bi;
+    bi.x1 = __shfl_sync(SSDBOX_FULL_MASK, me.x1, i);
+    bi.y1 = __shfl_sync(SSDBOX_FULL_MASK, me.y1, i);
+    bi.x2 = __shfl_sync(SSDBOX_FULL_MASK, me.x2, i);
+    bi.y2 = __shfl_sync(SSDBOX_FULL_MASK, me.y2, i);
+    float ai = __shfl_sync(SSDBOX_FULL_MASK, my_area, i);
+    if (lane > i && lane < m && !(iou_nms(bi, ai, me, my_area) <= a.nms_thr)) supp_by |= 1u << i;
+  }
+  uint32_t removed = 0u, kept = 0u;
+  for (int i = 0; i < m; ++i) {
+    uint32_t col = __ballot_sync(SSDBOX_FULL_MASK, (supp_by >> i) & 1u);
+    if (!((removed >> i) & 1u)) {
+      kept |= 1u << i;
+      removed |= col;
+    }
+  }
+  __syncwarp();                                        // orders the zero fill before the row writes
+  if (lane < m && ((kept >> lane) & 1u)) {
+    float* r = o + __popc(kept & ((1u << lane) - 1u)) * 5;
+    r[0] = ord2f((uint32_t)(key >> 32));
+    r[1] = me.x1; r[2] = me.y1; r[3] = me.x2; r[4] = me.y2;
+  }
+  if (lane == 0 && a.counts) a.counts[seg] = __popc(kept);
+}
+
 constexpr int kSegThreads = 256;
 
 __global__ void __launch_bounds__(kSegThreads) detect_segment_kernel(DetSegArgs a) {
   extern __shared__ __align__(16) unsigned char smem_seg[];
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_seg);
   NmsSmem ns = carve_nms(smem_seg + (size_t)a.cap * 8, a.top_k);
-  const int seg = blockIdx.x, tid = threadIdx.x;
-  const int b = seg / a.C, c = seg - b * a.C;
-  const uint32_t total = c == 0 ? 0u : a.cnt[seg];
-  if (total > (uint32_t)a.cap) {         // detect_overflow_kernel owns this segment
-    if (tid == 0) a.ovf_list[atomicAdd(a.ovf_count, 1u)] = seg;
-    return;
+  const int tid = threadIdx.x;
+  const int nbig = (int)*a.big_count;                 // written by detect_segment_small_kernel
+  for (int w = blockIdx.x; w < nbig; w += gridDim.x) {
+    const int seg = a.big_list[w];
+    const int b = seg / a.C;
+    const int n = (int)a.cnt[seg];                    // 32 < n <= cap
+    int npad = 64;
+    while (npad < n) npad <<= 1;
+    const unsigned long long* src = a.cand + (size_t)seg * a.cap;
+    for (int i = tid; i < npad; i += kSegThreads) keys[i] = i < n ? src[i] : 0ull;
+    __syncthreads();
+    segment_finish(a, b, seg, keys, n, npad, ns);
+    __syncthreads();
   }
-  if (total == 0u) {                     // background plane / no candidate: zeros (detection.py:37,50-51)
-    float* o = a.out + (size_t)seg * a.top_k * 5;
-    for (int e = tid; e < a.top_k * 5; e += kSegThreads) o[e] = 0.0f;
-    if (tid == 0 && a.counts) a.counts[seg] = 0;
-    return;
-  }
-  const int n = (int)total;
-  int npad = 32;
-  while (npad < n) npad <<= 1;
-  const unsigned long long* src = a.cand + (size_t)seg * a.cap;
-  for (int i = tid; i < npad; i += kSegThreads) keys[i] = i < n ? src[i] : 0ull;
-  __syncthreads();
-  segment_finish(a, b, seg, keys, n, npad, ns);
 }
 
 constexpr int kOvfThreads = 1024;
@@ -370,12 +453,13 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
   if (rc) return rc;
   const int cap = detect_cand_cap(top_k);
   Carver cv(ws);
-  uint32_t* cnt = cv.take<uint32_t>((size_t)B * C + 1);   // [B*C] counters + overflow count
+  uint32_t* cnt = cv.take<uint32_t>((size_t)B * C + 2);   // [B*C] counters + overflow / big counts
   int32_t* ovf_list = cv.take<int32_t>((size_t)B * C);
+  int32_t* big_list = cv.take<int32_t>((size_t)B * C);
   unsigned long long* cand = cv.take<unsigned long long>((size_t)B * C * cap);
   uint32_t* scratch = cv.take<uint32_t>((size_t)kOverflowSlots * P);
 
-  rc = launch_init(nullptr, 0, cnt, (size_t)B * C + 1, nullptr, 0, nullptr, 0, st);
+  rc = launch_init(nullptr, 0, cnt, (size_t)B * C + 2, nullptr, 0, nullptr, 0, st);
   if (rc) return rc;
 
   if (P > 0) {
@@ -404,12 +488,19 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
   g.nms_thr = cfg->nms_thresh; g.conf_thr = cfg->conf_thresh; g.var0 = cfg->var0; g.var1 = cfg->var1;
   g.prior_stride = (long long)cfg->prior_batch_stride;
   g.loc = loc; g.scores = scores; g.priors = priors; g.keep = score_keep;
-  g.cnt = cnt; g.cand = cand; g.ovf_count = cnt + (size_t)B * C; g.ovf_list = ovf_list; g.scratch = scratch; g.out = out; g.counts = counts;
+  g.cnt = cnt; g.cand = cand; g.ovf_count = cnt + (size_t)B * C; g.ovf_list = ovf_list; g.big_count = cnt + (size_t)B * C + 1; g.big_list = big_list; g.scratch = scratch; g.out = out; g.counts = counts;
+  {
+    TimerScope ts__(KID_DET_SEGMENT, st);
+    int per = kSmallThreads / 32;
+    detect_segment_small_kernel<<<(B * C + per - 1) / per, kSmallThreads, 0, st>>>(g);
+  }
+  SSDBOX_LAUNCH_OK("detect_segment_small_kernel");
   size_t seg_smem = (size_t)cap * 8 + nms_smem_bytes(top_k);
   SSDBOX_CUDA(cudaFuncSetAttribute(detect_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem));
-{
-    TimerScope ts__(KID_DET_SEGMENT, st);
-    detect_segment_kernel<<<B * C, kSegThreads, seg_smem, st>>>(g);
+  {
+    TimerScope ts__(KID_DET_SEGMENT_BIG, st);
+    int big_grid = dev.sm_count * 4 < B * C ? dev.sm_count * 4 : B * C;
+    detect_segment_kernel<<<big_grid, kSegThreads, seg_smem, st>>>(g);
   }
   SSDBOX_LAUNCH_OK("detect_segment_kernel");
 

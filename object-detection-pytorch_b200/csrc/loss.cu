@@ -151,6 +151,26 @@ struct MineArgs {
   float* dbg_keys;
 };
 
+// per-prior work of pass A: returns the ordered mining key (0 = outside the ranking)
+__device__ __forceinline__ uint32_t mine_visit(const MineArgs& a, size_t i, int p, int g0, const float* pri,
+                                               float key, int lb, int inpool, int& npos, double& ce, double& l1) {
+  if (!inpool) return 0u;
+  if (lb > 0) {
+    ++npos;
+    ce += (double)key;
+    const float* row = a.gt + (size_t)(g0 + a.tidx[i]) * 5;
+    Box m;
+    m.x1 = row[0]; m.y1 = row[1]; m.x2 = row[2]; m.y2 = row[3];
+    float4 t = encode_box(m, *reinterpret_cast<const float4*>(pri + (size_t)p * 4), a.var0, a.var1);
+    float4 l = *reinterpret_cast<const float4*>(a.loc + i * 4);
+    l1 += (double)(smooth_l1(l.x, t.x) + smooth_l1(l.y, t.y) + smooth_l1(l.z, t.z) + smooth_l1(l.w, t.w));
+    return f2ord(0.0f);                                   // multibox_loss.py:97 positives rank as 0
+  }
+  return f2ord(key);
+}
+
+// VEC = 4: four consecutive priors per thread and 16/8/4-byte vector accesses (needs P % 4 == 0)
+template <int VEC>
 __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a) {
   extern __shared__ __align__(16) unsigned char smem_mine[];
   unsigned char* smem_raw = smem_mine;
@@ -168,49 +188,57 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
   const size_t off = (size_t)b * P;
   const int g0 = a.gt_offsets[b];
   const float* pri = a.priors + (size_t)b * (size_t)a.prior_stride;
-  const uint32_t ord_zero = f2ord(0.0f);
   const bool in_smem = a.uk_in_smem != 0;
 
-  // pass A: positives (count, CE, smooth-L1) and the ordered mining keys; loads batched 4 deep
+  // pass A: positives (count, CE, smooth-L1) and the ordered mining keys
   int npos = 0;
   double ce = 0.0, l1 = 0.0;
-  for (int p0 = tid; p0 < P; p0 += 4 * kMineThreads) {
-    float key[4];
-    int lb[4], inp[4];
+  if (VEC == 4) {
+    const float4* k4 = reinterpret_cast<const float4*>(a.keys + off);
+    const short4* l4 = reinterpret_cast<const short4*>(a.lab + off);
+    const uchar4* p4 = a.pool ? reinterpret_cast<const uchar4*>(a.pool + off) : nullptr;
+    const int n4 = P >> 2;
+    for (int q0 = tid; q0 < n4; q0 += 2 * kMineThreads) {
+      float4 kk[2];
+      short4 ll[2];
+      uchar4 pp[2];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      int p = p0 + u * kMineThreads;
-      key[u] = 0.f; lb[u] = 0; inp[u] = 0;
-      if (p < P) {
-        key[u] = a.keys[off + p];
-        lb[u] = a.lab[off + p];
-        inp[u] = a.pool ? a.pool[off + p] : 1;
+      for (int u = 0; u < 2; ++u) {
+        int q = q0 + u * kMineThreads;
+        kk[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ll[u] = make_short4(0, 0, 0, 0);
+        pp[u] = make_uchar4(1, 1, 1, 1);
+        if (q < n4) {
+          kk[u] = k4[q];
+          ll[u] = l4[q];
+          if (p4) pp[u] = p4[q];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        int q = q0 + u * kMineThreads;
+        if (q >= n4) continue;
+        int p = q * 4;
+        size_t i = off + p;
+        if (a.dbg_keys) *reinterpret_cast<float4*>(a.dbg_keys + i) = kk[u];
+        uint4 uo;
+        uo.x = mine_visit(a, i, p, g0, pri, kk[u].x, ll[u].x, pp[u].x, npos, ce, l1);
+        uo.y = mine_visit(a, i + 1, p + 1, g0, pri, kk[u].y, ll[u].y, pp[u].y, npos, ce, l1);
+        uo.z = mine_visit(a, i + 2, p + 2, g0, pri, kk[u].z, ll[u].z, pp[u].z, npos, ce, l1);
+        uo.w = mine_visit(a, i + 3, p + 3, g0, pri, kk[u].w, ll[u].w, pp[u].w, npos, ce, l1);
+        *reinterpret_cast<uint4*>(uk + p) = uo;
+        if (in_smem) *reinterpret_cast<short4*>(s_lab + p) = ll[u];
       }
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      int p = p0 + u * kMineThreads;
-      if (p >= P) continue;
+  } else {
+    for (int p = tid; p < P; p += kMineThreads) {
       size_t i = off + p;
-      if (a.dbg_keys) a.dbg_keys[i] = key[u];
-      uint32_t uo;
-      if (!inp[u]) {
-        uo = 0u;
-      } else if (lb[u] > 0) {
-        ++npos;
-        ce += (double)key[u];
-        const float* row = a.gt + (size_t)(g0 + a.tidx[i]) * 5;
-        Box m;
-        m.x1 = row[0]; m.y1 = row[1]; m.x2 = row[2]; m.y2 = row[3];
-        float4 t = encode_box(m, *reinterpret_cast<const float4*>(pri + (size_t)p * 4), a.var0, a.var1);
-        float4 l = *reinterpret_cast<const float4*>(a.loc + i * 4);
-        l1 += (double)(smooth_l1(l.x, t.x) + smooth_l1(l.y, t.y) + smooth_l1(l.z, t.z) + smooth_l1(l.w, t.w));
-        uo = ord_zero;
-      } else {
-        uo = f2ord(key[u]);
-      }
-      uk[p] = uo;
-      if (in_smem) s_lab[p] = (int16_t)lb[u];
+      float key = a.keys[i];
+      int lb = a.lab[i];
+      int inpool = a.pool ? a.pool[i] : 1;
+      if (a.dbg_keys) a.dbg_keys[i] = key;
+      uk[p] = mine_visit(a, i, p, g0, pri, key, lb, inpool, npos, ce, l1);
+      if (in_smem) s_lab[p] = (int16_t)lb;
     }
   }
   int npos_blk = (int)(block_sum((double)npos, s_dscr) + 0.5);
@@ -222,22 +250,42 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
   if (kk > P - 1) kk = P - 1;
   const int K = (int)kk;
   uint32_t Tu = 0xffffffffu;
-  if (K > 0) Tu = cta_select_threshold<false>(uk, P, K, a.hist + (size_t)b * kHistBins, s_hist, s_iscr, s_res);
+  if (K > 0) Tu = cta_select_threshold<false, VEC>(uk, P, K, a.hist + (size_t)b * kHistBins, s_hist, s_iscr, s_res);
   __syncthreads();
 
   // final pass: neg = rank < num_neg (:103); CE over pos U neg (:106-110).  The CE of a selected
   // negative is its mining key, recovered exactly from the ordered key (no second read of keys).
   double ce_neg = 0.0;
-  for (int p = tid; p < P; p += kMineThreads) {
-    size_t i = off + p;
-    uint32_t u = uk[p];
-    int lb = in_smem ? (int)s_lab[p] : (int)a.lab[i];
+  auto decide = [&](uint32_t u, int lb, bool& negsel) -> int16_t {
     bool inpool = u != 0u;
     bool is_pos = inpool && lb > 0;
-    bool negsel = K > 0 && inpool && u >= Tu;
-    a.sel[i] = is_pos ? (int16_t)lb : (negsel ? (int16_t)0 : (int16_t)-1);
+    negsel = K > 0 && inpool && u >= Tu;
     if (negsel && !is_pos) ce_neg += (double)ord2f(u);
-    if (a.dbg_neg) a.dbg_neg[i] = negsel ? 1 : 0;
+    return is_pos ? (int16_t)lb : (negsel ? (int16_t)0 : (int16_t)-1);
+  };
+  if (VEC == 4) {
+    const int n4 = P >> 2;
+    for (int q = tid; q < n4; q += kMineThreads) {
+      int p = q * 4;
+      size_t i = off + p;
+      uint4 u = *reinterpret_cast<const uint4*>(uk + p);
+      short4 lb = in_smem ? *reinterpret_cast<const short4*>(s_lab + p) : *reinterpret_cast<const short4*>(a.lab + i);
+      bool n0, n1, n2, n3;
+      short4 so;
+      so.x = decide(u.x, lb.x, n0);
+      so.y = decide(u.y, lb.y, n1);
+      so.z = decide(u.z, lb.z, n2);
+      so.w = decide(u.w, lb.w, n3);
+      *reinterpret_cast<short4*>(a.sel + i) = so;
+      if (a.dbg_neg) *reinterpret_cast<uchar4*>(a.dbg_neg + i) = make_uchar4(n0, n1, n2, n3);
+    }
+  } else {
+    for (int p = tid; p < P; p += kMineThreads) {
+      size_t i = off + p;
+      bool ns;
+      a.sel[i] = decide(uk[p], in_smem ? (int)s_lab[p] : (int)a.lab[i], ns);
+      if (a.dbg_neg) a.dbg_neg[i] = ns ? 1 : 0;
+    }
   }
   ce_neg = block_sum(ce_neg, s_dscr);
 
@@ -498,10 +546,14 @@ extern "C" int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float*
   m.partial = w.partial; m.ticket = w.ticket; m.sums = sums; m.losses = losses; m.sel = sel;
   m.dbg_neg = dbg_neg; m.dbg_keys = dbg_keys;
   size_t smem = fixed + (m.uk_in_smem ? (size_t)P * 6 + 16 : 0);
-  SSDBOX_CUDA(cudaFuncSetAttribute(mine_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-{
+  // vector mode needs every per-image row of keys / lab / pool / sel / debug arrays 16-byte friendly
+  const bool vec4 = (P % 4 == 0) && aligned16(sel) && (!pool || (reinterpret_cast<uintptr_t>(pool) & 3u) == 0) &&
+                    (!dbg_neg || (reinterpret_cast<uintptr_t>(dbg_neg) & 3u) == 0) && (!dbg_keys || aligned16(dbg_keys));
+  void (*mkern)(MineArgs) = vec4 ? mine_reduce_kernel<4> : mine_reduce_kernel<1>;
+  SSDBOX_CUDA(cudaFuncSetAttribute(mkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
     TimerScope ts__(KID_MINE, st);
-    mine_reduce_kernel<<<B, kMineThreads, smem, st>>>(m);
+    mkern<<<B, kMineThreads, smem, st>>>(m);
   }
   SSDBOX_LAUNCH_OK("mine_reduce_kernel");
 

@@ -86,7 +86,7 @@ match_kernel(MatchArgs a, unsigned long long* __restrict__ gt_best, uint32_t* __
   float wx1 = INFINITY, wy1 = INFINITY, wx2 = -INFINITY, wy2 = -INFINITY;
 #pragma unroll
   for (int k = 0; k < kMatchPPT; ++k) {
-    int p = blockIdx.x * kMatchTile + tid * kMatchPPT + k;
+    int p = (gridDim.x - 1 - blockIdx.x) * kMatchTile + tid * kMatchPPT + k;   // heavy coarse-layer tiles first
     pidx[k] = p;
     valid[k] = p < a.P;
     if (valid[k]) {

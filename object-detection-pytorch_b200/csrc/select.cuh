@@ -9,11 +9,26 @@
 
 namespace ssdbox {
 
+// visits every ordered key once; VEC = 4 reads them as 16-byte vectors (P % 4 == 0, 16-byte aligned)
+template <int VEC, class F>
+__device__ __forceinline__ void for_each_key(const uint32_t* uk, int P, F f) {
+  if (VEC == 4) {
+    const uint4* u4 = reinterpret_cast<const uint4*>(uk);
+    const int n4 = P >> 2;
+    for (int q = threadIdx.x; q < n4; q += blockDim.x) {
+      uint4 u = u4[q];
+      f(u.x); f(u.y); f(u.z); f(u.w);
+    }
+  } else {
+    for (int p = threadIdx.x; p < P; p += blockDim.x) f(uk[p]);
+  }
+}
+
 // After the call an element is selected iff uk[p] != 0 && uk[p] >= T (returned); equal-to-T
 // elements that lose the tie are demoted to T-1 in place.  K >= 1.  uk[p] == 0 marks elements
 // outside the ranking.  hist1 (nullable, global) = precomputed level-1 histogram.
 // s_hist: 2048 uint32, s_iscr: >= 64 ints, s_res: >= 2 ints (all shared memory).
-template <bool kPreferHighIndex>
+template <bool kPreferHighIndex, int VEC = 1>
 __device__ uint32_t cta_select_threshold(uint32_t* uk, int P, int K, const uint32_t* hist1, uint32_t* s_hist,
                                          int* s_iscr, int* s_res) {
   const int tid = threadIdx.x, T = blockDim.x;
@@ -21,10 +36,9 @@ __device__ uint32_t cta_select_threshold(uint32_t* uk, int P, int K, const uint3
   for (int i = tid; i < kHistBins; i += T) s_hist[i] = hist1 ? hist1[i] : 0u;
   __syncthreads();
   if (!hist1) {
-    for (int p = tid; p < P; p += T) {
-      uint32_t u = uk[p];
+    for_each_key<VEC>(uk, P, [&](uint32_t u) {
       if (u) atomicAdd(&s_hist[u >> 21], 1u);
-    }
+    });
     __syncthreads();
   }
   find_digit(s_hist, kHistBins, K, s_iscr, s_res);
@@ -37,10 +51,9 @@ __device__ uint32_t cta_select_threshold(uint32_t* uk, int P, int K, const uint3
   // level 2: bits 20..10 of the elements in bin d1
   for (int i = tid; i < 2048; i += T) s_hist[i] = 0u;
   __syncthreads();
-  for (int p = tid; p < P; p += T) {
-    uint32_t u = uk[p];
+  for_each_key<VEC>(uk, P, [&](uint32_t u) {
     if (u && (int)(u >> 21) == d1) atomicAdd(&s_hist[(u >> 10) & 2047u], 1u);
-  }
+  });
   __syncthreads();
   find_digit(s_hist, 2048, K2, s_iscr, s_res);
   int d2 = s_res[0];
@@ -52,10 +65,9 @@ __device__ uint32_t cta_select_threshold(uint32_t* uk, int P, int K, const uint3
   // level 3: bits 9..0
   for (int i = tid; i < 1024; i += T) s_hist[i] = 0u;
   __syncthreads();
-  for (int p = tid; p < P; p += T) {
-    uint32_t u = uk[p];
+  for_each_key<VEC>(uk, P, [&](uint32_t u) {
     if (u && (u >> 10) == pre2) atomicAdd(&s_hist[u & 1023u], 1u);
-  }
+  });
   __syncthreads();
   find_digit(s_hist, 1024, K3, s_iscr, s_res);
   int d3 = s_res[0];

@@ -27,7 +27,7 @@ SYMBOLS = [
 ]
 
 KERNEL_NAMES = ["init", "match", "loss_stream", "mine_reduce", "loss_bwd", "detect_stream", "detect_segment",
-                "detect_overflow", "materialize"]
+                "detect_overflow", "materialize", "detect_segment_big"]
 
 
 class PriorCfg(C.Structure):

@@ -3,6 +3,8 @@
 Skipped where /root/reference is not mounted (the GPU box): there the committed golden
 vectors (tests/test_oracle_golden.py) pin the oracle instead.
 """
+import os
+
 import pytest
 import torch
 
@@ -116,3 +118,36 @@ def test_nms_bit_exact(ref):
     rk, rc = ref.nms(torch.zeros(0, 4), torch.zeros(0), 0.45, 200)
     ok, oc = O.greedy_nms(torch.zeros(0, 4), torch.zeros(0), 0.45, 200)
     assert rc == oc == 0
+
+
+def test_compat_install_rebinds_reference_symbols():
+    """ssdbox.compat.install() swaps the CUDA-backed classes into the reference's namespaces
+    (run in a subprocess: it patches lib.layers globally)."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, os
+root = %r
+sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "object-detection-pytorch_b200"))
+import warnings; warnings.filterwarnings("ignore")
+from oracle import ref_loader
+ref_loader._install_stubs()
+sys.path.insert(0, ref_loader.REFERENCE_ROOT)
+import lib.layers
+import ssdbox, ssdbox.compat
+cls = ssdbox.compat.install()
+from lib.layers import *            # what train.py:16 / evaluate_utils.py:9 do
+import lib.layers.box_utils as bu
+assert PriorBoxSSD is ssdbox.PriorBoxSSD and DetectOut is ssdbox.DetectOut
+assert MultiBoxLoss is cls and issubclass(cls, ssdbox.MultiBoxLoss)
+assert bu.nms is ssdbox.box_utils.nms and bu.match is ssdbox.box_utils.match
+from lib.utils.config import cfg
+crit = MultiBoxLoss(21, 0.5, True, 0, True, 3, 0.5, False, True)     # train.py:99-100
+assert crit.variance == list(cfg.MODEL.VARIANCE)
+pb = PriorBoxSSD(cfg)                                                 # models/__init__.py:28
+assert pb.num_priors == [4, 6, 6, 6, 4, 4]
+det = DetectOut(21, 0, 200, 0.01, 0.45, cfg.MODEL.VARIANCE)           # evaluate_utils.py:16-17
+print("ok")
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
