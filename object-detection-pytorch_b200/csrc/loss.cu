@@ -123,7 +123,7 @@ static int launch_stream(StreamArgs a, const float* conf, long long rows, int C,
 // per-image selection of the K largest ordered keys (descending, ties by ascending index)
 // ------------------------------------------------------------------------------------------------
 constexpr int kMineThreads = 1024;
-constexpr int kMineFixedSmem = 8192 + 320 + 288;   // level histogram + reduction scratch
+constexpr int kMineFixedSmem = 8192 + 800 + 288;   // level histogram + reduction scratch (99 doubles) + int scratch
 
 struct MineArgs {
   int B, P, C;
@@ -151,6 +151,13 @@ struct MineArgs {
   float* dbg_keys;
 };
 
+#ifdef SSDBOX_PHASE_TIMING
+__device__ long long g_phase[16];
+#define PHASE_MARK(k) do { __syncthreads(); if (blockIdx.x == 1 && threadIdx.x == 0) g_phase[k] = clock64(); } while (0)
+#else
+#define PHASE_MARK(k) do { } while (0)
+#endif
+
 // per-prior work of pass A: returns the ordered mining key (0 = outside the ranking)
 __device__ __forceinline__ uint32_t mine_visit(const MineArgs& a, size_t i, int p, int g0, const float* pri,
                                                float key, int lb, int inpool, int& npos, double& ce, double& l1) {
@@ -175,8 +182,8 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
   extern __shared__ __align__(16) unsigned char smem_mine[];
   unsigned char* smem_raw = smem_mine;
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw);             // 2048
-  double* s_dscr = reinterpret_cast<double*>(smem_raw + 8192);          // 40
-  int* s_iscr = reinterpret_cast<int*>(smem_raw + 8192 + 320);          // 64
+  double* s_dscr = reinterpret_cast<double*>(smem_raw + 8192);          // 100
+  int* s_iscr = reinterpret_cast<int*>(smem_raw + 8192 + 800);          // 64
   int* s_res = s_iscr + 64;                                             // 8
   // smem mode: ordered keys + class targets of the whole image stay on chip between the passes
   uint32_t* uk = a.uk_in_smem ? reinterpret_cast<uint32_t*>(smem_raw + kMineFixedSmem)
@@ -191,6 +198,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
   const bool in_smem = a.uk_in_smem != 0;
 
   // pass A: positives (count, CE, smooth-L1) and the ordered mining keys
+  PHASE_MARK(0);
   int npos = 0;
   double ce = 0.0, l1 = 0.0;
   if (VEC == 4) {
@@ -241,9 +249,11 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
       if (in_smem) s_lab[p] = (int16_t)lb;
     }
   }
-  int npos_blk = (int)(block_sum((double)npos, s_dscr) + 0.5);
-  ce = block_sum(ce, s_dscr);
-  l1 = block_sum(l1, s_dscr);
+  PHASE_MARK(1);
+  double npos_d = (double)npos;
+  block_sum3(npos_d, ce, l1, s_dscr);
+  int npos_blk = (int)(npos_d + 0.5);
+  PHASE_MARK(2);
 
   // multibox_loss.py:101-102  num_neg = clamp(ratio * num_pos, max = P - 1)
   long long kk = (long long)a.negpos_ratio * npos_blk;
@@ -252,6 +262,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
   uint32_t Tu = 0xffffffffu;
   if (K > 0) Tu = cta_select_threshold<false, VEC>(uk, P, K, a.hist + (size_t)b * kHistBins, s_hist, s_iscr, s_res);
   __syncthreads();
+  PHASE_MARK(3);
 
   // final pass: neg = rank < num_neg (:103); CE over pos U neg (:106-110).  The CE of a selected
   // negative is its mining key, recovered exactly from the ordered key (no second read of keys).
@@ -287,7 +298,9 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
       if (a.dbg_neg) a.dbg_neg[i] = ns ? 1 : 0;
     }
   }
+  PHASE_MARK(4);
   ce_neg = block_sum(ce_neg, s_dscr);
+  PHASE_MARK(5);
 
   if (tid == 0) {
     a.partial[(size_t)b * 3 + 0] = l1;
@@ -300,14 +313,26 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  // last CTA: fold the per-image partials in image order (bit-reproducible run to run)
-  if (tid == 0) {
-    double sl = 0.0, sc = 0.0, sn = 0.0;
-    for (int i = 0; i < a.B; ++i) {
-      sl += __ldcg(&a.partial[(size_t)i * 3 + 0]);
-      sc += __ldcg(&a.partial[(size_t)i * 3 + 1]);
-      sn += __ldcg(&a.partial[(size_t)i * 3 + 2]);
+  // last CTA: fold the per-image partials in image order (bit-reproducible run to run); the loads
+  // are spread over the threads (one L2 round trip), the fp64 adds stay sequential in image order
+  double sl = 0.0, sc = 0.0, sn = 0.0;
+  for (int base = 0; base < a.B; base += 32) {
+    __syncthreads();
+    if (tid < 96) {
+      int i = base + (tid & 31), f = tid >> 5;
+      s_dscr[f * 32 + (tid & 31)] = i < a.B ? __ldcg(&a.partial[(size_t)i * 3 + f]) : 0.0;
     }
+    __syncthreads();
+    if (tid == 0) {
+      int n = a.B - base < 32 ? a.B - base : 32;
+      for (int i = 0; i < n; ++i) {
+        sl += s_dscr[i];
+        sc += s_dscr[32 + i];
+        sn += s_dscr[64 + i];
+      }
+    }
+  }
+  if (tid == 0) {
     a.sums[0] = sl;
     a.sums[1] = sc;
     a.sums[2] = sn;
@@ -332,9 +357,9 @@ mine_only_kernel(const float* __restrict__ keys, const uint8_t* __restrict__ pos
   unsigned char* smem_raw = smem_mine;
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw);
   double* s_dscr = reinterpret_cast<double*>(smem_raw + 8192);
-  int* s_iscr = reinterpret_cast<int*>(smem_raw + 8192 + 320);
+  int* s_iscr = reinterpret_cast<int*>(smem_raw + 8192 + 800);
   int* s_res = s_iscr + 64;
-  uint32_t* uk = uk_in_smem ? reinterpret_cast<uint32_t*>(smem_raw + 8192 + 320 + 288)
+  uint32_t* uk = uk_in_smem ? reinterpret_cast<uint32_t*>(smem_raw + kMineFixedSmem)
                             : ukey_global + (size_t)blockIdx.x * P;
   const int tid = threadIdx.x;
   const size_t off = (size_t)blockIdx.x * P;
@@ -565,6 +590,12 @@ extern "C" int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float*
   return SSDBOX_OK;
 }
 
+#ifdef SSDBOX_PHASE_TIMING
+extern "C" __attribute__((visibility("default"))) int ssdbox_debug_phases(long long* out16) {
+  return cudaMemcpyFromSymbol(out16, ssdbox::g_phase, sizeof(long long) * 16) == cudaSuccess ? 0 : -5;
+}
+#endif
+
 extern "C" int ssdbox_multibox_loss_finalize(const double* sums, float* losses, ssdbox_stream_t stream) {
   SSDBOX_REQUIRE(sums && losses, SSDBOX_EINVAL, "finalize: null pointer");
   finalize_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(sums, losses);
@@ -619,7 +650,7 @@ extern "C" int ssdbox_hard_negative_mine(const float* keys, const uint8_t* pos, 
   DevInfo dev;
   int rc = get_dev_info(&dev);
   if (rc) return rc;
-  size_t fixed = 8192 + 320 + 288;
+  size_t fixed = kMineFixedSmem;
   int in_smem = (fixed + (size_t)P * 4 <= (size_t)dev.max_smem_optin - 1024) ? 1 : 0;
   size_t smem = fixed + (in_smem ? (size_t)P * 4 : 0);
   SSDBOX_CUDA(cudaFuncSetAttribute(mine_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -44,6 +44,13 @@ int launch_init(unsigned long long* best, size_t nbest, uint32_t* z0, size_t n0,
   return SSDBOX_OK;
 }
 
+#ifdef SSDBOX_PHASE_TIMING
+__device__ long long g_mphase[32];
+#define MPHASE(k) do { __syncthreads(); if (blockIdx.y == 1 && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) g_mphase[(blockIdx.x == 0 ? 0 : 16) + (k)] = clock64(); } while (0)
+#else
+#define MPHASE(k) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kMatchThreads)
 match_kernel(MatchArgs a, unsigned long long* __restrict__ gt_best, uint32_t* __restrict__ done,
              int16_t* __restrict__ lab, int16_t* __restrict__ tidx, float* __restrict__ overlap, int gpad) {
@@ -56,6 +63,7 @@ match_kernel(MatchArgs a, unsigned long long* __restrict__ gt_best, uint32_t* __
 
   const int b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31;
+  MPHASE(0);
   const int g0 = a.gt_offsets[b];
   int G = a.gt_offsets[b + 1] - g0;
   G = G < 0 ? 0 : (G > a.gmax ? a.gmax : G);
@@ -70,6 +78,7 @@ match_kernel(MatchArgs a, unsigned long long* __restrict__ gt_best, uint32_t* __
     s_best[g] = kBestInit;
   }
   __syncthreads();
+  MPHASE(1);
 
   const size_t img_off = (size_t)b * (size_t)a.P;
   const float* pri = a.priors + (size_t)b * (size_t)a.prior_stride;
@@ -115,6 +124,7 @@ match_kernel(MatchArgs a, unsigned long long* __restrict__ gt_best, uint32_t* __
     wy2 = fmaxf(wy2, __shfl_xor_sync(SSDBOX_FULL_MASK, wy2, d));
   }
 
+  MPHASE(2);
   for (int g = 0; g < G; ++g) {
     float4 tv = s_box[g];
     if (!(tv.x < wx2 && tv.z > wx1 && tv.y < wy2 && tv.w > wy1)) continue;   // warp-uniform
@@ -146,6 +156,7 @@ match_kernel(MatchArgs a, unsigned long long* __restrict__ gt_best, uint32_t* __
     }
   }
 
+  MPHASE(3);
 #pragma unroll
   for (int k = 0; k < kMatchPPT; ++k) {
     if (valid[k]) {
@@ -158,6 +169,7 @@ match_kernel(MatchArgs a, unsigned long long* __restrict__ gt_best, uint32_t* __
   }
 
   // publish this CTA's per-truth candidates, then elect the last CTA of the image
+  MPHASE(4);
   __syncthreads();
   for (int g = tid; g < G; g += kMatchThreads) {
     unsigned long long v = s_best[g];
@@ -170,6 +182,7 @@ match_kernel(MatchArgs a, unsigned long long* __restrict__ gt_best, uint32_t* __
     s_last = (t == gridDim.x - 1);
   }
   __syncthreads();
+  MPHASE(5);
   if (!s_last) return;
   __threadfence();
 
@@ -253,6 +266,12 @@ int launch_materialize(const MatchArgs& a, float var0, float var1, const int16_t
 }  // namespace ssdbox
 
 using namespace ssdbox;
+
+#ifdef SSDBOX_PHASE_TIMING
+extern "C" __attribute__((visibility("default"))) int ssdbox_debug_match_phases(long long* out32) {
+  return cudaMemcpyFromSymbol(out32, ssdbox::g_mphase, sizeof(long long) * 32) == cudaSuccess ? 0 : -5;
+}
+#endif
 
 extern "C" int ssdbox_match_encode(const float* gt, const int32_t* gt_offsets, int32_t gmax, const float* priors,
                                    int64_t prior_batch_stride, const float* anchors_xyxy, int32_t B, int32_t P,
