@@ -164,7 +164,15 @@ typedef struct {
   int32_t binarize_labels;    /* RefineDet ARM: every truth label becomes class 1 */
   int32_t finalize;           /* 1: losses = sums / N on device; 0: leave sums for an all-reduce */
   int64_t prior_batch_stride; /* 0 or 4*P (see ssdbox_match_encode) */
+  int32_t flags;              /* SSDBOX_LOSS_* bits */
+  int32_t reserved;
 } ssdbox_loss_cfg;
+
+/* By default the matching runs on dedicated warps inside the streaming kernel (it overlaps the
+ * HBM-bound pass over conf).  This flag runs it as its own kernel before the streaming pass
+ * instead (same results; the library also falls back to it when a CTA's truths do not fit in
+ * shared memory beside the ring). */
+#define SSDBOX_LOSS_SEPARATE_MATCH 1
 
 /* forward.
  *   loc [B,P,4], conf [B,P,C] raw logits, priors, anchors_xyxy (nullable), gt/gt_offsets

@@ -1,19 +1,27 @@
 // MultiBoxLoss forward / backward: lib/layers/modules/multibox_loss.py:48-117 (+ autograd).
 //
-// Forward = 4 launches on the caller's stream (CUDA-graph capturable, no host sync):
+// Forward = 3 launches on the caller's stream (CUDA-graph capturable, no host sync):
 //   init_kernel        per-truth best-prior keys := (0, prior 0); tickets / histograms := 0
-//   match_kernel       (match.cu) class target + matched truth per prior, IoU matrix never stored
-//   loss_stream_kernel THE HBM-bound kernel: conf [B*P, C] streamed once through a ring of
-//                      TMA bulk-copy (cp.async.bulk + mbarrier) stages; one thread per prior row
-//                      computes log-sum-exp, key = lse - x[target] and bumps the image's level-1
-//                      mining histogram (top 11 bits of the order-preserving key)
-//   mine_reduce_kernel one CTA per image: radix-select of the num_neg-th largest mining key
-//                      (level 1 comes from the streamed histogram, levels 2/3 touch only the
-//                      winning bin), canonical tie order, fixed-order fp64 reduction of
-//                      smooth-L1 / CE, last CTA folds the per-image partials (deterministic).
-// The final CE over pos U neg needs no second pass over conf: CE(row) = lse - x[target] is the
-// very key the stream kernel wrote.  Backward zero-fills grad_conf and touches conf only on the
-// selected rows.
+//   loss_stream_kernel THE HBM-bound kernel, warp-specialised, one persistent CTA per SM:
+//                        1 producer warp   streams conf [B*P, C] through a ring of TMA bulk-copy
+//                                          stages (cp.async.bulk + mbarrier)
+//                        8 consumer warps  one thread per prior row: lse and the background key
+//                                          lse - x[0]; level-1 mining histogram (top 11 bits of the
+//                                          order-preserving key).  Independent of the class targets.
+//                        8 match warps     box_utils.match for the CTA's rows while the consumers
+//                                          wait on memory: truths in shared memory, 4 consecutive
+//                                          priors per thread, warp bounding-box pruning, per-truth
+//                                          argmax by REDUX + atomicMax.  The IoU matrix never exists.
+//   mine_reduce_kernel one CTA per image: replays the forced assignment ("every truth keeps its
+//                      best prior, last truth wins"), positives get CE = lse - x[target] (one
+//                      gathered logit each) and move to the zero bin; radix-select of the
+//                      num_neg-th largest mining key (level 1 from the streamed histogram, levels
+//                      2/3 touch only the winning bin), canonical tie order, fixed-order fp64
+//                      reduction of smooth-L1 / CE, last CTA folds the per-image partials.
+// (With SSDBOX_LOSS_SEPARATE_MATCH, or when the truths of a CTA's images do not fit beside the ring,
+// match_kernel of match.cu runs as a fourth launch before the stream kernel instead.)
+// The final CE over pos U neg needs no second pass over conf: CE of a negative is its mining key.
+// Backward zero-fills grad_conf and touches conf only on the selected rows.
 #include "ops.h"
 #include "ring.cuh"
 #include "select.cuh"
@@ -25,18 +33,45 @@ namespace ssdbox {
 // streaming pass
 // ------------------------------------------------------------------------------------------------
 constexpr float kLog2e = 1.4426950408889634f;
+#ifdef SSDBOX_PHASE_TIMING
+__device__ long long g_sphase[8 * 160];
+__device__ long long g_mstat[8 * 160];
+#define SMARK(k) do { if (blockIdx.x < 160 && lane == 0) g_sphase[blockIdx.x * 8 + (k)] = clock64(); } while (0)
+#else
+#define SMARK(k) do { } while (0)
+#endif
+
+constexpr int kMatchWarps = 8;
+constexpr int kStreamThreads = kRingThreads + kMatchWarps * 32;   // consumers + producer + match warps
 
 struct StreamArgs {
   RingPlan ring;       // conf [B*P, C]
-  const int16_t* lab;
   const uint8_t* pool;
-  float* keys;
+  float* key0;         // [B*P]  lse - x[0]   (mining key of a non-positive prior, multibox_loss.py:94)
+  float* lse;          // [B*P]  log-sum-exp of the row
   uint32_t* hist;
   int P;
+  // fused matching (box_utils.py:92-130 on dedicated warps)
+  int fuse;
+  int B;
+  const float* gt;
+  const int32_t* gt_offsets;
+  int gmax, gpad;
+  const float* priors;
+  long long prior_stride;
+  const float* anchors_xyxy;
+  float threshold;
+  int binarize;
+  unsigned long long* gt_best;
+  int16_t* lab_out;
+  int16_t* tidx_out;
+  int img_slots;       // images one CTA can touch; their truths are cached in shared memory
 };
 
+// log-sum-exp of one row with the row maximum (box_utils.py:273 uses one global maximum; same value
+// up to fp32 rounding).  4 independent accumulators; ex2.approx on (x - m) * log2(e).
 template <int CT>
-__device__ __forceinline__ float row_key(const float* __restrict__ rp, int C, int lb) {
+__device__ __forceinline__ float row_lse(const float* __restrict__ rp, int C) {
   float m, s;
   if (CT > 0) {
     float v[CT > 0 ? CT : 1];
@@ -58,62 +93,328 @@ __device__ __forceinline__ float row_key(const float* __restrict__ rp, int C, in
     s = 0.f;
     for (int c = 0; c < C; ++c) s += ex2_approx(fmaf(rp[c], kLog2e, nml));
   }
-  float lse = logf(s) + m;        // box_utils.py:273 log(sum(exp(x - max))) + max (row max here)
-  return lse - rp[lb];            // multibox_loss.py:94  lse - gather(conf_t)
+  return logf(s) + m;
+}
+
+// ---- match warps --------------------------------------------------------------------------------
+struct GtCache {
+  const float4* box;          // [slots, gpad] xyxy
+  const float* area;          // [slots, gpad]
+  const int* lab;             // [slots, gpad] class target (label + 1)
+  const int* count;           // [slots]
+  unsigned long long* best;   // [slots, gpad] CTA-local per-truth best prior, flushed once at the end
+};
+
+// max IoU, lowest prior index on ties (box_utils.py:116); shared-memory copy first: the global
+// atomic happens once per (CTA, truth) at the end, never inside the truth loop
+__device__ __forceinline__ void best_prior_update(unsigned long long* dst, uint32_t iou_bits, uint32_t p) {
+  unsigned long long key = ((unsigned long long)iou_bits << 32) | (unsigned long long)(uint32_t)(~p);
+  if (key > *reinterpret_cast<volatile unsigned long long*>(dst)) atomicMax(dst, key);
+}
+
+// One warp matches 128 consecutive rows (4 consecutive priors per thread) per iteration.
+//  * the next iteration's priors are prefetched (their L2 latency is several microseconds while the
+//    consumers saturate HBM),
+//  * truths are pruned 32 at a time: lane g tests truth g against the warp's bounding box, the
+//    ballot is the list of truths to compute (a disjoint truth has IoU 0 with all 128 priors and
+//    cannot move either running maximum, both update on strict >),
+//  * the four IoUs of a thread are branch-free so their IEEE divisions overlap.
+struct PriorQuad {
+  float4 v[4];
+};
+
+__device__ __forceinline__ void load_quad(const StreamArgs& a, long long row0, long long row_end, PriorQuad& q) {
+  const float* src = a.anchors_xyxy ? a.anchors_xyxy : a.priors;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    long long row = row0 + k;
+    q.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < row_end) {
+      uint32_t b = (uint32_t)row / (uint32_t)a.P;
+      uint32_t p = (uint32_t)row - b * (uint32_t)a.P;
+      q.v[k] = *reinterpret_cast<const float4*>(src + (size_t)b * (size_t)a.prior_stride + (size_t)p * 4);
+    }
+  }
+}
+
+__device__ void match_warp_loop(const StreamArgs& a, const GtCache& gc, int b_lo, long long row_begin,
+                                long long row_end, int mw, int lane) {
+  constexpr int K = 4;
+  const long long step = (long long)kMatchWarps * (32 * K);
+  long long base = row_begin + (long long)mw * (32 * K);
+  PriorQuad nxt;
+  if (base < row_end) load_quad(a, base + lane * K, row_end, nxt);
+  for (; base < row_end; base += step) {
+    const long long row0 = base + lane * K;
+    PriorQuad cur = nxt;
+    if (base + step < row_end) load_quad(a, row0 + step, row_end, nxt);     // prefetch
+    Box box[K];
+    float area[K], bt_ov[K];
+    int bt_idx[K];
+    uint32_t bb[K], pp[K];
+    bool valid[K];
+    float wx1 = INFINITY, wy1 = INFINITY, wx2 = -INFINITY, wy2 = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      long long row = row0 + k;
+      valid[k] = row < row_end;
+      bb[k] = 0; pp[k] = 0;
+      box[k].x1 = box[k].y1 = box[k].x2 = box[k].y2 = 0.f;
+      if (valid[k]) {
+        bb[k] = (uint32_t)row / (uint32_t)a.P;
+        pp[k] = (uint32_t)row - bb[k] * (uint32_t)a.P;
+        if (a.anchors_xyxy) {
+          box[k].x1 = cur.v[k].x; box[k].y1 = cur.v[k].y; box[k].x2 = cur.v[k].z; box[k].y2 = cur.v[k].w;
+        } else {
+          box[k] = point_form(cur.v[k]);
+        }
+        wx1 = fminf(wx1, box[k].x1); wy1 = fminf(wy1, box[k].y1);
+        wx2 = fmaxf(wx2, box[k].x2); wy2 = fmaxf(wy2, box[k].y2);
+      }
+      area[k] = box_area(box[k]);
+      bt_ov[k] = 0.0f;     // all-zero IoU column -> truth 0 (first index), overlap 0
+      bt_idx[k] = 0;
+    }
+    // rows of the warp are consecutive: one image iff the first and the last valid row agree
+    const uint32_t vmask = __ballot_sync(SSDBOX_FULL_MASK, valid[0]);
+    if (vmask == 0u) continue;
+    const uint32_t b_first = __shfl_sync(SSDBOX_FULL_MASK, bb[0], 0);
+    uint32_t my_last = valid[3] ? bb[3] : (valid[2] ? bb[2] : (valid[1] ? bb[1] : bb[0]));
+    const uint32_t b_last = __shfl_sync(SSDBOX_FULL_MASK, my_last, 31 - __clz(vmask));
+    if (b_first == b_last) {
+      const int slot = (int)b_first - b_lo;
+      const int G = gc.count[slot];
+      const float4* gb = gc.box + (size_t)slot * a.gpad;
+      const float* ga = gc.area + (size_t)slot * a.gpad;
+      const int* gl = gc.lab + (size_t)slot * a.gpad;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        wx1 = fminf(wx1, __shfl_xor_sync(SSDBOX_FULL_MASK, wx1, d));
+        wy1 = fminf(wy1, __shfl_xor_sync(SSDBOX_FULL_MASK, wy1, d));
+        wx2 = fmaxf(wx2, __shfl_xor_sync(SSDBOX_FULL_MASK, wx2, d));
+        wy2 = fmaxf(wy2, __shfl_xor_sync(SSDBOX_FULL_MASK, wy2, d));
+      }
+      for (int gbase = 0; gbase < G; gbase += 32) {
+        bool touch = false;
+        if (gbase + lane < G) {
+          float4 tv = gb[gbase + lane];
+          touch = tv.x < wx2 && tv.z > wx1 && tv.y < wy2 && tv.w > wy1;
+        }
+        uint32_t todo = __ballot_sync(SSDBOX_FULL_MASK, touch);
+        while (todo) {                    // ascending truth index: first truth wins ties (box_utils.py:118)
+          const int g = gbase + __ffs(todo) - 1;
+          todo &= todo - 1;
+          float4 tv = gb[g];
+          Box t;
+          t.x1 = tv.x; t.y1 = tv.y; t.x2 = tv.z; t.y2 = tv.w;
+          const float ta = ga[g];
+          float iou[K];
+          iou_jaccard_multi<K>(t, ta, box, area, iou);
+          float lm = 0.0f;
+          uint32_t lp = 0xffffffffu;
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            float v = valid[k] ? iou[k] : 0.0f;
+            if (v > bt_ov[k]) {           // strict
+              bt_ov[k] = v;
+              bt_idx[k] = g;
+            }
+            if (v > lm) {                 // strict + ascending p: lowest prior wins ties (:116)
+              lm = v;
+              lp = pp[k];
+            }
+          }
+          uint32_t mb = __reduce_max_sync(SSDBOX_FULL_MASK, __float_as_uint(lm));
+          if (mb != 0u) {
+            uint32_t pm = __reduce_min_sync(SSDBOX_FULL_MASK, (__float_as_uint(lm) == mb) ? lp : 0xffffffffu);
+            if (lane == 0) best_prior_update(&gc.best[(size_t)slot * a.gpad + g], mb, pm);
+          }
+        }
+      }
+      short4 lo, to;
+      int16_t* lop = reinterpret_cast<int16_t*>(&lo);
+      int16_t* top = reinterpret_cast<int16_t*>(&to);
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        lop[k] = (int16_t)((G > 0 && !(bt_ov[k] < a.threshold)) ? gl[bt_idx[k]] : 0);   // :130
+        top[k] = (int16_t)bt_idx[k];
+      }
+      if (valid[K - 1]) {                 // row0 is a multiple of 4: 8-byte stores
+        *reinterpret_cast<short4*>(a.lab_out + row0) = lo;
+        *reinterpret_cast<short4*>(a.tidx_out + row0) = to;
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if (valid[k]) {
+            a.lab_out[row0 + k] = lop[k];
+            a.tidx_out[row0 + k] = top[k];
+          }
+      }
+    } else {
+      // the 128 rows straddle an image boundary (once per image at most): plain per-prior loops
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (!valid[k]) continue;
+        const int slot = (int)bb[k] - b_lo;
+        const int G = gc.count[slot];
+        const float4* gb = gc.box + (size_t)slot * a.gpad;
+        const float* ga = gc.area + (size_t)slot * a.gpad;
+        float ov = 0.0f;
+        int ti = 0;
+        for (int g = 0; g < G; ++g) {
+          float4 tv = gb[g];
+          Box t;
+          t.x1 = tv.x; t.y1 = tv.y; t.x2 = tv.z; t.y2 = tv.w;
+          float iou = iou_jaccard(t, ga[g], box[k], area[k]);
+          if (iou > ov) {
+            ov = iou;
+            ti = g;
+          }
+          if (iou > 0.0f) best_prior_update(&gc.best[(size_t)slot * a.gpad + g], __float_as_uint(iou), pp[k]);
+        }
+        a.lab_out[row0 + k] = (int16_t)((G > 0 && !(ov < a.threshold)) ? gc.lab[(size_t)slot * a.gpad + ti] : 0);
+        a.tidx_out[row0 + k] = (int16_t)ti;
+      }
+    }
+  }
+  // all match warps of the CTA are done: publish the CTA's per-truth candidates
+  asm volatile("bar.sync 1, %0;" ::"n"(kMatchWarps * 32) : "memory");
+  const int mt = mw * 32 + lane;
+  for (int sl = 0; sl < a.img_slots; ++sl) {
+    const int b = b_lo + sl;
+    if (b >= a.B) break;
+    const int G = gc.count[sl];
+    for (int g = mt; g < G; g += kMatchWarps * 32) {
+      unsigned long long v = gc.best[(size_t)sl * a.gpad + g];
+      if (v > kBestInit) atomicMax(&a.gt_best[(size_t)b * a.gpad + g], v);
+    }
+  }
 }
 
 template <int CT>
-__global__ void __launch_bounds__(kRingThreads, 1) loss_stream_kernel(StreamArgs a) {
+__global__ void __launch_bounds__(kStreamThreads, 1) loss_stream_kernel(StreamArgs a) {
   extern __shared__ __align__(128) unsigned char smem_ring[];
-  RingCtx rc = ring_setup(a.ring, smem_ring);
   const int C = CT > 0 ? CT : a.ring.C;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int R = a.ring.R, NS = a.ring.NS;
+
+  // truths of every image this CTA touches -> shared memory (behind the ring stages)
+  GtCache gc;
+  gc.box = nullptr; gc.area = nullptr; gc.lab = nullptr; gc.count = nullptr; gc.best = nullptr;
+  int b_lo = 0;
+  if (a.fuse) {
+    unsigned char* base = smem_ring + kRingHeaderBytes + (size_t)NS * R * C * 4;
+    unsigned long long* s_best = reinterpret_cast<unsigned long long*>(base);
+    base += (size_t)a.img_slots * a.gpad * 8;
+    float4* s_box = reinterpret_cast<float4*>(base);
+    float* s_area = reinterpret_cast<float*>(s_box + (size_t)a.img_slots * a.gpad);
+    int* s_lab = reinterpret_cast<int*>(s_area + (size_t)a.img_slots * a.gpad);
+    int* s_cnt = s_lab + (size_t)a.img_slots * a.gpad;
+    long long first_row = (long long)blockIdx.x * a.ring.tiles_per_cta * R;
+    b_lo = (int)(first_row / a.P);
+    for (int sl = 0; sl < a.img_slots; ++sl) {
+      int b = b_lo + sl;
+      int g0 = 0, G = 0;
+      if (b < a.B) {
+        g0 = a.gt_offsets[b];
+        G = a.gt_offsets[b + 1] - g0;
+        G = G < 0 ? 0 : (G > a.gmax ? a.gmax : G);
+      }
+      if (tid == 0) s_cnt[sl] = G;
+      for (int g = tid; g < G; g += kStreamThreads) {
+        const float* r = a.gt + (size_t)(g0 + g) * 5;
+        Box t;
+        t.x1 = r[0]; t.y1 = r[1]; t.x2 = r[2]; t.y2 = r[3];
+        s_box[(size_t)sl * a.gpad + g] = make_float4(t.x1, t.y1, t.x2, t.y2);
+        s_area[(size_t)sl * a.gpad + g] = box_area(t);
+        s_lab[(size_t)sl * a.gpad + g] = a.binarize ? 1 : (int)(r[4] + 1.0f);   // box_utils.py:129
+        s_best[(size_t)sl * a.gpad + g] = kBestInit;
+      }
+    }
+    gc.box = s_box; gc.area = s_area; gc.lab = s_lab; gc.count = s_cnt; gc.best = s_best;
+  }
+  if (warp == 0) SMARK(0);
+  RingCtx rc = ring_setup(a.ring, smem_ring);   // its __syncthreads() also publishes the truth cache
+  if (warp == 0) SMARK(1);
   if (warp == kRingConsumerWarps) {
     ring_produce(a.ring, rc);
+    SMARK(2);
+    return;
+  }
+  if (warp > kRingConsumerWarps) {
+    if (warp == kRingConsumerWarps + 1) SMARK(3);
+    if (a.fuse) {
+      long long row_begin = rc.t0 * R;
+      long long row_end = (rc.t0 + rc.n_local) * R;
+      if (row_end > a.ring.rows) row_end = a.ring.rows;
+      match_warp_loop(a, gc, b_lo, row_begin, row_end, warp - kRingConsumerWarps - 1, lane);
+    }
+    if (warp == kRingConsumerWarps + 1) SMARK(4);
+    if (warp == kRingConsumerWarps + 8) SMARK(5);
     return;
   }
   const int wg = warp >> 2;
   const int r = tid & 127;
-  const int R = a.ring.R, NS = a.ring.NS;
   for (int it = wg; it < rc.n_local; it += 2) {
     const int s = it % NS, j = it % (2 * NS), ph = it / (2 * NS);
     long long row = (rc.t0 + it) * R + r;
     bool valid = (r < R) && (row < a.ring.rows);
-    int lb = 0;
     int inpool = 1;
-    if (valid) {
-      lb = a.lab[row];
-      if (a.pool) inpool = a.pool[row];
-    }
+    if (valid && a.pool) inpool = a.pool[row];
     mbar_wait(&rc.full[j], (uint32_t)(ph & 1));
-    float key = 0.f;
-    if (valid) key = row_key<CT>(rc.stages + (size_t)s * rc.stage_floats + (size_t)r * C, C, lb);
+    float lse = 0.f, k0 = 0.f;
+    if (valid) {
+      const float* rp = rc.stages + (size_t)s * rc.stage_floats + (size_t)r * C;
+      lse = row_lse<CT>(rp, C);
+      k0 = lse - rp[0];                                    // multibox_loss.py:94 with conf_t = 0
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive(&rc.empty[j]);
     if (valid) {
-      a.keys[row] = key;
+      a.lse[row] = lse;
+      a.key0[row] = k0;
       if (inpool) {
-        float mk = lb > 0 ? 0.0f : key;                    // multibox_loss.py:97 positives -> 0
         uint32_t b = (uint32_t)row / (uint32_t)a.P;
-        atomicAdd(&a.hist[(size_t)b * kHistBins + (f2ord(mk) >> 21)], 1u);
+        atomicAdd(&a.hist[(size_t)b * kHistBins + (f2ord(k0) >> 21)], 1u);
       }
     }
   }
+  if (warp == 0) SMARK(6);
+  if (warp == 7) SMARK(7);
 }
 
-static int launch_stream(StreamArgs a, const float* conf, long long rows, int C, int sm_count, int max_smem,
-                         cudaStream_t st) {
-  if (rows == 0) return SSDBOX_OK;
-  int rc = plan_ring(&a.ring, conf, rows, C, sm_count, max_smem);
+// StreamArgs.fuse must be decided by the caller (plan_stream) before the launch
+static int plan_stream(StreamArgs* a, const float* conf, long long rows, int C, int sm_count, int max_smem,
+                       bool want_fuse, size_t* smem_out) {
+  int rc = plan_ring(&a->ring, conf, rows, C, sm_count, max_smem);
   if (rc) return rc;
+  size_t smem = a->ring.smem_bytes;
+  a->fuse = 0;
+  a->img_slots = 0;
+  if (want_fuse) {
+    long long rows_per_cta = (long long)a->ring.tiles_per_cta * a->ring.R;
+    long long slots = (rows_per_cta + a->P - 2) / a->P + 1;
+    size_t need = (size_t)slots * a->gpad * 32 + (size_t)slots * 4 + 64;
+    if (slots <= 256 && smem + need <= (size_t)max_smem - 1024) {
+      a->fuse = 1;
+      a->img_slots = (int)slots;
+      smem += need;
+    }
+  }
+  *smem_out = smem;
+  return SSDBOX_OK;
+}
+
+static int launch_stream(const StreamArgs& a, size_t smem, cudaStream_t st) {
+  const int C = a.ring.C;
   void (*kern)(StreamArgs) = loss_stream_kernel<0>;
   if (C == 81) kern = loss_stream_kernel<81>;
   else if (C == 21) kern = loss_stream_kernel<21>;
   else if (C == 2) kern = loss_stream_kernel<2>;
-  SSDBOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.ring.smem_bytes));
-{
+  SSDBOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
     TimerScope ts__(KID_LOSS_STREAM, st);
-    kern<<<a.ring.grid, kRingThreads, a.ring.smem_bytes, st>>>(a);
+    kern<<<a.ring.grid, kStreamThreads, smem, st>>>(a);
   }
   SSDBOX_LAUNCH_OK("loss_stream_kernel");
   return SSDBOX_OK;
@@ -136,10 +437,18 @@ struct MineArgs {
   const float* gt;
   const int32_t* gt_offsets;
   const uint8_t* pool;
-  const float* keys;
+  const float* keys;       // key0 = lse - x[0] from the stream kernel
+  const float* lse;
+  const float* conf;       // gathered once per positive: x[target]
   const int16_t* lab;
   const int16_t* tidx;
-  const uint32_t* hist;
+  uint32_t* hist;          // level-1 histogram; positives are moved to the zero bin here
+  // fused matching: the forced assignment (box_utils.py:123-127) is replayed here
+  int fuse;
+  int gmax, gpad, binarize;
+  const unsigned long long* gt_best;
+  int16_t* lab_w;
+  int16_t* tidx_w;
   uint32_t* ukey_global;   // used when the ordered keys do not fit in shared memory
   int uk_in_smem;
   double* partial;
@@ -159,19 +468,26 @@ __device__ long long g_phase[16];
 #endif
 
 // per-prior work of pass A: returns the ordered mining key (0 = outside the ranking)
-__device__ __forceinline__ uint32_t mine_visit(const MineArgs& a, size_t i, int p, int g0, const float* pri,
+__device__ __forceinline__ uint32_t mine_visit(const MineArgs& a, size_t i, int p, int b, int g0, const float* pri,
                                                float key, int lb, int inpool, int& npos, double& ce, double& l1) {
+  if (a.dbg_keys) a.dbg_keys[i] = key;
   if (!inpool) return 0u;
   if (lb > 0) {
     ++npos;
-    ce += (double)key;
+    // CE of a positive = lse - x[target] (multibox_loss.py:94,110); it leaves its streamed bin
+    // and ranks as 0 (multibox_loss.py:97)
+    float cep = a.lse[i] - a.conf[i * (size_t)a.C + lb];
+    if (a.dbg_keys) a.dbg_keys[i] = cep;
+    ce += (double)cep;
+    atomicSub(&a.hist[(size_t)b * kHistBins + (f2ord(key) >> 21)], 1u);
+    atomicAdd(&a.hist[(size_t)b * kHistBins + (f2ord(0.0f) >> 21)], 1u);
     const float* row = a.gt + (size_t)(g0 + a.tidx[i]) * 5;
     Box m;
     m.x1 = row[0]; m.y1 = row[1]; m.x2 = row[2]; m.y2 = row[3];
     float4 t = encode_box(m, *reinterpret_cast<const float4*>(pri + (size_t)p * 4), a.var0, a.var1);
     float4 l = *reinterpret_cast<const float4*>(a.loc + i * 4);
     l1 += (double)(smooth_l1(l.x, t.x) + smooth_l1(l.y, t.y) + smooth_l1(l.z, t.z) + smooth_l1(l.w, t.w));
-    return f2ord(0.0f);                                   // multibox_loss.py:97 positives rank as 0
+    return f2ord(0.0f);
   }
   return f2ord(key);
 }
@@ -196,6 +512,31 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
   const int g0 = a.gt_offsets[b];
   const float* pri = a.priors + (size_t)b * (size_t)a.prior_stride;
   const bool in_smem = a.uk_in_smem != 0;
+
+  // phase F (fused matching only): every truth claims its best prior, sequentially, last truth
+  // wins; a claimed prior becomes positive with that truth's label (box_utils.py:123-130)
+  if (a.fuse) {
+    int G = a.gt_offsets[b + 1] - g0;
+    G = G < 0 ? 0 : (G > a.gmax ? a.gmax : G);
+    const unsigned long long* best = a.gt_best + (size_t)b * a.gpad;
+    unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_hist);   // 1024 entries
+    const bool cached = G <= 1024;
+    if (cached) {
+      for (int j = tid; j < G; j += kMineThreads) s_best[j] = __ldcg(&best[j]);
+      __syncthreads();
+    }
+    for (int j = tid; j < G; j += kMineThreads) {
+      const uint32_t pj = ~(uint32_t)((cached ? s_best[j] : __ldcg(&best[j])) & 0xffffffffull);
+      bool winner = pj < (uint32_t)P;
+      for (int j2 = j + 1; winner && j2 < G; ++j2)
+        if (~(uint32_t)((cached ? s_best[j2] : __ldcg(&best[j2])) & 0xffffffffull) == pj) winner = false;
+      if (winner) {
+        a.lab_w[off + pj] = (int16_t)(a.binarize ? 1 : (int)(a.gt[(size_t)(g0 + j) * 5 + 4] + 1.0f));
+        a.tidx_w[off + pj] = (int16_t)j;
+      }
+    }
+    __syncthreads();
+  }
 
   // pass A: positives (count, CE, smooth-L1) and the ordered mining keys
   PHASE_MARK(0);
@@ -228,12 +569,11 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
         if (q >= n4) continue;
         int p = q * 4;
         size_t i = off + p;
-        if (a.dbg_keys) *reinterpret_cast<float4*>(a.dbg_keys + i) = kk[u];
         uint4 uo;
-        uo.x = mine_visit(a, i, p, g0, pri, kk[u].x, ll[u].x, pp[u].x, npos, ce, l1);
-        uo.y = mine_visit(a, i + 1, p + 1, g0, pri, kk[u].y, ll[u].y, pp[u].y, npos, ce, l1);
-        uo.z = mine_visit(a, i + 2, p + 2, g0, pri, kk[u].z, ll[u].z, pp[u].z, npos, ce, l1);
-        uo.w = mine_visit(a, i + 3, p + 3, g0, pri, kk[u].w, ll[u].w, pp[u].w, npos, ce, l1);
+        uo.x = mine_visit(a, i, p, b, g0, pri, kk[u].x, ll[u].x, pp[u].x, npos, ce, l1);
+        uo.y = mine_visit(a, i + 1, p + 1, b, g0, pri, kk[u].y, ll[u].y, pp[u].y, npos, ce, l1);
+        uo.z = mine_visit(a, i + 2, p + 2, b, g0, pri, kk[u].z, ll[u].z, pp[u].z, npos, ce, l1);
+        uo.w = mine_visit(a, i + 3, p + 3, b, g0, pri, kk[u].w, ll[u].w, pp[u].w, npos, ce, l1);
         *reinterpret_cast<uint4*>(uk + p) = uo;
         if (in_smem) *reinterpret_cast<short4*>(s_lab + p) = ll[u];
       }
@@ -244,8 +584,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
       float key = a.keys[i];
       int lb = a.lab[i];
       int inpool = a.pool ? a.pool[i] : 1;
-      if (a.dbg_keys) a.dbg_keys[i] = key;
-      uk[p] = mine_visit(a, i, p, g0, pri, key, lb, inpool, npos, ce, l1);
+      uk[p] = mine_visit(a, i, p, b, g0, pri, key, lb, inpool, npos, ce, l1);
       if (in_smem) s_lab[p] = (int16_t)lb;
     }
   }
@@ -524,6 +863,8 @@ extern "C" int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float*
                      (!dbg_loc_t || aligned16(dbg_loc_t)),
                  SSDBOX_EALIGN, "loss: box pointers must be 16-byte aligned");
   SSDBOX_REQUIRE((reinterpret_cast<uintptr_t>(conf) & 3u) == 0, SSDBOX_EALIGN, "loss: conf must be 4-byte aligned");
+  SSDBOX_REQUIRE((reinterpret_cast<uintptr_t>(tidx) & 7u) == 0 && (reinterpret_cast<uintptr_t>(sel) & 7u) == 0,
+                 SSDBOX_EALIGN, "loss: sel / tidx must be 8-byte aligned");
   SSDBOX_REQUIRE(ws_bytes >= loss_ws_bytes(B, P, C, cfg->gmax), SSDBOX_EWORKSPACE, "loss: workspace too small");
   DevInfo dev;
   rc = get_dev_info(&dev);
@@ -540,21 +881,44 @@ extern "C" int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float*
   w.partial = c.take<double>((size_t)B * 3);
   w.ticket = c.take<uint32_t>(1);
 
+  w.lse = c.take<float>((size_t)B * P);
+
   rc = launch_init(w.m.gt_best, (size_t)(B + 1) * gt_pad(cfg->gmax), w.m.done, (size_t)B + 1, w.hist,
                    (size_t)B * kHistBins, w.ticket, 1, st);
   if (rc) return rc;
+
+  // Matching runs on dedicated warps of the streaming kernel unless the caller asked for the
+  // separate kernel or the truths of a CTA's images do not fit in shared memory beside the ring.
   MatchArgs ma{gt, gt_offsets, cfg->gmax, priors, (long long)cfg->prior_batch_stride, anchors_xyxy, B, P,
                cfg->threshold, cfg->binarize_labels};
-  rc = launch_match(ma, w.m, w.m.lab, tidx, nullptr, st);
-  if (rc) return rc;
-
   StreamArgs sa{};
-  sa.lab = w.m.lab;
   sa.pool = pool;
-  sa.keys = w.keys;
+  sa.key0 = w.keys;
+  sa.lse = w.lse;
   sa.hist = w.hist;
   sa.P = P;
-  rc = launch_stream(sa, conf, (long long)B * P, C, dev.sm_count, dev.max_smem_optin, st);
+  sa.B = B;
+  sa.gt = gt;
+  sa.gt_offsets = gt_offsets;
+  sa.gmax = cfg->gmax;
+  sa.gpad = gt_pad(cfg->gmax);
+  sa.priors = priors;
+  sa.prior_stride = (long long)cfg->prior_batch_stride;
+  sa.anchors_xyxy = anchors_xyxy;
+  sa.threshold = cfg->threshold;
+  sa.binarize = cfg->binarize_labels;
+  sa.gt_best = w.m.gt_best;
+  sa.lab_out = w.m.lab;
+  sa.tidx_out = tidx;
+  size_t stream_smem = 0;
+  rc = plan_stream(&sa, conf, (long long)B * P, C, dev.sm_count, dev.max_smem_optin,
+                   !(cfg->flags & SSDBOX_LOSS_SEPARATE_MATCH), &stream_smem);
+  if (rc) return rc;
+  if (!sa.fuse) {
+    rc = launch_match(ma, w.m, w.m.lab, tidx, nullptr, st);
+    if (rc) return rc;
+  }
+  rc = launch_stream(sa, stream_smem, st);
   if (rc) return rc;
 
   MineArgs m{};
@@ -564,7 +928,9 @@ extern "C" int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float*
   m.finalize = cfg->finalize;
   m.prior_stride = (long long)cfg->prior_batch_stride;
   m.loc = loc; m.priors = priors; m.gt = gt; m.gt_offsets = gt_offsets; m.pool = pool;
-  m.keys = w.keys; m.lab = w.m.lab; m.tidx = tidx; m.hist = w.hist;
+  m.keys = w.keys; m.lse = w.lse; m.conf = conf; m.lab = w.m.lab; m.tidx = tidx; m.hist = w.hist;
+  m.fuse = sa.fuse; m.gmax = cfg->gmax; m.gpad = sa.gpad; m.binarize = cfg->binarize_labels;
+  m.gt_best = w.m.gt_best; m.lab_w = w.m.lab; m.tidx_w = tidx;
   m.ukey_global = w.ukey;
   size_t fixed = kMineFixedSmem;
   m.uk_in_smem = (fixed + (size_t)P * 6 + 16 <= (size_t)dev.max_smem_optin - 1024) ? 1 : 0;
@@ -591,6 +957,12 @@ extern "C" int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float*
 }
 
 #ifdef SSDBOX_PHASE_TIMING
+extern "C" __attribute__((visibility("default"))) int ssdbox_debug_mstat(long long* out) {
+  return cudaMemcpyFromSymbol(out, ssdbox::g_mstat, sizeof(long long) * 8 * 160) == cudaSuccess ? 0 : -5;
+}
+extern "C" __attribute__((visibility("default"))) int ssdbox_debug_sphases(long long* out16) {
+  return cudaMemcpyFromSymbol(out16, ssdbox::g_sphase, sizeof(long long) * 8 * 160) == cudaSuccess ? 0 : -5;
+}
 extern "C" __attribute__((visibility("default"))) int ssdbox_debug_phases(long long* out16) {
   return cudaMemcpyFromSymbol(out16, ssdbox::g_phase, sizeof(long long) * 16) == cudaSuccess ? 0 : -5;
 }

@@ -35,7 +35,8 @@ static inline void carve_match_core(Carver& c, int B, int gmax, MatchWs* w) {
 // ---- loss ----------------------------------------------------------------------------------
 struct LossWs {
   MatchWs m;
-  float* keys;        // [B,P]  lse - x[target]
+  float* keys;        // [B,P]  lse - x[0]
+  float* lse;         // [B,P]
   uint32_t* hist;     // [B, kHistBins]
   uint32_t* ukey;     // [B,P]  ordered mining keys (only used when they do not fit in smem)
   double* partial;    // [B,3]
@@ -43,7 +44,7 @@ struct LossWs {
 };
 static inline size_t loss_ws_bytes(int B, int P, int C, int gmax) {
   (void)C;
-  return match_core_bytes(B, gmax) + align_up((size_t)B * P * 2) + align_up((size_t)B * P * 4) * 2 +
+  return match_core_bytes(B, gmax) + align_up((size_t)B * P * 2) + align_up((size_t)B * P * 4) * 3 +
          align_up((size_t)B * kHistBins * 4) + align_up((size_t)B * 3 * 8) + 256;
 }
 

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libssdbox.so")
 
 OK, EINVAL, ESHAPE, EALIGN, EWORKSPACE, ECUDA = 0, -1, -2, -3, -4, -5
+LOSS_SEPARATE_MATCH = 1
 OP_MATCH, OP_LOSS_FWD, OP_DETECT, OP_NMS, OP_LSE, OP_MINE = 1, 2, 3, 4, 5, 6
 MAX_LAYERS, MAX_MIN_SIZES, MAX_RATIOS = 16, 4, 6
 
@@ -49,6 +50,7 @@ class LossCfg(C.Structure):
         ("B", C.c_int32), ("P", C.c_int32), ("C", C.c_int32), ("gmax", C.c_int32),
         ("threshold", C.c_float), ("negpos_ratio", C.c_int32), ("var0", C.c_float), ("var1", C.c_float),
         ("binarize_labels", C.c_int32), ("finalize", C.c_int32), ("prior_batch_stride", C.c_int64),
+        ("flags", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -51,7 +51,7 @@ class _State(object):
 
 def loss_forward_raw(state, loc, conf, priors, gt, offsets, gmax, num_classes, threshold, negpos_ratio,
                      variance, anchors_xyxy=None, pool=None, binarize=False, finalize=True, debug=None,
-                     fresh=False):
+                     fresh=False, flags=0):
     """One call of ssdbox_multibox_loss_fwd on validated CUDA tensors.  Returns
     (cfg, sums[3] f64, losses[2] f32, sel[B,P] i16, tidx[B,P] i16).  With fresh=False the outputs are
     the module's persistent buffers (overwritten by the next call); fresh=True allocates new ones
@@ -69,7 +69,7 @@ def loss_forward_raw(state, loc, conf, priors, gt, offsets, gmax, num_classes, t
     per_image = priors.dim() == 3
     cfg = _abi.LossCfg(B, P, int(num_classes), int(gmax), float(threshold), int(negpos_ratio),
                        float(variance[0]), float(variance[1]), 1 if binarize else 0, 1 if finalize else 0,
-                       4 * P if per_image else 0)
+                       4 * P if per_image else 0, int(flags), 0)
     ws, n = state.ws.get(_abi.workspace_bytes(_abi.OP_LOSS_FWD, B, P, num_classes, gmax), dev)
     dbg = debug or {}
     _abi.check(_abi.lib().ssdbox_multibox_loss_fwd(
@@ -92,7 +92,7 @@ class _MultiBoxLossFn(torch.autograd.Function):
         cfg, sums, losses, sel, tidx = loss_forward_raw(
             st, loc, conf, priors, gt, offsets, gmax, mod.num_classes, mod.threshold, mod.negpos_ratio,
             mod.variance, anchors_xyxy, pool, mod.binarize_labels, finalize=not distributed, debug=mod._debug,
-            fresh=need_grad)
+            fresh=need_grad, flags=mod.abi_flags)
         if distributed:
             # the only collective of the path: {sum smooth-L1, sum CE, N_pos} summed over ranks
             import torch.distributed as dist
@@ -145,6 +145,7 @@ class MultiBoxLoss(nn.Module):
         self.binarize_labels = False
         self.distributed = distributed
         self.process_group = process_group
+        self.abi_flags = 0          # _abi.LOSS_SEPARATE_MATCH: matching as its own kernel
         self._state = _State()
         self._debug = None
         self._last = None

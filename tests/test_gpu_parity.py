@@ -321,6 +321,32 @@ def test_multibox_loss_edge_cases(dev):
     assert float(ll2) == float(ll) and float(lc2) == float(lc)
 
 
+@pytest.mark.parametrize("name,B,seed", [("ssd300_voc", 5, 0), ("ssd512_coco", 3, 1), ("refinedet320_voc", 7, 2)])
+def test_fused_and_separate_matching_agree(dev, name, B, seed):
+    """The matching runs on dedicated warps of the streaming kernel by default and as its own kernel
+    on request: both must give bit-identical targets, selections and sums."""
+    from ssdbox import _abi
+    x = U.seeded_inputs(name, B, seed)
+    # make the batch interesting: duplicate truths (shared best prior) and an empty image
+    tg = list(x["targets"])
+    tg[0] = torch.cat([tg[0], tg[0][:1] * torch.tensor([1, 1, 1, 1, 0.0]) + torch.tensor([0, 0, 0, 0, 5.0])], 0)
+    tg[1] = torch.zeros(0, 5)
+    res = []
+    for flags in (0, _abi.LOSS_SEPARATE_MATCH):
+        crit = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False)
+        crit.abi_flags = flags
+        res.append(crit.intermediates((x["loc"].to(dev), x["conf"].to(dev), x["priors"].to(dev)), _gpu_targets(tg, dev)))
+    a, b = res
+    for k in ("conf_t", "neg", "sel", "tidx", "keys", "sums", "loc_t"):
+        assert torch.equal(a[k], b[k]), k
+    # oracle check on the non-empty images
+    keep = [i for i, t in enumerate(tg) if t.size(0) > 0]
+    r = O.multibox_loss(x["loc"][keep], x["conf"][keep], x["priors"], [tg[i] for i in keep], x["C"], detail=True)
+    assert torch.equal(a["conf_t"].cpu()[keep], r["conf_t"])
+    U.assert_close_rel(a["loss_l"], r["loss_l"], REL, 0, "loss_l")
+    U.assert_close_rel(a["loss_c"], r["loss_c"], REL, 0, "loss_c")
+
+
 def test_cuda_graph_capture(dev):
     x = U.seeded_inputs("ssd300_voc", 4, 0)
     crit = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False)
