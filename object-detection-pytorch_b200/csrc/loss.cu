@@ -8,8 +8,10 @@
 //                        8 consumer warps  one thread per prior row: lse and the background key
 //                                          lse - x[0]; level-1 mining histogram (top 11 bits of the
 //                                          order-preserving key).  Independent of the class targets.
-//                        8 match warps     box_utils.match for the CTA's rows while the consumers
-//                                          wait on memory: truths in shared memory, 4 consecutive
+//                        1 scheduler warp + 8 match warps: box_utils.match while the consumers wait
+//                                          on memory.  Work units (1024 priors of one image) come
+//                                          from a global counter, the unit's truths and priors are
+//                                          staged in shared memory (priors by TMA); 4 consecutive
 //                                          priors per thread, warp bounding-box pruning, per-truth
 //                                          argmax by REDUX + atomicMax.  The IoU matrix never exists.
 //   mine_reduce_kernel one CTA per image: replays the forced assignment ("every truth keeps its
@@ -18,7 +20,7 @@
 //                      num_neg-th largest mining key (level 1 from the streamed histogram, levels
 //                      2/3 touch only the winning bin), canonical tie order, fixed-order fp64
 //                      reduction of smooth-L1 / CE, last CTA folds the per-image partials.
-// (With SSDBOX_LOSS_SEPARATE_MATCH, or when the truths of a CTA's images do not fit beside the ring,
+// (With SSDBOX_LOSS_SEPARATE_MATCH, or when two unit buffers do not fit beside the ring,
 // match_kernel of match.cu runs as a fourth launch before the stream kernel instead.)
 // The final CE over pos U neg needs no second pass over conf: CE of a negative is its mining key.
 // Backward zero-fills grad_conf and touches conf only on the selected rows.
@@ -42,7 +44,11 @@ __device__ long long g_mstat[8 * 160];
 #endif
 
 constexpr int kMatchWarps = 8;
-constexpr int kStreamThreads = kRingThreads + kMatchWarps * 32;   // consumers + producer + match warps
+constexpr int kMatchTile = kMatchWarps * 128;                      // priors of one matching work unit
+constexpr int kSchedWarp = kRingConsumerWarps + 1;                 // warp 8 = conf producer, 9 = unit scheduler
+constexpr int kFirstMatchWarp = kRingConsumerWarps + 2;
+constexpr int kStreamThreads = (kRingConsumerWarps + 2 + kMatchWarps) * 32;
+constexpr int kMatchBarBytes = 64;                                 // mfull[2], mempty[2]
 
 struct StreamArgs {
   RingPlan ring;       // conf [B*P, C]
@@ -65,7 +71,9 @@ struct StreamArgs {
   unsigned long long* gt_best;
   int16_t* lab_out;
   int16_t* tidx_out;
-  int img_slots;       // images one CTA can touch; their truths are cached in shared memory
+  uint32_t* unit_counter;   // next matching work unit (zeroed by init_kernel)
+  int unit_bytes;           // one unit buffer in shared memory
+  int dbg;                  // SSDBOX_PHASE_TIMING builds: 1 = do not stream conf (matching alone)
 };
 
 // log-sum-exp of one row with the row maximum (box_utils.py:273 uses one global maximum; same value
@@ -96,97 +104,145 @@ __device__ __forceinline__ float row_lse(const float* __restrict__ rp, int C) {
   return logf(s) + m;
 }
 
-// ---- match warps --------------------------------------------------------------------------------
-struct GtCache {
-  const float4* box;          // [slots, gpad] xyxy
-  const float* area;          // [slots, gpad]
-  const int* lab;             // [slots, gpad] class target (label + 1)
-  const int* count;           // [slots]
-  unsigned long long* best;   // [slots, gpad] CTA-local per-truth best prior, flushed once at the end
+// ---- matching on dedicated warps -----------------------------------------------------------------
+// Work unit = kMatchTile consecutive priors of one image.  Units are handed out dynamically (one
+// global counter, heavy coarse-layer tiles first) so the matching load is balanced over the SMs
+// whatever the truth counts of the images a CTA happens to stream.  The scheduler warp stages a
+// unit in one of two shared-memory buffers: the unit's truths (+area, +label, +CTA-local best-prior
+// keys) with plain loads and its priors with one TMA bulk copy; the match warps therefore never wait
+// on a global load while the consumers saturate HBM.
+struct MatchUnit {
+  int b, p0, nrows, G;      // b < 0: no more work
 };
+struct UnitBuf {
+  MatchUnit* hd;
+  float4* pri;                // [kMatchTile] centre-form priors (or xyxy anchors)
+  float4* box;                // [gpad] truth xyxy
+  unsigned long long* best;   // [gpad] per-truth best prior over this unit
+  float* area;                // [gpad]
+  int* lab;                   // [gpad] class target (label + 1)
+};
+__device__ __forceinline__ UnitBuf unit_buf(unsigned char* mbase, int buf, int unit_bytes, int gpad) {
+  unsigned char* ub = mbase + kMatchBarBytes + (size_t)buf * unit_bytes;
+  UnitBuf u;
+  u.hd = reinterpret_cast<MatchUnit*>(ub);
+  u.pri = reinterpret_cast<float4*>(ub + 16);
+  u.box = u.pri + kMatchTile;
+  u.best = reinterpret_cast<unsigned long long*>(u.box + gpad);
+  u.area = reinterpret_cast<float*>(u.best + gpad);
+  u.lab = reinterpret_cast<int*>(u.area + gpad);
+  return u;
+}
+static inline int unit_buf_bytes(int gpad) { return (int)align_up((size_t)16 + (size_t)kMatchTile * 16 + (size_t)gpad * 32, 128); }
 
 // max IoU, lowest prior index on ties (box_utils.py:116); shared-memory copy first: the global
-// atomic happens once per (CTA, truth) at the end, never inside the truth loop
+// atomic happens once per (unit, truth), never inside the truth loop
 __device__ __forceinline__ void best_prior_update(unsigned long long* dst, uint32_t iou_bits, uint32_t p) {
   unsigned long long key = ((unsigned long long)iou_bits << 32) | (unsigned long long)(uint32_t)(~p);
   if (key > *reinterpret_cast<volatile unsigned long long*>(dst)) atomicMax(dst, key);
 }
 
-// One warp matches 128 consecutive rows (4 consecutive priors per thread) per iteration.
-//  * the next iteration's priors are prefetched (their L2 latency is several microseconds while the
-//    consumers saturate HBM),
-//  * truths are pruned 32 at a time: lane g tests truth g against the warp's bounding box, the
-//    ballot is the list of truths to compute (a disjoint truth has IoU 0 with all 128 priors and
-//    cannot move either running maximum, both update on strict >),
-//  * the four IoUs of a thread are branch-free so their IEEE divisions overlap.
-struct PriorQuad {
-  float4 v[4];
-};
-
-__device__ __forceinline__ void load_quad(const StreamArgs& a, long long row0, long long row_end, PriorQuad& q) {
-  const float* src = a.anchors_xyxy ? a.anchors_xyxy : a.priors;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    long long row = row0 + k;
-    q.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < row_end) {
-      uint32_t b = (uint32_t)row / (uint32_t)a.P;
-      uint32_t p = (uint32_t)row - b * (uint32_t)a.P;
-      q.v[k] = *reinterpret_cast<const float4*>(src + (size_t)b * (size_t)a.prior_stride + (size_t)p * 4);
+// whole scheduler warp
+__device__ void match_sched_loop(const StreamArgs& a, unsigned char* mbase, int lane) {
+  uint64_t* mfull = reinterpret_cast<uint64_t*>(mbase);
+  uint64_t* mempty = mfull + 2;
+  const int ntile = (a.P + kMatchTile - 1) / kMatchTile;
+  const unsigned nunits = (unsigned)ntile * (unsigned)a.B;
+  const float* src_base = a.anchors_xyxy ? a.anchors_xyxy : a.priors;
+  for (int k = 0;; ++k) {
+    const int buf = k & 1;
+    UnitBuf ub = unit_buf(mbase, buf, a.unit_bytes, a.gpad);
+    if (k >= 2) {    // the match warps have released the unit staged two rounds ago
+      if (lane == 0) mbar_wait(&mempty[buf], (uint32_t)(((k >> 1) - 1) & 1));
+      __syncwarp();
+    }
+    unsigned u = 0;
+    if (lane == 0) u = atomicAdd(a.unit_counter, 1u);
+    u = __shfl_sync(SSDBOX_FULL_MASK, u, 0);
+    if (u >= nunits) {
+      if (lane == 0) {
+        ub.hd->b = -1;
+        mbar_arrive(&mfull[buf]);
+      }
+      return;
+    }
+    const int tile = ntile - 1 - (int)(u / (unsigned)a.B);     // coarse layers (most truths per warp) first
+    const int b = (int)(u % (unsigned)a.B);
+    const int p0 = tile * kMatchTile;
+    const int nrows = a.P - p0 < kMatchTile ? a.P - p0 : kMatchTile;
+    const int g0 = a.gt_offsets[b];
+    int G = a.gt_offsets[b + 1] - g0;
+    G = G < 0 ? 0 : (G > a.gmax ? a.gmax : G);
+    for (int g = lane; g < G; g += 32) {
+      const float* r = a.gt + (size_t)(g0 + g) * 5;
+      Box t;
+      t.x1 = r[0]; t.y1 = r[1]; t.x2 = r[2]; t.y2 = r[3];
+      ub.box[g] = make_float4(t.x1, t.y1, t.x2, t.y2);
+      ub.area[g] = box_area(t);
+      ub.lab[g] = a.binarize ? 1 : (int)(r[4] + 1.0f);   // box_utils.py:129
+      ub.best[g] = kBestInit;
+    }
+    if (lane == 0) *ub.hd = MatchUnit{b, p0, nrows, G};
+    __syncwarp();
+    if (lane == 0) {
+      const float* src = src_base + (size_t)b * (size_t)a.prior_stride + (size_t)p0 * 4;
+      mbar_arrive_expect_tx(&mfull[buf], (uint32_t)nrows * 16u);
+      bulk_g2s_plain(ub.pri, src, (uint32_t)nrows * 16u, &mfull[buf]);
     }
   }
 }
 
-__device__ void match_warp_loop(const StreamArgs& a, const GtCache& gc, int b_lo, long long row_begin,
-                                long long row_end, int mw, int lane) {
+// One match warp owns 128 consecutive priors of the unit (4 consecutive priors per thread).
+//  * truths are pruned 32 at a time: lane g tests truth g against the warp's bounding box, the
+//    ballot is the list of truths to compute (a disjoint truth has IoU 0 with all 128 priors and
+//    cannot move either running maximum, both update on strict >),
+//  * the four IoUs of a thread are branch-free so their IEEE divisions overlap.
+__device__ void match_unit_loop(const StreamArgs& a, unsigned char* mbase, int mw, int lane) {
   constexpr int K = 4;
-  const long long step = (long long)kMatchWarps * (32 * K);
-  long long base = row_begin + (long long)mw * (32 * K);
-  PriorQuad nxt;
-  if (base < row_end) load_quad(a, base + lane * K, row_end, nxt);
-  for (; base < row_end; base += step) {
-    const long long row0 = base + lane * K;
-    PriorQuad cur = nxt;
-    if (base + step < row_end) load_quad(a, row0 + step, row_end, nxt);     // prefetch
+  uint64_t* mfull = reinterpret_cast<uint64_t*>(mbase);
+  uint64_t* mempty = mfull + 2;
+#ifdef SSDBOX_PHASE_TIMING
+  long long t_wait = 0, t_busy = 0, n_units = 0, n_truths = 0;
+#endif
+  for (int k = 0;; ++k) {
+    const int buf = k & 1;
+    UnitBuf ub = unit_buf(mbase, buf, a.unit_bytes, a.gpad);
+#ifdef SSDBOX_PHASE_TIMING
+    long long c0 = clock64();
+#endif
+    mbar_wait(&mfull[buf], (uint32_t)((k >> 1) & 1));
+#ifdef SSDBOX_PHASE_TIMING
+    long long c1 = clock64();
+    t_wait += c1 - c0;
+#endif
+    const MatchUnit hd = *ub.hd;
+    if (hd.b < 0) break;
+    const int G = hd.G;
+    const int r0 = mw * (32 * K) + lane * K;      // first prior of this thread inside the unit
     Box box[K];
     float area[K], bt_ov[K];
     int bt_idx[K];
-    uint32_t bb[K], pp[K];
     bool valid[K];
     float wx1 = INFINITY, wy1 = INFINITY, wx2 = -INFINITY, wy2 = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      long long row = row0 + k;
-      valid[k] = row < row_end;
-      bb[k] = 0; pp[k] = 0;
-      box[k].x1 = box[k].y1 = box[k].x2 = box[k].y2 = 0.f;
-      if (valid[k]) {
-        bb[k] = (uint32_t)row / (uint32_t)a.P;
-        pp[k] = (uint32_t)row - bb[k] * (uint32_t)a.P;
+    for (int q = 0; q < K; ++q) {
+      valid[q] = r0 + q < hd.nrows;
+      box[q].x1 = box[q].y1 = box[q].x2 = box[q].y2 = 0.f;
+      if (valid[q]) {
+        float4 v = ub.pri[r0 + q];
         if (a.anchors_xyxy) {
-          box[k].x1 = cur.v[k].x; box[k].y1 = cur.v[k].y; box[k].x2 = cur.v[k].z; box[k].y2 = cur.v[k].w;
+          box[q].x1 = v.x; box[q].y1 = v.y; box[q].x2 = v.z; box[q].y2 = v.w;
         } else {
-          box[k] = point_form(cur.v[k]);
+          box[q] = point_form(v);
         }
-        wx1 = fminf(wx1, box[k].x1); wy1 = fminf(wy1, box[k].y1);
-        wx2 = fmaxf(wx2, box[k].x2); wy2 = fmaxf(wy2, box[k].y2);
+        wx1 = fminf(wx1, box[q].x1); wy1 = fminf(wy1, box[q].y1);
+        wx2 = fmaxf(wx2, box[q].x2); wy2 = fmaxf(wy2, box[q].y2);
       }
-      area[k] = box_area(box[k]);
-      bt_ov[k] = 0.0f;     // all-zero IoU column -> truth 0 (first index), overlap 0
-      bt_idx[k] = 0;
+      area[q] = box_area(box[q]);
+      bt_ov[q] = 0.0f;     // all-zero IoU column -> truth 0 (first index), overlap 0
+      bt_idx[q] = 0;
     }
-    // rows of the warp are consecutive: one image iff the first and the last valid row agree
-    const uint32_t vmask = __ballot_sync(SSDBOX_FULL_MASK, valid[0]);
-    if (vmask == 0u) continue;
-    const uint32_t b_first = __shfl_sync(SSDBOX_FULL_MASK, bb[0], 0);
-    uint32_t my_last = valid[3] ? bb[3] : (valid[2] ? bb[2] : (valid[1] ? bb[1] : bb[0]));
-    const uint32_t b_last = __shfl_sync(SSDBOX_FULL_MASK, my_last, 31 - __clz(vmask));
-    if (b_first == b_last) {
-      const int slot = (int)b_first - b_lo;
-      const int G = gc.count[slot];
-      const float4* gb = gc.box + (size_t)slot * a.gpad;
-      const float* ga = gc.area + (size_t)slot * a.gpad;
-      const int* gl = gc.lab + (size_t)slot * a.gpad;
+    if (__ballot_sync(SSDBOX_FULL_MASK, valid[0]) != 0u) {
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) {
         wx1 = fminf(wx1, __shfl_xor_sync(SSDBOX_FULL_MASK, wx1, d));
@@ -194,40 +250,44 @@ __device__ void match_warp_loop(const StreamArgs& a, const GtCache& gc, int b_lo
         wx2 = fmaxf(wx2, __shfl_xor_sync(SSDBOX_FULL_MASK, wx2, d));
         wy2 = fmaxf(wy2, __shfl_xor_sync(SSDBOX_FULL_MASK, wy2, d));
       }
+      const uint32_t pbase = (uint32_t)(hd.p0 + r0);
       for (int gbase = 0; gbase < G; gbase += 32) {
         bool touch = false;
         if (gbase + lane < G) {
-          float4 tv = gb[gbase + lane];
+          float4 tv = ub.box[gbase + lane];
           touch = tv.x < wx2 && tv.z > wx1 && tv.y < wy2 && tv.w > wy1;
         }
         uint32_t todo = __ballot_sync(SSDBOX_FULL_MASK, touch);
+#ifdef SSDBOX_PHASE_TIMING
+        n_truths += __popc(todo);
+#endif
         while (todo) {                    // ascending truth index: first truth wins ties (box_utils.py:118)
           const int g = gbase + __ffs(todo) - 1;
           todo &= todo - 1;
-          float4 tv = gb[g];
+          float4 tv = ub.box[g];
           Box t;
           t.x1 = tv.x; t.y1 = tv.y; t.x2 = tv.z; t.y2 = tv.w;
-          const float ta = ga[g];
+          const float ta = ub.area[g];
           float iou[K];
           iou_jaccard_multi<K>(t, ta, box, area, iou);
           float lm = 0.0f;
           uint32_t lp = 0xffffffffu;
 #pragma unroll
-          for (int k = 0; k < K; ++k) {
-            float v = valid[k] ? iou[k] : 0.0f;
-            if (v > bt_ov[k]) {           // strict
-              bt_ov[k] = v;
-              bt_idx[k] = g;
+          for (int q = 0; q < K; ++q) {
+            float v = valid[q] ? iou[q] : 0.0f;
+            if (v > bt_ov[q]) {           // strict
+              bt_ov[q] = v;
+              bt_idx[q] = g;
             }
             if (v > lm) {                 // strict + ascending p: lowest prior wins ties (:116)
               lm = v;
-              lp = pp[k];
+              lp = pbase + q;
             }
           }
           uint32_t mb = __reduce_max_sync(SSDBOX_FULL_MASK, __float_as_uint(lm));
           if (mb != 0u) {
             uint32_t pm = __reduce_min_sync(SSDBOX_FULL_MASK, (__float_as_uint(lm) == mb) ? lp : 0xffffffffu);
-            if (lane == 0) best_prior_update(&gc.best[(size_t)slot * a.gpad + g], mb, pm);
+            if (lane == 0) best_prior_update(&ub.best[g], mb, pm);
           }
         }
       }
@@ -235,60 +295,44 @@ __device__ void match_warp_loop(const StreamArgs& a, const GtCache& gc, int b_lo
       int16_t* lop = reinterpret_cast<int16_t*>(&lo);
       int16_t* top = reinterpret_cast<int16_t*>(&to);
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        lop[k] = (int16_t)((G > 0 && !(bt_ov[k] < a.threshold)) ? gl[bt_idx[k]] : 0);   // :130
-        top[k] = (int16_t)bt_idx[k];
+      for (int q = 0; q < K; ++q) {
+        lop[q] = (int16_t)((G > 0 && !(bt_ov[q] < a.threshold)) ? ub.lab[bt_idx[q]] : 0);   // :130
+        top[q] = (int16_t)bt_idx[q];
       }
-      if (valid[K - 1]) {                 // row0 is a multiple of 4: 8-byte stores
+      const size_t row0 = (size_t)hd.b * (size_t)a.P + (size_t)(hd.p0 + r0);
+      if (valid[K - 1] && (row0 & 3u) == 0) {        // 8-byte stores
         *reinterpret_cast<short4*>(a.lab_out + row0) = lo;
         *reinterpret_cast<short4*>(a.tidx_out + row0) = to;
       } else {
 #pragma unroll
-        for (int k = 0; k < K; ++k)
-          if (valid[k]) {
-            a.lab_out[row0 + k] = lop[k];
-            a.tidx_out[row0 + k] = top[k];
+        for (int q = 0; q < K; ++q)
+          if (valid[q]) {
+            a.lab_out[row0 + q] = lop[q];
+            a.tidx_out[row0 + q] = top[q];
           }
       }
-    } else {
-      // the 128 rows straddle an image boundary (once per image at most): plain per-prior loops
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        if (!valid[k]) continue;
-        const int slot = (int)bb[k] - b_lo;
-        const int G = gc.count[slot];
-        const float4* gb = gc.box + (size_t)slot * a.gpad;
-        const float* ga = gc.area + (size_t)slot * a.gpad;
-        float ov = 0.0f;
-        int ti = 0;
-        for (int g = 0; g < G; ++g) {
-          float4 tv = gb[g];
-          Box t;
-          t.x1 = tv.x; t.y1 = tv.y; t.x2 = tv.z; t.y2 = tv.w;
-          float iou = iou_jaccard(t, ga[g], box[k], area[k]);
-          if (iou > ov) {
-            ov = iou;
-            ti = g;
-          }
-          if (iou > 0.0f) best_prior_update(&gc.best[(size_t)slot * a.gpad + g], __float_as_uint(iou), pp[k]);
-        }
-        a.lab_out[row0 + k] = (int16_t)((G > 0 && !(ov < a.threshold)) ? gc.lab[(size_t)slot * a.gpad + ti] : 0);
-        a.tidx_out[row0 + k] = (int16_t)ti;
-      }
     }
-  }
-  // all match warps of the CTA are done: publish the CTA's per-truth candidates
-  asm volatile("bar.sync 1, %0;" ::"n"(kMatchWarps * 32) : "memory");
-  const int mt = mw * 32 + lane;
-  for (int sl = 0; sl < a.img_slots; ++sl) {
-    const int b = b_lo + sl;
-    if (b >= a.B) break;
-    const int G = gc.count[sl];
-    for (int g = mt; g < G; g += kMatchWarps * 32) {
-      unsigned long long v = gc.best[(size_t)sl * a.gpad + g];
-      if (v > kBestInit) atomicMax(&a.gt_best[(size_t)b * a.gpad + g], v);
+    // every match warp is done with the unit: publish its per-truth candidates, release the buffer
+    asm volatile("bar.sync 1, %0;" ::"n"(kMatchWarps * 32) : "memory");
+    for (int g = mw * 32 + lane; g < G; g += kMatchWarps * 32) {
+      unsigned long long v = ub.best[g];
+      if (v > kBestInit) atomicMax(&a.gt_best[(size_t)hd.b * a.gpad + g], v);
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&mempty[buf]);
+#ifdef SSDBOX_PHASE_TIMING
+    t_busy += clock64() - c1;
+    ++n_units;
+#endif
   }
+#ifdef SSDBOX_PHASE_TIMING
+  if (mw == 0 && lane == 0 && blockIdx.x < 160) {
+    g_mstat[blockIdx.x * 8 + 0] = t_wait;
+    g_mstat[blockIdx.x * 8 + 1] = t_busy;
+    g_mstat[blockIdx.x * 8 + 2] = n_units;
+    g_mstat[blockIdx.x * 8 + 3] = n_truths;
+  }
+#endif
 }
 
 template <int CT>
@@ -298,59 +342,34 @@ __global__ void __launch_bounds__(kStreamThreads, 1) loss_stream_kernel(StreamAr
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int R = a.ring.R, NS = a.ring.NS;
 
-  // truths of every image this CTA touches -> shared memory (behind the ring stages)
-  GtCache gc;
-  gc.box = nullptr; gc.area = nullptr; gc.lab = nullptr; gc.count = nullptr; gc.best = nullptr;
-  int b_lo = 0;
-  if (a.fuse) {
-    unsigned char* base = smem_ring + kRingHeaderBytes + (size_t)NS * R * C * 4;
-    unsigned long long* s_best = reinterpret_cast<unsigned long long*>(base);
-    base += (size_t)a.img_slots * a.gpad * 8;
-    float4* s_box = reinterpret_cast<float4*>(base);
-    float* s_area = reinterpret_cast<float*>(s_box + (size_t)a.img_slots * a.gpad);
-    int* s_lab = reinterpret_cast<int*>(s_area + (size_t)a.img_slots * a.gpad);
-    int* s_cnt = s_lab + (size_t)a.img_slots * a.gpad;
-    long long first_row = (long long)blockIdx.x * a.ring.tiles_per_cta * R;
-    b_lo = (int)(first_row / a.P);
-    for (int sl = 0; sl < a.img_slots; ++sl) {
-      int b = b_lo + sl;
-      int g0 = 0, G = 0;
-      if (b < a.B) {
-        g0 = a.gt_offsets[b];
-        G = a.gt_offsets[b + 1] - g0;
-        G = G < 0 ? 0 : (G > a.gmax ? a.gmax : G);
-      }
-      if (tid == 0) s_cnt[sl] = G;
-      for (int g = tid; g < G; g += kStreamThreads) {
-        const float* r = a.gt + (size_t)(g0 + g) * 5;
-        Box t;
-        t.x1 = r[0]; t.y1 = r[1]; t.x2 = r[2]; t.y2 = r[3];
-        s_box[(size_t)sl * a.gpad + g] = make_float4(t.x1, t.y1, t.x2, t.y2);
-        s_area[(size_t)sl * a.gpad + g] = box_area(t);
-        s_lab[(size_t)sl * a.gpad + g] = a.binarize ? 1 : (int)(r[4] + 1.0f);   // box_utils.py:129
-        s_best[(size_t)sl * a.gpad + g] = kBestInit;
-      }
-    }
-    gc.box = s_box; gc.area = s_area; gc.lab = s_lab; gc.count = s_cnt; gc.best = s_best;
+  unsigned char* mbase = smem_ring + kRingHeaderBytes + (size_t)NS * R * C * 4;   // matching area behind the ring
+  if (a.fuse && tid == 0) {
+    uint64_t* mfull = reinterpret_cast<uint64_t*>(mbase);
+    mbar_init(&mfull[0], 1);
+    mbar_init(&mfull[1], 1);
+    mbar_init(&mfull[2], kMatchWarps);
+    mbar_init(&mfull[3], kMatchWarps);
   }
   if (warp == 0) SMARK(0);
-  RingCtx rc = ring_setup(a.ring, smem_ring);   // its __syncthreads() also publishes the truth cache
+  RingCtx rc = ring_setup(a.ring, smem_ring);   // fences the barrier inits, __syncthreads()
+#ifdef SSDBOX_PHASE_TIMING
+  if (a.dbg & 1) rc.n_local = 0;
+#endif
   if (warp == 0) SMARK(1);
   if (warp == kRingConsumerWarps) {
     ring_produce(a.ring, rc);
     SMARK(2);
     return;
   }
-  if (warp > kRingConsumerWarps) {
-    if (warp == kRingConsumerWarps + 1) SMARK(3);
-    if (a.fuse) {
-      long long row_begin = rc.t0 * R;
-      long long row_end = (rc.t0 + rc.n_local) * R;
-      if (row_end > a.ring.rows) row_end = a.ring.rows;
-      match_warp_loop(a, gc, b_lo, row_begin, row_end, warp - kRingConsumerWarps - 1, lane);
-    }
-    if (warp == kRingConsumerWarps + 1) SMARK(4);
-    if (warp == kRingConsumerWarps + 8) SMARK(5);
+  if (warp == kSchedWarp) {
+    if (a.fuse) match_sched_loop(a, mbase, lane);
+    return;
+  }
+  if (warp >= kFirstMatchWarp) {
+    if (warp == kFirstMatchWarp) SMARK(3);
+    if (a.fuse) match_unit_loop(a, mbase, warp - kFirstMatchWarp, lane);
+    if (warp == kFirstMatchWarp) SMARK(4);
+    if (warp == kFirstMatchWarp + kMatchWarps - 1) SMARK(5);
     return;
   }
   const int wg = warp >> 2;
@@ -383,25 +402,29 @@ __global__ void __launch_bounds__(kStreamThreads, 1) loss_stream_kernel(StreamAr
   if (warp == 7) SMARK(7);
 }
 
-// StreamArgs.fuse must be decided by the caller (plan_stream) before the launch
+// Decides whether the matching is fused (its two unit buffers must fit beside >= 3 ring stages).
 static int plan_stream(StreamArgs* a, const float* conf, long long rows, int C, int sm_count, int max_smem,
                        bool want_fuse, size_t* smem_out) {
-  int rc = plan_ring(&a->ring, conf, rows, C, sm_count, max_smem);
-  if (rc) return rc;
-  size_t smem = a->ring.smem_bytes;
   a->fuse = 0;
-  a->img_slots = 0;
+  a->unit_bytes = 0;
   if (want_fuse) {
-    long long rows_per_cta = (long long)a->ring.tiles_per_cta * a->ring.R;
-    long long slots = (rows_per_cta + a->P - 2) / a->P + 1;
-    size_t need = (size_t)slots * a->gpad * 32 + (size_t)slots * 4 + 64;
-    if (slots <= 256 && smem + need <= (size_t)max_smem - 1024) {
-      a->fuse = 1;
-      a->img_slots = (int)slots;
-      smem += need;
+    int ub = unit_buf_bytes(a->gpad);
+    size_t need = (size_t)kMatchBarBytes + 2 * (size_t)ub;
+    if (need + 65536 < (size_t)max_smem) {
+      RingPlan rp;
+      int rc = plan_ring(&rp, conf, rows, C, sm_count, max_smem - (int)need);
+      if (rc == SSDBOX_OK && rp.NS >= 3) {
+        a->ring = rp;
+        a->fuse = 1;
+        a->unit_bytes = ub;
+        *smem_out = rp.smem_bytes + need;
+        return SSDBOX_OK;
+      }
     }
   }
-  *smem_out = smem;
+  int rc = plan_ring(&a->ring, conf, rows, C, sm_count, max_smem);
+  if (rc) return rc;
+  *smem_out = a->ring.smem_bytes;
   return SSDBOX_OK;
 }
 
@@ -879,12 +902,12 @@ extern "C" int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float*
   w.ukey = c.take<uint32_t>((size_t)B * P);
   w.hist = c.take<uint32_t>((size_t)B * kHistBins);
   w.partial = c.take<double>((size_t)B * 3);
-  w.ticket = c.take<uint32_t>(1);
+  w.ticket = c.take<uint32_t>(2);      // [0] mine_reduce ticket, [1] next matching unit
 
   w.lse = c.take<float>((size_t)B * P);
 
   rc = launch_init(w.m.gt_best, (size_t)(B + 1) * gt_pad(cfg->gmax), w.m.done, (size_t)B + 1, w.hist,
-                   (size_t)B * kHistBins, w.ticket, 1, st);
+                   (size_t)B * kHistBins, w.ticket, 2, st);
   if (rc) return rc;
 
   // Matching runs on dedicated warps of the streaming kernel unless the caller asked for the
@@ -910,6 +933,8 @@ extern "C" int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float*
   sa.gt_best = w.m.gt_best;
   sa.lab_out = w.m.lab;
   sa.tidx_out = tidx;
+  sa.unit_counter = w.ticket + 1;
+  sa.dbg = (cfg->flags >> 8) & 0xff;
   size_t stream_smem = 0;
   rc = plan_stream(&sa, conf, (long long)B * P, C, dev.sm_count, dev.max_smem_optin,
                    !(cfg->flags & SSDBOX_LOSS_SEPARATE_MATCH), &stream_smem);

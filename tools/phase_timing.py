@@ -14,10 +14,14 @@ tg = [t.to(dev) for t in synth.gen_targets(B, Cn, 32, 0)]
 loc = torch.randn(B, P, 4, device=dev) * 0.5
 conf = torch.randn(B, P, Cn, device=dev); conf[..., 0] += 4
 crit = ssdbox.MultiBoxLoss(Cn, 0.5, True, 0, True, 3, 0.5, False)
-for _ in range(3):
+import time
+for it in range(4):
+    crit.abi_flags = {0: 0, 1: 0, 2: 256, 3: 1}[it]
+    print('--- flags', crit.abi_flags, '(0 fused, 256 fused without conf streaming, 1 separate match kernel)')
+    torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record()
     with torch.no_grad():
         crit((loc, conf, pri), tg)
-    torch.cuda.synchronize()
+    e1.record(); torch.cuda.synchronize(); print('  forward total %.1f us' % (1e3 * e0.elapsed_time(e1)))
     buf = (C.c_longlong * 16)()
     _abi.lib().ssdbox_debug_phases.argtypes = [C.c_void_p]
     print(_abi.lib().ssdbox_debug_phases(buf), [buf[i + 1] - buf[i] for i in range(5)], "cycles: passA, sums, select, final, sum")
@@ -33,10 +37,9 @@ for _ in range(3):
     _abi.lib().ssdbox_debug_mstat.argtypes = [C.c_void_p]
     _abi.lib().ssdbox_debug_mstat(ms)
     st = np.array(list(ms), dtype=np.int64).reshape(160, 8)[:148]
-    for i in (3, 138, 57, 70):
-        print("  CTA %d warp0: load %d cyc, g-loop %d cyc over %d iters; truths visited %d, computed %d; match_end %d" % (i, st[i,0], st[i,1], st[i,2], st[i,4], st[i,3], rel[i,4]))
-    worst = np.argsort(-rel[:, 4])[:6]
-    print(" slowest match CTAs:", [(int(i), int(rel[i, 4]), int(rel[i, 6])) for i in worst])
+    print("  match warp 0 per CTA: wait cyc min/med/max %s | busy cyc min/med/max %s | units min/med/max %s | truths/unit %.1f | busy cyc/unit %.0f"
+          % (np.percentile(st[:, 0], [0, 50, 100]).astype(int).tolist(), np.percentile(st[:, 1], [0, 50, 100]).astype(int).tolist(),
+             np.percentile(st[:, 2], [0, 50, 100]).astype(int).tolist(), st[:, 3].sum() / max(st[:, 2].sum(), 1), st[:, 1].sum() / max(st[:, 2].sum(), 1)))
     buf = (C.c_longlong * 32)()
     _abi.lib().ssdbox_debug_match_phases.argtypes = [C.c_void_p]
     _abi.lib().ssdbox_debug_match_phases(buf)
