@@ -173,6 +173,9 @@ typedef struct {
  * instead (same results; the library also falls back to it when a CTA's truths do not fit in
  * shared memory beside the ring). */
 #define SSDBOX_LOSS_SEPARATE_MATCH 1
+/* Use the generic (shared-memory) mining kernel even when the register-resident one applies
+ * (P % 4 == 0 and P <= 24576); same results, for testing. */
+#define SSDBOX_LOSS_GENERIC_MINE 2
 
 /* forward.
  *   loc [B,P,4], conf [B,P,C] raw logits, priors, anchors_xyxy (nullable), gt/gt_offsets

@@ -484,11 +484,43 @@ struct MineArgs {
 };
 
 #ifdef SSDBOX_PHASE_TIMING
-__device__ long long g_phase[16];
-#define PHASE_MARK(k) do { __syncthreads(); if (blockIdx.x == 1 && threadIdx.x == 0) g_phase[k] = clock64(); } while (0)
+__device__ long long g_phase[16 * 64];
+#define PHASE_MARK(k) do { __syncthreads(); if (blockIdx.x < 64 && threadIdx.x == 0) g_phase[blockIdx.x * 16 + (k)] = clock64(); } while (0)
 #else
 #define PHASE_MARK(k) do { } while (0)
 #endif
+
+// last CTA: fold the per-image partials in image order (bit-reproducible run to run); the loads
+// are spread over the threads (one L2 round trip), the fp64 adds stay sequential in image order
+__device__ void fold_partials(const MineArgs& a, double* s_dscr) {
+  const int tid = threadIdx.x;
+  double sl = 0.0, sc = 0.0, sn = 0.0;
+  for (int base = 0; base < a.B; base += 32) {
+    __syncthreads();
+    if (tid < 96) {
+      int i = base + (tid & 31), f = tid >> 5;
+      s_dscr[f * 32 + (tid & 31)] = i < a.B ? __ldcg(&a.partial[(size_t)i * 3 + f]) : 0.0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int n = a.B - base < 32 ? a.B - base : 32;
+      for (int i = 0; i < n; ++i) {
+        sl += s_dscr[i];
+        sc += s_dscr[32 + i];
+        sn += s_dscr[64 + i];
+      }
+    }
+  }
+  if (tid == 0) {
+    a.sums[0] = sl;
+    a.sums[1] = sc;
+    a.sums[2] = sn;
+    if (a.finalize && a.losses) {     // multibox_loss.py:114-116 (N == 0 -> 0 instead of inf/nan)
+      a.losses[0] = sn > 0.0 ? (float)(sl / sn) : 0.0f;
+      a.losses[1] = sn > 0.0 ? (float)(sc / sn) : 0.0f;
+    }
+  }
+}
 
 // per-prior work of pass A: returns the ordered mining key (0 = outside the ranking)
 __device__ __forceinline__ uint32_t mine_visit(const MineArgs& a, size_t i, int p, int b, int g0, const float* pri,
@@ -675,34 +707,332 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  // last CTA: fold the per-image partials in image order (bit-reproducible run to run); the loads
-  // are spread over the threads (one L2 round trip), the fp64 adds stay sequential in image order
-  double sl = 0.0, sc = 0.0, sn = 0.0;
-  for (int base = 0; base < a.B; base += 32) {
-    __syncthreads();
-    if (tid < 96) {
-      int i = base + (tid & 31), f = tid >> 5;
-      s_dscr[f * 32 + (tid & 31)] = i < a.B ? __ldcg(&a.partial[(size_t)i * 3 + f]) : 0.0;
+  fold_partials(a, s_dscr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Register-resident variant for P % 4 == 0 and P <= 4 * kMineQ * 1024 (every SSD / RFB / FSSD head):
+// each thread keeps its 24 mining keys and class targets in registers from the single load to the
+// final store, so the kernel is one chain of a few memory round trips instead of several sweeps:
+//   (1) keys, class targets, level-1 histogram, per-truth best priors and the truth rows are all
+//       requested at once; (2) the forced assignment is replayed on a small shared list and patched
+//       into the owners' registers; (3) positives are compacted (deterministic block scan) and
+//       handled one per thread, so their dependent gathers (lse, the target logit from DRAM, loc,
+//       prior) cost one round trip for the whole image; (4) radix select on the registers;
+//   (5) sel / ce are produced from the registers.  Same results as mine_reduce_kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMineQ = 6;
+constexpr int kForceListMax = 128;
+
+__device__ __forceinline__ int reg_find(const uint32_t* s_hist, int nbins, int K, int* s_iscr, int* s_res, int* above) {
+  find_digit(s_hist, nbins, K, s_iscr, s_res);
+  *above = s_res[1];
+  return s_res[0];
+}
+
+__global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_mine[];
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_mine);                        // 2048
+  double* s_dscr = reinterpret_cast<double*>(smem_mine + 8192);                     // 100
+  int* s_iscr = reinterpret_cast<int*>(smem_mine + 8192 + 800);                     // 64
+  int* s_res = s_iscr + 64;                                                         // 8
+  unsigned long long* s_best = reinterpret_cast<unsigned long long*>(smem_mine + kMineFixedSmem);   // kForceListMax
+  uint32_t* s_force = reinterpret_cast<uint32_t*>(s_best + kForceListMax);          // kForceListMax x 2
+  float* s_gt = reinterpret_cast<float*>(s_force + 2 * kForceListMax);              // kForceListMax x 5 (+3 pad)
+  uint32_t* s_list = reinterpret_cast<uint32_t*>(s_gt + 5 * kForceListMax + 8);     // P: prior | class << 16
+  __shared__ int s_last, s_nforce;
+
+  const int b = blockIdx.x, tid = threadIdx.x, P = a.P;
+  const size_t off = (size_t)b * P;
+  const int g0 = a.gt_offsets[b];
+  int G = a.gt_offsets[b + 1] - g0;
+  G = G < 0 ? 0 : (G > a.gmax ? a.gmax : G);
+  const float* pri = a.priors + (size_t)b * (size_t)a.prior_stride;
+  const int n4 = P >> 2;
+  const bool small_g = a.fuse && G <= kForceListMax;
+
+  PHASE_MARK(0);
+  // (1) everything this CTA needs from memory, requested together
+  if (tid == 0) s_nforce = 0;
+  unsigned long long my_best = 0ull;
+  if (small_g && tid < G) my_best = __ldcg(&a.gt_best[(size_t)b * a.gpad + tid]);
+  const bool gt_cached = G <= kForceListMax;
+  float my_gt = 0.f;
+  if (gt_cached && tid < 5 * G) my_gt = a.gt[(size_t)g0 * 5 + tid];
+  uint32_t h0 = a.hist[(size_t)b * kHistBins + tid], h1 = a.hist[(size_t)b * kHistBins + 1024 + tid];
+  uint32_t uk[kMineQ][4];     // ordered mining keys (0 = outside the ranking)
+  short4 ll[kMineQ];
+  uint32_t poolmask = 0u;     // bit j*4+e: prior is ranked (inside P and inside the caller's pool)
+  const float4* k4 = reinterpret_cast<const float4*>(a.keys + off);
+  const short4* l4 = reinterpret_cast<const short4*>(a.lab + off);
+  const uchar4* p4 = a.pool ? reinterpret_cast<const uchar4*>(a.pool + off) : nullptr;
+#pragma unroll
+  for (int j = 0; j < kMineQ; ++j) {
+    const int q = tid + j * kMineThreads;
+    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < n4) {
+      kv = k4[q];
+      uint32_t m = 0xfu;
+      if (p4) {
+        uchar4 pv = p4[q];
+        m = (pv.x ? 1u : 0u) | (pv.y ? 2u : 0u) | (pv.z ? 4u : 0u) | (pv.w ? 8u : 0u);
+      }
+      poolmask |= m << (4 * j);
+    }
+    uk[j][0] = f2ord(kv.x); uk[j][1] = f2ord(kv.y); uk[j][2] = f2ord(kv.z); uk[j][3] = f2ord(kv.w);
+  }
+  if (a.fuse && !small_g) {
+    // many truths: replay the forced assignment through global memory first (box_utils.py:123-130)
+    const unsigned long long* best = a.gt_best + (size_t)b * a.gpad;
+    for (int j = tid; j < G; j += kMineThreads) {
+      const uint32_t pj = ~(uint32_t)(__ldcg(&best[j]) & 0xffffffffull);
+      bool winner = pj < (uint32_t)P;
+      for (int j2 = j + 1; winner && j2 < G; ++j2)
+        if (~(uint32_t)(__ldcg(&best[j2]) & 0xffffffffull) == pj) winner = false;
+      if (winner) {
+        a.lab_w[off + pj] = (int16_t)(a.binarize ? 1 : (int)(a.gt[(size_t)(g0 + j) * 5 + 4] + 1.0f));
+        a.tidx_w[off + pj] = (int16_t)j;
+      }
     }
     __syncthreads();
-    if (tid == 0) {
-      int n = a.B - base < 32 ? a.B - base : 32;
-      for (int i = 0; i < n; ++i) {
-        sl += s_dscr[i];
-        sc += s_dscr[32 + i];
-        sn += s_dscr[64 + i];
+  }
+#pragma unroll
+  for (int j = 0; j < kMineQ; ++j) {
+    const int q = tid + j * kMineThreads;
+    ll[j] = make_short4(0, 0, 0, 0);
+    if (q < n4) ll[j] = l4[q];
+  }
+  s_hist[tid] = h0;
+  s_hist[1024 + tid] = h1;
+  if (small_g && tid < G) s_best[tid] = my_best;
+  if (gt_cached && tid < 5 * G) s_gt[tid] = my_gt;
+  __syncthreads();
+
+  PHASE_MARK(1);
+  // (2) forced assignment on the shared list: truth j keeps its best prior unless a later truth
+  // claims the same prior (last truth wins); winners are patched into the owner's registers
+  if (small_g) {
+    if (tid < G) {
+      const uint32_t pj = ~(uint32_t)(s_best[tid] & 0xffffffffull);
+      bool winner = pj < (uint32_t)P;
+      for (int j2 = tid + 1; winner && j2 < G; ++j2)
+        if (~(uint32_t)(s_best[j2] & 0xffffffffull) == pj) winner = false;
+      if (winner) {
+        const int lb = a.binarize ? 1 : (int)(s_gt[tid * 5 + 4] + 1.0f);
+        a.lab_w[off + pj] = (int16_t)lb;
+        a.tidx_w[off + pj] = (int16_t)tid;
+        const int slot = atomicAdd(&s_nforce, 1);
+        s_force[2 * slot] = pj;
+        s_force[2 * slot + 1] = (uint32_t)lb;
+      }
+    }
+    __syncthreads();
+    const int nf = s_nforce;
+    for (int f = 0; f < nf; ++f) {
+      const uint32_t pj = s_force[2 * f];
+      const uint32_t q = pj >> 2;
+      if ((q & (kMineThreads - 1)) == (uint32_t)tid) {
+        const int16_t lb = (int16_t)s_force[2 * f + 1];
+        const int j = (int)(q / kMineThreads), e = (int)(pj & 3u);
+#pragma unroll
+        for (int jj = 0; jj < kMineQ; ++jj)
+          if (jj == j) {
+            if (e == 0) ll[jj].x = lb;
+            else if (e == 1) ll[jj].y = lb;
+            else if (e == 2) ll[jj].z = lb;
+            else ll[jj].w = lb;
+          }
       }
     }
   }
-  if (tid == 0) {
-    a.sums[0] = sl;
-    a.sums[1] = sc;
-    a.sums[2] = sn;
-    if (a.finalize && a.losses) {     // multibox_loss.py:114-116 (N == 0 -> 0 instead of inf/nan)
-      a.losses[0] = sn > 0.0 ? (float)(sl / sn) : 0.0f;
-      a.losses[1] = sn > 0.0 ? (float)(sc / sn) : 0.0f;
+
+  PHASE_MARK(2);
+  // (3) ordered keys in registers; positives leave their streamed bin for the zero bin and are
+  // compacted into s_list in a fixed (thread-major) order
+  int mypos = 0;
+  const uint32_t zero_ord = f2ord(0.0f);
+#pragma unroll
+  for (int j = 0; j < kMineQ; ++j) {
+    const int q = tid + j * kMineThreads;
+    if (a.dbg_keys && q < n4)
+      *reinterpret_cast<float4*>(a.dbg_keys + off + (size_t)q * 4) =
+          make_float4(ord2f(uk[j][0]), ord2f(uk[j][1]), ord2f(uk[j][2]), ord2f(uk[j][3]));
+    const int lb[4] = {ll[j].x, ll[j].y, ll[j].z, ll[j].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      uint32_t u = 0u;
+      if ((poolmask >> (4 * j + e)) & 1u) {
+        u = uk[j][e];
+        if (lb[e] > 0) {
+          ++mypos;
+          atomicSub(&s_hist[u >> 21], 1u);
+          atomicAdd(&s_hist[zero_ord >> 21], 1u);
+          u = zero_ord;
+        }
+      }
+      uk[j][e] = u;
     }
   }
+  int npos_blk;
+  int slot = block_exclusive_scan(mypos, s_iscr, &npos_blk);
+  if (mypos) {
+#pragma unroll
+    for (int j = 0; j < kMineQ; ++j) {
+      const int lb[4] = {ll[j].x, ll[j].y, ll[j].z, ll[j].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (((poolmask >> (4 * j + e)) & 1u) && lb[e] > 0) s_list[slot++] = (uint32_t)((tid + j * kMineThreads) * 4 + e) | ((uint32_t)lb[e] << 16);
+    }
+  }
+  __syncthreads();
+
+  PHASE_MARK(3);
+  // one positive per thread: CE = lse - x[target] (multibox_loss.py:94,110) and smooth-L1 against
+  // the encoded truth (:87-90, box_utils.py:215-222)
+  double ce = 0.0, l1 = 0.0;
+  for (int sidx = tid; sidx < npos_blk; sidx += kMineThreads) {
+    const uint32_t ent = s_list[sidx];
+    const int p = (int)(ent & 0xffffu), lb = (int)(ent >> 16);
+    const size_t i = off + p;
+    const float lse = a.lse[i];
+    const float xt = a.conf[i * (size_t)a.C + lb];
+    const int t = a.tidx[i];
+    const float4 l = *reinterpret_cast<const float4*>(a.loc + i * 4);
+    const float4 pr = *reinterpret_cast<const float4*>(pri + (size_t)p * 4);
+    const float* row = gt_cached ? s_gt + t * 5 : a.gt + (size_t)(g0 + t) * 5;
+    Box m;
+    m.x1 = row[0]; m.y1 = row[1]; m.x2 = row[2]; m.y2 = row[3];
+    const float cep = lse - xt;
+    if (a.dbg_keys) a.dbg_keys[i] = cep;
+    ce += (double)cep;
+    float4 tt = encode_box(m, pr, a.var0, a.var1);
+    l1 += (double)(smooth_l1(l.x, tt.x) + smooth_l1(l.y, tt.y) + smooth_l1(l.z, tt.z) + smooth_l1(l.w, tt.w));
+  }
+  double dummy = 0.0;
+  block_sum3(dummy, ce, l1, s_dscr);
+
+  PHASE_MARK(4);
+  // multibox_loss.py:101-102  num_neg = clamp(ratio * num_pos, max = P - 1)
+  long long kk64 = (long long)a.negpos_ratio * npos_blk;
+  if (kk64 > P - 1) kk64 = P - 1;
+  const int K = (int)kk64;
+
+  // (4) radix select of the K-th largest ordered key, 11 + 11 + 10 bits, keys in registers
+  uint32_t Tu = 0xffffffffu;
+  if (K > 0) {
+    int above;
+    int d1 = reg_find(s_hist, kHistBins, K, s_iscr, s_res, &above);
+    if (d1 < 0) {
+      Tu = 1u;      // fewer than K ranked elements: take them all
+    } else {
+      int K2 = K - above;
+      int n1 = (int)s_hist[d1];
+      __syncthreads();
+      if (K2 == n1) {
+        Tu = ((uint32_t)d1 << 21) ? ((uint32_t)d1 << 21) : 1u;
+      } else {
+        s_hist[tid] = 0u;
+        s_hist[1024 + tid] = 0u;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kMineQ; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint32_t u = uk[j][e];
+            if (u && (int)(u >> 21) == d1) atomicAdd(&s_hist[(u >> 10) & 2047u], 1u);
+          }
+        __syncthreads();
+        int d2 = reg_find(s_hist, 2048, K2, s_iscr, s_res, &above);
+        int K3 = K2 - above;
+        int n2 = (int)s_hist[d2];
+        __syncthreads();
+        const uint32_t pre2 = ((uint32_t)d1 << 11) | (uint32_t)d2;
+        if (K3 == n2) {
+          Tu = (pre2 << 10) ? (pre2 << 10) : 1u;
+        } else {
+          s_hist[tid] = 0u;
+          __syncthreads();
+#pragma unroll
+          for (int j = 0; j < kMineQ; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              uint32_t u = uk[j][e];
+              if (u && (u >> 10) == pre2) atomicAdd(&s_hist[u & 1023u], 1u);
+            }
+          __syncthreads();
+          int d3 = reg_find(s_hist, 1024, K3, s_iscr, s_res, &above);
+          int need = K3 - above;
+          int n3 = (int)s_hist[d3];
+          __syncthreads();
+          Tu = (pre2 << 10) | (uint32_t)d3;
+          if (need != n3) {
+            // ties straddle the cut: equal keys win in ascending prior order (stable descending sort)
+            int running = 0;
+#pragma unroll
+            for (int j = 0; j < kMineQ; ++j) {
+              int cnt = 0;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) cnt += uk[j][e] == Tu ? 1 : 0;
+              int total;
+              int ex = block_exclusive_scan(cnt, s_iscr, &total);
+              int rank = running + ex;
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (uk[j][e] == Tu) {
+                  if (rank >= need) uk[j][e] = Tu - 1u;
+                  ++rank;
+                }
+              running += total;
+              __syncthreads();
+            }
+          }
+        }
+      }
+    }
+  }
+
+  PHASE_MARK(5);
+  // (5) neg = rank < num_neg (:103); CE over pos U neg (:106-110); the CE of a selected negative is
+  // its mining key, recovered exactly from the ordered key
+  double ce_neg = 0.0;
+#pragma unroll
+  for (int j = 0; j < kMineQ; ++j) {
+    const int q = tid + j * kMineThreads;
+    const int lb[4] = {ll[j].x, ll[j].y, ll[j].z, ll[j].w};
+    int16_t so[4];
+    unsigned char ng[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t u = uk[j][e];
+      const bool inpool = u != 0u;
+      const bool is_pos = inpool && lb[e] > 0;
+      const bool negsel = K > 0 && inpool && u >= Tu;
+      if (negsel && !is_pos) ce_neg += (double)ord2f(u);
+      so[e] = is_pos ? (int16_t)lb[e] : (negsel ? (int16_t)0 : (int16_t)-1);
+      ng[e] = negsel ? 1 : 0;
+    }
+    if (q < n4) {
+      *reinterpret_cast<short4*>(a.sel + off + (size_t)q * 4) = make_short4(so[0], so[1], so[2], so[3]);
+      if (a.dbg_neg) *reinterpret_cast<uchar4*>(a.dbg_neg + off + (size_t)q * 4) = make_uchar4(ng[0], ng[1], ng[2], ng[3]);
+    }
+  }
+  PHASE_MARK(6);
+  ce_neg = block_sum(ce_neg, s_dscr);
+  PHASE_MARK(7);
+
+  if (tid == 0) {
+    a.partial[(size_t)b * 3 + 0] = l1;
+    a.partial[(size_t)b * 3 + 1] = ce + ce_neg;
+    a.partial[(size_t)b * 3 + 2] = (double)npos_blk;
+    __threadfence();
+    unsigned t = atomicAdd(a.ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  fold_partials(a, s_dscr);
+  PHASE_MARK(8);
 }
 
 __global__ void finalize_kernel(const double* __restrict__ sums, float* __restrict__ losses) {
@@ -966,6 +1296,10 @@ extern "C" int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float*
   const bool vec4 = (P % 4 == 0) && aligned16(sel) && (!pool || (reinterpret_cast<uintptr_t>(pool) & 3u) == 0) &&
                     (!dbg_neg || (reinterpret_cast<uintptr_t>(dbg_neg) & 3u) == 0) && (!dbg_keys || aligned16(dbg_keys));
   void (*mkern)(MineArgs) = vec4 ? mine_reduce_kernel<4> : mine_reduce_kernel<1>;
+  if (vec4 && P <= 4 * kMineQ * kMineThreads && !(cfg->flags & SSDBOX_LOSS_GENERIC_MINE)) {
+    mkern = mine_reduce_reg_kernel;     // keys and class targets stay in registers
+    smem = kMineFixedSmem + (size_t)kForceListMax * 16 + (size_t)(5 * kForceListMax + 8) * 4 + (size_t)P * 4;
+  }
   SSDBOX_CUDA(cudaFuncSetAttribute(mkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     TimerScope ts__(KID_MINE, st);
@@ -989,7 +1323,7 @@ extern "C" __attribute__((visibility("default"))) int ssdbox_debug_sphases(long 
   return cudaMemcpyFromSymbol(out16, ssdbox::g_sphase, sizeof(long long) * 8 * 160) == cudaSuccess ? 0 : -5;
 }
 extern "C" __attribute__((visibility("default"))) int ssdbox_debug_phases(long long* out16) {
-  return cudaMemcpyFromSymbol(out16, ssdbox::g_phase, sizeof(long long) * 16) == cudaSuccess ? 0 : -5;
+  return cudaMemcpyFromSymbol(out16, ssdbox::g_phase, sizeof(long long) * 16 * 64) == cudaSuccess ? 0 : -5;
 }
 #endif
 

@@ -324,7 +324,8 @@ def test_multibox_loss_edge_cases(dev):
 @pytest.mark.parametrize("name,B,seed", [("ssd300_voc", 5, 0), ("ssd512_coco", 3, 1), ("refinedet320_voc", 7, 2)])
 def test_fused_and_separate_matching_agree(dev, name, B, seed):
     """The matching runs on dedicated warps of the streaming kernel by default and as its own kernel
-    on request: both must give bit-identical targets, selections and sums."""
+    on request; the mining runs register-resident when P % 4 == 0 and P <= 24576 and through shared
+    memory otherwise / on request: all variants must give bit-identical targets, selections and sums."""
     from ssdbox import _abi
     x = U.seeded_inputs(name, B, seed)
     # make the batch interesting: duplicate truths (shared best prior) and an empty image
@@ -332,19 +333,65 @@ def test_fused_and_separate_matching_agree(dev, name, B, seed):
     tg[0] = torch.cat([tg[0], tg[0][:1] * torch.tensor([1, 1, 1, 1, 0.0]) + torch.tensor([0, 0, 0, 0, 5.0])], 0)
     tg[1] = torch.zeros(0, 5)
     res = []
-    for flags in (0, _abi.LOSS_SEPARATE_MATCH):
+    for flags in (0, _abi.LOSS_SEPARATE_MATCH, _abi.LOSS_GENERIC_MINE, _abi.LOSS_SEPARATE_MATCH | _abi.LOSS_GENERIC_MINE):
         crit = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False)
         crit.abi_flags = flags
         res.append(crit.intermediates((x["loc"].to(dev), x["conf"].to(dev), x["priors"].to(dev)), _gpu_targets(tg, dev)))
-    a, b = res
-    for k in ("conf_t", "neg", "sel", "tidx", "keys", "sums", "loc_t"):
-        assert torch.equal(a[k], b[k]), k
+    a = res[0]
+    for b in res[1:]:
+        for k in ("conf_t", "neg", "sel", "tidx", "keys", "sums", "loc_t"):
+            assert torch.equal(a[k], b[k]), k
     # oracle check on the non-empty images
     keep = [i for i, t in enumerate(tg) if t.size(0) > 0]
     r = O.multibox_loss(x["loc"][keep], x["conf"][keep], x["priors"], [tg[i] for i in keep], x["C"], detail=True)
     assert torch.equal(a["conf_t"].cpu()[keep], r["conf_t"])
     U.assert_close_rel(a["loss_l"], r["loss_l"], REL, 0, "loss_l")
     U.assert_close_rel(a["loss_c"], r["loss_c"], REL, 0, "loss_c")
+
+
+def test_loss_many_truths_and_tied_keys(dev):
+    """(1) more truths per image than the shared forced-assignment list holds (the mining kernel then
+    replays the forced assignment through global memory); (2) constant logits: every mining key is
+    equal, so the whole negative set is decided by the tie rule (stable descending sort: lowest prior
+    index first, multibox_loss.py:99-103).  All kernel variants must agree bit for bit."""
+    from ssdbox import _abi
+    pri = U.oracle_priors("ssd300_voc")
+    P, C, B = pri.size(0), 21, 2
+    tg = synth.gen_targets(B, C, 200, 11, gt_min=150)
+    loc = synth.gen_loc(B, P, 11)
+    conf = synth.gen_train_logits(B, P, C, 11)
+    r = O.multibox_loss(loc, conf, pri, tg, C, detail=True)
+    res = []
+    for flags in (0, _abi.LOSS_GENERIC_MINE, _abi.LOSS_SEPARATE_MATCH):
+        crit = ssdbox.MultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False)
+        crit.abi_flags = flags
+        d = crit.intermediates((loc.to(dev), conf.to(dev), pri.to(dev)), _gpu_targets(tg, dev))
+        _check_neg_sets(d, r, P)
+        U.assert_close_rel(d["loss_l"], r["loss_l"], REL, 0, "loss_l")
+        U.assert_close_rel(d["loss_c"], r["loss_c"], REL, 0, "loss_c")
+        res.append(d)
+    for b in res[1:]:
+        for k in ("conf_t", "neg", "sel", "tidx", "keys", "sums"):
+            assert torch.equal(res[0][k], b[k]), k
+    # tied keys
+    tg = synth.gen_targets(B, C, 6, 12)
+    flat = torch.zeros(B, P, C)
+    res = []
+    for flags in (0, _abi.LOSS_GENERIC_MINE):
+        crit = ssdbox.MultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False)
+        crit.abi_flags = flags
+        res.append(crit.intermediates((loc.to(dev), flat.to(dev), pri.to(dev)), _gpu_targets(tg, dev)))
+    for k in ("conf_t", "neg", "sel", "sums"):
+        assert torch.equal(res[0][k], res[1][k]), k
+    d = res[0]
+    pos = d["conf_t"].cpu() > 0
+    neg = d["neg"].cpu().bool()
+    for b in range(B):
+        k = min(3 * int(pos[b].sum()), P - 1)
+        # all keys tie at log(C); positives rank as 0 and come last: the first k non-positive priors win
+        want = torch.zeros(P, dtype=torch.bool)
+        want[(~pos[b]).nonzero().flatten()[:k]] = True
+        assert torch.equal(neg[b], want), b
 
 
 def test_cuda_graph_capture(dev):

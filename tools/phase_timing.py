@@ -22,9 +22,14 @@ for it in range(4):
     with torch.no_grad():
         crit((loc, conf, pri), tg)
     e1.record(); torch.cuda.synchronize(); print('  forward total %.1f us' % (1e3 * e0.elapsed_time(e1)))
-    buf = (C.c_longlong * 16)()
+    buf = (C.c_longlong * (16 * 64))()
     _abi.lib().ssdbox_debug_phases.argtypes = [C.c_void_p]
-    print(_abi.lib().ssdbox_debug_phases(buf), [buf[i + 1] - buf[i] for i in range(5)], "cycles: passA, sums, select, final, sum")
+    _abi.lib().ssdbox_debug_phases(buf)
+    import numpy as np
+    ph = np.array(list(buf), dtype=np.int64).reshape(64, 16)
+    d = np.diff(ph[:, :8], axis=1)
+    print("  mine phases (cycles, median over CTAs / max): load %d/%d  forced %d/%d  keys+scan %d/%d  positives %d/%d  select %d/%d  final %d/%d  sum %d/%d ; total med %d max %d; kernel span %d"
+          % tuple([x for i in range(7) for x in (int(np.median(d[:, i])), int(d[:, i].max()))] + [int(np.median(ph[:, 7] - ph[:, 0])), int((ph[:, 7] - ph[:, 0]).max()), int(ph[:, :8].max() - ph[:, 0].min())]))
     sb = (C.c_longlong * (8 * 160))()
     _abi.lib().ssdbox_debug_sphases.argtypes = [C.c_void_p]
     _abi.lib().ssdbox_debug_sphases(sb)
