@@ -199,6 +199,7 @@ def run_reference(args):
 # GPU arm
 # ----------------------------------------------------------------------------------------------
 def main():
+    T0 = time.perf_counter()
     args = parse()
     if args.impl == "reference":
         run_reference(args)
@@ -217,8 +218,24 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL announces its version on stdout at communicator creation: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     n_gpus = world
+
+    def log(msg):
+        if rank == 0:
+            sys.stderr.write("bench[%.1fs]: %s\n" % (time.perf_counter() - T0, msg))
+            sys.stderr.flush()
 
     cfg, c = configs.get(args.workload)
     C = cfg.MODEL.NUM_CLASSES
@@ -250,6 +267,7 @@ def main():
             out = det.forward(loc, sc, priors, out=det_out)
         return ll, lc, out
 
+    log("inputs ready")
     # eager warm-up (lazy init, workspace allocation), also the functional sanity of the step
     for _ in range(2):
         ll, lc, out = step()
@@ -282,6 +300,7 @@ def main():
     bwd_us = 1e3 * kb["loss_bwd"][0] / max(kb["loss_bwd"][1], 1)
     del loc_g, conf_g
 
+    log("per-kernel timers done")
     # ---- the timed region: K replays of the captured step (or eager launches) -------------------
     use_graph = not args.no_graph
     graph = None
@@ -306,6 +325,7 @@ def main():
         else:
             step()
 
+    log("graph captured" if graph is not None else "eager mode")
     for _ in range(max(args.warmup, 3)):
         run_once()
     torch.cuda.synchronize()
@@ -325,20 +345,21 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     elapsed_ms = e0.elapsed_time(e1)
-    # keep the GPU busy a little longer so the clock sampler sees load even for short K
-    if rank == 0:
-        t_end = time.perf_counter() + 0.6
-        while time.perf_counter() < t_end:
-            run_once()
-        torch.cuda.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
+    # keep the GPUs busy a little longer so the clock sampler sees load even for short K; the step
+    # holds a collective when N > 1, so every rank runs the SAME number of extra steps
+    n_extra = int(min(20000, max(1, 0.6 / max(elapsed_ms / args.steps * 1e-3, 1e-6))))
+    for _ in range(n_extra):
+        run_once()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
     ms_per_step = elapsed_ms / args.steps
     value = n_gpus * B / (ms_per_step * 1e-3)
 
+    log("timed region done")
     # ---- e2e: public modules, pinned host inputs, H2D + D2H inside the timed region -------------
     loc_d, conf_d, sc_d = torch.empty_like(loc), torch.empty_like(conf), torch.empty_like(sc)
     out_h = torch.empty(B, C, top_k, 5, dtype=torch.float32).pin_memory()
@@ -374,9 +395,21 @@ def main():
            "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
            "api": "ssdbox.MultiBoxLoss.forward + ssdbox.DetectOut.__call__ from pinned host tensors"}
 
-    if rank != 0:
+    log("e2e done")
+
+    def teardown():
+        # a process group whose collectives were captured in a CUDA graph can block in
+        # destroy_process_group(): drop the graph, drain, rendezvous, then leave without it
         if dist is not None:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        teardown()
         return
 
     # ---- roofline of the dominant kernel + per-phase fractions ----------------------------------
@@ -438,13 +471,14 @@ def main():
                    "global_batch": n_gpus * B, "detect_scores": "dense (bkg bias 4)" if args.dense else "sparse/realistic (bkg bias 10)",
                    "l2": "inputs larger than L2 (conf and scores are %.0f MB each vs 126 MB L2)" % (conf.numel() * 4 / 1e6),
                    "launch": "CUDA graph replay" if graph is not None else "eager launches",
-                   "parallelism": "images sharded by rank; one all-reduce of {sum_l, sum_c, N_pos} per step" if n_gpus > 1 else "single GPU"},
+                   "parallelism": ("images sharded by rank; {sum_l, sum_c, N_pos} reduced per step: %s" % (
+                       "inside the mining kernel over NVLink peer memory (no collective launch)" if crit.reduce_used == "p2p"
+                       else "one NCCL all-reduce")) if n_gpus > 1 else "single GPU"},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "phases": phases, "sanity": sanity,
     }
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    teardown()
 
 
 if __name__ == "__main__":

@@ -193,6 +193,31 @@ SSDBOX_API int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float*
                              int16_t* sel, int16_t* tidx, int64_t* dbg_conf_t, float* dbg_loc_t,
                              uint8_t* dbg_neg, float* dbg_keys, void* ws, size_t ws_bytes,
                              ssdbox_stream_t stream);
+
+/* ---- multi-GPU: loss sums reduced over NVLink peer memory inside the mining kernel ------------
+ * The only cross-image coupling of MultiBoxLoss is { sum smooth-L1, sum CE, N } (multibox_loss.py:
+ * 114-116).  With one process per GPU, every rank owns an exchange buffer of
+ * ssdbox_peer_buffer_bytes() bytes, ZERO-FILLED ONCE at creation and mapped into every peer
+ * (CUDA IPC / symmetric memory; the library never allocates).  The last CTA of the mining kernel
+ * stores the rank's three sums into its slot of every peer's buffer (st.release.sys through
+ * NVLink), waits for the slots of its own buffer (ld.acquire.sys), adds them in rank order
+ * (bit-identical on every rank) and finalises: `sums` / `losses` then hold the GLOBAL values.
+ * There is no separate collective launch.  Like any collective, every rank must issue the same
+ * sequence of peer-reduced forwards; a call epoch kept in the buffer makes the call replayable
+ * from a CUDA graph.  A peer that never arrives traps the kernel after ~4 s instead of hanging. */
+#define SSDBOX_MAX_PEERS 16
+typedef struct {
+  int32_t rank, world;                 /* 1 <= world <= SSDBOX_MAX_PEERS */
+  void* bufs[SSDBOX_MAX_PEERS];        /* bufs[r]: rank r's exchange buffer as addressable from THIS device */
+} ssdbox_peer_group;
+SSDBOX_API size_t ssdbox_peer_buffer_bytes(void);
+/* ssdbox_multibox_loss_fwd with the reduction above; peers == NULL behaves like the plain call. */
+SSDBOX_API int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const float* loc, const float* conf,
+                             const float* priors, const float* anchors_xyxy, const uint8_t* pool,
+                             const float* gt, const int32_t* gt_offsets, double* sums, float* losses,
+                             int16_t* sel, int16_t* tidx, int64_t* dbg_conf_t, float* dbg_loc_t,
+                             uint8_t* dbg_neg, float* dbg_keys, const ssdbox_peer_group* peers, void* ws, size_t ws_bytes,
+                             ssdbox_stream_t stream);
 /* losses = sums[0..1] / sums[2]  (after the caller all-reduced `sums` across ranks) */
 SSDBOX_API int ssdbox_multibox_loss_finalize(const double* sums, float* losses, ssdbox_stream_t stream);
 /* backward: grad_loc [B,P,4], grad_conf [B,P,C] (both fully written);

@@ -38,7 +38,14 @@ constexpr float kLog2e = 1.4426950408889634f;
 #ifdef SSDBOX_PHASE_TIMING
 __device__ long long g_sphase[8 * 160];
 __device__ long long g_mstat[8 * 160];
-#define SMARK(k) do { if (blockIdx.x < 160 && lane == 0) g_sphase[blockIdx.x * 8 + (k)] = clock64(); } while (0)
+__device__ unsigned long long g_sgt[2 * 160];
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define SMARK(k) do { if (blockIdx.x < 160 && lane == 0) { g_sphase[blockIdx.x * 8 + (k)] = clock64(); \
+    if ((k) == 0) g_sgt[blockIdx.x * 2] = gtimer_ns(); if ((k) == 7) g_sgt[blockIdx.x * 2 + 1] = gtimer_ns(); } } while (0)
 #else
 #define SMARK(k) do { } while (0)
 #endif
@@ -352,9 +359,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) loss_stream_kernel(StreamAr
   }
   if (warp == 0) SMARK(0);
   RingCtx rc = ring_setup(a.ring, smem_ring);   // fences the barrier inits, __syncthreads()
-#ifdef SSDBOX_PHASE_TIMING
-  if (a.dbg & 1) rc.n_local = 0;
-#endif
   if (warp == 0) SMARK(1);
   if (warp == kRingConsumerWarps) {
     ring_produce(a.ring, rc);
@@ -481,6 +485,9 @@ struct MineArgs {
   int16_t* sel;
   uint8_t* dbg_neg;
   float* dbg_keys;
+  // multi-GPU: exchange buffers of every rank (world == 0: single GPU)
+  int peer_rank, peer_world;
+  void* peer_bufs[SSDBOX_MAX_PEERS];
 };
 
 #ifdef SSDBOX_PHASE_TIMING
@@ -489,6 +496,71 @@ __device__ long long g_phase[16 * 64];
 #else
 #define PHASE_MARK(k) do { } while (0)
 #endif
+
+// ---- NVLink peer-memory reduction of {sum smooth-L1, sum CE, N} (see ssdbox_peer_group) ----------
+// Exchange buffer of a rank: [0] call epoch (u64, touched by the owner only), then at byte 64 two
+// banks (epoch parity) of `world` 32-byte slots { double s[3]; u64 epoch }.  Slot (parity, r) of
+// rank q's buffer is written by rank r only.  A rank can run at most one call ahead of a peer's
+// reads (it needs that peer's slot of the current call to finish), so two banks are enough.
+constexpr int kPeerHeaderBytes = 64;
+constexpr int kPeerSlotBytes = 32;
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// one warp; s[0..2] in shared memory holds this rank's sums on entry and the global sums on exit
+__device__ void peer_exchange(const MineArgs& a, double* s, int lane) {
+  const int world = a.peer_world, me = a.peer_rank;
+  unsigned long long* mine = reinterpret_cast<unsigned long long*>(a.peer_bufs[me]);
+  unsigned long long epoch = 0;
+  if (lane == 0) {
+    epoch = mine[0] + 1ull;
+    mine[0] = epoch;
+  }
+  epoch = __shfl_sync(SSDBOX_FULL_MASK, epoch, 0);
+  const size_t bank = kPeerHeaderBytes + (size_t)(epoch & 1ull) * world * kPeerSlotBytes;
+  const double v0 = s[0], v1 = s[1], v2 = s[2];
+  __syncwarp();
+  double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+  if (lane < world) {
+    // my sums -> slot `me` of rank `lane`'s buffer (peer store over NVLink; own buffer for lane == me)
+    char* dst = static_cast<char*>(a.peer_bufs[lane]) + bank + (size_t)me * kPeerSlotBytes;
+    volatile double* d = reinterpret_cast<volatile double*>(dst);
+    d[0] = v0;
+    d[1] = v1;
+    d[2] = v2;
+    st_release_sys(reinterpret_cast<unsigned long long*>(dst + 24), epoch);
+    // rank `lane`'s sums <- slot `lane` of my buffer
+    const char* src = reinterpret_cast<const char*>(mine) + bank + (size_t)lane * kPeerSlotBytes;
+    const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(src + 24);
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) != epoch) {
+      if (clock64() - t0 > 8000000000LL) __trap();     // a peer never arrived
+    }
+    const volatile double* q = reinterpret_cast<const volatile double*>(src);
+    r0 = q[0];
+    r1 = q[1];
+    r2 = q[2];
+  }
+  // rank order: the same fp64 result on every rank
+  double t0s = 0.0, t1s = 0.0, t2s = 0.0;
+  for (int r = 0; r < world; ++r) {
+    t0s += __shfl_sync(SSDBOX_FULL_MASK, r0, r);
+    t1s += __shfl_sync(SSDBOX_FULL_MASK, r1, r);
+    t2s += __shfl_sync(SSDBOX_FULL_MASK, r2, r);
+  }
+  if (lane == 0) {
+    s[0] = t0s;
+    s[1] = t1s;
+    s[2] = t2s;
+  }
+}
 
 // last CTA: fold the per-image partials in image order (bit-reproducible run to run); the loads
 // are spread over the threads (one L2 round trip), the fp64 adds stay sequential in image order
@@ -510,6 +582,19 @@ __device__ void fold_partials(const MineArgs& a, double* s_dscr) {
         sn += s_dscr[64 + i];
       }
     }
+  }
+  if (a.peer_world > 0) {     // uniform over the CTA
+    if (tid == 0) {
+      s_dscr[0] = sl;
+      s_dscr[1] = sc;
+      s_dscr[2] = sn;
+    }
+    __syncthreads();
+    if (tid < 32) peer_exchange(a, s_dscr, tid);
+    __syncthreads();
+    sl = s_dscr[0];
+    sc = s_dscr[1];
+    sn = s_dscr[2];
   }
   if (tid == 0) {
     a.sums[0] = sl;
@@ -1194,14 +1279,36 @@ static int check_loss_cfg(const ssdbox_loss_cfg* c) {
   return SSDBOX_OK;
 }
 
+extern "C" size_t ssdbox_peer_buffer_bytes(void) {
+  return (size_t)kPeerHeaderBytes + 2 * (size_t)SSDBOX_MAX_PEERS * kPeerSlotBytes;
+}
+
 extern "C" int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float* loc, const float* conf,
                                         const float* priors, const float* anchors_xyxy, const uint8_t* pool,
                                         const float* gt, const int32_t* gt_offsets, double* sums, float* losses,
                                         int16_t* sel, int16_t* tidx, int64_t* dbg_conf_t, float* dbg_loc_t,
                                         uint8_t* dbg_neg, float* dbg_keys, void* ws, size_t ws_bytes,
                                         ssdbox_stream_t stream) {
+  return ssdbox_multibox_loss_fwd_peers(cfg, loc, conf, priors, anchors_xyxy, pool, gt, gt_offsets, sums, losses, sel,
+                                        tidx, dbg_conf_t, dbg_loc_t, dbg_neg, dbg_keys, nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const float* loc, const float* conf,
+                                              const float* priors, const float* anchors_xyxy, const uint8_t* pool,
+                                              const float* gt, const int32_t* gt_offsets, double* sums, float* losses,
+                                              int16_t* sel, int16_t* tidx, int64_t* dbg_conf_t, float* dbg_loc_t,
+                                              uint8_t* dbg_neg, float* dbg_keys, const ssdbox_peer_group* peers,
+                                              void* ws, size_t ws_bytes, ssdbox_stream_t stream) {
   int rc = check_loss_cfg(cfg);
   if (rc) return rc;
+  if (peers) {
+    SSDBOX_REQUIRE(peers->world >= 1 && peers->world <= SSDBOX_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world,
+                   SSDBOX_EINVAL, "loss: bad peer group (rank %d of %d)", peers->rank, peers->world);
+    for (int r = 0; r < peers->world; ++r)
+      SSDBOX_REQUIRE(peers->bufs[r] && (reinterpret_cast<uintptr_t>(peers->bufs[r]) & 15u) == 0, SSDBOX_EINVAL,
+                     "loss: peer buffer %d is null or misaligned", r);
+    SSDBOX_REQUIRE(cfg->B > 0 && cfg->P > 0, SSDBOX_EINVAL, "loss: a peer-reduced call needs a non-empty local batch");
+  }
   const int B = cfg->B, P = cfg->P, C = cfg->C;
   SSDBOX_REQUIRE(sums && ws && gt_offsets, SSDBOX_EINVAL, "loss: null pointer");
   SSDBOX_REQUIRE(!cfg->finalize || losses, SSDBOX_EINVAL, "loss: finalize needs `losses`");
@@ -1269,6 +1376,9 @@ extern "C" int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float*
   rc = plan_stream(&sa, conf, (long long)B * P, C, dev.sm_count, dev.max_smem_optin,
                    !(cfg->flags & SSDBOX_LOSS_SEPARATE_MATCH), &stream_smem);
   if (rc) return rc;
+#ifdef SSDBOX_PHASE_TIMING
+  if (sa.dbg & 1) sa.ring.tiles = 0, sa.ring.tiles_per_cta = 0;     // matching alone
+#endif
   if (!sa.fuse) {
     rc = launch_match(ma, w.m, w.m.lab, tidx, nullptr, st);
     if (rc) return rc;
@@ -1291,6 +1401,12 @@ extern "C" int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float*
   m.uk_in_smem = (fixed + (size_t)P * 6 + 16 <= (size_t)dev.max_smem_optin - 1024) ? 1 : 0;
   m.partial = w.partial; m.ticket = w.ticket; m.sums = sums; m.losses = losses; m.sel = sel;
   m.dbg_neg = dbg_neg; m.dbg_keys = dbg_keys;
+  m.peer_world = 0;
+  if (peers) {
+    m.peer_rank = peers->rank;
+    m.peer_world = peers->world;
+    for (int r = 0; r < peers->world; ++r) m.peer_bufs[r] = peers->bufs[r];
+  }
   size_t smem = fixed + (m.uk_in_smem ? (size_t)P * 6 + 16 : 0);
   // vector mode needs every per-image row of keys / lab / pool / sel / debug arrays 16-byte friendly
   const bool vec4 = (P % 4 == 0) && aligned16(sel) && (!pool || (reinterpret_cast<uintptr_t>(pool) & 3u) == 0) &&
@@ -1318,6 +1434,9 @@ extern "C" int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float*
 #ifdef SSDBOX_PHASE_TIMING
 extern "C" __attribute__((visibility("default"))) int ssdbox_debug_mstat(long long* out) {
   return cudaMemcpyFromSymbol(out, ssdbox::g_mstat, sizeof(long long) * 8 * 160) == cudaSuccess ? 0 : -5;
+}
+extern "C" __attribute__((visibility("default"))) int ssdbox_debug_sgt(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, ssdbox::g_sgt, sizeof(unsigned long long) * 2 * 160) == cudaSuccess ? 0 : -5;
 }
 extern "C" __attribute__((visibility("default"))) int ssdbox_debug_sphases(long long* out16) {
   return cudaMemcpyFromSymbol(out16, ssdbox::g_sphase, sizeof(long long) * 8 * 160) == cudaSuccess ? 0 : -5;

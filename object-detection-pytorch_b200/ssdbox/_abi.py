@@ -24,7 +24,8 @@ SYMBOLS = [
     "ssdbox_abi_version", "ssdbox_last_error", "ssdbox_workspace_bytes", "ssdbox_priorbox_count",
     "ssdbox_priorbox", "ssdbox_point_form", "ssdbox_center_form", "ssdbox_jaccard", "ssdbox_encode",
     "ssdbox_decode", "ssdbox_log_sum_exp", "ssdbox_match_encode", "ssdbox_hard_negative_mine",
-    "ssdbox_multibox_loss_fwd", "ssdbox_multibox_loss_finalize", "ssdbox_multibox_loss_bwd",
+    "ssdbox_multibox_loss_fwd", "ssdbox_multibox_loss_fwd_peers", "ssdbox_peer_buffer_bytes",
+    "ssdbox_multibox_loss_finalize", "ssdbox_multibox_loss_bwd",
     "ssdbox_nms", "ssdbox_detect", "ssdbox_arm_filter", "ssdbox_timers_enable", "ssdbox_timers_read",
 ]
 
@@ -63,6 +64,14 @@ class DetectCfg(C.Structure):
     ]
 
 
+MAX_PEERS = 16
+
+
+class PeerGroup(C.Structure):
+    """ssdbox_peer_group: every rank's exchange buffer as addressable from this device."""
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("bufs", C.c_void_p * MAX_PEERS)]
+
+
 _lib = None
 _lock = threading.Lock()
 P_ = C.c_void_p
@@ -76,6 +85,8 @@ def _declare(lib):
     lib.ssdbox_last_error.argtypes = [C.c_char_p, sz]
     lib.ssdbox_workspace_bytes.restype = sz
     lib.ssdbox_workspace_bytes.argtypes = [C.c_int] * 6
+    lib.ssdbox_peer_buffer_bytes.restype = sz
+    lib.ssdbox_peer_buffer_bytes.argtypes = []
     lib.ssdbox_priorbox_count.restype = i64
     lib.ssdbox_priorbox_count.argtypes = [C.POINTER(PriorCfg)]
     sigs = {
@@ -89,6 +100,7 @@ def _declare(lib):
         "ssdbox_match_encode": [P_, P_, i32, P_, i64, P_, i32, i32, f32, f32, f32, i32, P_, P_, P_, P_, P_, sz, P_],
         "ssdbox_hard_negative_mine": [P_, P_, P_, i32, i32, i32, P_, P_, sz, P_],
         "ssdbox_multibox_loss_fwd": [C.POINTER(LossCfg)] + [P_] * 15 + [P_, sz, P_],
+        "ssdbox_multibox_loss_fwd_peers": [C.POINTER(LossCfg)] + [P_] * 15 + [C.POINTER(PeerGroup), P_, sz, P_],
         "ssdbox_multibox_loss_finalize": [P_, P_, P_],
         "ssdbox_multibox_loss_bwd": [C.POINTER(LossCfg)] + [P_] * 11 + [P_],
         "ssdbox_nms": [P_, P_, i32, f32, i32, P_, P_, P_, sz, P_],

@@ -31,3 +31,63 @@ def finalize_losses(sums):
     if n <= 0:
         return torch.zeros((), dtype=torch.float32), torch.zeros((), dtype=torch.float32)
     return (sums[0] / n).to(torch.float32), (sums[1] / n).to(torch.float32)
+
+
+class PeerExchange(object):
+    """Exchange buffers for the NVLink peer-memory reduction of the loss sums (ssdbox_peer_group,
+    include/ssdbox.h): one small zero-filled buffer per rank, allocated in symmetric memory
+    (torch.distributed._symmetric_memory) so that every rank holds a device pointer to every peer's
+    buffer.  Built once per (process group, device); collective: every rank of the group must
+    construct it at the same point.  Raises when symmetric memory / peer access is unavailable --
+    MultiBoxLoss then keeps the NCCL all-reduce."""
+
+    def __init__(self, device, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _abi
+        grp = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(grp)
+        self.rank = dist.get_rank(grp)
+        if self.world > _abi.MAX_PEERS:
+            raise RuntimeError("ssdbox: peer reduction supports at most %d ranks" % _abi.MAX_PEERS)
+        nbytes = int(_abi.lib().ssdbox_peer_buffer_bytes())
+        gname = grp.group_name if hasattr(grp, "group_name") else grp
+        enable = getattr(symm_mem, "enable_symm_mem_for_group", None)
+        if enable is not None:           # needed by older torch releases, a no-op / deprecated later
+            try:
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    enable(gname)
+            except Exception:
+                pass
+        self.buf = symm_mem.empty((nbytes + 7) // 8, dtype=torch.int64, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, gname)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(group=grp)          # every buffer is zero before any rank stores into a peer
+        ptrs = [int(x) for x in self.handle.buffer_ptrs]
+        if len(ptrs) != self.world or int(self.handle.rank) != self.rank:
+            raise RuntimeError("ssdbox: symmetric-memory rendezvous returned an unexpected layout")
+        self.group = _abi.PeerGroup()
+        self.group.rank = self.rank
+        self.group.world = self.world
+        for r, ptr in enumerate(ptrs):
+            self.group.bufs[r] = C.c_void_p(ptr)
+
+
+class LocalPeerExchange(object):
+    """World-size-1 peer group on ordinary device memory (tests: drives the exchange code path of the
+    mining kernel on a single GPU; the rank stores into and reads from its own buffer)."""
+
+    def __init__(self, device):
+        import ctypes as C
+        from . import _abi
+        nbytes = int(_abi.lib().ssdbox_peer_buffer_bytes())
+        self.buf = torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device=device)
+        self.world, self.rank = 1, 0
+        self.group = _abi.PeerGroup()
+        self.group.rank = 0
+        self.group.world = 1
+        self.group.bufs[0] = C.c_void_p(self.buf.data_ptr())

@@ -51,7 +51,7 @@ class _State(object):
 
 def loss_forward_raw(state, loc, conf, priors, gt, offsets, gmax, num_classes, threshold, negpos_ratio,
                      variance, anchors_xyxy=None, pool=None, binarize=False, finalize=True, debug=None,
-                     fresh=False, flags=0):
+                     fresh=False, flags=0, peers=None):
     """One call of ssdbox_multibox_loss_fwd on validated CUDA tensors.  Returns
     (cfg, sums[3] f64, losses[2] f32, sel[B,P] i16, tidx[B,P] i16).  With fresh=False the outputs are
     the module's persistent buffers (overwritten by the next call); fresh=True allocates new ones
@@ -72,14 +72,15 @@ def loss_forward_raw(state, loc, conf, priors, gt, offsets, gmax, num_classes, t
                        4 * P if per_image else 0, int(flags), 0)
     ws, n = state.ws.get(_abi.workspace_bytes(_abi.OP_LOSS_FWD, B, P, num_classes, gmax), dev)
     dbg = debug or {}
-    _abi.check(_abi.lib().ssdbox_multibox_loss_fwd(
+    _abi.check(_abi.lib().ssdbox_multibox_loss_fwd_peers(
         C.byref(cfg), _abi.ptr(loc, torch.float32, "loc_data"), _abi.ptr(conf, torch.float32, "conf_data"),
         _abi.ptr(priors, torch.float32, "priors"), _abi.ptr(anchors_xyxy, torch.float32, "anchors", True),
         _abi.ptr(pool, torch.uint8, "pool", True), _abi.ptr(gt, torch.float32, "gt"),
         _abi.ptr(offsets, torch.int32, "gt_offsets"), _abi.ptr(sums), _abi.ptr(losses),
         _abi.ptr(sel), _abi.ptr(tidx), _abi.ptr(dbg.get("conf_t"), torch.int64, "conf_t", True),
         _abi.ptr(dbg.get("loc_t"), torch.float32, "loc_t", True), _abi.ptr(dbg.get("neg"), torch.uint8, "neg", True),
-        _abi.ptr(dbg.get("keys"), torch.float32, "keys", True), ws, n, _abi.stream_ptr(dev)))
+        _abi.ptr(dbg.get("keys"), torch.float32, "keys", True),
+        C.byref(peers) if peers is not None else None, ws, n, _abi.stream_ptr(dev)))
     return cfg, sums, losses, sel, tidx
 
 
@@ -88,13 +89,18 @@ class _MultiBoxLossFn(torch.autograd.Function):
     def forward(ctx, loc, conf, priors, gt, offsets, anchors_xyxy, pool, mod, gmax):
         st = mod._state
         distributed = mod._is_distributed()
+        # the only collective of the path: {sum smooth-L1, sum CE, N_pos} summed over ranks.  Preferred:
+        # inside the mining kernel over NVLink peer memory; otherwise one NCCL all-reduce + finalize.
+        if getattr(mod, "_force_peers", False):
+            peers = mod._peers.group
+        else:
+            peers = mod._peer_group(loc.device) if distributed else None
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         cfg, sums, losses, sel, tidx = loss_forward_raw(
             st, loc, conf, priors, gt, offsets, gmax, mod.num_classes, mod.threshold, mod.negpos_ratio,
-            mod.variance, anchors_xyxy, pool, mod.binarize_labels, finalize=not distributed, debug=mod._debug,
-            fresh=need_grad, flags=mod.abi_flags)
-        if distributed:
-            # the only collective of the path: {sum smooth-L1, sum CE, N_pos} summed over ranks
+            mod.variance, anchors_xyxy, pool, mod.binarize_labels, finalize=(not distributed) or peers is not None,
+            debug=mod._debug, fresh=need_grad, flags=mod.abi_flags, peers=peers)
+        if distributed and peers is None:
             import torch.distributed as dist
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=mod.process_group)
             _abi.check(_abi.lib().ssdbox_multibox_loss_finalize(_abi.ptr(sums), _abi.ptr(losses),
@@ -125,12 +131,14 @@ class MultiBoxLoss(nn.Module):
     """SSD weighted loss (multibox_loss.py:10-46).  Arguments as in the reference; as there,
     prior_for_matching / bkg_label / neg_mining / neg_overlap / encode_target are stored but
     unused.  `variance` replaces the reference's read of the global cfg (multibox_loss.py:46);
-    `distributed=True` (or an initialised default process group with world size > 1) all-reduces
-    the loss numerators and the positive count across ranks (images are sharded by rank)."""
+    `distributed=True` (or an initialised default process group with world size > 1) sums the loss
+    numerators and the positive count across ranks (images are sharded by rank).  `reduce`:
+    "p2p" = inside the mining kernel over NVLink peer memory (ssdbox.dist.PeerExchange), "nccl" = one
+    all-reduce after it, "auto" = p2p when symmetric memory is available, else nccl."""
 
     def __init__(self, num_classes, overlap_thresh, prior_for_matching, bkg_label, neg_mining, neg_pos,
                  neg_overlap, encode_target, use_gpu=True, variance=(0.1, 0.2), distributed=None,
-                 process_group=None):
+                 process_group=None, reduce="auto"):
         super(MultiBoxLoss, self).__init__()
         self.use_gpu = use_gpu
         self.num_classes = num_classes
@@ -145,6 +153,11 @@ class MultiBoxLoss(nn.Module):
         self.binarize_labels = False
         self.distributed = distributed
         self.process_group = process_group
+        if reduce not in ("auto", "p2p", "nccl"):
+            raise ValueError("reduce must be 'auto', 'p2p' or 'nccl'")
+        self.reduce = reduce
+        self.reduce_used = None     # "p2p" / "nccl" once the first distributed forward has run
+        self._peers = None
         self.abi_flags = 0          # _abi.LOSS_SEPARATE_MATCH: matching as its own kernel
         self._state = _State()
         self._debug = None
@@ -158,6 +171,37 @@ class MultiBoxLoss(nn.Module):
         if self.distributed and not ok:
             raise RuntimeError("ssdbox: distributed=True but no process group with world size > 1 is initialised")
         return ok
+
+    def _peer_group(self, device):
+        """ctypes ssdbox_peer_group for the peer-memory reduction, or None (use NCCL).  Built lazily at
+        the first distributed forward (collective: all ranks get here together)."""
+        if self.reduce == "nccl":
+            self.reduce_used = "nccl"
+            return None
+        if self._peers is None:
+            from . import dist as sdist
+            try:
+                self._peers = sdist.PeerExchange(device, self.process_group)
+            except Exception as e:
+                self._peers = False
+                self._peers_error = repr(e)
+            # all ranks must take the same route: fall back together if any rank failed
+            import torch.distributed as dist
+            ok = torch.tensor([1 if self._peers else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.process_group)
+            if int(ok.item()) == 0:
+                if self.reduce == "p2p":
+                    raise RuntimeError("ssdbox: reduce='p2p' but the peer exchange could not be set up: %s"
+                                       % getattr(self, "_peers_error", "failed on another rank"))
+                self._peers = False
+        self.reduce_used = "p2p" if self._peers else "nccl"
+        return self._peers.group if self._peers else None
+
+    def use_local_peer_exchange(self, device):
+        """tests: run the peer-exchange path with a world of one rank (no process group needed)."""
+        from . import dist as sdist
+        self._peers = sdist.LocalPeerExchange(device)
+        self._force_peers = True
 
     def forward(self, predictions, targets):
         loc_data, conf_data, priors = predictions

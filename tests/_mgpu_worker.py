@@ -1,0 +1,66 @@
+"""torchrun worker of tests/test_multi_gpu.py: one process per GPU, NCCL.  Every rank computes the
+loss of its image shard with (a) the NVLink peer-memory reduction inside the mining kernel and
+(b) the NCCL all-reduce; both must equal the single-GPU loss over the whole batch (computed on rank
+0's GPU by the same library, itself pinned to the oracle by test_gpu_parity.py)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "object-detection-pytorch_b200"))
+import torch
+import torch.distributed as dist
+
+
+def main():
+    import ssdbox
+    from ssdbox import dist as sdist
+    from tests import _util as U
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    B = 2 * world + 1                                       # uneven shards
+    x = U.seeded_inputs("ssd300_voc", B, 21)
+    loc, conf, tg = sdist.shard_batch(x["loc"], x["conf"], x["targets"], rank, world)
+    pri = x["priors"].to(dev)
+    tgd = [t.to(dev) for t in tg]
+    res = {}
+    for mode in ("p2p", "nccl"):
+        crit = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False, distributed=True, reduce=mode)
+        for it in range(3):                                 # several calls: both epoch banks of the exchange
+            lo = loc.to(dev).requires_grad_(True)
+            co = conf.to(dev).requires_grad_(True)
+            ll, lc = crit((lo, co, pri), tgd)
+            (ll + lc).backward()
+        assert crit.reduce_used == mode, (crit.reduce_used, mode)
+        res[mode] = (float(ll), float(lc), crit._last[0].clone(), lo.grad.clone(), co.grad.clone())
+    # single-GPU reference over the whole batch
+    full = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False, distributed=False)
+    lo = x["loc"].to(dev).requires_grad_(True)
+    co = x["conf"].to(dev).requires_grad_(True)
+    fl, fc = full((lo, co, pri), [t.to(dev) for t in x["targets"]])
+    (fl + fc).backward()
+    b, e = sdist.shard_range(B, rank, world)
+    for mode in ("p2p", "nccl"):
+        ll, lc, sums, gl, gc = res[mode]
+        assert int(sums[2]) == int(full._last[0][2]), (mode, sums, full._last[0])
+        assert abs(ll - float(fl)) <= 1e-6 * abs(float(fl)) and abs(lc - float(fc)) <= 1e-6 * abs(float(fc)), (mode, ll, lc, float(fl), float(fc))
+        U.assert_close_rel(gl, lo.grad[b:e], 1e-5, 1e-8, mode + " grad_loc shard")
+        U.assert_close_rel(gc, co.grad[b:e], 1e-5, 1e-8, mode + " grad_conf shard")
+    # every rank holds bit-identical global sums (rank-ordered fp64 adds)
+    mine = res["p2p"][2]
+    allv = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    for v in allv:
+        assert torch.equal(v, allv[0])
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        print("MGPU_OK world=%d p2p=(%.6f, %.6f) nccl=(%.6f, %.6f)" % (world, res["p2p"][0], res["p2p"][1], res["nccl"][0], res["nccl"][1]), flush=True)
+    sys.stdout.flush()
+    os._exit(0)
+
+
+if __name__ == "__main__":
+    main()

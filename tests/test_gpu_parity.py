@@ -394,6 +394,38 @@ def test_loss_many_truths_and_tied_keys(dev):
         assert torch.equal(neg[b], want), b
 
 
+def test_peer_exchange_single_rank(dev):
+    """The NVLink peer-memory reduction of the loss sums (ssdbox_multibox_loss_fwd_peers) with a world
+    of one rank: the mining kernel stores into / reads from its own exchange buffer.  Same sums and
+    losses as the plain call, over several calls (both epoch banks) and under CUDA-graph replay."""
+    x = U.seeded_inputs("ssd300_voc", 4, 5)
+    args = ((x["loc"].to(dev), x["conf"].to(dev), x["priors"].to(dev)), _gpu_targets(x["targets"], dev))
+    plain = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False)
+    a = plain.intermediates(*args)
+    crit = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False)
+    crit.use_local_peer_exchange(dev)
+    for _ in range(3):
+        b = crit.intermediates(*args)
+        for k in ("sums", "sel", "loss_l", "loss_c"):
+            assert torch.equal(a[k], b[k]), k
+    assert int(crit._peers.buf[0]) == 3            # call epoch kept in the exchange buffer
+    gt, offs = synth.pack_targets(x["targets"])
+    gt, offs = gt.to(dev), offs.to(dev)
+    gmax = max(int(t.size(0)) for t in x["targets"])
+    loc, conf, pri = args[0]
+    with torch.no_grad():
+        crit.forward_packed(loc, conf, pri, gt, offs, gmax)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            ll, lc = crit.forward_packed(loc, conf, pri, gt, offs, gmax)
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+    assert float(ll) == float(a["loss_l"]) and float(lc) == float(a["loss_c"])
+    assert int(crit._peers.buf[0]) == 7
+
+
 def test_cuda_graph_capture(dev):
     x = U.seeded_inputs("ssd300_voc", 4, 0)
     crit = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False)

@@ -1,0 +1,21 @@
+"""N > 1 on real GPUs (skipped on a box with fewer than two): the sharded MultiBoxLoss with the
+NVLink peer-memory reduction and with the NCCL all-reduce against the single-GPU result."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+def test_sharded_loss_two_gpus():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n = min(torch.cuda.device_count(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "_mgpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT)
+    assert r.returncode == 0 and "MGPU_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])

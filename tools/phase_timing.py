@@ -38,6 +38,13 @@ for it in range(4):
     rel = arr - arr[:, :1]
     print(" stream per-CTA cycles: match_w0_end min/med/max %s | cons_w0_end min/med/max %s | producer_end max %d"
           % (np.percentile(rel[:, 4], [0, 50, 100]).astype(int).tolist(), np.percentile(rel[:, 6], [0, 50, 100]).astype(int).tolist(), rel[:, 2].max()))
+    gt_ = (C.c_ulonglong * (2 * 160))()
+    _abi.lib().ssdbox_debug_sgt.argtypes = [C.c_void_p]
+    _abi.lib().ssdbox_debug_sgt(gt_)
+    g = np.array(list(gt_), dtype=np.int64).reshape(160, 2)[:148]
+    span_ns = g[:, 1].max() - g[:, 0].min()
+    print("  stream kernel span (globaltimer, first CTA start -> last consumer end): %.1f us; CTA start spread %.1f us; consumer-end spread %.1f us; cycles/ns of CTA 0: %.3f"
+          % (span_ns / 1e3, (g[:, 0].max() - g[:, 0].min()) / 1e3, (g[:, 1].max() - g[:, 1].min()) / 1e3, rel[0, 7] / max(g[0, 1] - g[0, 0], 1)))
     ms = (C.c_longlong * (8 * 160))()
     _abi.lib().ssdbox_debug_mstat.argtypes = [C.c_void_p]
     _abi.lib().ssdbox_debug_mstat(ms)
