@@ -176,6 +176,9 @@ typedef struct {
 /* Use the generic (shared-memory) mining kernel even when the register-resident one applies
  * (P % 4 == 0 and P <= 24576); same results, for testing. */
 #define SSDBOX_LOSS_GENERIC_MINE 2
+/* Keep the register-resident mining kernel on one CTA per image (by default images with P >= 8192
+ * are split over a thread-block cluster of two CTAs); same results, for testing. */
+#define SSDBOX_LOSS_NO_CLUSTER 4
 
 /* forward.
  *   loc [B,P,4], conf [B,P,C] raw logits, priors, anchors_xyxy (nullable), gt/gt_offsets

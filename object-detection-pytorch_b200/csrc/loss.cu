@@ -564,18 +564,18 @@ __device__ void peer_exchange(const MineArgs& a, double* s, int lane) {
 
 // last CTA: fold the per-image partials in image order (bit-reproducible run to run); the loads
 // are spread over the threads (one L2 round trip), the fp64 adds stay sequential in image order
-__device__ void fold_partials(const MineArgs& a, double* s_dscr) {
+__device__ void fold_partials(const MineArgs& a, double* s_dscr, int nparts) {
   const int tid = threadIdx.x;
   double sl = 0.0, sc = 0.0, sn = 0.0;
-  for (int base = 0; base < a.B; base += 32) {
+  for (int base = 0; base < nparts; base += 32) {
     __syncthreads();
     if (tid < 96) {
       int i = base + (tid & 31), f = tid >> 5;
-      s_dscr[f * 32 + (tid & 31)] = i < a.B ? __ldcg(&a.partial[(size_t)i * 3 + f]) : 0.0;
+      s_dscr[f * 32 + (tid & 31)] = i < nparts ? __ldcg(&a.partial[(size_t)i * 3 + f]) : 0.0;
     }
     __syncthreads();
     if (tid == 0) {
-      int n = a.B - base < 32 ? a.B - base : 32;
+      int n = nparts - base < 32 ? nparts - base : 32;
       for (int i = 0; i < n; ++i) {
         sl += s_dscr[i];
         sc += s_dscr[32 + i];
@@ -792,7 +792,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  fold_partials(a, s_dscr);
+  fold_partials(a, s_dscr, a.B);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -815,7 +815,9 @@ __device__ __forceinline__ int reg_find(const uint32_t* s_hist, int nbins, int K
   return s_res[0];
 }
 
+template <int CL>
 __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineArgs a) {
+  constexpr int Q = kMineQ / CL;     // quads (4 priors) per thread
   extern __shared__ __align__(16) unsigned char smem_mine[];
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_mine);                        // 2048
   double* s_dscr = reinterpret_cast<double*>(smem_mine + 8192);                     // 100
@@ -824,16 +826,23 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   unsigned long long* s_best = reinterpret_cast<unsigned long long*>(smem_mine + kMineFixedSmem);   // kForceListMax
   uint32_t* s_force = reinterpret_cast<uint32_t*>(s_best + kForceListMax);          // kForceListMax x 2
   float* s_gt = reinterpret_cast<float*>(s_force + 2 * kForceListMax);              // kForceListMax x 5 (+3 pad)
-  uint32_t* s_list = reinterpret_cast<uint32_t*>(s_gt + 5 * kForceListMax + 8);     // P: prior | class << 16
+  uint32_t* s_list = reinterpret_cast<uint32_t*>(s_gt + 5 * kForceListMax + 8);     // P / CL + 4: prior | class << 16
   __shared__ int s_last, s_nforce;
+  __shared__ uint32_t s_xch[4];      // [0..1] positives per CTA of the cluster, [2..3] tie counts
 
-  const int b = blockIdx.x, tid = threadIdx.x, P = a.P;
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int b = blockIdx.x / CL, tid = threadIdx.x, P = a.P;
   const size_t off = (size_t)b * P;
   const int g0 = a.gt_offsets[b];
   int G = a.gt_offsets[b + 1] - g0;
   G = G < 0 ? 0 : (G > a.gmax ? a.gmax : G);
   const float* pri = a.priors + (size_t)b * (size_t)a.prior_stride;
   const int n4 = P >> 2;
+  const int n4h = (n4 + CL - 1) / CL;          // quads owned by one CTA of the cluster (contiguous range)
+  const int q0 = rank * n4h;
+  auto sync_all = [&]() {
+    if (CL > 1) cluster_sync_all(); else __syncthreads();
+  };
   const bool small_g = a.fuse && G <= kForceListMax;
 
   PHASE_MARK(0);
@@ -845,17 +854,17 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   float my_gt = 0.f;
   if (gt_cached && tid < 5 * G) my_gt = a.gt[(size_t)g0 * 5 + tid];
   uint32_t h0 = a.hist[(size_t)b * kHistBins + tid], h1 = a.hist[(size_t)b * kHistBins + 1024 + tid];
-  uint32_t uk[kMineQ][4];     // ordered mining keys (0 = outside the ranking)
-  short4 ll[kMineQ];
+  uint32_t uk[Q][4];     // ordered mining keys (0 = outside the ranking)
+  short4 ll[Q];
   uint32_t poolmask = 0u;     // bit j*4+e: prior is ranked (inside P and inside the caller's pool)
   const float4* k4 = reinterpret_cast<const float4*>(a.keys + off);
   const short4* l4 = reinterpret_cast<const short4*>(a.lab + off);
   const uchar4* p4 = a.pool ? reinterpret_cast<const uchar4*>(a.pool + off) : nullptr;
 #pragma unroll
-  for (int j = 0; j < kMineQ; ++j) {
-    const int q = tid + j * kMineThreads;
+  for (int j = 0; j < Q; ++j) {
+    const int ql = tid + j * kMineThreads, q = q0 + ql;
     float4 kv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q < n4) {
+    if (ql < n4h && q < n4) {
       kv = k4[q];
       uint32_t m = 0xfu;
       if (p4) {
@@ -869,7 +878,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   if (a.fuse && !small_g) {
     // many truths: replay the forced assignment through global memory first (box_utils.py:123-130)
     const unsigned long long* best = a.gt_best + (size_t)b * a.gpad;
-    for (int j = tid; j < G; j += kMineThreads) {
+    for (int j = tid; j < G && rank == 0; j += kMineThreads) {
       const uint32_t pj = ~(uint32_t)(__ldcg(&best[j]) & 0xffffffffull);
       bool winner = pj < (uint32_t)P;
       for (int j2 = j + 1; winner && j2 < G; ++j2)
@@ -879,19 +888,20 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
         a.tidx_w[off + pj] = (int16_t)j;
       }
     }
-    __syncthreads();
+    if (CL > 1) __threadfence();
+    sync_all();
   }
 #pragma unroll
-  for (int j = 0; j < kMineQ; ++j) {
-    const int q = tid + j * kMineThreads;
+  for (int j = 0; j < Q; ++j) {
+    const int ql = tid + j * kMineThreads, q = q0 + ql;
     ll[j] = make_short4(0, 0, 0, 0);
-    if (q < n4) ll[j] = l4[q];
+    if (ql < n4h && q < n4) ll[j] = l4[q];
   }
   s_hist[tid] = h0;
   s_hist[1024 + tid] = h1;
   if (small_g && tid < G) s_best[tid] = my_best;
   if (gt_cached && tid < 5 * G) s_gt[tid] = my_gt;
-  __syncthreads();
+  sync_all();          // cluster: the peer's histogram copy is in place before it receives remote updates
 
   PHASE_MARK(1);
   // (2) forced assignment on the shared list: truth j keeps its best prior unless a later truth
@@ -904,8 +914,8 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
         if (~(uint32_t)(s_best[j2] & 0xffffffffull) == pj) winner = false;
       if (winner) {
         const int lb = a.binarize ? 1 : (int)(s_gt[tid * 5 + 4] + 1.0f);
-        a.lab_w[off + pj] = (int16_t)lb;
-        a.tidx_w[off + pj] = (int16_t)tid;
+        if (rank == 0) a.lab_w[off + pj] = (int16_t)lb;
+        a.tidx_w[off + pj] = (int16_t)tid;      // every CTA of the cluster: its positives read it back below
         const int slot = atomicAdd(&s_nforce, 1);
         s_force[2 * slot] = pj;
         s_force[2 * slot + 1] = (uint32_t)lb;
@@ -915,12 +925,12 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
     const int nf = s_nforce;
     for (int f = 0; f < nf; ++f) {
       const uint32_t pj = s_force[2 * f];
-      const uint32_t q = pj >> 2;
-      if ((q & (kMineThreads - 1)) == (uint32_t)tid) {
+      const int ql = (int)(pj >> 2) - q0;
+      if (ql >= 0 && ql < n4h && (ql & (kMineThreads - 1)) == tid) {
         const int16_t lb = (int16_t)s_force[2 * f + 1];
-        const int j = (int)(q / kMineThreads), e = (int)(pj & 3u);
+        const int j = ql / kMineThreads, e = (int)(pj & 3u);
 #pragma unroll
-        for (int jj = 0; jj < kMineQ; ++jj)
+        for (int jj = 0; jj < Q; ++jj)
           if (jj == j) {
             if (e == 0) ll[jj].x = lb;
             else if (e == 1) ll[jj].y = lb;
@@ -936,10 +946,11 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   // compacted into s_list in a fixed (thread-major) order
   int mypos = 0;
   const uint32_t zero_ord = f2ord(0.0f);
+  const uint32_t rhist = CL > 1 ? peer_smem(s_hist, (uint32_t)(rank ^ 1)) : 0u;
 #pragma unroll
-  for (int j = 0; j < kMineQ; ++j) {
-    const int q = tid + j * kMineThreads;
-    if (a.dbg_keys && q < n4)
+  for (int j = 0; j < Q; ++j) {
+    const int ql = tid + j * kMineThreads, q = q0 + ql;
+    if (a.dbg_keys && ql < n4h && q < n4)
       *reinterpret_cast<float4*>(a.dbg_keys + off + (size_t)q * 4) =
           make_float4(ord2f(uk[j][0]), ord2f(uk[j][1]), ord2f(uk[j][2]), ord2f(uk[j][3]));
     const int lb[4] = {ll[j].x, ll[j].y, ll[j].z, ll[j].w};
@@ -952,6 +963,10 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
           ++mypos;
           atomicSub(&s_hist[u >> 21], 1u);
           atomicAdd(&s_hist[zero_ord >> 21], 1u);
+          if (CL > 1) {
+            peer_red_add(rhist + (u >> 21) * 4u, 0xffffffffu);
+            peer_red_add(rhist + (zero_ord >> 21) * 4u, 1u);
+          }
           u = zero_ord;
         }
       }
@@ -962,12 +977,17 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   int slot = block_exclusive_scan(mypos, s_iscr, &npos_blk);
   if (mypos) {
 #pragma unroll
-    for (int j = 0; j < kMineQ; ++j) {
+    for (int j = 0; j < Q; ++j) {
       const int lb[4] = {ll[j].x, ll[j].y, ll[j].z, ll[j].w};
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        if (((poolmask >> (4 * j + e)) & 1u) && lb[e] > 0) s_list[slot++] = (uint32_t)((tid + j * kMineThreads) * 4 + e) | ((uint32_t)lb[e] << 16);
+        if (((poolmask >> (4 * j + e)) & 1u) && lb[e] > 0)
+          s_list[slot++] = (uint32_t)((q0 + tid + j * kMineThreads) * 4 + e) | ((uint32_t)lb[e] << 16);
     }
+  }
+  if (CL > 1 && tid == 0) {       // positives of this CTA -> both CTAs of the cluster
+    s_xch[rank] = (uint32_t)npos_blk;
+    peer_st_u32(peer_smem(&s_xch[rank], (uint32_t)(rank ^ 1)), (uint32_t)npos_blk);
   }
   __syncthreads();
 
@@ -995,10 +1015,15 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   }
   double dummy = 0.0;
   block_sum3(dummy, ce, l1, s_dscr);
+  int npos_img = npos_blk;
+  if (CL > 1) {
+    cluster_sync_all();           // remote histogram updates and positive counts have landed
+    npos_img = (int)(s_xch[0] + s_xch[1]);
+  }
 
   PHASE_MARK(4);
   // multibox_loss.py:101-102  num_neg = clamp(ratio * num_pos, max = P - 1)
-  long long kk64 = (long long)a.negpos_ratio * npos_blk;
+  long long kk64 = (long long)a.negpos_ratio * npos_img;
   if (kk64 > P - 1) kk64 = P - 1;
   const int K = (int)kk64;
 
@@ -1018,15 +1043,18 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
       } else {
         s_hist[tid] = 0u;
         s_hist[1024 + tid] = 0u;
-        __syncthreads();
+        sync_all();
 #pragma unroll
-        for (int j = 0; j < kMineQ; ++j)
+        for (int j = 0; j < Q; ++j)
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             uint32_t u = uk[j][e];
-            if (u && (int)(u >> 21) == d1) atomicAdd(&s_hist[(u >> 10) & 2047u], 1u);
+            if (u && (int)(u >> 21) == d1) {
+              atomicAdd(&s_hist[(u >> 10) & 2047u], 1u);
+              if (CL > 1) peer_red_add(rhist + ((u >> 10) & 2047u) * 4u, 1u);
+            }
           }
-        __syncthreads();
+        sync_all();
         int d2 = reg_find(s_hist, 2048, K2, s_iscr, s_res, &above);
         int K3 = K2 - above;
         int n2 = (int)s_hist[d2];
@@ -1036,15 +1064,18 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
           Tu = (pre2 << 10) ? (pre2 << 10) : 1u;
         } else {
           s_hist[tid] = 0u;
-          __syncthreads();
+          sync_all();
 #pragma unroll
-          for (int j = 0; j < kMineQ; ++j)
+          for (int j = 0; j < Q; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               uint32_t u = uk[j][e];
-              if (u && (u >> 10) == pre2) atomicAdd(&s_hist[u & 1023u], 1u);
+              if (u && (u >> 10) == pre2) {
+                atomicAdd(&s_hist[u & 1023u], 1u);
+                if (CL > 1) peer_red_add(rhist + (u & 1023u) * 4u, 1u);
+              }
             }
-          __syncthreads();
+          sync_all();
           int d3 = reg_find(s_hist, 1024, K3, s_iscr, s_res, &above);
           int need = K3 - above;
           int n3 = (int)s_hist[d3];
@@ -1053,8 +1084,23 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
           if (need != n3) {
             // ties straddle the cut: equal keys win in ascending prior order (stable descending sort)
             int running = 0;
+            if (CL > 1) {         // the lower half of the priors (CTA 0) ranks first
+              int mine_ties = 0;
 #pragma unroll
-            for (int j = 0; j < kMineQ; ++j) {
+              for (int j = 0; j < Q; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) mine_ties += uk[j][e] == Tu ? 1 : 0;
+              int total_ties;
+              block_exclusive_scan(mine_ties, s_iscr, &total_ties);
+              if (tid == 0) {
+                s_xch[2 + rank] = (uint32_t)total_ties;
+                peer_st_u32(peer_smem(&s_xch[2 + rank], (uint32_t)(rank ^ 1)), (uint32_t)total_ties);
+              }
+              cluster_sync_all();
+              running = rank == 0 ? 0 : (int)s_xch[2];
+            }
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
               int cnt = 0;
 #pragma unroll
               for (int e = 0; e < 4; ++e) cnt += uk[j][e] == Tu ? 1 : 0;
@@ -1081,8 +1127,8 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   // its mining key, recovered exactly from the ordered key
   double ce_neg = 0.0;
 #pragma unroll
-  for (int j = 0; j < kMineQ; ++j) {
-    const int q = tid + j * kMineThreads;
+  for (int j = 0; j < Q; ++j) {
+    const int ql = tid + j * kMineThreads, q = q0 + ql;
     const int lb[4] = {ll[j].x, ll[j].y, ll[j].z, ll[j].w};
     int16_t so[4];
     unsigned char ng[4];
@@ -1096,7 +1142,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
       so[e] = is_pos ? (int16_t)lb[e] : (negsel ? (int16_t)0 : (int16_t)-1);
       ng[e] = negsel ? 1 : 0;
     }
-    if (q < n4) {
+    if (ql < n4h && q < n4) {
       *reinterpret_cast<short4*>(a.sel + off + (size_t)q * 4) = make_short4(so[0], so[1], so[2], so[3]);
       if (a.dbg_neg) *reinterpret_cast<uchar4*>(a.dbg_neg + off + (size_t)q * 4) = make_uchar4(ng[0], ng[1], ng[2], ng[3]);
     }
@@ -1106,9 +1152,9 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   PHASE_MARK(7);
 
   if (tid == 0) {
-    a.partial[(size_t)b * 3 + 0] = l1;
-    a.partial[(size_t)b * 3 + 1] = ce + ce_neg;
-    a.partial[(size_t)b * 3 + 2] = (double)npos_blk;
+    a.partial[(size_t)blockIdx.x * 3 + 0] = l1;
+    a.partial[(size_t)blockIdx.x * 3 + 1] = ce + ce_neg;
+    a.partial[(size_t)blockIdx.x * 3 + 2] = (double)npos_blk;
     __threadfence();
     unsigned t = atomicAdd(a.ticket, 1u);
     s_last = (t == gridDim.x - 1);
@@ -1116,7 +1162,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  fold_partials(a, s_dscr);
+  fold_partials(a, s_dscr, (int)gridDim.x);
   PHASE_MARK(8);
 }
 
@@ -1338,7 +1384,7 @@ extern "C" int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const 
   w.keys = c.take<float>((size_t)B * P);
   w.ukey = c.take<uint32_t>((size_t)B * P);
   w.hist = c.take<uint32_t>((size_t)B * kHistBins);
-  w.partial = c.take<double>((size_t)B * 3);
+  w.partial = c.take<double>((size_t)B * 6);     // {l1, ce, npos} per mining CTA (two per image when clustered)
   w.ticket = c.take<uint32_t>(2);      // [0] mine_reduce ticket, [1] next matching unit
 
   w.lse = c.take<float>((size_t)B * P);
@@ -1412,12 +1458,36 @@ extern "C" int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const 
   const bool vec4 = (P % 4 == 0) && aligned16(sel) && (!pool || (reinterpret_cast<uintptr_t>(pool) & 3u) == 0) &&
                     (!dbg_neg || (reinterpret_cast<uintptr_t>(dbg_neg) & 3u) == 0) && (!dbg_keys || aligned16(dbg_keys));
   void (*mkern)(MineArgs) = vec4 ? mine_reduce_kernel<4> : mine_reduce_kernel<1>;
+  bool launched = false;
   if (vec4 && P <= 4 * kMineQ * kMineThreads && !(cfg->flags & SSDBOX_LOSS_GENERIC_MINE)) {
-    mkern = mine_reduce_reg_kernel;     // keys and class targets stay in registers
+    // keys and class targets stay in registers; images with many priors are split over a cluster of
+    // two CTAs (two SMs pull the image's keys, histograms merged through distributed shared memory)
+    const bool pair = P >= 8192 && !(cfg->flags & SSDBOX_LOSS_NO_CLUSTER);
+    mkern = pair ? mine_reduce_reg_kernel<2> : mine_reduce_reg_kernel<1>;
     smem = kMineFixedSmem + (size_t)kForceListMax * 16 + (size_t)(5 * kForceListMax + 8) * 4 + (size_t)P * 4;
+    if (pair) {
+      SSDBOX_CUDA(cudaFuncSetAttribute(mkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3(2 * B);
+      lc.blockDim = dim3(kMineThreads);
+      lc.dynamicSmemBytes = smem;
+      lc.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      lc.attrs = at;
+      lc.numAttrs = 1;
+      {
+        TimerScope ts__(KID_MINE, st);
+        SSDBOX_CUDA(cudaLaunchKernelEx(&lc, mkern, m));
+      }
+      launched = true;
+    }
   }
-  SSDBOX_CUDA(cudaFuncSetAttribute(mkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  {
+  if (!launched) {
+    SSDBOX_CUDA(cudaFuncSetAttribute(mkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TimerScope ts__(KID_MINE, st);
     mkern<<<B, kMineThreads, smem, st>>>(m);
   }

@@ -39,13 +39,13 @@ struct LossWs {
   float* lse;         // [B,P]
   uint32_t* hist;     // [B, kHistBins]
   uint32_t* ukey;     // [B,P]  ordered mining keys (only used when they do not fit in smem)
-  double* partial;    // [B,3]
+  double* partial;    // [2B,3]
   uint32_t* ticket;   // [1]
 };
 static inline size_t loss_ws_bytes(int B, int P, int C, int gmax) {
   (void)C;
   return match_core_bytes(B, gmax) + align_up((size_t)B * P * 2) + align_up((size_t)B * P * 4) * 3 +
-         align_up((size_t)B * kHistBins * 4) + align_up((size_t)B * 3 * 8) + 256;
+         align_up((size_t)B * kHistBins * 4) + align_up((size_t)B * 6 * 8) + 256;
 }
 
 // ---- mining in isolation ---------------------------------------------------------------------

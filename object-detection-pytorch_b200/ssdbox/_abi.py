@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libssdbox.so")
 OK, EINVAL, ESHAPE, EALIGN, EWORKSPACE, ECUDA = 0, -1, -2, -3, -4, -5
 LOSS_SEPARATE_MATCH = 1
 LOSS_GENERIC_MINE = 2
+LOSS_NO_CLUSTER = 4
 OP_MATCH, OP_LOSS_FWD, OP_DETECT, OP_NMS, OP_LSE, OP_MINE = 1, 2, 3, 4, 5, 6
 MAX_LAYERS, MAX_MIN_SIZES, MAX_RATIOS = 16, 4, 6
 

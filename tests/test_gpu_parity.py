@@ -333,7 +333,8 @@ def test_fused_and_separate_matching_agree(dev, name, B, seed):
     tg[0] = torch.cat([tg[0], tg[0][:1] * torch.tensor([1, 1, 1, 1, 0.0]) + torch.tensor([0, 0, 0, 0, 5.0])], 0)
     tg[1] = torch.zeros(0, 5)
     res = []
-    for flags in (0, _abi.LOSS_SEPARATE_MATCH, _abi.LOSS_GENERIC_MINE, _abi.LOSS_SEPARATE_MATCH | _abi.LOSS_GENERIC_MINE):
+    for flags in (0, _abi.LOSS_SEPARATE_MATCH, _abi.LOSS_GENERIC_MINE, _abi.LOSS_NO_CLUSTER,
+                  _abi.LOSS_SEPARATE_MATCH | _abi.LOSS_GENERIC_MINE):
         crit = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False)
         crit.abi_flags = flags
         res.append(crit.intermediates((x["loc"].to(dev), x["conf"].to(dev), x["priors"].to(dev)), _gpu_targets(tg, dev)))
@@ -362,7 +363,7 @@ def test_loss_many_truths_and_tied_keys(dev):
     conf = synth.gen_train_logits(B, P, C, 11)
     r = O.multibox_loss(loc, conf, pri, tg, C, detail=True)
     res = []
-    for flags in (0, _abi.LOSS_GENERIC_MINE, _abi.LOSS_SEPARATE_MATCH):
+    for flags in (0, _abi.LOSS_GENERIC_MINE, _abi.LOSS_SEPARATE_MATCH, _abi.LOSS_NO_CLUSTER):
         crit = ssdbox.MultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False)
         crit.abi_flags = flags
         d = crit.intermediates((loc.to(dev), conf.to(dev), pri.to(dev)), _gpu_targets(tg, dev))
@@ -377,12 +378,13 @@ def test_loss_many_truths_and_tied_keys(dev):
     tg = synth.gen_targets(B, C, 6, 12)
     flat = torch.zeros(B, P, C)
     res = []
-    for flags in (0, _abi.LOSS_GENERIC_MINE):
+    for flags in (0, _abi.LOSS_GENERIC_MINE, _abi.LOSS_NO_CLUSTER):
         crit = ssdbox.MultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False)
         crit.abi_flags = flags
         res.append(crit.intermediates((loc.to(dev), flat.to(dev), pri.to(dev)), _gpu_targets(tg, dev)))
-    for k in ("conf_t", "neg", "sel", "sums"):
-        assert torch.equal(res[0][k], res[1][k]), k
+    for other in res[1:]:
+        for k in ("conf_t", "neg", "sel", "sums"):
+            assert torch.equal(res[0][k], other[k]), k
     d = res[0]
     pos = d["conf_t"].cpu() > 0
     neg = d["neg"].cpu().bool()
