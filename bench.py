@@ -300,6 +300,33 @@ def main():
     bwd_us = 1e3 * kb["loss_bwd"][0] / max(kb["loss_bwd"][1], 1)
     del loc_g, conf_g
 
+    # SURVEY 8f rank 2 (reported beside the headline): DetectOut on raw logits with the softmax fused
+    # into the candidate pass, against torch.softmax + the plain DetectOut of the step
+    det_lg = ssdbox.DetectOut(C, 0, top_k, 0.01, 0.45, VAR, conf_is_logits=True)
+    lg = torch.log(sc.clamp_min(1e-30))          # logits whose softmax is the step's score tensor
+    with torch.no_grad():
+        det_lg.forward(loc, lg, priors, out=det_out)
+        torch.cuda.synchronize()
+        _abi.timers_enable(True)
+        for _ in range(5):
+            det_lg.forward(loc, lg, priors, out=det_out)
+        torch.cuda.synchronize()
+        kl = _abi.timers_read()
+        _abi.timers_enable(False)
+        fused_us = sum(1e3 * kl[k][0] / kl[k][1] for k in ("init", "detect_stream", "detect_segment", "detect_segment_big", "detect_overflow") if kl[k][1])
+        fused_stream_us = 1e3 * kl["detect_stream"][0] / max(kl["detect_stream"][1], 1)
+        fused_dets = int((det_out[..., 0] > 0).sum())
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        sm_out = torch.empty_like(lg)
+        torch.softmax(lg, -1, out=sm_out)
+        ev[0].record()
+        for _ in range(5):
+            torch.softmax(lg, -1, out=sm_out)
+        ev[1].record()
+        torch.cuda.synchronize()
+        softmax_us = 1e3 * ev[0].elapsed_time(ev[1]) / 5
+    del lg, sm_out
+
     log("per-kernel timers done")
     # ---- the timed region: K replays of the captured step (or eager launches) -------------------
     use_graph = not args.no_graph
@@ -434,6 +461,10 @@ def main():
                       "hbm_frac": P * (4 * C + 16) * B / (bwd_us * 1e-6) / 1e9 / peak if bwd_us else None},
         "detect": {"kernel_us_sum": d_us, "bytes_per_image": bytes_D(P, C, top_k),
                    "hbm_frac_of_kernel_sum": bytes_D(P, C, top_k) * B / (d_us * 1e-6) / 1e9 / peak if d_us else None},
+        "detect_fused_softmax": {"note": "DetectOut(conf_is_logits=True): softmax of ssd_v3.py:123-124 fused into the candidate pass (SURVEY 8f rank 2), same detections",
+                                 "kernel_us_sum": fused_us, "detect_stream_us": fused_stream_us, "detections": fused_dets,
+                                 "unfused_us": softmax_us + d_us, "torch_softmax_us": softmax_us,
+                                 "hbm_frac_of_kernel_sum": bytes_D(P, C, top_k) * B / (fused_us * 1e-6) / 1e9 / peak if fused_us else None},
         "step_hbm_frac": (bytes_T(P, C, g_avg, B) + bytes_D(P, C, top_k)) * B / (ms_per_step * 1e-3) / 1e9 / peak,
         other + "_kernel": {"avg_launch_us": kernels_us.get(other), "achieved_GBps": dom_bytes / (kernels_us[other] * 1e-6) / 1e9 if other in kernels_us else None,
                             "traffic": traffic.get(other)},

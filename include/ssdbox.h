@@ -254,7 +254,16 @@ typedef struct {
   float conf_thresh, nms_thresh;
   float var0, var1;
   int64_t prior_batch_stride;
+  int32_t flags;              /* SSDBOX_DETECT_* bits */
+  int32_t reserved;
 } ssdbox_detect_cfg;
+
+/* `scores` holds RAW LOGITS: the softmax every model applies right before DetectOut (ssd_v3.py:
+ * 123-124, rfb_net.py:222-226) is fused into the streaming pass -- score = expf(x - rowmax) /
+ * sum_c expf(x_c - rowmax), computed only for rows that can hold a candidate.  Saves the separate
+ * softmax kernel's read + write of conf (2 x 4*B*P*C bytes).  Scores then agree with
+ * torch.softmax to fp32 rounding (<= 1e-6 relative) instead of bit for bit. */
+#define SSDBOX_DETECT_LOGITS 1
 
 SSDBOX_API int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, const float* scores,
                   const float* priors, const uint8_t* score_keep, float* out, int32_t* counts, void* ws,

@@ -33,6 +33,8 @@ struct DetStreamArgs {
   int P;
   int cap;
   float thr;
+  float* row_m;             // [B*P] logits mode: row maximum ...
+  float* row_s;             // [B*P] ... and sum_c expf(x_c - max) of rows that can hold a candidate, else 0
 };
 
 // One (row, class) score above the threshold (rare: ~5e-4 of the elements with a trained detector).
@@ -49,7 +51,12 @@ __device__ __forceinline__ void emit_candidate(const DetStreamArgs& a, int C, ui
 // Consumer: one thread per prior row computes the maximum over the foreground classes (conflict-
 // free LDS, 4 independent FMNMX chains); rows with a hit (a few per cent) are then re-scanned by
 // the whole warp, lane = class, so the per-hit work never serialises a warp over 80 classes.
-template <int CT>
+// LOGITS: the rows are raw class logits.  Every row pays one cheap softmax denominator (ex2.approx,
+// like the loss kernel) to decide conservatively whether any foreground class can exceed the
+// threshold; rows that can are re-scanned by the whole warp with expf and a correctly rounded division.
+constexpr float kDetLog2e = 1.4426950408889634f;
+
+template <int CT, bool LOGITS>
 __global__ void __launch_bounds__(kRingThreads, 1) detect_stream_kernel(DetStreamArgs a) {
   extern __shared__ __align__(128) unsigned char smem_ring[];
   RingCtx rc = ring_setup(a.ring, smem_ring);
@@ -72,19 +79,48 @@ __global__ void __launch_bounds__(kRingThreads, 1) detect_stream_kernel(DetStrea
     const float* st = rc.stages + (size_t)s * rc.stage_floats;
     const float* rp = st + (size_t)r * C;
     mbar_wait(&rc.full[j], (uint32_t)(ph & 1));
-    float m = -INFINITY;
+    float m = -INFINITY;        // scores: max over the foreground classes; logits: max over all classes
+    bool hit = false;
     if (valid) {
-      if (CT > 1) {
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (LOGITS) {
+        float mfg = -INFINITY, sum = 0.f;
+        if (CT > 1) {
+          float v[CT > 1 ? CT : 1];
 #pragma unroll
-        for (int c = 1; c < CT; ++c) m4[c & 3] = fmaxf(m4[c & 3], rp[c]);
-        m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          for (int c = 0; c < CT; ++c) v[c] = rp[c];
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int c = 1; c < CT; ++c) m4[c & 3] = fmaxf(m4[c & 3], v[c]);
+          mfg = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          m = fmaxf(mfg, v[0]);
+          const float nml = -m * kDetLog2e;
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < CT; ++c) s4[c & 3] += ex2_approx(fmaf(v[c], kDetLog2e, nml));
+          sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        } else {
+          for (int c = 1; c < C; ++c) mfg = fmaxf(mfg, rp[c]);
+          m = fmaxf(mfg, rp[0]);
+          const float nml = -m * kDetLog2e;
+          for (int c = 0; c < C; ++c) sum += ex2_approx(fmaf(rp[c], kDetLog2e, nml));
+        }
+        // conservative: the approximate ratio is within ~1e-5 of the exact one
+        hit = kept ? ex2_approx((mfg - m) * kDetLog2e) > thr * sum * 0.9999f : 0.0f > thr;
+        if (!hit) a.row_s[row] = 0.0f;
       } else {
-        for (int c = 1; c < C; ++c) m = fmaxf(m, rp[c]);
+        if (CT > 1) {
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int c = 1; c < CT; ++c) m4[c & 3] = fmaxf(m4[c & 3], rp[c]);
+          m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        } else {
+          for (int c = 1; c < C; ++c) m = fmaxf(m, rp[c]);
+        }
+        if (!kept) m = 0.0f;
+        hit = m > thr;                                     // detection.py:48 strict >
       }
-      if (!kept) m = 0.0f;
     }
-    uint32_t hits = __ballot_sync(SSDBOX_FULL_MASK, valid && m > thr);     // detection.py:48 strict >
+    uint32_t hits = __ballot_sync(SSDBOX_FULL_MASK, valid && hit);
     while (hits) {
       const int src = __ffs(hits) - 1;
       hits &= hits - 1;
@@ -93,9 +129,25 @@ __global__ void __launch_bounds__(kRingThreads, 1) detect_stream_kernel(DetStrea
       const uint32_t b = (uint32_t)hrow / (uint32_t)a.P;
       const uint32_t p = (uint32_t)hrow - b * (uint32_t)a.P;
       const float* hp = st + (size_t)(r - lane + src) * C;
-      for (int c = 1 + lane; c < C; c += 32) {
-        float v = hkept ? hp[c] : 0.0f;
-        if (v > thr) emit_candidate(a, C, b, p, c, v);
+      if (LOGITS) {
+        const float hm = __shfl_sync(SSDBOX_FULL_MASK, m, src);
+        float part = 0.f;
+        for (int c = lane; c < C; c += 32) part += expf(hp[c] - hm);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(SSDBOX_FULL_MASK, part, d);
+        if (lane == 0) {
+          a.row_m[hrow] = hm;
+          a.row_s[hrow] = part;
+        }
+        for (int c = 1 + lane; c < C; c += 32) {
+          float v = hkept ? __fdiv_rn(expf(hp[c] - hm), part) : 0.0f;
+          if (v > thr) emit_candidate(a, C, b, p, c, v);
+        }
+      } else {
+        for (int c = 1 + lane; c < C; c += 32) {
+          float v = hkept ? hp[c] : 0.0f;
+          if (v > thr) emit_candidate(a, C, b, p, c, v);
+        }
       }
     }
     __syncwarp();
@@ -184,6 +236,8 @@ struct DetSegArgs {
   uint32_t* big_count; // [1] number of lists with 32 < n <= cap
   int32_t* big_list;   // [B*C]
   uint32_t* scratch;   // [kOverflowSlots, P]
+  const float* row_m;  // logits mode (nullptr otherwise): softmax row max / denominator from the stream pass
+  const float* row_s;
   float* out;
   int32_t* counts;
 };
@@ -350,6 +404,10 @@ __global__ void __launch_bounds__(kOvfThreads, 1) detect_overflow_kernel(DetSegA
     for (int p = tid; p < a.P; p += kOvfThreads) {
       size_t row = (size_t)b * a.P + p;
       float v = a.scores[row * a.C + c];
+      if (a.row_s) {           // logits: the same expression as the candidate pass
+        const float sden = a.row_s[row];
+        v = sden > 0.0f ? __fdiv_rn(expf(v - a.row_m[row]), sden) : 0.0f;
+      }
       if (a.keep && !a.keep[row]) v = 0.0f;
       uk[p] = v > a.conf_thr ? f2ord(v) : 0u;
     }
@@ -458,6 +516,9 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
   int32_t* big_list = cv.take<int32_t>((size_t)B * C);
   unsigned long long* cand = cv.take<unsigned long long>((size_t)B * C * cap);
   uint32_t* scratch = cv.take<uint32_t>((size_t)kOverflowSlots * P);
+  float* row_m = cv.take<float>((size_t)B * P);
+  float* row_s = cv.take<float>((size_t)B * P);
+  const bool logits = (cfg->flags & SSDBOX_DETECT_LOGITS) != 0;
 
   rc = launch_init(nullptr, 0, cnt, (size_t)B * C + 2, nullptr, 0, nullptr, 0, st);
   if (rc) return rc;
@@ -472,9 +533,11 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
     sa.P = P;
     sa.cap = cap;
     sa.thr = cfg->conf_thresh;
-    void (*kern)(DetStreamArgs) = detect_stream_kernel<0>;
-    if (C == 81) kern = detect_stream_kernel<81>;
-    else if (C == 21) kern = detect_stream_kernel<21>;
+    sa.row_m = row_m;
+    sa.row_s = row_s;
+    void (*kern)(DetStreamArgs) = logits ? detect_stream_kernel<0, true> : detect_stream_kernel<0, false>;
+    if (C == 81) kern = logits ? detect_stream_kernel<81, true> : detect_stream_kernel<81, false>;
+    else if (C == 21) kern = logits ? detect_stream_kernel<21, true> : detect_stream_kernel<21, false>;
     SSDBOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa.ring.smem_bytes));
 {
     TimerScope ts__(KID_DET_STREAM, st);
@@ -489,6 +552,7 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
   g.prior_stride = (long long)cfg->prior_batch_stride;
   g.loc = loc; g.scores = scores; g.priors = priors; g.keep = score_keep;
   g.cnt = cnt; g.cand = cand; g.ovf_count = cnt + (size_t)B * C; g.ovf_list = ovf_list; g.big_count = cnt + (size_t)B * C + 1; g.big_list = big_list; g.scratch = scratch; g.out = out; g.counts = counts;
+  g.row_m = logits ? row_m : nullptr; g.row_s = logits ? row_s : nullptr;
   {
     TimerScope ts__(KID_DET_SEGMENT, st);
     int per = kSmallThreads / 32;

@@ -61,10 +61,11 @@ class DetectCfg(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("P", C.c_int32), ("C", C.c_int32), ("top_k", C.c_int32),
         ("conf_thresh", C.c_float), ("nms_thresh", C.c_float), ("var0", C.c_float), ("var1", C.c_float),
-        ("prior_batch_stride", C.c_int64),
+        ("prior_batch_stride", C.c_int64), ("flags", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
+DETECT_LOGITS = 1
 MAX_PEERS = 16
 
 

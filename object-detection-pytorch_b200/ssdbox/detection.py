@@ -1,7 +1,10 @@
 """DetectOut -- drop-in for lib/layers/functions/detection.py:6-64.  Same constructor; call it
 as `detector(loc_data, conf_data, prior_data)` (the reference relies on the legacy
 Function.__call__ -> forward dispatch, evaluate_utils.py:60).  Returns the [B, C, top_k, 5]
-tensor of (score, x1, y1, x2, y2) rows in NMS order, zero padded, on the input's device."""
+tensor of (score, x1, y1, x2, y2) rows in NMS order, zero padded, on the input's device.
+
+`conf_is_logits=True` (extension): conf_data holds the raw class logits and the
+softmax of ssd_v3.py:123-124 / rfb_net.py:222-226 is fused into the candidate pass."""
 import ctypes as C
 
 import torch
@@ -10,7 +13,7 @@ from . import _abi
 
 
 class DetectOut(object):
-    def __init__(self, num_classes, bkg_label, top_k, conf_thresh, nms_thresh, variance):
+    def __init__(self, num_classes, bkg_label, top_k, conf_thresh, nms_thresh, variance, conf_is_logits=False):
         self.num_classes = num_classes
         self.background_label = bkg_label
         self.top_k = top_k
@@ -19,6 +22,7 @@ class DetectOut(object):
             raise ValueError('nms_threshold must be non negative.')
         self.conf_thresh = conf_thresh
         self.variance = variance
+        self.conf_is_logits = bool(conf_is_logits)
         self._ws = _abi.Workspace()
         self.last_counts = None
 
@@ -37,7 +41,7 @@ class DetectOut(object):
         counts = torch.empty(num, self.num_classes, dtype=torch.int32, device=dev)
         cfg = _abi.DetectCfg(num, P, self.num_classes, int(self.top_k), float(self.conf_thresh),
                              float(self.nms_thresh), float(self.variance[0]), float(self.variance[1]),
-                             4 * P if per_image else 0)
+                             4 * P if per_image else 0, _abi.DETECT_LOGITS if self.conf_is_logits else 0, 0)
         ws, n = self._ws.get(_abi.workspace_bytes(_abi.OP_DETECT, num, P, self.num_classes, 0, self.top_k), dev)
         keep = score_keep.to(dev).to(torch.uint8).contiguous() if score_keep is not None else None
         _abi.check(_abi.lib().ssdbox_detect(

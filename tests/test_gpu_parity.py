@@ -528,6 +528,32 @@ def test_detect_dense_overflow_path(dev):
     _compare_detect(out, O.detect(x["loc"], x["scores"], x["priors"], x["C"], top_k=17, conf_thresh=0.05, nms_thresh=0.3), "dense/17")
 
 
+@pytest.mark.parametrize("name,B,seed,bias", [("ssd300_voc", 3, 0, 10.0), ("ssd512_coco", 2, 1, 10.0), ("rfb300_voc", 2, 2, 8.0),
+                                              ("ssd300_voc", 1, 3, 1.0)])
+def test_detect_fused_softmax(dev, name, B, seed, bias):
+    """DetectOut on raw logits with the softmax of ssd_v3.py:123-124 fused into
+    the candidate pass, against the oracle run on torch.softmax(logits).  Scores agree to fp32
+    rounding of the softmax (2e-6 relative, stated here), keep-lists / counts are identical and
+    boxes agree to 1e-5; bias 1.0 drives every class through the dense overflow path."""
+    cfg, c = configs.get(name)
+    pri = U.oracle_priors(name)
+    P, C = pri.size(0), cfg.MODEL.NUM_CLASSES
+    g = torch.Generator().manual_seed(seed + 4000)
+    logits = torch.randn(B, P, C, generator=g)
+    logits[..., 0] += bias
+    loc = synth.gen_loc(B, P, seed)
+    det = ssdbox.DetectOut(C, 0, 200, 0.01, 0.45, VAR, conf_is_logits=True)
+    out = det(loc.to(dev), logits.to(dev), pri.to(dev)).cpu()
+    ref = O.detect(loc, torch.softmax(logits, -1), pri, C)
+    assert torch.equal((out[..., 0] > 0).sum(-1), (ref[..., 0] > 0).sum(-1)), "detections per (image, class)"
+    assert torch.equal(det.last_counts.cpu().long(), (ref[..., 0] > 0).sum(-1))
+    U.assert_close_rel(out[..., 0], ref[..., 0], 2e-6, 0, name + " fused-softmax scores")
+    U.assert_close_rel(out[..., 1:], ref[..., 1:], REL, 1e-6, name + " fused-softmax boxes")
+    # the plain path on the same softmax scores gives the reference's rows bit for bit (control)
+    plain = ssdbox.DetectOut(C, 0, 200, 0.01, 0.45, VAR)(loc.to(dev), torch.softmax(logits, -1).to(dev), pri.to(dev)).cpu()
+    assert torch.equal(plain[..., 0], ref[..., 0])
+
+
 def test_detect_empty_and_uniform(dev):
     pri = U.oracle_priors("refinedet320_voc")
     P, C = pri.size(0), 21
