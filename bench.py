@@ -327,6 +327,24 @@ def main():
         softmax_us = 1e3 * ev[0].elapsed_time(ev[1]) / 5
     del lg, sm_out
 
+    # SURVEY 8f rank 1 (reported beside the headline): detections -> flat [n,7] result rows
+    from ssdbox import evaluate_utils as EU
+    extra_hw = torch.tensor([[480.0, 640.0]] * B, device=dev)
+    img_ids = torch.arange(B, dtype=torch.float32, device=dev)
+    with torch.no_grad():
+        det.forward(loc, sc, priors, out=det_out)
+        EU.coco_result_rows(det_out, extra_hw, img_ids, sync=False)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(10):
+            rows_buf, rows_total, _ = EU.coco_result_rows(det_out, extra_hw, img_ids, sync=False)
+        ev[1].record()
+        torch.cuda.synchronize()
+        evalpost_us = 1e3 * ev[0].elapsed_time(ev[1]) / 10
+        evalpost_rows = int(rows_total)
+    del rows_buf
+
     log("per-kernel timers done")
     # ---- the timed region: K replays of the captured step (or eager launches) -------------------
     use_graph = not args.no_graph
@@ -465,6 +483,8 @@ def main():
                                  "kernel_us_sum": fused_us, "detect_stream_us": fused_stream_us, "detections": fused_dets,
                                  "unfused_us": softmax_us + d_us, "torch_softmax_us": softmax_us,
                                  "hbm_frac_of_kernel_sum": bytes_D(P, C, top_k) * B / (fused_us * 1e-6) / 1e9 / peak if fused_us else None},
+        "eval_post": {"note": "ssdbox_detections_compact after DetectOut: rescale + convert_ssd_result + COCO post_proc (evaluate_utils.py:63-70,175-203), 2 launches incl. host launch overhead",
+                      "us": evalpost_us, "rows": evalpost_rows, "bytes_read": B * C * top_k * 5 * 4},
         "step_hbm_frac": (bytes_T(P, C, g_avg, B) + bytes_D(P, C, top_k)) * B / (ms_per_step * 1e-3) / 1e9 / peak,
         other + "_kernel": {"avg_launch_us": kernels_us.get(other), "achieved_GBps": dom_bytes / (kernels_us[other] * 1e-6) / 1e9 if other in kernels_us else None,
                             "traffic": traffic.get(other)},

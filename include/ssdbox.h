@@ -60,7 +60,8 @@ enum {
   SSDBOX_OP_DETECT = 3,
   SSDBOX_OP_NMS = 4,
   SSDBOX_OP_LSE = 5,
-  SSDBOX_OP_MINE = 6
+  SSDBOX_OP_MINE = 6,
+  SSDBOX_OP_COMPACT = 7       /* ssdbox_detections_compact: B, C used */
 };
 
 SSDBOX_API int ssdbox_abi_version(void);
@@ -268,6 +269,26 @@ typedef struct {
 SSDBOX_API int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, const float* scores,
                   const float* priors, const uint8_t* score_keep, float* out, int32_t* counts, void* ws,
                   size_t ws_bytes, ssdbox_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Eval post-processing right after DetectOut -- replaces
+ * lib/utils/evaluate_utils.py:63-70 (rescale), :127-139 / :175-190 (convert_ssd_result) and
+ * :193-203 (EvalCOCO.post_proc).
+ *   det        [B,C,K,5] rows (score, x1, y1, x2, y2), e.g. the output of ssdbox_detect
+ *   extra      [B,2] (h, w) of each image, nullable (no rescale)          evaluate_utils.py:63-68
+ *   image_ids  [B] fp32 nullable: dataset ids of the images (COCO modes)   :180
+ *   mode 0  VOC  rows [xmin, ymin, xmax, ymax, score, image, cls]          :127-139
+ *        1  COCO rows [xmin, ymin, xmax, ymax, score, image, cls, cocoid]  :175-190
+ *        2  COCO result rows [cocoid, x1, y1, w, h, score, cls]            :193-199
+ *   out        [capacity_rows, 7 | 8]; rows with score > 0 in (image, class, k) order (the order
+ *              masked_select yields); rows beyond capacity_rows are dropped, *total still counts them
+ *   total      int32[1] number of rows;  seg_offsets int32 [B*C+1] nullable: first row of every
+ *              (image, class) segment (what EvalVOC.post_proc re-derives with numpy masks)
+ * ws: SSDBOX_OP_COMPACT. */
+SSDBOX_API int ssdbox_detections_compact(const float* det, int32_t B, int32_t C, int32_t K, const float* extra,
+                              const float* image_ids, int32_t mode, float* out, int64_t capacity_rows,
+                              int32_t* total, int32_t* seg_offsets, void* ws, size_t ws_bytes,
+                              ssdbox_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * RefineDet glue (not in the reference snapshot; arXiv 1711.06897).

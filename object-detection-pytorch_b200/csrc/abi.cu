@@ -147,6 +147,7 @@ extern "C" size_t ssdbox_workspace_bytes(int op, int B, int P, int C, int gmax, 
     case SSDBOX_OP_NMS: return nms_ws_bytes(P, top_k) + 256;
     case SSDBOX_OP_LSE: return 256;
     case SSDBOX_OP_MINE: return mine_ws_bytes(B, P) + 256;
+    case SSDBOX_OP_COMPACT: return compact_ws_bytes(B, C) + 256;
     default: return 0;
   }
 }

@@ -60,6 +60,11 @@ static inline size_t detect_ws_bytes(int B, int P, int C, int top_k) {
          align_up((size_t)kOverflowSlots * P * 4) + 2 * align_up((size_t)B * P * 4);   // + softmax row max / sum (logits mode)
 }
 
+// ---- eval post-processing (detections -> flat list) -----------------------------------------
+static inline size_t compact_ws_bytes(int B, int C) {
+  return align_up((size_t)B * C * 4) + align_up(((size_t)B * C + 1) * 4) + 256;
+}
+
 // ---- nms -----------------------------------------------------------------------------------
 static inline size_t nms_ws_bytes(int n, int top_k) {
   (void)top_k;

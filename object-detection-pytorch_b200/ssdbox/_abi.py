@@ -17,7 +17,7 @@ OK, EINVAL, ESHAPE, EALIGN, EWORKSPACE, ECUDA = 0, -1, -2, -3, -4, -5
 LOSS_SEPARATE_MATCH = 1
 LOSS_GENERIC_MINE = 2
 LOSS_NO_CLUSTER = 4
-OP_MATCH, OP_LOSS_FWD, OP_DETECT, OP_NMS, OP_LSE, OP_MINE = 1, 2, 3, 4, 5, 6
+OP_MATCH, OP_LOSS_FWD, OP_DETECT, OP_NMS, OP_LSE, OP_MINE, OP_COMPACT = 1, 2, 3, 4, 5, 6, 7
 MAX_LAYERS, MAX_MIN_SIZES, MAX_RATIOS = 16, 4, 6
 
 # every symbol include/ssdbox.h declares (tests check the library exports exactly these)
@@ -27,7 +27,7 @@ SYMBOLS = [
     "ssdbox_decode", "ssdbox_log_sum_exp", "ssdbox_match_encode", "ssdbox_hard_negative_mine",
     "ssdbox_multibox_loss_fwd", "ssdbox_multibox_loss_fwd_peers", "ssdbox_peer_buffer_bytes",
     "ssdbox_multibox_loss_finalize", "ssdbox_multibox_loss_bwd",
-    "ssdbox_nms", "ssdbox_detect", "ssdbox_arm_filter", "ssdbox_timers_enable", "ssdbox_timers_read",
+    "ssdbox_nms", "ssdbox_detect", "ssdbox_detections_compact", "ssdbox_arm_filter", "ssdbox_timers_enable", "ssdbox_timers_read",
 ]
 
 KERNEL_NAMES = ["init", "match", "loss_stream", "mine_reduce", "loss_bwd", "detect_stream", "detect_segment",
@@ -108,6 +108,7 @@ def _declare(lib):
         "ssdbox_nms": [P_, P_, i32, f32, i32, P_, P_, P_, sz, P_],
         "ssdbox_detect": [C.POINTER(DetectCfg), P_, P_, P_, P_, P_, P_, P_, sz, P_],
         "ssdbox_arm_filter": [P_, i64, f32, P_, P_],
+        "ssdbox_detections_compact": [P_, i32, i32, i32, P_, P_, i32, P_, i64, P_, P_, P_, sz, P_],
     }
     sigs["ssdbox_timers_enable"] = [C.c_int]
     sigs["ssdbox_timers_read"] = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]

@@ -133,6 +133,34 @@ def main():
         seeded[key + "_det_counts"] = nz.sum(-1).numpy().astype(np.int16)
         seeded[key + "_det_rows"] = np32(det[nz])
     np.savez_compressed(os.path.join(OUT, "seeded.npz"), **seeded)
+    # ---- eval post-processing after Detect (evaluate_utils.py:63-70,127-139,175-203) -------
+    import importlib
+    import types
+    eu = importlib.import_module("lib.utils.evaluate_utils")
+    g = torch.Generator().manual_seed(17)
+    B, Cn, K = 4, 6, 9
+    det = torch.zeros(B, Cn, K, 5)
+    for b in range(B):
+        for c in range(1, Cn):
+            n = int(torch.randint(0, K + 1, (1,), generator=g))
+            det[b, c, :n, 0] = torch.rand(n, generator=g).sort(descending=True).values * 0.98 + 0.01
+            det[b, c, :n, 1:] = torch.rand(n, 4, generator=g)
+    extra = torch.tensor([[375.0, 500.0], [333.0, 500.0], [480.0, 640.0], [427.0, 640.0]])
+    ids = [139, 285, 632, 724]
+    scaled = det.clone()
+    h = extra[:, 0].unsqueeze(-1).unsqueeze(-1)          # evaluate_utils.py:63-68, verbatim order
+    w = extra[:, 1].unsqueeze(-1).unsqueeze(-1)
+    scaled[:, :, :, 1] *= w
+    scaled[:, :, :, 3] *= w
+    scaled[:, :, :, 2] *= h
+    scaled[:, :, :, 4] *= h
+    voc, _ = eu.EvalVOC.convert_ssd_result(None, scaled.clone(), 0)
+    holder = types.SimpleNamespace(dataset=types.SimpleNamespace(ids=ids), results=[])
+    coco, idt = eu.EvalCOCO.convert_ssd_result(holder, scaled.clone(), 0)
+    eu.EvalCOCO.post_proc(holder, coco.clone(), 0, idt)
+    np.savez_compressed(os.path.join(OUT, "evalpost.npz"), det=np32(det), extra=np32(extra),
+                        ids=np.array(ids, dtype=np.float32), voc=np32(voc), coco=np32(coco),
+                        coco_rows=holder.results[0].astype(np.float32))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

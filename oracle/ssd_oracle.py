@@ -371,3 +371,45 @@ def refine_detect(arm_loc, arm_conf, odm_loc, odm_scores, priors, num_classes, t
     keep = arm_objectness(arm_conf) > theta
     return detect(odm_loc, odm_scores, priors, num_classes, top_k, conf_thresh, nms_thresh,
                   variances, stable=stable, score_mask=keep, anchors_center=cf)
+
+
+# --------------------------------------------------------------------------------------
+# 8f rank 1: eval post-processing after Detect (lib/utils/evaluate_utils.py)
+# --------------------------------------------------------------------------------------
+def rescale_detections(det, extra):
+    """evaluate_utils.py:63-68 on a copy: x *= w, y *= h with extra[:,0]=h, extra[:,1]=w."""
+    det = det.clone()
+    h = extra[:, 0].unsqueeze(-1).unsqueeze(-1)
+    w = extra[:, 1].unsqueeze(-1).unsqueeze(-1)
+    det[:, :, :, 1] *= w
+    det[:, :, :, 3] *= w
+    det[:, :, :, 2] *= h
+    det[:, :, :, 4] *= h
+    return det
+
+
+def convert_ssd_result(det, coco_ids=None):
+    """EvalVOC.convert_ssd_result (:127-139) / EvalCOCO.convert_ssd_result (:175-190): append the image
+    index, the class index (and the coco id), keep rows with score > 0, reorder the columns to
+    xmin, ymin, xmax, ymax, score, image, cls(, cocoid)."""
+    B, C, K = det.shape[:3]
+    idx = torch.arange(0, B).view(B, 1, 1, 1).expand(B, C, K, 1).to(det.dtype)
+    cls = torch.arange(0, C).view(1, C, 1, 1).expand(B, C, K, 1).to(det.dtype)
+    cols = [det, idx, cls]
+    if coco_ids is not None:
+        cid = torch.Tensor(list(coco_ids)).view(B, 1, 1, 1).expand(B, C, K, 1)
+        cols.append(cid)
+    full = torch.cat(cols, 3)
+    n = full.size(3)
+    mask = full[:, :, :, 0].gt(0.).unsqueeze(-1).expand(full.size())
+    flat = torch.masked_select(full, mask).view(-1, n)
+    order = [1, 2, 3, 4, 0, 5, 6] + ([7] if coco_ids is not None else [])
+    return flat[:, order]
+
+
+def coco_post_proc(rows):
+    """EvalCOCO.post_proc (:193-199): x2,y2 -> w,h then cocoid, x1, y1, w, h, score, cls."""
+    rows = rows.clone()
+    rows[:, 2] -= rows[:, 0]
+    rows[:, 3] -= rows[:, 1]
+    return rows[:, [7, 0, 1, 2, 3, 4, 6]]

@@ -678,3 +678,51 @@ def test_full_size_rfb300_detect_b256(dev):
     assert bool((s[..., :-1] >= s[..., 1:]).all())
     sub = [0, 100, 255]
     _compare_detect(out[sub], O.detect(loc[sub], sc[sub], pri, C), "rfb300 b256 subset")
+
+
+# ------------------------------------------------------------------------------------------------
+# 8f rank 1: eval post-processing after Detect (evaluate_utils.py:63-70,127-139,175-203) -- bit-exact
+# ------------------------------------------------------------------------------------------------
+def test_eval_post_processing_golden(dev):
+    from ssdbox import evaluate_utils as EU
+    g = U.golden("evalpost.npz")
+    det, extra, ids = torch.tensor(g["det"]).to(dev), torch.tensor(g["extra"]).to(dev), g["ids"].tolist()
+    keep = det.clone()
+    voc, seg = EU.convert_ssd_result(det, extra)
+    assert torch.equal(det, keep)                                   # the input is not scaled in place
+    assert np.array_equal(voc.cpu().numpy(), g["voc"])
+    coco, _ = EU.convert_ssd_result(det, extra, coco_ids=ids)
+    assert np.array_equal(coco.cpu().numpy(), g["coco"])
+    rows, _ = EU.coco_result_rows(det, extra, coco_ids=ids)
+    assert np.array_equal(rows.cpu().numpy(), g["coco_rows"])
+    # seg = first row of every (image, class) segment: the slices EvalVOC.post_proc cuts (:141-151)
+    seg = seg.cpu().numpy()
+    B, C = det.size(0), det.size(1)
+    vocn = voc.cpu().numpy()
+    for b in range(B):
+        for c in range(C):
+            sl = vocn[seg[b * C + c]:seg[b * C + c + 1]]
+            want = g["voc"][(g["voc"][:, 5] == b) & (g["voc"][:, 6] == c)]
+            assert np.array_equal(sl, want)
+
+
+def test_eval_post_processing_after_detect(dev):
+    """DetectOut -> convert_ssd_result on a full-size batch against the oracle restatement; a tight
+    output capacity truncates the rows but still reports the full count."""
+    from ssdbox import evaluate_utils as EU
+    x = U.seeded_inputs("ssd512_coco", 3, 4)
+    det = ssdbox.DetectOut(x["C"], 0, 200, 0.01, 0.45, VAR)(x["loc"].to(dev), x["scores"].to(dev), x["priors"].to(dev))
+    extra = torch.tensor([[375.0, 500.0], [512.0, 512.0], [480.0, 641.0]])
+    ids = [9, 25, 30]
+    scaled = O.rescale_detections(det.cpu(), extra)
+    voc, seg = EU.convert_ssd_result(det, extra.to(dev))
+    assert torch.equal(voc.cpu(), O.convert_ssd_result(scaled))
+    rows, _ = EU.coco_result_rows(det, extra.to(dev), ids)
+    assert torch.equal(rows.cpu(), O.coco_post_proc(O.convert_ssd_result(scaled, coco_ids=ids)))
+    assert int(seg[-1]) == voc.size(0) == int((det[..., 0] > 0).sum())
+    buf, total, _ = EU.convert_ssd_result(det, extra.to(dev), capacity=10, sync=False)
+    assert int(total) == voc.size(0) and torch.equal(buf.cpu(), voc[:10].cpu())
+    # no rescale, empty detections
+    z = torch.zeros(2, 4, 5, 5, device=dev)
+    e, s0 = EU.convert_ssd_result(z)
+    assert e.shape == (0, 7) and int(s0.abs().sum()) == 0

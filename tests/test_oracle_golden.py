@@ -137,3 +137,15 @@ def test_empty_truth_image_is_all_background():
     pri = U.oracle_priors("refinedet320_voc")
     m = O.match_image(0.5, torch.zeros(0, 4), pri, VAR, torch.zeros(0))
     assert int(m["conf"].abs().sum()) == 0 and float(m["loc"].abs().sum()) == 0.0
+
+
+def test_eval_post_processing_golden():
+    """oracle convert_ssd_result / coco_post_proc against rows recorded from the reference's
+    EvalVOC / EvalCOCO (lib/utils/evaluate_utils.py:63-70,127-139,175-203)."""
+    g = U.golden("evalpost.npz")
+    det, extra = torch.tensor(g["det"]), torch.tensor(g["extra"])
+    scaled = O.rescale_detections(det, extra)
+    assert np.array_equal(O.convert_ssd_result(scaled).numpy(), g["voc"])
+    coco = O.convert_ssd_result(scaled, coco_ids=g["ids"].tolist())
+    assert np.array_equal(coco.numpy(), g["coco"])
+    assert np.array_equal(O.coco_post_proc(coco).numpy(), g["coco_rows"])

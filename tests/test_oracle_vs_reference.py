@@ -151,3 +151,34 @@ print("ok")
 ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_eval_post_processing_bit_exact(ref):
+    """oracle convert_ssd_result / coco_post_proc == the reference's EvalVOC / EvalCOCO methods
+    (lib/utils/evaluate_utils.py:63-68,127-139,175-203), called unbound on a stand-in object."""
+    import importlib
+    import types
+    eu = importlib.import_module("lib.utils.evaluate_utils")
+    g = torch.Generator().manual_seed(3)
+    B, C, K = 3, 5, 7
+    det = torch.zeros(B, C, K, 5)
+    for b in range(B):
+        for c in range(1, C):
+            n = int(torch.randint(0, K + 1, (1,), generator=g))
+            det[b, c, :n, 0] = torch.rand(n, generator=g).sort(descending=True).values * 0.98 + 0.01
+            det[b, c, :n, 1:] = torch.rand(n, 4, generator=g)
+    extra = torch.tensor([[375.0, 500.0], [333.0, 500.0], [480.0, 640.0]])
+    scaled = O.rescale_detections(det, extra)
+    want = det.clone()
+    h = extra[:, 0].unsqueeze(-1).unsqueeze(-1)
+    w = extra[:, 1].unsqueeze(-1).unsqueeze(-1)
+    want[:, :, :, 1] *= w; want[:, :, :, 3] *= w; want[:, :, :, 2] *= h; want[:, :, :, 4] *= h
+    assert torch.equal(scaled, want)
+    rv, _ = eu.EvalVOC.convert_ssd_result(None, scaled.clone(), 0)
+    assert torch.equal(O.convert_ssd_result(scaled), rv)
+    ids = [139, 285, 632]
+    holder = types.SimpleNamespace(dataset=types.SimpleNamespace(ids=ids), results=[])
+    rc, idt = eu.EvalCOCO.convert_ssd_result(holder, scaled.clone(), 0)
+    assert torch.equal(O.convert_ssd_result(scaled, coco_ids=ids), rc)
+    eu.EvalCOCO.post_proc(holder, rc.clone(), 0, idt)
+    assert (holder.results[0] == O.coco_post_proc(rc).numpy()).all()
