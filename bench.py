@@ -262,9 +262,11 @@ def main():
     det_out = torch.empty(B, C, top_k, 5, dtype=torch.float32, device=dev)
 
     def step():
+        # T, then D, then the (multi-GPU) wait for the other ranks' loss sums: D overlaps that wait
         with torch.no_grad():
-            ll, lc = crit.forward_packed(loc, conf, priors, gt, offs, gmax)
+            pending = crit.forward_packed_deferred(loc, conf, priors, gt, offs, gmax)
             out = det.forward(loc, sc, priors, out=det_out)
+            ll, lc = pending.wait()
         return ll, lc, out
 
     log("inputs ready")
@@ -390,8 +392,12 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     elapsed_ms = e0.elapsed_time(e1)
+    rank_ms = [elapsed_ms / args.steps]
     if dist is not None:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        rank_ms = [float(x.item()) / args.steps for x in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
     # keep the GPUs busy a little longer so the clock sampler sees load even for short K; the step
@@ -512,7 +518,8 @@ def main():
                                   % (reps, bt, bd, cores),
                         "train_fwd_images_per_s": reps * bt / tt, "detect_images_per_s": reps * bd / td}
 
-    launches_per_step = 9
+    # T: init, loss_stream, mine_reduce; D: init, detect_stream, segment (warp / CTA), overflow; N > 1: + the collect kernel
+    launches_per_step = 8 + (1 if n_gpus > 1 else 0)
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -523,10 +530,10 @@ def main():
                    "l2": "inputs larger than L2 (conf and scores are %.0f MB each vs 126 MB L2)" % (conf.numel() * 4 / 1e6),
                    "launch": "CUDA graph replay" if graph is not None else "eager launches",
                    "parallelism": ("images sharded by rank; {sum_l, sum_c, N_pos} reduced per step: %s" % (
-                       "inside the mining kernel over NVLink peer memory (no collective launch)" if crit.reduce_used == "p2p"
+                       "posted over NVLink peer memory by the mining kernel, collected by a 1-warp kernel after DetectOut (no NCCL launch)" if crit.reduce_used == "p2p"
                        else "one NCCL all-reduce")) if n_gpus > 1 else "single GPU"},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
-        "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "phases": phases, "sanity": sanity,
+        "gpu_launches": launches_per_step * args.steps, "rank_ms_per_step": rank_ms, "clocks": clocks, "phases": phases, "sanity": sanity,
     }
     print(json.dumps(line), flush=True)
     teardown()

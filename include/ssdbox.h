@@ -180,6 +180,11 @@ typedef struct {
 /* Keep the register-resident mining kernel on one CTA per image (by default images with P >= 8192
  * are split over a thread-block cluster of two CTAs); same results, for testing. */
 #define SSDBOX_LOSS_NO_CLUSTER 4
+/* Peer-reduced calls only: the mining kernel posts this rank's sums to the peers but does not wait
+ * for theirs; `sums` / `losses` hold LOCAL values until ssdbox_multibox_loss_peer_finish runs on
+ * the same stream.  Work enqueued in between (e.g. DetectOut of the same step) overlaps the wait, so
+ * rank skew no longer stalls the step. */
+#define SSDBOX_LOSS_DEFER_PEER_WAIT 8
 
 /* forward.
  *   loc [B,P,4], conf [B,P,C] raw logits, priors, anchors_xyxy (nullable), gt/gt_offsets
@@ -215,6 +220,10 @@ typedef struct {
   void* bufs[SSDBOX_MAX_PEERS];        /* bufs[r]: rank r's exchange buffer as addressable from THIS device */
 } ssdbox_peer_group;
 SSDBOX_API size_t ssdbox_peer_buffer_bytes(void);
+/* completes a call made with SSDBOX_LOSS_DEFER_PEER_WAIT: waits for every rank's sums, adds them in
+ * rank order, writes the global sums[3] and losses[2] (nullable). */
+SSDBOX_API int ssdbox_multibox_loss_peer_finish(const ssdbox_peer_group* peers, double* sums, float* losses,
+                                     ssdbox_stream_t stream);
 /* ssdbox_multibox_loss_fwd with the reduction above; peers == NULL behaves like the plain call. */
 SSDBOX_API int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const float* loc, const float* conf,
                              const float* priors, const float* anchors_xyxy, const uint8_t* pool,

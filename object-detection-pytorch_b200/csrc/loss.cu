@@ -486,7 +486,7 @@ struct MineArgs {
   uint8_t* dbg_neg;
   float* dbg_keys;
   // multi-GPU: exchange buffers of every rank (world == 0: single GPU)
-  int peer_rank, peer_world;
+  int peer_rank, peer_world, peer_defer;
   void* peer_bufs[SSDBOX_MAX_PEERS];
 };
 
@@ -514,10 +514,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
-// one warp; s[0..2] in shared memory holds this rank's sums on entry and the global sums on exit
-__device__ void peer_exchange(const MineArgs& a, double* s, int lane) {
-  const int world = a.peer_world, me = a.peer_rank;
-  unsigned long long* mine = reinterpret_cast<unsigned long long*>(a.peer_bufs[me]);
+// one warp: this rank's sums -> slot `me` of every rank's buffer (peer stores over NVLink; own buffer
+// for lane == me).  Returns the call epoch (advanced here, kept in the owner's buffer).
+__device__ unsigned long long peer_post(void* const* bufs, int me, int world, double v0, double v1, double v2, int lane) {
+  unsigned long long* mine = reinterpret_cast<unsigned long long*>(bufs[me]);
   unsigned long long epoch = 0;
   if (lane == 0) {
     epoch = mine[0] + 1ull;
@@ -525,19 +525,25 @@ __device__ void peer_exchange(const MineArgs& a, double* s, int lane) {
   }
   epoch = __shfl_sync(SSDBOX_FULL_MASK, epoch, 0);
   const size_t bank = kPeerHeaderBytes + (size_t)(epoch & 1ull) * world * kPeerSlotBytes;
-  const double v0 = s[0], v1 = s[1], v2 = s[2];
-  __syncwarp();
-  double r0 = 0.0, r1 = 0.0, r2 = 0.0;
   if (lane < world) {
-    // my sums -> slot `me` of rank `lane`'s buffer (peer store over NVLink; own buffer for lane == me)
-    char* dst = static_cast<char*>(a.peer_bufs[lane]) + bank + (size_t)me * kPeerSlotBytes;
+    char* dst = static_cast<char*>(bufs[lane]) + bank + (size_t)me * kPeerSlotBytes;
     volatile double* d = reinterpret_cast<volatile double*>(dst);
     d[0] = v0;
     d[1] = v1;
     d[2] = v2;
     st_release_sys(reinterpret_cast<unsigned long long*>(dst + 24), epoch);
-    // rank `lane`'s sums <- slot `lane` of my buffer
-    const char* src = reinterpret_cast<const char*>(mine) + bank + (size_t)lane * kPeerSlotBytes;
+  }
+  return epoch;
+}
+
+// one warp: waits for every rank's slot of call `epoch` in MY buffer and adds them in rank order (the
+// same fp64 result on every rank); result valid in lane 0
+__device__ void peer_collect(void* const* bufs, int me, int world, unsigned long long epoch, int lane, double* out) {
+  const char* mine = static_cast<const char*>(bufs[me]);
+  const size_t bank = kPeerHeaderBytes + (size_t)(epoch & 1ull) * world * kPeerSlotBytes;
+  double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+  if (lane < world) {
+    const char* src = mine + bank + (size_t)lane * kPeerSlotBytes;
     const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(src + 24);
     const long long t0 = clock64();
     while (ld_acquire_sys(flag) != epoch) {
@@ -548,17 +554,53 @@ __device__ void peer_exchange(const MineArgs& a, double* s, int lane) {
     r1 = q[1];
     r2 = q[2];
   }
-  // rank order: the same fp64 result on every rank
   double t0s = 0.0, t1s = 0.0, t2s = 0.0;
   for (int r = 0; r < world; ++r) {
     t0s += __shfl_sync(SSDBOX_FULL_MASK, r0, r);
     t1s += __shfl_sync(SSDBOX_FULL_MASK, r1, r);
     t2s += __shfl_sync(SSDBOX_FULL_MASK, r2, r);
   }
+  out[0] = t0s;
+  out[1] = t1s;
+  out[2] = t2s;
+}
+
+// one warp; s[0..2] in shared memory holds this rank's sums on entry and (unless the wait is
+// deferred to ssdbox_multibox_loss_peer_finish) the global sums on exit
+__device__ void peer_exchange(const MineArgs& a, double* s, int lane) {
+  const double v0 = s[0], v1 = s[1], v2 = s[2];
+  __syncwarp();
+  unsigned long long epoch = peer_post(a.peer_bufs, a.peer_rank, a.peer_world, v0, v1, v2, lane);
+  if (a.peer_defer) return;
+  double g[3];
+  peer_collect(a.peer_bufs, a.peer_rank, a.peer_world, epoch, lane, g);
   if (lane == 0) {
-    s[0] = t0s;
-    s[1] = t1s;
-    s[2] = t2s;
+    s[0] = g[0];
+    s[1] = g[1];
+    s[2] = g[2];
+  }
+}
+
+struct PeerFinishArgs {
+  int rank, world;
+  void* bufs[SSDBOX_MAX_PEERS];
+  double* sums;
+  float* losses;
+};
+
+__global__ void peer_finish_kernel(PeerFinishArgs a) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long epoch = *reinterpret_cast<const unsigned long long*>(a.bufs[a.rank]);   // posted by the forward
+  double g[3];
+  peer_collect(a.bufs, a.rank, a.world, epoch, lane, g);
+  if (lane == 0) {
+    a.sums[0] = g[0];
+    a.sums[1] = g[1];
+    a.sums[2] = g[2];
+    if (a.losses) {
+      a.losses[0] = g[2] > 0.0 ? (float)(g[0] / g[2]) : 0.0f;
+      a.losses[1] = g[2] > 0.0 ? (float)(g[1] / g[2]) : 0.0f;
+    }
   }
 }
 
@@ -1448,6 +1490,7 @@ extern "C" int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const 
   m.partial = w.partial; m.ticket = w.ticket; m.sums = sums; m.losses = losses; m.sel = sel;
   m.dbg_neg = dbg_neg; m.dbg_keys = dbg_keys;
   m.peer_world = 0;
+  m.peer_defer = (cfg->flags & SSDBOX_LOSS_DEFER_PEER_WAIT) ? 1 : 0;
   if (peers) {
     m.peer_rank = peers->rank;
     m.peer_world = peers->world;
@@ -1515,6 +1558,22 @@ extern "C" __attribute__((visibility("default"))) int ssdbox_debug_phases(long l
   return cudaMemcpyFromSymbol(out16, ssdbox::g_phase, sizeof(long long) * 16 * 64) == cudaSuccess ? 0 : -5;
 }
 #endif
+
+extern "C" int ssdbox_multibox_loss_peer_finish(const ssdbox_peer_group* peers, double* sums, float* losses,
+                                               ssdbox_stream_t stream) {
+  SSDBOX_REQUIRE(peers && sums, SSDBOX_EINVAL, "peer_finish: null pointer");
+  SSDBOX_REQUIRE(peers->world >= 1 && peers->world <= SSDBOX_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world,
+                 SSDBOX_EINVAL, "peer_finish: bad peer group");
+  PeerFinishArgs a{};
+  a.rank = peers->rank;
+  a.world = peers->world;
+  for (int r = 0; r < peers->world; ++r) a.bufs[r] = peers->bufs[r];
+  a.sums = sums;
+  a.losses = losses;
+  peer_finish_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  SSDBOX_LAUNCH_OK("peer_finish_kernel");
+  return SSDBOX_OK;
+}
 
 extern "C" int ssdbox_multibox_loss_finalize(const double* sums, float* losses, ssdbox_stream_t stream) {
   SSDBOX_REQUIRE(sums && losses, SSDBOX_EINVAL, "finalize: null pointer");

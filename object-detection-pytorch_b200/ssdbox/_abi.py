@@ -17,6 +17,7 @@ OK, EINVAL, ESHAPE, EALIGN, EWORKSPACE, ECUDA = 0, -1, -2, -3, -4, -5
 LOSS_SEPARATE_MATCH = 1
 LOSS_GENERIC_MINE = 2
 LOSS_NO_CLUSTER = 4
+LOSS_DEFER_PEER_WAIT = 8
 OP_MATCH, OP_LOSS_FWD, OP_DETECT, OP_NMS, OP_LSE, OP_MINE, OP_COMPACT = 1, 2, 3, 4, 5, 6, 7
 MAX_LAYERS, MAX_MIN_SIZES, MAX_RATIOS = 16, 4, 6
 
@@ -25,7 +26,8 @@ SYMBOLS = [
     "ssdbox_abi_version", "ssdbox_last_error", "ssdbox_workspace_bytes", "ssdbox_priorbox_count",
     "ssdbox_priorbox", "ssdbox_point_form", "ssdbox_center_form", "ssdbox_jaccard", "ssdbox_encode",
     "ssdbox_decode", "ssdbox_log_sum_exp", "ssdbox_match_encode", "ssdbox_hard_negative_mine",
-    "ssdbox_multibox_loss_fwd", "ssdbox_multibox_loss_fwd_peers", "ssdbox_peer_buffer_bytes",
+    "ssdbox_multibox_loss_fwd", "ssdbox_multibox_loss_fwd_peers", "ssdbox_multibox_loss_peer_finish",
+    "ssdbox_peer_buffer_bytes",
     "ssdbox_multibox_loss_finalize", "ssdbox_multibox_loss_bwd",
     "ssdbox_nms", "ssdbox_detect", "ssdbox_detections_compact", "ssdbox_arm_filter", "ssdbox_timers_enable", "ssdbox_timers_read",
 ]
@@ -104,6 +106,7 @@ def _declare(lib):
         "ssdbox_multibox_loss_fwd": [C.POINTER(LossCfg)] + [P_] * 15 + [P_, sz, P_],
         "ssdbox_multibox_loss_fwd_peers": [C.POINTER(LossCfg)] + [P_] * 15 + [C.POINTER(PeerGroup), P_, sz, P_],
         "ssdbox_multibox_loss_finalize": [P_, P_, P_],
+        "ssdbox_multibox_loss_peer_finish": [C.POINTER(PeerGroup), P_, P_, P_],
         "ssdbox_multibox_loss_bwd": [C.POINTER(LossCfg)] + [P_] * 11 + [P_],
         "ssdbox_nms": [P_, P_, i32, f32, i32, P_, P_, P_, sz, P_],
         "ssdbox_detect": [C.POINTER(DetectCfg), P_, P_, P_, P_, P_, P_, P_, sz, P_],

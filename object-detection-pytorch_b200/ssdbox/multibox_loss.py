@@ -127,6 +127,23 @@ class _MultiBoxLossFn(torch.autograd.Function):
         return grad_loc, grad_conf, None, None, None, None, None, None, None
 
 
+class PendingLoss(object):
+    """Result of MultiBoxLoss.forward_packed_deferred: wait() enqueues ssdbox_multibox_loss_peer_finish
+    on the current stream and returns (loss_l, loss_c) of the GLOBAL batch."""
+
+    def __init__(self, peers, sums, losses, ready):
+        self._peers, self._sums, self._losses, self._ready = peers, sums, losses, ready
+
+    def wait(self):
+        if self._ready is None:
+            _abi.check(_abi.lib().ssdbox_multibox_loss_peer_finish(
+                C.byref(self._peers), _abi.ptr(self._sums), _abi.ptr(self._losses),
+                _abi.stream_ptr(self._losses.device)))
+            out = self._losses.clone()
+            self._ready = (out[0], out[1])
+        return self._ready
+
+
 class MultiBoxLoss(nn.Module):
     """SSD weighted loss (multibox_loss.py:10-46).  Arguments as in the reference; as there,
     prior_for_matching / bkg_label / neg_mining / neg_overlap / encode_target are stored but
@@ -219,6 +236,27 @@ class MultiBoxLoss(nn.Module):
     def forward_packed(self, loc, conf, priors, gt, offsets, gmax, anchors_xyxy=None, pool=None):
         """Same as forward with the targets already in the C-ABI layout (no host work: capturable)."""
         return _MultiBoxLossFn.apply(loc, conf, priors, gt, offsets, anchors_xyxy, pool, self, int(gmax))
+
+    def forward_packed_deferred(self, loc, conf, priors, gt, offsets, gmax):
+        """Inference-style (no autograd) forward whose cross-rank wait is deferred: returns a
+        PendingLoss; kernels enqueued before `pending.wait()` (e.g. DetectOut of the same step) overlap
+        the wait for the other ranks' sums, so rank skew does not stall the step.  Without the
+        peer-memory reduction (single GPU, reduce='nccl') it simply runs the normal forward."""
+        with torch.no_grad():
+            distributed = self._is_distributed()
+            if getattr(self, "_force_peers", False):
+                peers = self._peers.group
+            else:
+                peers = self._peer_group(loc.device) if distributed else None
+            if peers is None:
+                ll, lc = self.forward_packed(loc, conf, priors, gt, offsets, gmax)
+                return PendingLoss(None, None, None, (ll, lc))
+            cfg, sums, losses, sel, tidx = loss_forward_raw(
+                self._state, loc, conf, priors, gt, offsets, gmax, self.num_classes, self.threshold,
+                self.negpos_ratio, self.variance, None, None, self.binarize_labels, finalize=True,
+                debug=None, fresh=False, flags=self.abi_flags | _abi.LOSS_DEFER_PEER_WAIT, peers=peers)
+            self._last = (sums, sel, tidx)
+            return PendingLoss(peers, sums, losses, None)
 
     def intermediates(self, predictions, targets):
         """Runs the forward and also materialises the reference's intermediates

@@ -48,6 +48,17 @@ def main():
         assert abs(ll - float(fl)) <= 1e-6 * abs(float(fl)) and abs(lc - float(fc)) <= 1e-6 * abs(float(fc)), (mode, ll, lc, float(fl), float(fc))
         U.assert_close_rel(gl, lo.grad[b:e], 1e-5, 1e-8, mode + " grad_loc shard")
         U.assert_close_rel(gc, co.grad[b:e], 1e-5, 1e-8, mode + " grad_conf shard")
+    # deferred wait: post in the mining kernel, other work, then collect -- same global losses
+    from ssdbox import synth
+    crit = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False, distributed=True, reduce="p2p")
+    gt, offs = synth.pack_targets(tg)
+    gmax = max(int(t.size(0)) for t in tg)
+    for it in range(3):
+        pend = crit.forward_packed_deferred(loc.to(dev), conf.to(dev), pri, gt.to(dev), offs.to(dev), gmax)
+        _ = torch.zeros(1 << 20, device=dev).sum()          # unrelated work between post and collect
+        dl, dc = pend.wait()
+    assert abs(float(dl) - res["p2p"][0]) <= 1e-7 * abs(res["p2p"][0]) and abs(float(dc) - res["p2p"][1]) <= 1e-7 * abs(res["p2p"][1])
+    assert torch.equal(crit._last[0], res["p2p"][2])
     # every rank holds bit-identical global sums (rank-ordered fp64 adds)
     mine = res["p2p"][2]
     allv = [torch.empty_like(mine) for _ in range(world)]

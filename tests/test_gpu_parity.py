@@ -426,6 +426,11 @@ def test_peer_exchange_single_rank(dev):
         torch.cuda.synchronize()
     assert float(ll) == float(a["loss_l"]) and float(lc) == float(a["loss_c"])
     assert int(crit._peers.buf[0]) == 7
+    # deferred wait (post in the mining kernel, collect in ssdbox_multibox_loss_peer_finish)
+    pend = crit.forward_packed_deferred(loc, conf, pri, gt, offs, gmax)
+    dl, dc = pend.wait()
+    assert float(dl) == float(a["loss_l"]) and float(dc) == float(a["loss_c"]) and int(crit._peers.buf[0]) == 8
+    assert torch.equal(crit._last[0], a["sums"])
 
 
 def test_cuda_graph_capture(dev):
