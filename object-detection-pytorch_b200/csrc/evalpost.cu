@@ -15,7 +15,7 @@
 
 namespace ssdbox {
 
-constexpr int kCompactThreads = 256;
+constexpr int kCompactThreads = 1024;
 
 struct CompactArgs {
   const float* det;       // [B,C,K,5] (score, x1, y1, x2, y2)
