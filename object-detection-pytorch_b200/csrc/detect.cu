@@ -66,11 +66,11 @@ __global__ void __launch_bounds__(kRingThreads, 1) detect_stream_kernel(DetStrea
     ring_produce(a.ring, rc);
     return;
   }
-  const int wg = warp >> 2;
-  const int r = tid & 127;
+  const int wg = warp / kRingGroupWarps;
+  const int r = tid % (32 * kRingGroupWarps);
   const int R = a.ring.R, NS = a.ring.NS;
   const float thr = a.thr;
-  for (int it = wg; it < rc.n_local; it += 2) {
+  for (int it = wg; it < rc.n_local; it += kRingGroups) {
     const int s = it % NS, j = it % (2 * NS), ph = it / (2 * NS);
     const long long row = (rc.t0 + it) * R + r;
     const bool valid = (r < R) && (row < a.ring.rows);

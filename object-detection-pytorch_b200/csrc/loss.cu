@@ -376,9 +376,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) loss_stream_kernel(StreamAr
     if (warp == kFirstMatchWarp + kMatchWarps - 1) SMARK(5);
     return;
   }
-  const int wg = warp >> 2;
-  const int r = tid & 127;
-  for (int it = wg; it < rc.n_local; it += 2) {
+  const int wg = warp / kRingGroupWarps;
+  const int r = tid % (32 * kRingGroupWarps);
+  for (int it = wg; it < rc.n_local; it += kRingGroups) {
     const int s = it % NS, j = it % (2 * NS), ph = it / (2 * NS);
     long long row = (rc.t0 + it) * R + r;
     bool valid = (r < R) && (row < a.ring.rows);
