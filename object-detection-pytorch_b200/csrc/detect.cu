@@ -67,86 +67,90 @@ __global__ void __launch_bounds__(kRingThreads, 1) detect_stream_kernel(DetStrea
     return;
   }
   const int wg = warp / kRingGroupWarps;
-  const int r = tid % (32 * kRingGroupWarps);
+  const int rbase = tid % (32 * kRingGroupWarps);
+  const int KR = a.ring.KR;
   const int R = a.ring.R, NS = a.ring.NS;
   const float thr = a.thr;
   for (int it = wg; it < rc.n_local; it += kRingGroups) {
     const int s = it % NS, j = it % (2 * NS), ph = it / (2 * NS);
-    const long long row = (rc.t0 + it) * R + r;
-    const bool valid = (r < R) && (row < a.ring.rows);
-    bool kept = true;
-    if (valid && a.keep) kept = a.keep[row] != 0;          // RefineDet: filtered anchors score 0
     const float* st = rc.stages + (size_t)s * rc.stage_floats;
-    const float* rp = st + (size_t)r * C;
     mbar_wait(&rc.full[j], (uint32_t)(ph & 1));
-    float m = -INFINITY;        // scores: max over the foreground classes; logits: max over all classes
-    bool hit = false;
-    if (valid) {
-      if (LOGITS) {
-        float mfg = -INFINITY, sum = 0.f;
-        if (CT > 1) {
-          float v[CT > 1 ? CT : 1];
-#pragma unroll
-          for (int c = 0; c < CT; ++c) v[c] = rp[c];
-          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-          for (int c = 1; c < CT; ++c) m4[c & 3] = fmaxf(m4[c & 3], v[c]);
-          mfg = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-          m = fmaxf(mfg, v[0]);
-          const float nml = -m * kDetLog2e;
-          float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int c = 0; c < CT; ++c) s4[c & 3] += ex2_approx(fmaf(v[c], kDetLog2e, nml));
-          sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    for (int k = 0; k < KR; ++k) {
+      const int r = k * (32 * kRingGroupWarps) + rbase;
+      const long long row = (rc.t0 + it) * R + r;
+      const bool valid = (r < R) && (row < a.ring.rows);
+      bool kept = true;
+      if (valid && a.keep) kept = a.keep[row] != 0;          // RefineDet: filtered anchors score 0
+      const float* rp = st + (size_t)r * C;
+      float m = -INFINITY;        // scores: max over the foreground classes; logits: max over all classes
+      bool hit = false;
+      if (valid) {
+        if (LOGITS) {
+          float mfg = -INFINITY, sum = 0.f;
+          if (CT > 1) {
+            float v[CT > 1 ? CT : 1];
+  #pragma unroll
+            for (int c = 0; c < CT; ++c) v[c] = rp[c];
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  #pragma unroll
+            for (int c = 1; c < CT; ++c) m4[c & 3] = fmaxf(m4[c & 3], v[c]);
+            mfg = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            m = fmaxf(mfg, v[0]);
+            const float nml = -m * kDetLog2e;
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
+  #pragma unroll
+            for (int c = 0; c < CT; ++c) s4[c & 3] += ex2_approx(fmaf(v[c], kDetLog2e, nml));
+            sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+          } else {
+            for (int c = 1; c < C; ++c) mfg = fmaxf(mfg, rp[c]);
+            m = fmaxf(mfg, rp[0]);
+            const float nml = -m * kDetLog2e;
+            for (int c = 0; c < C; ++c) sum += ex2_approx(fmaf(rp[c], kDetLog2e, nml));
+          }
+          // conservative: the approximate ratio is within ~1e-5 of the exact one
+          hit = kept ? ex2_approx((mfg - m) * kDetLog2e) > thr * sum * 0.9999f : 0.0f > thr;
+          if (!hit) a.row_s[row] = 0.0f;
         } else {
-          for (int c = 1; c < C; ++c) mfg = fmaxf(mfg, rp[c]);
-          m = fmaxf(mfg, rp[0]);
-          const float nml = -m * kDetLog2e;
-          for (int c = 0; c < C; ++c) sum += ex2_approx(fmaf(rp[c], kDetLog2e, nml));
+          if (CT > 1) {
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  #pragma unroll
+            for (int c = 1; c < CT; ++c) m4[c & 3] = fmaxf(m4[c & 3], rp[c]);
+            m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          } else {
+            for (int c = 1; c < C; ++c) m = fmaxf(m, rp[c]);
+          }
+          if (!kept) m = 0.0f;
+          hit = m > thr;                                     // detection.py:48 strict >
         }
-        // conservative: the approximate ratio is within ~1e-5 of the exact one
-        hit = kept ? ex2_approx((mfg - m) * kDetLog2e) > thr * sum * 0.9999f : 0.0f > thr;
-        if (!hit) a.row_s[row] = 0.0f;
-      } else {
-        if (CT > 1) {
-          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-          for (int c = 1; c < CT; ++c) m4[c & 3] = fmaxf(m4[c & 3], rp[c]);
-          m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-        } else {
-          for (int c = 1; c < C; ++c) m = fmaxf(m, rp[c]);
-        }
-        if (!kept) m = 0.0f;
-        hit = m > thr;                                     // detection.py:48 strict >
       }
-    }
-    uint32_t hits = __ballot_sync(SSDBOX_FULL_MASK, valid && hit);
-    while (hits) {
-      const int src = __ffs(hits) - 1;
-      hits &= hits - 1;
-      const long long hrow = row - lane + src;             // rows of a warp are consecutive
-      const bool hkept = __shfl_sync(SSDBOX_FULL_MASK, kept ? 1 : 0, src) != 0;
-      const uint32_t b = (uint32_t)hrow / (uint32_t)a.P;
-      const uint32_t p = (uint32_t)hrow - b * (uint32_t)a.P;
-      const float* hp = st + (size_t)(r - lane + src) * C;
-      if (LOGITS) {
-        const float hm = __shfl_sync(SSDBOX_FULL_MASK, m, src);
-        float part = 0.f;
-        for (int c = lane; c < C; c += 32) part += expf(hp[c] - hm);
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(SSDBOX_FULL_MASK, part, d);
-        if (lane == 0) {
-          a.row_m[hrow] = hm;
-          a.row_s[hrow] = part;
-        }
-        for (int c = 1 + lane; c < C; c += 32) {
-          float v = hkept ? __fdiv_rn(expf(hp[c] - hm), part) : 0.0f;
-          if (v > thr) emit_candidate(a, C, b, p, c, v);
-        }
-      } else {
-        for (int c = 1 + lane; c < C; c += 32) {
-          float v = hkept ? hp[c] : 0.0f;
-          if (v > thr) emit_candidate(a, C, b, p, c, v);
+      uint32_t hits = __ballot_sync(SSDBOX_FULL_MASK, valid && hit);
+      while (hits) {
+        const int src = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const long long hrow = row - lane + src;             // rows of a warp are consecutive
+        const bool hkept = __shfl_sync(SSDBOX_FULL_MASK, kept ? 1 : 0, src) != 0;
+        const uint32_t b = (uint32_t)hrow / (uint32_t)a.P;
+        const uint32_t p = (uint32_t)hrow - b * (uint32_t)a.P;
+        const float* hp = st + (size_t)(r - lane + src) * C;
+        if (LOGITS) {
+          const float hm = __shfl_sync(SSDBOX_FULL_MASK, m, src);
+          float part = 0.f;
+          for (int c = lane; c < C; c += 32) part += expf(hp[c] - hm);
+  #pragma unroll
+          for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(SSDBOX_FULL_MASK, part, d);
+          if (lane == 0) {
+            a.row_m[hrow] = hm;
+            a.row_s[hrow] = part;
+          }
+          for (int c = 1 + lane; c < C; c += 32) {
+            float v = hkept ? __fdiv_rn(expf(hp[c] - hm), part) : 0.0f;
+            if (v > thr) emit_candidate(a, C, b, p, c, v);
+          }
+        } else {
+          for (int c = 1 + lane; c < C; c += 32) {
+            float v = hkept ? hp[c] : 0.0f;
+            if (v > thr) emit_candidate(a, C, b, p, c, v);
+          }
         }
       }
     }

@@ -377,30 +377,28 @@ __global__ void __launch_bounds__(kStreamThreads, 1) loss_stream_kernel(StreamAr
     return;
   }
   const int wg = warp / kRingGroupWarps;
-  const int r = tid % (32 * kRingGroupWarps);
+  const int rbase = tid % (32 * kRingGroupWarps);
+  const int KR = a.ring.KR;
   for (int it = wg; it < rc.n_local; it += kRingGroups) {
     const int s = it % NS, j = it % (2 * NS), ph = it / (2 * NS);
-    long long row = (rc.t0 + it) * R + r;
-    bool valid = (r < R) && (row < a.ring.rows);
-    int inpool = 1;
-    if (valid && a.pool) inpool = a.pool[row];
     mbar_wait(&rc.full[j], (uint32_t)(ph & 1));
-    float lse = 0.f, k0 = 0.f;
-    if (valid) {
-      const float* rp = rc.stages + (size_t)s * rc.stage_floats + (size_t)r * C;
-      lse = row_lse<CT>(rp, C);
-      k0 = lse - rp[0];                                    // multibox_loss.py:94 with conf_t = 0
+    for (int k = 0; k < KR; ++k) {
+      const int r = k * (32 * kRingGroupWarps) + rbase;
+      const long long row = (rc.t0 + it) * R + r;
+      if ((r < R) && (row < a.ring.rows)) {
+        const float* rp = rc.stages + (size_t)s * rc.stage_floats + (size_t)r * C;
+        const float lse = row_lse<CT>(rp, C);
+        const float k0 = lse - rp[0];                        // multibox_loss.py:94 with conf_t = 0
+        a.lse[row] = lse;
+        a.key0[row] = k0;
+        if (!a.pool || a.pool[row]) {
+          uint32_t b = (uint32_t)row / (uint32_t)a.P;
+          atomicAdd(&a.hist[(size_t)b * kHistBins + (f2ord(k0) >> 21)], 1u);
+        }
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&rc.empty[j]);
-    if (valid) {
-      a.lse[row] = lse;
-      a.key0[row] = k0;
-      if (inpool) {
-        uint32_t b = (uint32_t)row / (uint32_t)a.P;
-        atomicAdd(&a.hist[(size_t)b * kHistBins + (f2ord(k0) >> 21)], 1u);
-      }
-    }
   }
   if (warp == 0) SMARK(6);
   if (warp == 7) SMARK(7);
@@ -1505,7 +1503,8 @@ extern "C" int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const 
   if (vec4 && P <= 4 * kMineQ * kMineThreads && !(cfg->flags & SSDBOX_LOSS_GENERIC_MINE)) {
     // keys and class targets stay in registers; images with many priors are split over a cluster of
     // two CTAs (two SMs pull the image's keys, histograms merged through distributed shared memory)
-    const bool pair = P >= 8192 && !(cfg->flags & SSDBOX_LOSS_NO_CLUSTER);
+    // (only while the 2*B CTAs still fit in one wave: one 1024-thread CTA per SM)
+    const bool pair = P >= 8192 && 2 * B <= dev.sm_count && !(cfg->flags & SSDBOX_LOSS_NO_CLUSTER);
     mkern = pair ? mine_reduce_reg_kernel<2> : mine_reduce_reg_kernel<1>;
     smem = kMineFixedSmem + (size_t)kForceListMax * 16 + (size_t)(5 * kForceListMax + 8) * 4 + (size_t)P * 4;
     if (pair) {

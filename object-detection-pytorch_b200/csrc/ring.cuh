@@ -32,7 +32,8 @@ struct RingPlan {
   long long rows;
   long long tiles;
   int C;
-  int R;
+  int R;         // rows per tile = 32 * kRingGroupWarps * KR
+  int KR;        // rows per consumer thread per tile (> 1 for narrow rows: keeps the bulk copies ~40 KB)
   int NS;
   int tiles_per_cta;
   int bulk_ok;
@@ -43,8 +44,16 @@ struct RingPlan {
 // host: choose R / NS / grid for `rows` x C given the device limits
 static inline int plan_ring(RingPlan* p, const float* src, long long rows, int C, int sm_count, int max_smem) {
   size_t budget = (size_t)max_smem - 1024 - kRingHeaderBytes;
-  int R = 32 * kRingGroupWarps;
-  while (R >= 32 && (size_t)2 * R * C * 4 > budget) R >>= 1;
+  // narrow rows (C = 21: 84 bytes): several rows per thread so that one bulk copy stays around 40 KB --
+  // the per-SM bulk-copy engine wants few large copies (10 KB tiles measured 3x off the roofline)
+  const int base = 32 * kRingGroupWarps;
+  int KR = 1;
+  while (KR < 32 && (size_t)base * (KR * 2) * C * 4 <= 49152) KR *= 2;
+  int R = base * KR;
+  while (R >= 32 && (size_t)2 * R * C * 4 > budget) {
+    R >>= 1;
+    if (KR > 1) KR >>= 1;
+  }
   if (R < 32) return fail(SSDBOX_ESHAPE, "%d classes do not fit the shared-memory ring", C);
   size_t stage_bytes = (size_t)R * C * 4;
   int NS = (int)(budget / stage_bytes);
@@ -54,6 +63,7 @@ static inline int plan_ring(RingPlan* p, const float* src, long long rows, int C
   p->rows = rows;
   p->C = C;
   p->R = R;
+  p->KR = KR;
   p->NS = NS;
   p->tiles = (rows + R - 1) / R;
   int grid = (int)(p->tiles < sm_count ? p->tiles : sm_count);
