@@ -37,20 +37,6 @@ struct DetStreamArgs {
   float* row_s;             // [B*P] ... and sum_c expf(x_c - max) of rows that can hold a candidate, else 0
 };
 
-// One (row, class) score above the threshold (rare: ~5e-4 of the elements with a trained detector).
-__device__ __forceinline__ void emit_candidate(const DetStreamArgs& a, int C, uint32_t b, uint32_t p, int c, float v) {
-  uint32_t* ctr = &a.cnt[(size_t)b * C + c];
-  // dense scores: once a list has overflowed its extra candidates are never read (the overflow
-  // kernel re-selects from the score column), so skip the atomic; a stale read only costs an atomic
-  if (__ldcg(ctr) > (uint32_t)a.cap) return;
-  uint32_t slot = atomicAdd(ctr, 1u);
-  if (slot < (uint32_t)a.cap)
-    a.cand[((size_t)b * C + c) * a.cap + slot] = ((unsigned long long)f2ord(v) << 32) | p;
-}
-
-// Consumer: one thread per prior row computes the maximum over the foreground classes (conflict-
-// free LDS, 4 independent FMNMX chains); rows with a hit (a few per cent) are then re-scanned by
-// the whole warp, lane = class, so the per-hit work never serialises a warp over 80 classes.
 // LOGITS: the rows are raw class logits.  Every row pays one cheap softmax denominator (ex2.approx,
 // like the loss kernel) to decide conservatively whether any foreground class can exceed the
 // threshold; rows that can are re-scanned by the whole warp with expf and a correctly rounded division.
@@ -71,6 +57,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) detect_stream_kernel(DetStrea
   const int KR = a.ring.KR;
   const int R = a.ring.R, NS = a.ring.NS;
   const float thr = a.thr;
+  uint32_t full = 0u, full_b = 0xffffffffu;     // saturated class slots of this lane, and the image they belong to
   for (int it = wg; it < rc.n_local; it += kRingGroups) {
     const int s = it % NS, j = it % (2 * NS), ph = it / (2 * NS);
     const float* st = rc.stages + (size_t)s * rc.stage_floats;
@@ -123,33 +110,90 @@ __global__ void __launch_bounds__(kRingThreads, 1) detect_stream_kernel(DetStrea
           hit = m > thr;                                     // detection.py:48 strict >
         }
       }
-      uint32_t hits = __ballot_sync(SSDBOX_FULL_MASK, valid && hit);
-      while (hits) {
-        const int src = __ffs(hits) - 1;
-        hits &= hits - 1;
-        const long long hrow = row - lane + src;             // rows of a warp are consecutive
-        const bool hkept = __shfl_sync(SSDBOX_FULL_MASK, kept ? 1 : 0, src) != 0;
-        const uint32_t b = (uint32_t)hrow / (uint32_t)a.P;
-        const uint32_t p = (uint32_t)hrow - b * (uint32_t)a.P;
-        const float* hp = st + (size_t)(r - lane + src) * C;
+      const uint32_t hits = __ballot_sync(SSDBOX_FULL_MASK, valid && hit);
+      if (hits) {
+        const uint32_t keptmask = __ballot_sync(SSDBOX_FULL_MASK, kept);
+        const int wrow0 = r - lane;                          // the warp's 32 rows are consecutive
+        const long long grow0 = row - lane;
+        float my_s = 0.f;                                    // LOGITS: softmax denominator of my row (m holds its max)
         if (LOGITS) {
-          const float hm = __shfl_sync(SSDBOX_FULL_MASK, m, src);
-          float part = 0.f;
-          for (int c = lane; c < C; c += 32) part += expf(hp[c] - hm);
-  #pragma unroll
-          for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(SSDBOX_FULL_MASK, part, d);
-          if (lane == 0) {
-            a.row_m[hrow] = hm;
-            a.row_s[hrow] = part;
+          uint32_t h = hits;
+          while (h) {
+            const int src = __ffs(h) - 1;
+            h &= h - 1;
+            const float* hp = st + (size_t)(wrow0 + src) * C;
+            const float hm = __shfl_sync(SSDBOX_FULL_MASK, m, src);
+            float part = 0.f;
+            for (int c = lane; c < C; c += 32) part += expf(hp[c] - hm);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(SSDBOX_FULL_MASK, part, d);
+            if (lane == src) my_s = part;
+            if (lane == 0) {
+              a.row_m[grow0 + src] = hm;
+              a.row_s[grow0 + src] = part;
+            }
           }
-          for (int c = 1 + lane; c < C; c += 32) {
-            float v = hkept ? __fdiv_rn(expf(hp[c] - hm), part) : 0.0f;
-            if (v > thr) emit_candidate(a, C, b, p, c, v);
+        }
+        // Class-major over the hit rows: lane = class, ONE atomicAdd per (class, 32 rows) reserves the
+        // slots of all its candidates (dense scores would otherwise serialise an atomic round trip per
+        // candidate).  All hit rows of a warp belong to one image except at an image boundary.
+        const uint32_t b_lo = (uint32_t)(grow0 + (__ffs(hits) - 1)) / (uint32_t)a.P;
+        const uint32_t b_hi = (uint32_t)(grow0 + (31 - __clz(hits))) / (uint32_t)a.P;
+        for (uint32_t b = b_lo; b <= b_hi; ++b) {
+          // hit rows of image b
+          uint32_t hb = hits;
+          if (b_lo != b_hi) {
+            hb = 0u;
+            uint32_t h = hits;
+            while (h) {
+              const int rb = __ffs(h) - 1;
+              h &= h - 1;
+              if ((uint32_t)(grow0 + rb) / (uint32_t)a.P == b) hb |= 1u << rb;
+            }
+            if (hb == 0u) continue;
           }
-        } else {
-          for (int c = 1 + lane; c < C; c += 32) {
-            float v = hkept ? hp[c] : 0.0f;
-            if (v > thr) emit_candidate(a, C, b, p, c, v);
+          if (b != full_b) {
+            full_b = b;
+            full = 0u;
+          }
+          const int p0 = (int)(grow0 - (long long)b * a.P);   // prior index of the warp's first row (may be < 0)
+          for (int sb = 0; 1 + 32 * sb < C; ++sb) {
+            const int c = 1 + lane + 32 * sb;
+            const bool act = c < C && !(sb < 32 && ((full >> sb) & 1u));
+            const int cc = act ? c : 0;
+            int cnt = 0;
+            uint32_t h = hb;
+            while (h) {
+              const int rb = __ffs(h) - 1;
+              h &= h - 1;
+              float v = st[(size_t)(wrow0 + rb) * C + cc];
+              if (LOGITS) v = __fdiv_rn(expf(v - __shfl_sync(SSDBOX_FULL_MASK, m, rb)), __shfl_sync(SSDBOX_FULL_MASK, my_s, rb));
+              if (!((keptmask >> rb) & 1u)) v = 0.0f;
+              cnt += (act && v > thr) ? 1 : 0;                // detection.py:48 strict >
+            }
+            uint32_t base = 0u;
+            if (cnt) {
+              base = atomicAdd(&a.cnt[(size_t)b * C + c], (uint32_t)cnt);
+              if (base >= (uint32_t)a.cap) {                 // list already full: its extra candidates are never read
+                if (sb < 32) full |= 1u << sb;
+                cnt = 0;
+              }
+            }
+            if (__any_sync(SSDBOX_FULL_MASK, cnt != 0)) {
+              h = hb;
+              while (h) {
+                const int rb = __ffs(h) - 1;
+                h &= h - 1;
+                float v = st[(size_t)(wrow0 + rb) * C + cc];
+                if (LOGITS) v = __fdiv_rn(expf(v - __shfl_sync(SSDBOX_FULL_MASK, m, rb)), __shfl_sync(SSDBOX_FULL_MASK, my_s, rb));
+                if (!((keptmask >> rb) & 1u)) v = 0.0f;
+                if (cnt && v > thr) {
+                  if (base < (uint32_t)a.cap)
+                    a.cand[((size_t)b * C + c) * a.cap + base] = ((unsigned long long)f2ord(v) << 32) | (uint32_t)(p0 + rb);
+                  ++base;
+                }
+              }
+            }
           }
         }
       }
