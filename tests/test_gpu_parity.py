@@ -731,3 +731,28 @@ def test_eval_post_processing_after_detect(dev):
     z = torch.zeros(2, 4, 5, 5, device=dev)
     e, s0 = EU.convert_ssd_result(z)
     assert e.shape == (0, 7) and int(s0.abs().sum()) == 0
+
+
+def test_tiny_shapes(dev):
+    """Degenerate sizes through every kernel: one image, a handful of priors, 2..3 classes, one truth."""
+    pri = torch.tensor([[0.25, 0.25, 0.3, 0.3], [0.5, 0.5, 0.4, 0.4], [0.75, 0.75, 0.3, 0.3], [0.5, 0.5, 0.9, 0.9], [0.1, 0.9, 0.1, 0.1]])
+    for P in (1, 4, 5):
+        for C in (2, 3):
+            p = pri[:P].contiguous()
+            g = torch.Generator().manual_seed(P * 10 + C)
+            loc = torch.randn(1, P, 4, generator=g) * 0.3
+            conf = torch.randn(1, P, C, generator=g)
+            tg = [torch.tensor([[0.3, 0.3, 0.7, 0.7, float(C - 2)]])]
+            crit = ssdbox.MultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False)
+            d = crit.intermediates((loc.to(dev), conf.to(dev), p.to(dev)), _gpu_targets(tg, dev))
+            r = O.multibox_loss(loc, conf, p, tg, C, detail=True)
+            assert torch.equal(d["conf_t"].cpu(), r["conf_t"]), (P, C)
+            assert torch.equal(d["neg"].cpu().bool(), r["neg"]), (P, C)
+            U.assert_close_rel(d["loss_l"], r["loss_l"], REL, 1e-7, "tiny loss_l")
+            U.assert_close_rel(d["loss_c"], r["loss_c"], REL, 1e-7, "tiny loss_c")
+            sc = torch.softmax(conf * 3, -1)
+            out = ssdbox.DetectOut(C, 0, 3, 0.01, 0.45, VAR)(loc.to(dev), sc.to(dev), p.to(dev)).cpu()
+            _compare_detect(out, O.detect(loc, sc, p, C, top_k=3), "tiny")
+            out2 = ssdbox.DetectOut(C, 0, 3, 0.01, 0.45, VAR, conf_is_logits=True)(loc.to(dev), (conf * 3).to(dev), p.to(dev)).cpu()
+            assert torch.equal(out2[..., 0] > 0, out[..., 0] > 0)
+            U.assert_close_rel(out2, out, 2e-6, 1e-7, "tiny logits")
