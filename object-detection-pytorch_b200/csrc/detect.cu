@@ -483,6 +483,241 @@ __global__ void __launch_bounds__(kOvfThreads, 1) detect_overflow_kernel(DetSegA
 }
 
 // ------------------------------------------------------------------------------------------------
+// Dense scores, chunked: one work item = (image, 8 consecutive classes).  The per-(image, class)
+// kernel above reads a strided score column per segment (24564 sectors for 24564 floats); here the 8
+// classes of a chunk share the sectors of every row, their radix-select histograms are built in the
+// same passes (8 x 2048 bins in shared memory, one warp per class finds the digit), and all
+// keys >= the class threshold are collected and sorted: the sort order (score desc, prior desc) IS
+// the reference's visiting order, so ties at the cut need no special handling as long as they fit the
+// 1024-entry list; a class whose ties do not fit (e.g. all scores equal) takes the column path.
+// ------------------------------------------------------------------------------------------------
+constexpr int kOvfClasses = 8;
+
+__device__ __forceinline__ float ovf_score(const DetSegArgs& a, size_t row, int c) {
+  float v = a.scores[row * a.C + c];
+  if (a.row_s) {           // logits: the same expression as the candidate pass
+    const float sden = a.row_s[row];
+    v = sden > 0.0f ? __fdiv_rn(expf(v - a.row_m[row]), sden) : 0.0f;
+  }
+  if (a.keep && !a.keep[row]) v = 0.0f;
+  return v;
+}
+
+// the scores of classes c0 .. c0+7 of one row: all loads issued together, row-wise state read once
+__device__ __forceinline__ void ovf_row_scores(const DetSegArgs& a, size_t row, int c0, float (&v)[kOvfClasses]) {
+  const float* x = a.scores + row * a.C + c0;
+#pragma unroll
+  for (int k = 0; k < kOvfClasses; ++k) v[k] = c0 + k < a.C ? x[k] : 0.0f;
+  const bool kept = !a.keep || a.keep[row];
+  if (a.row_s) {           // logits: the same expression as the candidate pass
+    const float sden = a.row_s[row], m = a.row_m[row];
+#pragma unroll
+    for (int k = 0; k < kOvfClasses; ++k) v[k] = sden > 0.0f ? __fdiv_rn(expf(v[k] - m), sden) : 0.0f;
+  }
+  if (!kept) {
+#pragma unroll
+    for (int k = 0; k < kOvfClasses; ++k) v[k] = 0.0f;
+  }
+}
+
+// one warp: digit d with  above = sum_{bin > d} hist < K <= above + hist[d]  (d = -1: fewer than K entries)
+__device__ __forceinline__ void warp_find_digit(const uint32_t* hist, int nbins, int K, int lane, int* d_out, int* above_out) {
+  const int span = nbins / 32;
+  const int hi = nbins - 1 - lane * span;       // lane owns bins hi, hi-1, ..., hi-span+1 (descending)
+  int local = 0;
+  for (int e = 0; e < span; ++e) local += (int)hist[hi - e];
+  const int incl = warp_inclusive_scan(local, lane);
+  int above = incl - local;
+  const bool mine = above < K && incl >= K;
+  int d = -1;
+  if (mine) {
+    for (int e = 0; e < span; ++e) {
+      const int h = (int)hist[hi - e];
+      if (above + h >= K) {
+        d = hi - e;
+        break;
+      }
+      above += h;
+    }
+  }
+  const uint32_t who = __ballot_sync(SSDBOX_FULL_MASK, mine);
+  if (who == 0u) {
+    *d_out = -1;
+    *above_out = 0;
+    return;
+  }
+  const int src = __ffs(who) - 1;
+  *d_out = __shfl_sync(SSDBOX_FULL_MASK, d, src);
+  *above_out = __shfl_sync(SSDBOX_FULL_MASK, above, src);
+}
+
+// the per-segment column path (any tie pattern): ordered scores -> scratch, exact select, collect
+__device__ void overflow_column_segment(const DetSegArgs& a, int b, int c, int seg, unsigned long long* keys,
+                                        uint32_t* s_hist, int* s_iscr, int* s_res, const NmsSmem& ns, uint32_t* uk) {
+  const int tid = threadIdx.x;
+  for (int p = tid; p < a.P; p += kOvfThreads) {
+    float v = ovf_score(a, (size_t)b * a.P + p, c);
+    uk[p] = v > a.conf_thr ? f2ord(v) : 0u;
+  }
+  if (tid == 0) s_res[4] = 0;
+  __syncthreads();
+  uint32_t Tu = cta_select_threshold<true>(uk, a.P, a.top_k, nullptr, s_hist, s_iscr, s_res);
+  __syncthreads();
+  for (int p = tid; p < a.P; p += kOvfThreads) {
+    uint32_t u = uk[p];
+    if (u != 0u && u >= Tu) {
+      int slot = atomicAdd(&s_res[4], 1);
+      if (slot < 1024) keys[slot] = ((unsigned long long)u << 32) | (uint32_t)p;
+    }
+  }
+  __syncthreads();
+  int n = s_res[4];
+  if (n > 1024) n = 1024;
+  int npad = 32;
+  while (npad < n) npad <<= 1;
+  for (int i = n + tid; i < npad; i += kOvfThreads) keys[i] = 0ull;
+  __syncthreads();
+  segment_finish(a, b, seg, keys, n, npad, ns);
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kOvfThreads, 1) detect_overflow_chunk_kernel(DetSegArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_ovc[];
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_ovc);                                   // [8][2048]
+  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_ovc + 65536);         // [8][1024]
+  int* s_iscr = reinterpret_cast<int*>(smem_ovc + 131072);                                      // 64
+  int* s_res = s_iscr + 64;                                                                     // 8
+  int* s_cls = s_res + 8;                                                                       // 8 x {active, K left, range lo, n collected, range size - 1, shift}
+  NmsSmem ns = carve_nms(smem_ovc + 131072 + 288 + 192, a.top_k);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nchunk = (a.C - 1 + kOvfClasses - 1) / kOvfClasses;
+  int* s_act = s_cls;
+  int* s_kleft = s_cls + 8;
+  uint32_t* s_pre = reinterpret_cast<uint32_t*>(s_cls + 16);     // key prefix fixed so far, finally the threshold key
+  int* s_n = s_cls + 24;
+  uint32_t* s_spanm1 = reinterpret_cast<uint32_t*>(s_cls + 32);   // current range size - 1 (0: the threshold key is s_pre)
+  int* s_shift = s_cls + 40;
+  uint32_t* uk = a.scratch + (size_t)blockIdx.x * a.P;
+  if (*a.ovf_count == 0u) return;       // no list overflowed (the normal case): written by detect_segment_small_kernel
+  for (int item = blockIdx.x; item < a.B * nchunk; item += gridDim.x) {
+    const int b = item / nchunk, c0 = 1 + (item - b * nchunk) * kOvfClasses;
+    __syncthreads();
+    if (tid < kOvfClasses) {
+      const int c = c0 + tid;
+      s_act[tid] = (c < a.C && a.cnt[(size_t)b * a.C + c] > (uint32_t)a.cap) ? 1 : 0;
+      s_kleft[tid] = a.top_k;
+      const uint32_t lo = f2ord(a.conf_thr), one = f2ord(1.0f);
+      const uint32_t nominal = one > lo ? one - lo : 0u;       // keys of the scores in (conf_thr, 1]
+      const int bits = nominal ? 32 - __clz(nominal) : 0;
+      s_pre[tid] = lo;
+      s_spanm1[tid] = 0xffffffffu - lo;                        // first level: everything above the threshold
+      s_shift[tid] = bits > 11 ? bits - 11 : 0;                // (nominal >> shift) <= 2047: the last bin also catches keys above 1.0
+      s_n[tid] = 0;
+    }
+    __syncthreads();
+    int actmask = 0;
+#pragma unroll
+    for (int k = 0; k < kOvfClasses; ++k) actmask |= s_act[k] << k;
+    if (actmask == 0) continue;
+
+    // Range-adaptive radix select, all active classes per pass: a level buckets the keys of the current
+    // range [lo, lo + span) into 2048 bins of 2^shift keys.  The first range is (key(conf_thr), key(1.0)]
+    // -- softmax scores -- with the last bin catching anything above, so the bins are spread over the
+    // scores' log-range (bucketing the top key bits would put every score in ~30 bins and serialise the
+    // shared-memory atomics).  Three levels in the normal case, at most five.
+    for (int level = 0; level < 5; ++level) {
+      if (level > 0) {
+        int pending = 0;
+#pragma unroll
+        for (int k = 0; k < kOvfClasses; ++k) pending |= ((actmask >> k) & 1) && s_spanm1[k] != 0u;
+        if (!pending) break;                      // uniform: shared state read after a barrier
+      }
+      for (int i = tid; i < kOvfClasses * 2048; i += kOvfThreads) s_hist[i] = 0u;
+      __syncthreads();
+      uint32_t lo_r[kOvfClasses], spanm1_r[kOvfClasses];
+      int shift_r[kOvfClasses];
+#pragma unroll
+      for (int k = 0; k < kOvfClasses; ++k) {
+        lo_r[k] = s_pre[k];
+        spanm1_r[k] = ((actmask >> k) & 1) ? s_spanm1[k] : 0u;     // 0: class inactive or already resolved
+        shift_r[k] = s_shift[k];
+      }
+      for (int p = tid; p < a.P; p += kOvfThreads) {
+        float v[kOvfClasses];
+        ovf_row_scores(a, (size_t)b * a.P + p, c0, v);
+#pragma unroll
+        for (int k = 0; k < kOvfClasses; ++k) {
+          const uint32_t u = f2ord(v[k]);
+          const uint32_t off = u - lo_r[k];
+          if (spanm1_r[k] != 0u && v[k] > a.conf_thr && u >= lo_r[k] && off <= spanm1_r[k]) {
+            const uint32_t bin = off >> shift_r[k];
+            atomicAdd(&s_hist[k * 2048 + (bin < 2047u ? bin : 2047u)], 1u);
+          }
+        }
+      }
+      __syncthreads();
+      if (warp < kOvfClasses && ((actmask >> warp) & 1) && s_spanm1[warp] != 0u) {
+        int d, above;
+        warp_find_digit(s_hist + warp * 2048, 2048, s_kleft[warp], lane, &d, &above);
+        if (lane == 0) {
+          if (d < 0) {               // cannot happen for an overflowed list (more than cap > top_k candidates)
+            d = 0;
+            above = 0;
+          }
+          s_kleft[warp] -= above;
+          const int sh = s_shift[warp];
+          const uint32_t lo = s_pre[warp] + ((uint32_t)d << sh);
+          // bin 2047 of the first level is open-ended; every other bin holds exactly 2^shift keys
+          uint32_t spanm1 = (level == 0 && d == 2047) ? (0xffffffffu - lo) : ((1u << sh) - 1u);
+          // everything above the bin plus the whole bin fits the list: stop refining, the sort of
+          // segment_finish orders the bin and keeps the first top_k
+          if ((a.top_k - s_kleft[warp]) + (int)s_hist[warp * 2048 + d] <= 1024) spanm1 = 0u;
+          int bits = spanm1 ? 32 - __clz(spanm1) : 0;
+          s_pre[warp] = lo;
+          s_spanm1[warp] = spanm1;
+          s_shift[warp] = bits > 11 ? bits - 11 : 0;
+        }
+      }
+      __syncthreads();
+    }
+    // s_pre[k] is now a key <= the top_k-th largest score with at most 1024 keys >= it (or the exact
+    // key of the top_k-th largest score): collect every key >= it
+    uint32_t thr_r[kOvfClasses];
+#pragma unroll
+    for (int k = 0; k < kOvfClasses; ++k) thr_r[k] = ((actmask >> k) & 1) ? s_pre[k] : 0xffffffffu;
+    for (int p = tid; p < a.P; p += kOvfThreads) {
+      float v[kOvfClasses];
+      ovf_row_scores(a, (size_t)b * a.P + p, c0, v);
+#pragma unroll
+      for (int k = 0; k < kOvfClasses; ++k) {
+        const uint32_t u = f2ord(v[k]);
+        if (v[k] > a.conf_thr && u >= thr_r[k] && thr_r[k] != 0xffffffffu) {
+          const int slot = atomicAdd(&s_n[k], 1);
+          if (slot < 1024) s_keys[k * 1024 + slot] = ((unsigned long long)u << 32) | (uint32_t)p;
+        }
+      }
+    }
+    __syncthreads();
+    for (int k = 0; k < kOvfClasses; ++k) {
+      if (!((actmask >> k) & 1)) continue;
+      const int c = c0 + k, seg = b * a.C + c;
+      const int n = s_n[k];
+      if (n > 1024) {              // ties at the cut do not fit: exact index-ordered selection on the column
+        overflow_column_segment(a, b, c, seg, s_keys + k * 1024, s_hist, s_iscr, s_res, ns, uk);
+        continue;
+      }
+      int npad = 32;
+      while (npad < n) npad <<= 1;
+      unsigned long long* keys = s_keys + k * 1024;
+      for (int i = n + tid; i < npad; i += kOvfThreads) keys[i] = 0ull;
+      __syncthreads();
+      segment_finish(a, b, seg, keys, n, npad, ns);     // sorts, keeps the first top_k, decodes, NMS, writes
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // stand-alone nms(boxes, scores, overlap, top_k), box_utils.py:279-343 -- one CTA
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kOvfThreads, 1)
@@ -616,11 +851,21 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
   }
   SSDBOX_LAUNCH_OK("detect_segment_kernel");
 
-  size_t ovf_smem = 16384 + 288 + nms_smem_bytes(top_k);
-  SSDBOX_CUDA(cudaFuncSetAttribute(detect_overflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ovf_smem));
   int ovf_grid = dev.sm_count < kOverflowSlots ? dev.sm_count : kOverflowSlots;
-  if (ovf_grid > B * C) ovf_grid = B * C;
-{
+  const size_t chunk_smem = 131072 + 288 + 192 + nms_smem_bytes(top_k);
+  if (top_k <= 256 && cap == 1024 && chunk_smem <= (size_t)dev.max_smem_optin - 1024) {
+    // chunked dense path: (image, 8 classes) work items, reads each score sector once per pass
+    SSDBOX_CUDA(cudaFuncSetAttribute(detect_overflow_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chunk_smem));
+    const int items = B * ((C - 1 + kOvfClasses - 1) / kOvfClasses);
+    if (ovf_grid > items) ovf_grid = items;
+    if (ovf_grid > 0) {
+      TimerScope ts__(KID_DET_OVERFLOW, st);
+      detect_overflow_chunk_kernel<<<ovf_grid, kOvfThreads, chunk_smem, st>>>(g);
+    }
+  } else {
+    size_t ovf_smem = 16384 + 288 + nms_smem_bytes(top_k);
+    SSDBOX_CUDA(cudaFuncSetAttribute(detect_overflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ovf_smem));
+    if (ovf_grid > B * C) ovf_grid = B * C;
     TimerScope ts__(KID_DET_OVERFLOW, st);
     detect_overflow_kernel<<<ovf_grid, kOvfThreads, ovf_smem, st>>>(g);
   }
