@@ -1,20 +1,26 @@
 // DetectOut.forward (lib/layers/functions/detection.py:25-64) and nms (box_utils.py:279-343).
 //
-// Detect = 4 launches on the caller's stream:
+// Detect = 5 launches on the caller's stream:
 //   init_kernel            candidate counters := 0
 //   detect_stream_kernel   THE HBM-bound kernel: scores [B*P, C] streamed once through the TMA
-//                          bulk-copy ring; one thread per prior row tests every class against
-//                          conf_thresh, warps aggregate the hits of a class with one ballot and
-//                          one atomicAdd and append (ordered score << 32 | prior) to the
-//                          (image, class) candidate list.  The transposed [C,P] view of
-//                          detection.py:38-39 is never materialised; decode runs only on candidates.
-//   detect_segment_kernel  one CTA per (image, class): bitonic sort of the candidates by
-//                          (score desc, prior desc) = the reference's visiting order, top_k cut,
-//                          decode of the survivors, 200x200 suppression bit-matrix built with warp
-//                          ballots in shared memory, one-warp greedy sweep, zero-padded output rows.
-//   detect_overflow_kernel only for (image, class) lists that exceeded the candidate capacity
-//                          (dense scores): exact radix-select of the top_k scores of the class
-//                          column straight from `scores`, then the same sort + NMS tail.
+//                          bulk-copy ring; one thread per prior row takes the row maximum over the
+//                          foreground classes; the few rows with a hit are re-scanned by the warp
+//                          class-major (lane = class, one atomicAdd per class per 32 rows) and append
+//                          (ordered score << 32 | prior) to the (image, class) candidate list.  With
+//                          raw logits (SSDBOX_DETECT_LOGITS) the softmax is fused in.  The transposed
+//                          [C,P] view of detection.py:38-39 is never materialised; decode runs only
+//                          on candidates.
+//   detect_segment_small_kernel  one WARP per (image, class) with <= 32 candidates (the normal case):
+//                          shuffle bitonic sort, decode, NMS and output rows entirely in registers;
+//                          larger lists are queued
+//   detect_overflow_chunk_kernel  only for lists that exceeded the candidate capacity (dense scores):
+//                          per (image, 8 classes) a range-adaptive radix select straight from
+//                          `scores` rewrites each list with the <= 1024 best keys and queues it
+//   detect_segment_kernel  one CTA per queued (image, class): bitonic sort by (score desc, prior desc)
+//                          = the reference's visiting order, top_k cut, decode of the survivors,
+//                          upper-triangular suppression bit-matrix built with warp ballots in shared
+//                          memory, one-warp greedy sweep, zero-padded output rows.
+// (top_k > 256: detect_overflow_kernel, one CTA per overflowed list, exact column select + NMS.)
 #include "ops.h"
 #include "ring.cuh"
 #include "select.cuh"
@@ -235,21 +241,25 @@ __device__ __forceinline__ NmsSmem carve_nms(unsigned char* base, int top_k) {
 __device__ __forceinline__ int nms_sweep(const NmsSmem& s, int m, float thr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   const int W = (m + 31) / 32;
-  for (int item = warp; item < m * W; item += nwarp) {
-    int i = item / W, wd = item - i * W;
-    int j = wd * 32 + lane;
-    bool bit = false;
-    if (wd * 32 + 31 > i) {
+  // suppression bits of row i, words at or right of the diagonal only (box j > i); rows are dealt to
+  // the warps round-robin
+  for (int i = warp; i < m; i += nwarp) {
+    const float4 bi = s.box[i];
+    Box I;
+    I.x1 = bi.x; I.y1 = bi.y; I.x2 = bi.z; I.y2 = bi.w;
+    const float ai = s.area[i];
+    for (int wd = i >> 5; wd < W; ++wd) {
+      const int j = wd * 32 + lane;
+      bool bit = false;
       if (j > i && j < m) {
-        float4 bi = s.box[i], bj = s.box[j];
-        Box I, J;
-        I.x1 = bi.x; I.y1 = bi.y; I.x2 = bi.z; I.y2 = bi.w;
+        const float4 bj = s.box[j];
+        Box J;
         J.x1 = bj.x; J.y1 = bj.y; J.x2 = bj.z; J.y2 = bj.w;
-        bit = !(iou_nms(I, s.area[i], J, s.area[j]) <= thr);     // :342 keeps IoU <= overlap
+        bit = !(iou_nms(I, ai, J, s.area[j]) <= thr);     // :342 keeps IoU <= overlap
       }
+      const uint32_t word = __ballot_sync(SSDBOX_FULL_MASK, bit);
+      if (lane == 0) s.mask[i * W + wd] = word;
     }
-    uint32_t word = __ballot_sync(SSDBOX_FULL_MASK, bit);
-    if (lane == 0) s.mask[item] = word;
   }
   __syncthreads();
   if (warp == 0) {
@@ -260,7 +270,7 @@ __device__ __forceinline__ int nms_sweep(const NmsSmem& s, int m, float thr) {
       if (!((w >> (i & 31)) & 1u)) {
         if (lane == 0) s.keep[cnt] = (uint16_t)i;
         ++cnt;
-        if (lane < W) removed |= s.mask[i * W + lane];
+        if (lane < W && lane >= (i >> 5)) removed |= s.mask[i * W + lane];
       }
     }
     if (lane == 0) *s.cnt = cnt;
@@ -277,8 +287,8 @@ struct DetSegArgs {
   const float* scores;
   const float* priors;
   const uint8_t* keep;
-  const uint32_t* cnt;
-  const unsigned long long* cand;
+  uint32_t* cnt;
+  unsigned long long* cand;
   uint32_t* ovf_count; // [1] number of (image, class) lists that overflowed
   int32_t* ovf_list;   // [B*C] their segment ids
   uint32_t* big_count; // [1] number of lists with 32 < n <= cap
@@ -706,13 +716,15 @@ __global__ void __launch_bounds__(kOvfThreads, 1) detect_overflow_chunk_kernel(D
         overflow_column_segment(a, b, c, seg, s_keys + k * 1024, s_hist, s_iscr, s_res, ns, uk);
         continue;
       }
-      int npad = 32;
-      while (npad < n) npad <<= 1;
-      unsigned long long* keys = s_keys + k * 1024;
-      for (int i = n + tid; i < npad; i += kOvfThreads) keys[i] = 0ull;
-      __syncthreads();
-      segment_finish(a, b, seg, keys, n, npad, ns);     // sorts, keeps the first top_k, decodes, NMS, writes
-      __syncthreads();
+      // hand the selected keys to detect_segment_kernel (next launch): several of its small CTAs share an
+      // SM, so the serial NMS sweep of one segment overlaps the IoU matrix of others
+      const unsigned long long* keys = s_keys + k * 1024;
+      unsigned long long* dst = a.cand + (size_t)seg * a.cap;
+      for (int i = tid; i < n; i += kOvfThreads) dst[i] = keys[i];
+      if (tid == 0) {
+        a.cnt[seg] = (uint32_t)n;
+        a.big_list[atomicAdd(a.big_count, 1u)] = seg;
+      }
     }
   }
 }
@@ -842,15 +854,8 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
     detect_segment_small_kernel<<<(B * C + per - 1) / per, kSmallThreads, 0, st>>>(g);
   }
   SSDBOX_LAUNCH_OK("detect_segment_small_kernel");
-  size_t seg_smem = (size_t)cap * 8 + nms_smem_bytes(top_k);
-  SSDBOX_CUDA(cudaFuncSetAttribute(detect_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem));
-  {
-    TimerScope ts__(KID_DET_SEGMENT_BIG, st);
-    int big_grid = dev.sm_count * 4 < B * C ? dev.sm_count * 4 : B * C;
-    detect_segment_kernel<<<big_grid, kSegThreads, seg_smem, st>>>(g);
-  }
-  SSDBOX_LAUNCH_OK("detect_segment_kernel");
-
+  // overflowed lists first: the chunked kernel only SELECTS (it rewrites the list with <= 1024 keys and
+  // queues the segment for the CTA-wide kernel below)
   int ovf_grid = dev.sm_count < kOverflowSlots ? dev.sm_count : kOverflowSlots;
   const size_t chunk_smem = 131072 + 288 + 192 + nms_smem_bytes(top_k);
   if (top_k <= 256 && cap == 1024 && chunk_smem <= (size_t)dev.max_smem_optin - 1024) {
@@ -870,6 +875,15 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
     detect_overflow_kernel<<<ovf_grid, kOvfThreads, ovf_smem, st>>>(g);
   }
   SSDBOX_LAUNCH_OK("detect_overflow_kernel");
+
+  size_t seg_smem = (size_t)cap * 8 + nms_smem_bytes(top_k);
+  SSDBOX_CUDA(cudaFuncSetAttribute(detect_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem));
+  {
+    TimerScope ts__(KID_DET_SEGMENT_BIG, st);
+    int big_grid = dev.sm_count * 4 < B * C ? dev.sm_count * 4 : B * C;
+    detect_segment_kernel<<<big_grid, kSegThreads, seg_smem, st>>>(g);
+  }
+  SSDBOX_LAUNCH_OK("detect_segment_kernel");
   return SSDBOX_OK;
 }
 
