@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) detect_stream_kernel(DetStrea
           for (int sb = 0; 1 + 32 * sb < C; ++sb) {
             const int c = 1 + lane + 32 * sb;
             const bool act = c < C && !(sb < 32 && ((full >> sb) & 1u));
+            if (!__any_sync(SSDBOX_FULL_MASK, act)) continue;      // every class of this slot is saturated (dense scores)
             const int cc = act ? c : 0;
             int cnt = 0;
             uint32_t h = hb;
