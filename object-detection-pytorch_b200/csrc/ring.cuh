@@ -15,6 +15,8 @@
 // stage and NS odd, a group would skip every other phase of a stage and could pass a wait two
 // phases early).
 #pragma once
+#include <cstdlib>
+
 #include "common.h"
 #include "ssdbox_dev.cuh"
 
@@ -58,6 +60,10 @@ static inline int plan_ring(RingPlan* p, const float* src, long long rows, int C
   size_t stage_bytes = (size_t)R * C * 4;
   int NS = (int)(budget / stage_bytes);
   if (NS > kRingMaxStages) NS = kRingMaxStages;
+  if (const char* e = getenv("SSDBOX_RING_MAX_STAGES")) {      // experiments only
+    int cap = atoi(e);
+    if (cap >= 2 && NS > cap) NS = cap;
+  }
   while (NS > 1 && (2 * NS) % kRingGroups) --NS;     // see the header comment
   p->src = src;
   p->rows = rows;
