@@ -14,12 +14,14 @@
 //                                          staged in shared memory (priors by TMA); 4 consecutive
 //                                          priors per thread, warp bounding-box pruning, per-truth
 //                                          argmax by REDUX + atomicMax.  The IoU matrix never exists.
-//   mine_reduce_kernel one CTA per image: replays the forced assignment ("every truth keeps its
-//                      best prior, last truth wins"), positives get CE = lse - x[target] (one
-//                      gathered logit each) and move to the zero bin; radix-select of the
+//   mine_reduce_*      per image (one CTA, or a cluster of two for many priors; keys register-resident
+//                      when P % 4 == 0 and P <= 24576): replays the forced assignment ("every truth
+//                      keeps its best prior, last truth wins"), positives get CE = lse - x[target]
+//                      (one gathered logit each) and move to the zero bin; radix-select of the
 //                      num_neg-th largest mining key (level 1 from the streamed histogram, levels
 //                      2/3 touch only the winning bin), canonical tie order, fixed-order fp64
-//                      reduction of smooth-L1 / CE, last CTA folds the per-image partials.
+//                      reduction of smooth-L1 / CE; the last CTA folds the partials and, multi-GPU,
+//                      exchanges {sum_l, sum_c, N} with the other ranks over NVLink peer memory.
 // (With SSDBOX_LOSS_SEPARATE_MATCH, or when two unit buffers do not fit beside the ring,
 // match_kernel of match.cu runs as a fourth launch before the stream kernel instead.)
 // The final CE over pos U neg needs no second pass over conf: CE of a negative is its mining key.
