@@ -559,6 +559,31 @@ def test_detect_fused_softmax(dev, name, B, seed, bias):
     assert torch.equal(plain[..., 0], ref[..., 0])
 
 
+def test_detect_mixed_density(dev):
+    """Some classes dense (lists overflow -> chunked top-k selection, chunks only partly active), some
+    with 33..1024 candidates (CTA-wide path), most sparse (warp path), in the same batch."""
+    name, B = "ssd512_coco", 2
+    cfg, c = configs.get(name)
+    pri = U.oracle_priors(name)
+    P, C = pri.size(0), cfg.MODEL.NUM_CLASSES
+    g = torch.Generator().manual_seed(77)
+    logits = torch.randn(B, P, C, generator=g)
+    logits[..., 0] += 9.0
+    logits[..., 3] += 6.5          # dense
+    logits[..., 12] += 6.0         # dense, another chunk
+    logits[..., 13] += 1.6         # a couple of hundred candidates
+    logits[1, :, 40] += 6.5        # dense in one image only
+    sc = torch.softmax(logits, -1)
+    loc = synth.gen_loc(B, P, 5)
+    n = (sc[..., 1:] > 0.01).sum(1)
+    assert int(n[0, 2]) > 1024 and int(n[0, 11]) > 1024 and 32 < int(n[0, 12]) < 1024 and int(n[0, 39]) <= 32 < 1024 < int(n[1, 39])
+    det = ssdbox.DetectOut(C, 0, 200, 0.01, 0.45, VAR)
+    out = det(loc.to(dev), sc.to(dev), pri.to(dev)).cpu()
+    ref = O.detect(loc, sc, pri, C)
+    _compare_detect(out, ref, "mixed density")
+    assert torch.equal(det.last_counts.cpu().long(), (ref[..., 0] > 0).sum(-1))
+
+
 def test_detect_empty_and_uniform(dev):
     pri = U.oracle_priors("refinedet320_voc")
     P, C = pri.size(0), 21
