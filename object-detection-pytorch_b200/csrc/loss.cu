@@ -866,10 +866,10 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   int* s_iscr = reinterpret_cast<int*>(smem_mine + 8192 + 800);                     // 64
   int* s_res = s_iscr + 64;                                                         // 8
   unsigned long long* s_best = reinterpret_cast<unsigned long long*>(smem_mine + kMineFixedSmem);   // kForceListMax
-  uint32_t* s_force = reinterpret_cast<uint32_t*>(s_best + kForceListMax);          // kForceListMax x 2
-  float* s_gt = reinterpret_cast<float*>(s_force + 2 * kForceListMax);              // kForceListMax x 5 (+3 pad)
+  float* s_gt = reinterpret_cast<float*>(s_best + 2 * kForceListMax);               // kForceListMax x 5 (+3 pad)
   uint32_t* s_list = reinterpret_cast<uint32_t*>(s_gt + 5 * kForceListMax + 8);     // P / CL + 4: prior | class << 16
-  __shared__ int s_last, s_nforce;
+  int16_t* s_ovr = reinterpret_cast<int16_t*>(s_list + ((a.P >> 2) + CL - 1) / CL * 4 + 4);   // forced label of a prior of this CTA, -1 = none
+  __shared__ int s_last;
   __shared__ uint32_t s_xch[4];      // [0..1] positives per CTA of the cluster, [2..3] tie counts
 
   const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
@@ -889,7 +889,6 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
 
   PHASE_MARK(0);
   // (1) everything this CTA needs from memory, requested together
-  if (tid == 0) s_nforce = 0;
   unsigned long long my_best = 0ull;
   if (small_g && tid < G) my_best = __ldcg(&a.gt_best[(size_t)b * a.gpad + tid]);
   const bool gt_cached = G <= kForceListMax;
@@ -941,44 +940,50 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   }
   s_hist[tid] = h0;
   s_hist[1024 + tid] = h1;
+  if (small_g) {
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+      const int ql = tid + j * kMineThreads;
+      if (ql < n4h) *reinterpret_cast<short4*>(s_ovr + ql * 4) = make_short4(-1, -1, -1, -1);
+    }
+  }
   if (small_g && tid < G) s_best[tid] = my_best;
   if (gt_cached && tid < 5 * G) s_gt[tid] = my_gt;
   sync_all();          // cluster: the peer's histogram copy is in place before it receives remote updates
 
   PHASE_MARK(1);
-  // (2) forced assignment on the shared list: truth j keeps its best prior unless a later truth
-  // claims the same prior (last truth wins); winners are patched into the owner's registers
+  // (2) forced assignment: truth j keeps its best prior unless a later truth claims the same prior
+  // (last truth wins); winners drop their label into a per-prior override array in shared memory
+  // that every thread merges into its registers (one 8-byte shared load per quad)
   if (small_g) {
     if (tid < G) {
       const uint32_t pj = ~(uint32_t)(s_best[tid] & 0xffffffffull);
       bool winner = pj < (uint32_t)P;
-      for (int j2 = tid + 1; winner && j2 < G; ++j2)
-        if (~(uint32_t)(s_best[j2] & 0xffffffffull) == pj) winner = false;
+      if (G <= 32) {                 // one warp holds every truth: the highest lane with this prior wins
+        const uint32_t same = __match_any_sync(__activemask(), pj);
+        winner = winner && (31 - __clz(same)) == (int)(tid & 31);
+      } else {
+        for (int j2 = tid + 1; winner && j2 < G; ++j2)
+          if (~(uint32_t)(s_best[j2] & 0xffffffffull) == pj) winner = false;
+      }
       if (winner) {
         const int lb = a.binarize ? 1 : (int)(s_gt[tid * 5 + 4] + 1.0f);
         if (rank == 0) a.lab_w[off + pj] = (int16_t)lb;
         a.tidx_w[off + pj] = (int16_t)tid;      // every CTA of the cluster: its positives read it back below
-        const int slot = atomicAdd(&s_nforce, 1);
-        s_force[2 * slot] = pj;
-        s_force[2 * slot + 1] = (uint32_t)lb;
+        const int ql = (int)(pj >> 2) - q0;
+        if (ql >= 0 && ql < n4h) s_ovr[ql * 4 + (int)(pj & 3u)] = (int16_t)lb;
       }
     }
     __syncthreads();
-    const int nf = s_nforce;
-    for (int f = 0; f < nf; ++f) {
-      const uint32_t pj = s_force[2 * f];
-      const int ql = (int)(pj >> 2) - q0;
-      if (ql >= 0 && ql < n4h && (ql & (kMineThreads - 1)) == tid) {
-        const int16_t lb = (int16_t)s_force[2 * f + 1];
-        const int j = ql / kMineThreads, e = (int)(pj & 3u);
 #pragma unroll
-        for (int jj = 0; jj < Q; ++jj)
-          if (jj == j) {
-            if (e == 0) ll[jj].x = lb;
-            else if (e == 1) ll[jj].y = lb;
-            else if (e == 2) ll[jj].z = lb;
-            else ll[jj].w = lb;
-          }
+    for (int j = 0; j < Q; ++j) {
+      const int ql = tid + j * kMineThreads;
+      if (ql < n4h) {
+        const short4 o = *reinterpret_cast<const short4*>(s_ovr + ql * 4);
+        if (o.x >= 0) ll[j].x = o.x;
+        if (o.y >= 0) ll[j].y = o.y;
+        if (o.z >= 0) ll[j].z = o.z;
+        if (o.w >= 0) ll[j].w = o.w;
       }
     }
   }
@@ -1034,33 +1039,29 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   __syncthreads();
 
   PHASE_MARK(3);
-  // one positive per thread: CE = lse - x[target] (multibox_loss.py:94,110) and smooth-L1 against
-  // the encoded truth (:87-90, box_utils.py:215-222)
-  double ce = 0.0, l1 = 0.0;
-  for (int sidx = tid; sidx < npos_blk; sidx += kMineThreads) {
-    const uint32_t ent = s_list[sidx];
-    const int p = (int)(ent & 0xffffu), lb = (int)(ent >> 16);
-    const size_t i = off + p;
-    const float lse = a.lse[i];
-    const float xt = a.conf[i * (size_t)a.C + lb];
-    const int t = a.tidx[i];
-    const float4 l = *reinterpret_cast<const float4*>(a.loc + i * 4);
-    const float4 pr = *reinterpret_cast<const float4*>(pri + (size_t)p * 4);
-    const float* row = gt_cached ? s_gt + t * 5 : a.gt + (size_t)(g0 + t) * 5;
-    Box m;
-    m.x1 = row[0]; m.y1 = row[1]; m.x2 = row[2]; m.y2 = row[3];
-    const float cep = lse - xt;
-    if (a.dbg_keys) a.dbg_keys[i] = cep;
-    ce += (double)cep;
-    float4 tt = encode_box(m, pr, a.var0, a.var1);
-    l1 += (double)(smooth_l1(l.x, tt.x) + smooth_l1(l.y, tt.y) + smooth_l1(l.z, tt.z) + smooth_l1(l.w, tt.w));
-  }
-  double dummy = 0.0;
-  block_sum3(dummy, ce, l1, s_dscr);
   int npos_img = npos_blk;
   if (CL > 1) {
     cluster_sync_all();           // remote histogram updates and positive counts have landed
     npos_img = (int)(s_xch[0] + s_xch[1]);
+  }
+  // one positive per thread: CE = lse - x[target] (multibox_loss.py:94,110) and smooth-L1 against
+  // the encoded truth (:87-90, box_utils.py:215-222).  The gathers of the first 1024 positives (all of
+  // them in practice) are only REQUESTED here -- the target logit comes from DRAM -- and consumed after
+  // the selection, which does not depend on them.
+  const bool havepos = tid < npos_blk;
+  float p_lse = 0.f, p_xt = 0.f;
+  int p_t = 0, p_p = 0;
+  float4 p_l = make_float4(0.f, 0.f, 0.f, 0.f), p_pr = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (havepos) {
+    const uint32_t ent = s_list[tid];
+    p_p = (int)(ent & 0xffffu);
+    const int lb = (int)(ent >> 16);
+    const size_t i = off + p_p;
+    p_lse = a.lse[i];
+    p_xt = a.conf[i * (size_t)a.C + lb];
+    p_t = a.tidx[i];
+    p_l = *reinterpret_cast<const float4*>(a.loc + i * 4);
+    p_pr = *reinterpret_cast<const float4*>(pri + (size_t)p_p * 4);
   }
 
   PHASE_MARK(4);
@@ -1165,6 +1166,25 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   }
 
   PHASE_MARK(5);
+  double ce = 0.0, l1 = 0.0;
+  auto positive = [&](size_t i, int p, float lse, float xt, int t, float4 l, float4 pr) {
+    const float* row = gt_cached ? s_gt + t * 5 : a.gt + (size_t)(g0 + t) * 5;
+    Box m;
+    m.x1 = row[0]; m.y1 = row[1]; m.x2 = row[2]; m.y2 = row[3];
+    const float cep = lse - xt;
+    if (a.dbg_keys) a.dbg_keys[i] = cep;
+    ce += (double)cep;
+    float4 tt = encode_box(m, pr, a.var0, a.var1);
+    l1 += (double)(smooth_l1(l.x, tt.x) + smooth_l1(l.y, tt.y) + smooth_l1(l.z, tt.z) + smooth_l1(l.w, tt.w));
+  };
+  if (havepos) positive(off + p_p, p_p, p_lse, p_xt, p_t, p_l, p_pr);
+  for (int sidx = tid + kMineThreads; sidx < npos_blk; sidx += kMineThreads) {
+    const uint32_t ent = s_list[sidx];
+    const int p = (int)(ent & 0xffffu), lb = (int)(ent >> 16);
+    const size_t i = off + p;
+    positive(i, p, a.lse[i], a.conf[i * (size_t)a.C + lb], a.tidx[i], *reinterpret_cast<const float4*>(a.loc + i * 4),
+             *reinterpret_cast<const float4*>(pri + (size_t)p * 4));
+  }
   // (5) neg = rank < num_neg (:103); CE over pos U neg (:106-110); the CE of a selected negative is
   // its mining key, recovered exactly from the ordered key
   double ce_neg = 0.0;
@@ -1190,7 +1210,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
     }
   }
   PHASE_MARK(6);
-  ce_neg = block_sum(ce_neg, s_dscr);
+  block_sum3(ce_neg, ce, l1, s_dscr);       // three independent fixed-shape trees, one set of barriers
   PHASE_MARK(7);
 
   if (tid == 0) {
@@ -1508,7 +1528,8 @@ extern "C" int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const 
     // (only while the 2*B CTAs still fit in one wave: one 1024-thread CTA per SM)
     const bool pair = P >= 8192 && 2 * B <= dev.sm_count && !(cfg->flags & SSDBOX_LOSS_NO_CLUSTER);
     mkern = pair ? mine_reduce_reg_kernel<2> : mine_reduce_reg_kernel<1>;
-    smem = kMineFixedSmem + (size_t)kForceListMax * 16 + (size_t)(5 * kForceListMax + 8) * 4 + (size_t)P * 4;
+    smem = kMineFixedSmem + (size_t)kForceListMax * 16 + (size_t)(5 * kForceListMax + 8) * 4 + (size_t)P * 4 + 16 +
+           (size_t)P * 2 + 16;      // ... + positives list + forced-label override array
     if (pair) {
       SSDBOX_CUDA(cudaFuncSetAttribute(mkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       cudaLaunchConfig_t lc = {};
