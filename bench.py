@@ -347,6 +347,31 @@ def main():
         evalpost_rows = int(rows_total)
     del rows_buf
 
+    # SURVEY 8f rank 3 (reported beside the headline): multibox head outputs (NCHW) -> conf [B,P,C]
+    from ssdbox import heads as HD
+    from oracle import ssd_oracle as _O   # only for the per-cell anchor counts of the config (host-side arithmetic)
+    per_cell = _O.num_priors_per_cell(cfg.MODEL)
+    with torch.no_grad():
+        head_outs = [torch.randn(B, a_ * C, h_, w_, device=dev) for a_, (h_, w_) in zip(per_cell, c["layer_dims"])]
+        rows_out = torch.empty(B, P, C, device=dev)
+        HD.heads_to_rows(head_outs, C, out=rows_out)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        for _ in range(5):
+            HD.heads_to_rows(head_outs, C, out=rows_out)
+        ev[1].record()
+        ref_rows = torch.cat([o.permute(0, 2, 3, 1).contiguous().view(B, -1) for o in head_outs], 1)
+        ev[2].record()
+        for _ in range(3):
+            ref_rows = torch.cat([o.permute(0, 2, 3, 1).contiguous().view(B, -1) for o in head_outs], 1)
+        ev[3].record()
+        torch.cuda.synchronize()
+        heads_us = 1e3 * ev[0].elapsed_time(ev[1]) / 5
+        heads_torch_us = 1e3 * ev[2].elapsed_time(ev[3]) / 3
+        heads_equal = bool(torch.equal(ref_rows.view(B, P, C), rows_out))
+    del head_outs, rows_out, ref_rows
+
     log("per-kernel timers done")
     # ---- the timed region: K replays of the captured step (or eager launches) -------------------
     use_graph = not args.no_graph
@@ -491,6 +516,9 @@ def main():
                                  "hbm_frac_of_kernel_sum": bytes_D(P, C, top_k) * B / (fused_us * 1e-6) / 1e9 / peak if fused_us else None},
         "eval_post": {"note": "ssdbox_detections_compact after DetectOut: rescale + convert_ssd_result + COCO post_proc (evaluate_utils.py:63-70,175-203), 2 launches incl. host launch overhead",
                       "us": evalpost_us, "rows": evalpost_rows, "bytes_read": B * C * top_k * 5 * 4},
+        "head_layout": {"note": "ssdbox_heads_to_rows: conf head outputs NCHW -> [B,P,C] in one launch (ssd_v3.py:114-121) against torch permute().contiguous() + cat",
+                        "us": heads_us, "torch_us": heads_torch_us, "bytes_moved": 2 * B * P * C * 4, "identical_to_torch": heads_equal,
+                        "hbm_frac": 2 * B * P * C * 4 / (heads_us * 1e-6) / 1e9 / peak},
         "step_hbm_frac": (bytes_T(P, C, g_avg, B) + bytes_D(P, C, top_k)) * B / (ms_per_step * 1e-3) / 1e9 / peak,
         other + "_kernel": {"avg_launch_us": kernels_us.get(other), "achieved_GBps": dom_bytes / (kernels_us[other] * 1e-6) / 1e9 if other in kernels_us else None,
                             "traffic": traffic.get(other)},

@@ -300,6 +300,22 @@ SSDBOX_API int ssdbox_detections_compact(const float* det, int32_t B, int32_t C,
                               ssdbox_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Head-output layout -- replaces lib/models/ssd_v3.py:114-121
+ * (rfb_net.py:213-220): permute(0,2,3,1).contiguous() of every multibox head output, view(B,-1)
+ * and cat(dim 1), i.e. the producer of loc [B,P,4] / conf [B,P,C].
+ *   src[k]   [B, channels_k, H_k, W_k] contiguous NCHW, channels_k = anchors_k * (4 | C), hw_k = H_k*W_k
+ *   out      [B, sum_k hw_k * channels_k]: per image the layers in order, each in (h, w, channel) order
+ * One launch, every element read once and written once. */
+#define SSDBOX_MAX_HEADS 16
+typedef struct {
+  int32_t num_layers, B;
+  int32_t channels[SSDBOX_MAX_HEADS];
+  int32_t hw[SSDBOX_MAX_HEADS];
+  const float* src[SSDBOX_MAX_HEADS];
+} ssdbox_heads_cfg;
+SSDBOX_API int ssdbox_heads_to_rows(const ssdbox_heads_cfg* cfg, float* out, ssdbox_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * RefineDet glue (not in the reference snapshot; arXiv 1711.06897).
  *   arm_conf [n,2] logits -> keep[n] uint8 = softmax(arm_conf)[:,1] > theta
  * (refined anchors come from ssdbox_decode with out_center).

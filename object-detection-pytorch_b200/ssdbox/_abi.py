@@ -29,7 +29,7 @@ SYMBOLS = [
     "ssdbox_multibox_loss_fwd", "ssdbox_multibox_loss_fwd_peers", "ssdbox_multibox_loss_peer_finish",
     "ssdbox_peer_buffer_bytes",
     "ssdbox_multibox_loss_finalize", "ssdbox_multibox_loss_bwd",
-    "ssdbox_nms", "ssdbox_detect", "ssdbox_detections_compact", "ssdbox_arm_filter", "ssdbox_timers_enable", "ssdbox_timers_read",
+    "ssdbox_nms", "ssdbox_detect", "ssdbox_detections_compact", "ssdbox_heads_to_rows", "ssdbox_arm_filter", "ssdbox_timers_enable", "ssdbox_timers_read",
 ]
 
 KERNEL_NAMES = ["init", "match", "loss_stream", "mine_reduce", "loss_bwd", "detect_stream", "detect_segment",
@@ -69,6 +69,14 @@ class DetectCfg(C.Structure):
 
 DETECT_LOGITS = 1
 MAX_PEERS = 16
+MAX_HEADS = 16
+
+
+class HeadsCfg(C.Structure):
+    """ssdbox_heads_cfg"""
+    _fields_ = [("num_layers", C.c_int32), ("B", C.c_int32), ("channels", C.c_int32 * MAX_HEADS),
+                ("hw", C.c_int32 * MAX_HEADS), ("src", C.c_void_p * MAX_HEADS)]
+
 
 
 class PeerGroup(C.Structure):
@@ -112,6 +120,7 @@ def _declare(lib):
         "ssdbox_detect": [C.POINTER(DetectCfg), P_, P_, P_, P_, P_, P_, P_, sz, P_],
         "ssdbox_arm_filter": [P_, i64, f32, P_, P_],
         "ssdbox_detections_compact": [P_, i32, i32, i32, P_, P_, i32, P_, i64, P_, P_, P_, sz, P_],
+        "ssdbox_heads_to_rows": [C.POINTER(HeadsCfg), P_, P_],
     }
     sigs["ssdbox_timers_enable"] = [C.c_int]
     sigs["ssdbox_timers_read"] = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]

@@ -161,6 +161,25 @@ def main():
     np.savez_compressed(os.path.join(OUT, "evalpost.npz"), det=np32(det), extra=np32(extra),
                         ids=np.array(ids, dtype=np.float32), voc=np32(voc), coco=np32(coco),
                         coco_rows=holder.results[0].astype(np.float32))
+    # ---- head-output layout (ssd_v3.py:113-121): the real model's forward on captured head outputs ----
+    from lib.models import model_factory
+    from lib.utils.config import cfg as ref_cfg
+    torch.manual_seed(0)
+    model, _, _ = model_factory(phase="train", cfg=ref_cfg)
+    outs = {"loc": [], "conf": []}
+    handles = []
+    for name in ("loc", "conf"):
+        for layer in getattr(model, name).children():
+            handles.append(layer.register_forward_hook(lambda m, i, o, name=name: outs[name].append(o.detach().clone())))
+    with torch.no_grad():
+        mloc, mconf = model(torch.randn(1, 3, 300, 300), phase="train")
+    for h in handles:
+        h.remove()
+    # the loc heads only (34928 floats): inputs and the reference's own output
+    heads = {"loc_out": np32(mloc)}
+    for k, o in enumerate(outs["loc"]):
+        heads["loc_in%d" % k] = np32(o)
+    np.savez_compressed(os.path.join(OUT, "heads.npz"), **heads)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

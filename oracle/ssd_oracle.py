@@ -413,3 +413,14 @@ def coco_post_proc(rows):
     rows[:, 2] -= rows[:, 0]
     rows[:, 3] -= rows[:, 1]
     return rows[:, [7, 0, 1, 2, 3, 4, 6]]
+
+
+# --------------------------------------------------------------------------------------
+# 8f rank 3: head-output layout (lib/models/ssd_v3.py:114-121, rfb_net.py:213-220)
+# --------------------------------------------------------------------------------------
+def heads_to_rows(outputs, k):
+    """outputs: list of multibox head outputs [B, A*k, H, W] -> [B, P, k]:
+    permute(0,2,3,1).contiguous() per layer (:115-116), view(B,-1) + cat(dim 1) (:118-119), view (:120-121)."""
+    rows = [o.permute(0, 2, 3, 1).contiguous() for o in outputs]
+    flat = torch.cat([o.view(o.size(0), -1) for o in rows], 1)
+    return flat.view(flat.size(0), -1, k)

@@ -781,3 +781,28 @@ def test_tiny_shapes(dev):
             out2 = ssdbox.DetectOut(C, 0, 3, 0.01, 0.45, VAR, conf_is_logits=True)(loc.to(dev), (conf * 3).to(dev), p.to(dev)).cpu()
             assert torch.equal(out2[..., 0] > 0, out[..., 0] > 0)
             U.assert_close_rel(out2, out, 2e-6, 1e-7, "tiny logits")
+
+
+# ------------------------------------------------------------------------------------------------
+# 8f rank 3: head-output layout (ssd_v3.py:114-121) -- pure data movement, bit-exact
+# ------------------------------------------------------------------------------------------------
+def test_head_output_layout(dev):
+    from ssdbox import heads as H
+    g = U.golden("heads.npz")
+    outs = [torch.tensor(g["loc_in%d" % k]).to(dev) for k in range(6)]
+    assert np.array_equal(H.heads_to_rows(outs, 4).cpu().numpy(), g["loc_out"])      # the reference model's own output
+    # SSD512-COCO head shapes (anchors x 81 channels, 64x64 ... 1x1), ragged tiles, B = 3
+    cfg, c = configs.get("ssd512_coco")
+    per_cell = O.num_priors_per_cell(cfg.MODEL)
+    gen = torch.Generator().manual_seed(5)
+    for K in (4, 81):
+        outs = [torch.randn(3, a * K, h, w, generator=gen) for a, (h, w) in zip(per_cell, c["layer_dims"])]
+        got = H.heads_to_rows([o.to(dev) for o in outs], K)
+        want = O.heads_to_rows(outs, K)
+        assert got.shape == (3, c["num_priors"], K) and torch.equal(got.cpu(), want)
+    # odd shapes: channels and H*W not multiples of the tile, one layer
+    o = torch.randn(2, 35, 7, 5, generator=gen)
+    assert torch.equal(H.heads_to_rows([o.to(dev)], 5).cpu(), O.heads_to_rows([o], 5))
+    # the result feeds the box path directly
+    loc = H.heads_to_rows([torch.randn(1, a * 4, h, w, generator=gen).to(dev) for a, (h, w) in zip(per_cell, c["layer_dims"])], 4)
+    assert loc.is_contiguous() and loc.shape == (1, c["num_priors"], 4)

@@ -149,3 +149,11 @@ def test_eval_post_processing_golden():
     coco = O.convert_ssd_result(scaled, coco_ids=g["ids"].tolist())
     assert np.array_equal(coco.numpy(), g["coco"])
     assert np.array_equal(O.coco_post_proc(coco).numpy(), g["coco_rows"])
+
+
+def test_head_output_layout_golden():
+    """oracle heads_to_rows against the loc tensor the reference's SSD300 model returned for the head
+    outputs recorded with it (lib/models/ssd_v3.py:113-121)."""
+    g = U.golden("heads.npz")
+    outs = [torch.tensor(g["loc_in%d" % k]) for k in range(6)]
+    assert np.array_equal(O.heads_to_rows(outs, 4).numpy(), g["loc_out"])

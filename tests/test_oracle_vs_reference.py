@@ -182,3 +182,25 @@ def test_eval_post_processing_bit_exact(ref):
     assert torch.equal(O.convert_ssd_result(scaled, coco_ids=ids), rc)
     eu.EvalCOCO.post_proc(holder, rc.clone(), 0, idt)
     assert (holder.results[0] == O.coco_post_proc(rc).numpy()).all()
+
+
+def test_head_output_layout_bit_exact(ref):
+    """oracle heads_to_rows == what the reference's SSD.forward (lib/models/ssd_v3.py:113-121) returns:
+    the real SSD300-VGG16 model (random weights) is run on CPU, its multibox head outputs are captured
+    with forward hooks and re-laid out by the oracle."""
+    from lib.models import model_factory
+    from lib.utils.config import cfg as ref_cfg
+    torch.manual_seed(0)
+    model, _, _ = model_factory(phase="train", cfg=ref_cfg)
+    outs = {"loc": [], "conf": []}
+    handles = []
+    for name in ("loc", "conf"):
+        for layer in getattr(model, name).children():
+            handles.append(layer.register_forward_hook(lambda m, i, o, name=name: outs[name].append(o.detach().clone())))
+    with torch.no_grad():
+        loc, conf = model(torch.randn(2, 3, 300, 300), phase="train")
+    for h in handles:
+        h.remove()
+    assert len(outs["loc"]) == 6 and outs["conf"][0].shape == (2, 84, 38, 38)
+    assert torch.equal(O.heads_to_rows(outs["loc"], 4), loc)
+    assert torch.equal(O.heads_to_rows(outs["conf"], ref_cfg.MODEL.NUM_CLASSES), conf)
