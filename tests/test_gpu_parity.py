@@ -806,3 +806,81 @@ def test_head_output_layout(dev):
     # the result feeds the box path directly
     loc = H.heads_to_rows([torch.randn(1, a * 4, h, w, generator=gen).to(dev) for a, (h, w) in zip(per_cell, c["layer_dims"])], 4)
     assert loc.is_contiguous() and loc.shape == (1, c["num_priors"], 4)
+
+
+# ------------------------------------------------------------------------------------------------
+# randomised shapes: arbitrary priors (not an SSD grid), odd sizes, every kernel variant by shape
+# ------------------------------------------------------------------------------------------------
+def _random_priors(P, g):
+    cxcy = torch.rand(P, 2, generator=g)
+    wh = torch.rand(P, 2, generator=g) * 0.45 + 0.03
+    return torch.cat([cxcy, wh], 1)
+
+
+@pytest.mark.parametrize("case", range(16))
+def test_random_shapes_against_oracle(dev, case):
+    g = torch.Generator().manual_seed(9000 + case)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+    B = ri(1, 4)
+    P = [ri(1, 40), ri(41, 700), ri(701, 2600), 4 * ri(180, 700)][case % 4]      # incl. P % 4 != 0 and P % 4 == 0
+    C = [2, 3, 7, 21, 33, 81, 90][case % 7]
+    gmax = [0, 1, 5, 37, 140][case % 5]
+    pri = _random_priors(P, g)
+    tg = []
+    for b in range(B):
+        n = ri(0, gmax) if gmax else 0
+        wh = torch.rand(n, 2, generator=g) * 0.5 + 0.04
+        xy = torch.rand(n, 2, generator=g) * (1 - wh)
+        tg.append(torch.cat([xy, xy + wh, torch.randint(0, C - 1, (n, 1), generator=g).float()], 1))
+    loc = torch.randn(B, P, 4, generator=g) * 0.4
+    conf = torch.randn(B, P, C, generator=g)
+    conf[..., 0] += float(ri(0, 5))
+    thr = [0.5, 0.35, 0.6][case % 3]
+    ratio = [3, 1, 5][case % 3]
+    # ---- loss (images without truths are legal for us; the oracle sees only the non-empty ones)
+    crit = ssdbox.MultiBoxLoss(C, thr, True, 0, True, ratio, 0.5, False)
+    d = crit.intermediates((loc.to(dev), conf.to(dev), pri.to(dev)), _gpu_targets(tg, dev))
+    keep = [b for b in range(B) if tg[b].size(0) > 0]
+    if keep:
+        r = O.multibox_loss(loc[keep], conf[keep], pri, [tg[b] for b in keep], C, threshold=thr, negpos_ratio=ratio, detail=True)
+        dk = {k: (v[keep] if torch.is_tensor(v) and v.dim() > 0 and v.size(0) == B else v) for k, v in d.items()}
+        _check_neg_sets(dk, r, P)
+        U.assert_close_rel(d["loss_l"], r["loss_l"], REL, 1e-7, "loss_l case %d" % case)
+        U.assert_close_rel(d["loss_c"], r["loss_c"], REL, 1e-7, "loss_c case %d" % case)
+    else:
+        assert float(d["loss_l"]) == 0.0 and float(d["loss_c"]) == 0.0
+    for b in range(B):
+        if tg[b].size(0) == 0:
+            assert int((d["sel"][b] >= 0).sum()) == 0
+    # ---- detect on scores and on logits, then the eval rows
+    top_k = [200, 5, 64][case % 3]
+    cthr = [0.01, 0.2, 0.05][case % 3]
+    sc = torch.softmax(conf * 2.0, -1)
+    det = ssdbox.DetectOut(C, 0, top_k, cthr, 0.45, VAR)
+    out = det(loc.to(dev), sc.to(dev), pri.to(dev))
+    ref = O.detect(loc, sc, pri, C, top_k=top_k, conf_thresh=cthr)
+    _compare_detect(out.cpu(), ref, "random case %d" % case)
+    from ssdbox import evaluate_utils as EU
+    extra = torch.rand(B, 2, generator=g) * 400 + 100
+    rows, _ = EU.convert_ssd_result(out, extra.to(dev))
+    assert torch.equal(rows.cpu(), O.convert_ssd_result(O.rescale_detections(out.cpu(), extra)))
+    # ---- fused softmax: same detections from the logits (scores to fp32 rounding of the softmax)
+    out_lg = ssdbox.DetectOut(C, 0, top_k, cthr, 0.45, VAR, conf_is_logits=True)(loc.to(dev), (conf * 2.0).to(dev), pri.to(dev)).cpu()
+    same = torch.equal(out_lg[..., 0] > 0, ref[..., 0] > 0)
+    if same:
+        U.assert_close_rel(out_lg[..., 0], ref[..., 0], 2e-6, 0, "logits scores case %d" % case)
+    else:       # a score within rounding of the threshold / of another score may flip a decision
+        assert int(((out_lg[..., 0] > 0) != (ref[..., 0] > 0)).sum()) <= 2
+    # ---- backward of the loss (all truths present) against autograd through the oracle
+    if keep and len(keep) == B and case % 2 == 0:
+        lo = loc.to(dev).requires_grad_(True)
+        co = conf.to(dev).requires_grad_(True)
+        ll, lc = crit((lo, co, pri.to(dev)), _gpu_targets(tg, dev))
+        (ll + 0.5 * lc).backward()
+        lr = loc.clone().requires_grad_(True)
+        cr = conf.clone().requires_grad_(True)
+        rl, rc = O.multibox_loss(lr, cr, pri, tg, C, threshold=thr, negpos_ratio=ratio)
+        (rl + 0.5 * rc).backward()
+        if torch.equal(d["neg"].cpu().bool(), r["neg"]):
+            U.assert_close_rel(lo.grad, lr.grad, REL, 1e-8, "grad_loc case %d" % case)
+            U.assert_close_rel(co.grad, cr.grad, REL, 1e-8, "grad_conf case %d" % case)
