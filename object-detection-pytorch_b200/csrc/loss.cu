@@ -26,6 +26,8 @@
 // match_kernel of match.cu runs as a fourth launch before the stream kernel instead.)
 // The final CE over pos U neg needs no second pass over conf: CE of a negative is its mining key.
 // Backward zero-fills grad_conf and touches conf only on the selected rows.
+#include <cstdlib>
+
 #include "ops.h"
 #include "ring.cuh"
 #include "select.cuh"
@@ -1370,6 +1372,184 @@ __global__ void __launch_bounds__(kBwdThreads) loss_bwd_kernel(BwdArgs a) {
   }
 }
 
+// ---- backward as ONE write-bound streaming kernel (aligned grad_conf, C <= 128) -------------------
+// Persistent CTAs; every warp owns one shared-memory tile of kBwdTileRows x C floats that is all zeros
+// except while it carries the gradient rows of the selected priors of the tile it is working on:
+//   1. `sel` of the tile (2 rows per lane; requested one tile ahead), ballot of the selected rows
+//   2. for each selected row: the logits row -> (softmax - onehot) * grad / N written into the tile
+//   3. fence.proxy.async, ONE TMA bulk store of the whole tile (zeros + rows) to grad_conf
+//   4. grad_loc rows of the tile with plain 16-byte stores (zeros, or smooth-L1' for positives)
+//   5. when the bulk store has read the tile, the patched rows are zeroed again
+// The zero fill therefore costs no store instructions, the few reads (3 MB of sel, 20 MB of logits rows)
+// run tiles ahead of the write stream in the other warps, and nothing is written twice.
+constexpr int kBwdTileRows = 64;
+constexpr int kBwdStreamWarps = 10;
+
+// per-tile read state of a warp: the class targets of its two rows (requested two tiles ahead) and the
+// logits of the first four selected rows
+struct BwdPre {
+  int lb[2];
+  int rl[4], tl[4];
+  float xv[4][4];
+  unsigned long long rest;     // selected rows beyond the first four
+};
+
+template <int CT>
+__global__ void __launch_bounds__(kBwdStreamWarps * 32, 1) loss_bwd_stream_kernel(BwdArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_bwd[];
+  const int C = CT > 0 ? CT : a.C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* tile = reinterpret_cast<float*>(smem_bwd) + (size_t)warp * kBwdTileRows * C;
+  const long long rows = (long long)a.B * a.P;
+  const long long tiles = (rows + kBwdTileRows - 1) / kBwdTileRows;
+  const long long per_cta = (tiles + gridDim.x - 1) / gridDim.x;
+  const long long t_begin = (long long)blockIdx.x * per_cta;
+  const long long t_end = t_begin + per_cta < tiles ? t_begin + per_cta : tiles;
+  const double n = a.sums[2];
+  const float scale_l = n > 0.0 ? (float)((double)a.grad_out[0] / n) : 0.0f;
+  const float scale_c = n > 0.0 ? (float)((double)a.grad_out[1] / n) : 0.0f;
+  for (int i = lane; i < kBwdTileRows * C; i += 32) tile[i] = 0.f;
+  __syncwarp();
+
+  // sel of a tile (2 rows per lane)
+  auto load_sel = [&](long long t, BwdPre& p) {
+    p.lb[0] = p.lb[1] = -1;
+    if (t < t_end) {
+      const long long r0 = t * kBwdTileRows + lane * 2;
+      if (r0 + 1 < rows) {
+        const short2 v = *reinterpret_cast<const short2*>(a.sel + r0);     // 8-byte aligned array, r0 even
+        p.lb[0] = v.x; p.lb[1] = v.y;
+      } else if (r0 < rows) {
+        p.lb[0] = a.sel[r0];
+      }
+    }
+  };
+  // the logits rows of the first four selected rows of the tile, requested together
+  auto load_rows = [&](long long t, BwdPre& p) {
+    const long long row0 = t * kBwdTileRows;
+    const uint32_t m0 = __ballot_sync(SSDBOX_FULL_MASK, p.lb[0] >= 0);
+    const uint32_t m1 = __ballot_sync(SSDBOX_FULL_MASK, p.lb[1] >= 0);
+    unsigned long long m = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      p.rl[j] = -1;
+      p.tl[j] = 0;
+      if (m) {
+        const int bit = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const int k = bit >> 5, src = bit & 31;
+        p.tl[j] = __shfl_sync(SSDBOX_FULL_MASK, k ? p.lb[1] : p.lb[0], src);
+        p.rl[j] = src * 2 + k;
+        const float* x = a.conf + (row0 + p.rl[j]) * C;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) p.xv[j][u] = lane + 32 * u < C ? x[lane + 32 * u] : -INFINITY;
+      }
+    }
+    p.rest = m;
+  };
+  auto put_row = [&](int rl, int tl, const float (&xv)[4]) {
+    float mx = fmaxf(fmaxf(xv[0], xv[1]), fmaxf(xv[2], xv[3]));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(SSDBOX_FULL_MASK, mx, d));
+    float e[4], sum = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      e[u] = lane + 32 * u < C ? expf(xv[u] - mx) : 0.f;
+      sum += e[u];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(SSDBOX_FULL_MASK, sum, d);
+    const float inv = 1.0f / sum;
+    float* g = tile + (size_t)rl * C;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = lane + 32 * u;
+      if (c < C) g[c] = scale_c * (e[u] * inv - (c == tl ? 1.0f : 0.0f));
+    }
+  };
+
+  BwdPre cur, nxt;
+  long long t = t_begin + warp;
+  load_sel(t, cur);
+  load_sel(t + kBwdStreamWarps, nxt);
+  uint32_t patched[2] = {0u, 0u};              // rows of my tile that currently hold non-zero data (bit = lane, per k)
+  for (; t < t_end; t += kBwdStreamWarps) {
+    const long long row0 = t * kBwdTileRows;
+    const int nrows = (int)(rows - row0 < kBwdTileRows ? rows - row0 : kBwdTileRows);
+    // the previous bulk store of this warp has read the tile: clear what it carried
+    bulk_wait_read_all();
+    __syncwarp();          // (lane 0 owns the bulk group: nobody touches the tile before its wait returns)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      uint32_t m = patched[k];
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        float* g = tile + (size_t)(src * 2 + k) * C;
+        for (int c = lane; c < C; c += 32) g[c] = 0.f;
+      }
+    }
+    // sel of this tile was requested two tiles ago; the rows it selects are requested now, four at a time
+    // (measured: requesting them one tile ahead, behind this warp's own stores, is slower)
+    load_rows(t, cur);
+    patched[0] = __ballot_sync(SSDBOX_FULL_MASK, cur.lb[0] >= 0);
+    patched[1] = __ballot_sync(SSDBOX_FULL_MASK, cur.lb[1] >= 0);
+    // gradient rows of the selected priors: (softmax - onehot) * grad / N
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (cur.rl[j] >= 0) put_row(cur.rl[j], cur.tl[j], cur.xv[j]);
+    unsigned long long m = cur.rest;           // more than four selected rows in the tile (rare)
+    while (m) {
+      const int bit = __ffsll((long long)m) - 1;
+      m &= m - 1;
+      const int k = bit >> 5, src = bit & 31;
+      const int tl = __shfl_sync(SSDBOX_FULL_MASK, k ? cur.lb[1] : cur.lb[0], src);
+      const int rl = src * 2 + k;
+      const float* x = a.conf + (row0 + rl) * C;
+      float xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) xv[u] = lane + 32 * u < C ? x[lane + 32 * u] : -INFINITY;
+      put_row(rl, tl, xv);
+    }
+    __syncwarp();
+    const uint32_t bytes = (uint32_t)nrows * (uint32_t)C * 4u;
+    float* dst = a.grad_conf + row0 * C;
+    if ((bytes & 15u) == 0u) {
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) bulk_s2g(dst, tile, bytes);
+    } else {                                   // ragged last tile: plain stores
+      for (int i = lane; i < nrows * C; i += 32) dst[i] = tile[i];
+    }
+    // grad_loc of the tile: zeros, or smooth-L1' for positives
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const long long row = row0 + lane * 2 + k;
+      if (row >= rows) continue;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (cur.lb[k] > 0) {
+        const int b = (int)((uint32_t)row / (uint32_t)a.P);
+        const int pi = (int)((uint32_t)row - (uint32_t)b * (uint32_t)a.P);
+        const float4 l = *reinterpret_cast<const float4*>(a.loc + row * 4);
+        const float4 pr = *reinterpret_cast<const float4*>(a.priors + (size_t)b * (size_t)a.prior_stride + (size_t)pi * 4);
+        const float* tr = a.gt + (size_t)(a.gt_offsets[b] + a.tidx[row]) * 5;
+        Box mbox;
+        mbox.x1 = tr[0]; mbox.y1 = tr[1]; mbox.x2 = tr[2]; mbox.y2 = tr[3];
+        float4 tt = encode_box(mbox, pr, a.var0, a.var1);
+        g.x = scale_l * fminf(fmaxf(l.x - tt.x, -1.f), 1.f);     // smooth-L1': d for |d|<1, sign(d) otherwise
+        g.y = scale_l * fminf(fmaxf(l.y - tt.y, -1.f), 1.f);
+        g.z = scale_l * fminf(fmaxf(l.z - tt.z, -1.f), 1.f);
+        g.w = scale_l * fminf(fmaxf(l.w - tt.w, -1.f), 1.f);
+      }
+      __stcs(reinterpret_cast<float4*>(a.grad_loc + row * 4), g);
+    }
+    // advance the read pipeline: sel two tiles ahead
+    cur = nxt;
+    load_sel(t + 2 * kBwdStreamWarps, nxt);
+  }
+  bulk_wait_all();          // the tile must outlive its last bulk store
+}
+
 }  // namespace ssdbox
 
 using namespace ssdbox;
@@ -1616,6 +1796,7 @@ extern "C" int ssdbox_multibox_loss_bwd(const ssdbox_loss_cfg* cfg, const float*
                  SSDBOX_EINVAL, "loss_bwd: null pointer");
   SSDBOX_REQUIRE(aligned16(loc) && aligned16(priors) && aligned16(grad_loc), SSDBOX_EALIGN,
                  "loss_bwd: box pointers must be 16-byte aligned");
+  SSDBOX_REQUIRE((reinterpret_cast<uintptr_t>(sel) & 7u) == 0, SSDBOX_EALIGN, "loss_bwd: sel must be 8-byte aligned");
   DevInfo dev;
   rc = get_dev_info(&dev);
   if (rc) return rc;
@@ -1629,7 +1810,15 @@ extern "C" int ssdbox_multibox_loss_bwd(const ssdbox_loss_cfg* cfg, const float*
   a.conf_aligned = aligned16(grad_conf) ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long rows = (long long)a.B * a.P;
-  {
+  const size_t stream_smem = (size_t)kBwdStreamWarps * kBwdTileRows * a.C * 4;
+  if (a.conf_aligned && a.C <= 128 && stream_smem <= (size_t)dev.max_smem_optin - 1024 && !getenv("SSDBOX_BWD_TWO_PASS")) {
+    void (*kern)(BwdArgs) = a.C == 81 ? loss_bwd_stream_kernel<81> : (a.C == 21 ? loss_bwd_stream_kernel<21> : loss_bwd_stream_kernel<0>);
+    SSDBOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem));
+    long long tiles = (rows + kBwdTileRows - 1) / kBwdTileRows;
+    int grid = (int)(tiles < dev.sm_count ? tiles : dev.sm_count);
+    TimerScope ts__(KID_LOSS_BWD, st);
+    kern<<<grid, kBwdStreamWarps * 32, stream_smem, st>>>(a);
+  } else {
     TimerScope ts__(KID_LOSS_BWD, st);
     zero_fill_kernel<<<dev.sm_count * 16, kBwdThreads, 0, st>>>(grad_conf, (size_t)rows * a.C, a.conf_aligned);
     long long groups = (rows + 31) / 32;
