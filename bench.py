@@ -518,7 +518,7 @@ def main():
         "step_bytes_model": "T: P*(4C+16)+20G+16P/B per image; D: P*(4C+16)+20*C*top_k per image (SURVEY.md 8d)",
         "train_fwd": {"kernel_us_sum": t_us, "bytes_per_image": bytes_T(P, C, g_avg, B),
                       "hbm_frac_of_kernel_sum": bytes_T(P, C, g_avg, B) * B / (t_us * 1e-6) / 1e9 / peak if t_us else None},
-        "train_bwd": {"kernel_us_sum": bwd_us, "note": "zero_fill + sparse-row kernels; grad_conf/grad_loc fully written",
+        "train_bwd": {"kernel_us_sum": bwd_us, "note": "loss_bwd_stream_kernel: one pass, TMA bulk stores of zero tiles carrying the selected rows; grad_conf/grad_loc fully written",
                       "bytes_written_per_image": P * (4 * C + 16),
                       "hbm_frac": P * (4 * C + 16) * B / (bwd_us * 1e-6) / 1e9 / peak if bwd_us else None},
         "detect": {"kernel_us_sum": d_us, "bytes_per_image": bytes_D(P, C, top_k),

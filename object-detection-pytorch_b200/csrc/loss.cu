@@ -1472,10 +1472,21 @@ __global__ void __launch_bounds__(kBwdStreamWarps * 32, 1) loss_bwd_stream_kerne
   long long t = t_begin + warp;
   load_sel(t, cur);
   load_sel(t + kBwdStreamWarps, nxt);
+  load_rows(t, cur);
   uint32_t patched[2] = {0u, 0u};              // rows of my tile that currently hold non-zero data (bit = lane, per k)
   for (; t < t_end; t += kBwdStreamWarps) {
     const long long row0 = t * kBwdTileRows;
     const int nrows = (int)(rows - row0 < kBwdTileRows ? rows - row0 : kBwdTileRows);
+    // read pipeline first (ahead of this iteration's stores): the selected logits rows of the NEXT tile
+    // of this warp (its sel arrived an iteration ago), sel of the one after
+    load_rows(t + kBwdStreamWarps, nxt);
+    int lb_nn[2];
+    {
+      BwdPre tmp;
+      load_sel(t + 2 * kBwdStreamWarps, tmp);
+      lb_nn[0] = tmp.lb[0];
+      lb_nn[1] = tmp.lb[1];
+    }
     // the previous bulk store of this warp has read the tile: clear what it carried
     bulk_wait_read_all();
     __syncwarp();          // (lane 0 owns the bulk group: nobody touches the tile before its wait returns)
@@ -1489,9 +1500,6 @@ __global__ void __launch_bounds__(kBwdStreamWarps * 32, 1) loss_bwd_stream_kerne
         for (int c = lane; c < C; c += 32) g[c] = 0.f;
       }
     }
-    // sel of this tile was requested two tiles ago; the rows it selects are requested now, four at a time
-    // (measured: requesting them one tile ahead, behind this warp's own stores, is slower)
-    load_rows(t, cur);
     patched[0] = __ballot_sync(SSDBOX_FULL_MASK, cur.lb[0] >= 0);
     patched[1] = __ballot_sync(SSDBOX_FULL_MASK, cur.lb[1] >= 0);
     // gradient rows of the selected priors: (softmax - onehot) * grad / N
@@ -1543,9 +1551,9 @@ __global__ void __launch_bounds__(kBwdStreamWarps * 32, 1) loss_bwd_stream_kerne
       }
       __stcs(reinterpret_cast<float4*>(a.grad_loc + row * 4), g);
     }
-    // advance the read pipeline: sel two tiles ahead
     cur = nxt;
-    load_sel(t + 2 * kBwdStreamWarps, nxt);
+    nxt.lb[0] = lb_nn[0];
+    nxt.lb[1] = lb_nn[1];
   }
   bulk_wait_all();          // the tile must outlive its last bulk store
 }
