@@ -1373,30 +1373,33 @@ __global__ void __launch_bounds__(kBwdThreads) loss_bwd_kernel(BwdArgs a) {
 }
 
 // ---- backward as ONE write-bound streaming kernel (aligned grad_conf, C <= 128) -------------------
-// Persistent CTAs; every warp owns one shared-memory tile of kBwdTileRows x C floats that is all zeros
+// Persistent CTAs; every warp owns one shared-memory tile of kBwdTileRows x C floats (41 KB at C = 81)
+// that is all zeros
 // except while it carries the gradient rows of the selected priors of the tile it is working on:
-//   1. `sel` of the tile (2 rows per lane; requested one tile ahead), ballot of the selected rows
+//   1. `sel` of the tile (4 rows per lane; requested two tiles ahead), ballot of the selected rows
 //   2. for each selected row: the logits row -> (softmax - onehot) * grad / N written into the tile
 //   3. fence.proxy.async, ONE TMA bulk store of the whole tile (zeros + rows) to grad_conf
 //   4. grad_loc rows of the tile with plain 16-byte stores (zeros, or smooth-L1' for positives)
 //   5. when the bulk store has read the tile, the patched rows are zeroed again
 // The zero fill therefore costs no store instructions, the few reads (3 MB of sel, 20 MB of logits rows)
 // run tiles ahead of the write stream in the other warps, and nothing is written twice.
-constexpr int kBwdTileRows = 64;
-constexpr int kBwdStreamWarps = 10;
+constexpr int kBwdRPL = 1;                          // rows of a tile per lane (1, 2 or 4)
+constexpr int kBwdTileRows = 32 * kBwdRPL;          // 32 rows = 10 KB bulk stores at C = 81
+constexpr int kBwdStreamWarps = 20;                 // measured: 5 warps x 128 rows 217 us, 10 x 64 134 us
 
-// per-tile read state of a warp: the class targets of its two rows (requested two tiles ahead) and the
-// logits of the first four selected rows
+// per-tile read state of a warp: the class targets of its rows (requested two tiles ahead) and the
+// logits of the first four selected rows (requested one tile ahead)
 struct BwdPre {
-  int lb[2];
+  int lb[kBwdRPL];
   int rl[4], tl[4];
   float xv[4][4];
-  unsigned long long rest;     // selected rows beyond the first four
+  uint32_t rest[kBwdRPL];      // selected rows beyond the first four, per row slot (bit = lane)
 };
 
 template <int CT>
 __global__ void __launch_bounds__(kBwdStreamWarps * 32, 1) loss_bwd_stream_kernel(BwdArgs a) {
   extern __shared__ __align__(128) unsigned char smem_bwd[];
+  constexpr int RPL = kBwdRPL;
   const int C = CT > 0 ? CT : a.C;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* tile = reinterpret_cast<float*>(smem_bwd) + (size_t)warp * kBwdTileRows * C;
@@ -1411,41 +1414,52 @@ __global__ void __launch_bounds__(kBwdStreamWarps * 32, 1) loss_bwd_stream_kerne
   for (int i = lane; i < kBwdTileRows * C; i += 32) tile[i] = 0.f;
   __syncwarp();
 
-  // sel of a tile (2 rows per lane)
-  auto load_sel = [&](long long t, BwdPre& p) {
-    p.lb[0] = p.lb[1] = -1;
+  // sel of a tile (RPL consecutive rows per lane; row r of the tile = lane * RPL + k)
+  auto load_sel = [&](long long t, int (&lb)[RPL]) {
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) lb[k] = -1;
     if (t < t_end) {
-      const long long r0 = t * kBwdTileRows + lane * 2;
-      if (r0 + 1 < rows) {
-        const short2 v = *reinterpret_cast<const short2*>(a.sel + r0);     // 8-byte aligned array, r0 even
-        p.lb[0] = v.x; p.lb[1] = v.y;
-      } else if (r0 < rows) {
-        p.lb[0] = a.sel[r0];
+      const long long r0 = t * kBwdTileRows + lane * RPL;
+      if (RPL == 4 && r0 + 3 < rows) {
+        const short4 v = *reinterpret_cast<const short4*>(a.sel + r0);     // 8-byte aligned array, r0 % 4 == 0
+        lb[0] = v.x; lb[1 % RPL] = v.y; lb[2 % RPL] = v.z; lb[3 % RPL] = v.w;
+      } else if (RPL == 2 && r0 + 1 < rows) {
+        const short2 v = *reinterpret_cast<const short2*>(a.sel + r0);
+        lb[0] = v.x; lb[1 % RPL] = v.y;
+      } else {
+#pragma unroll
+        for (int k = 0; k < RPL; ++k)
+          if (r0 + k < rows) lb[k] = a.sel[r0 + k];
       }
     }
   };
   // the logits rows of the first four selected rows of the tile, requested together
   auto load_rows = [&](long long t, BwdPre& p) {
     const long long row0 = t * kBwdTileRows;
-    const uint32_t m0 = __ballot_sync(SSDBOX_FULL_MASK, p.lb[0] >= 0);
-    const uint32_t m1 = __ballot_sync(SSDBOX_FULL_MASK, p.lb[1] >= 0);
-    unsigned long long m = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
+    int nfound = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      p.rl[j] = -1;
-      p.tl[j] = 0;
-      if (m) {
-        const int bit = __ffsll((long long)m) - 1;
+    for (int j = 0; j < 4; ++j) p.rl[j] = -1;
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {
+      uint32_t m = __ballot_sync(SSDBOX_FULL_MASK, p.lb[k] >= 0);
+      while (m && nfound < 4) {
+        const int src = __ffs(m) - 1;
         m &= m - 1;
-        const int k = bit >> 5, src = bit & 31;
-        p.tl[j] = __shfl_sync(SSDBOX_FULL_MASK, k ? p.lb[1] : p.lb[0], src);
-        p.rl[j] = src * 2 + k;
-        const float* x = a.conf + (row0 + p.rl[j]) * C;
+        const int tl = __shfl_sync(SSDBOX_FULL_MASK, p.lb[k], src);
+        const int rl = src * RPL + k;
+        const float* x = a.conf + (row0 + rl) * C;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) p.xv[j][u] = lane + 32 * u < C ? x[lane + 32 * u] : -INFINITY;
+        for (int j = 0; j < 4; ++j)
+          if (j == nfound) {
+            p.rl[j] = rl;
+            p.tl[j] = tl;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p.xv[j][u] = lane + 32 * u < C ? x[lane + 32 * u] : -INFINITY;
+          }
+        ++nfound;
       }
+      p.rest[k] = m;
     }
-    p.rest = m;
   };
   auto put_row = [&](int rl, int tl, const float (&xv)[4]) {
     float mx = fmaxf(fmaxf(xv[0], xv[1]), fmaxf(xv[2], xv[3]));
@@ -1470,54 +1484,52 @@ __global__ void __launch_bounds__(kBwdStreamWarps * 32, 1) loss_bwd_stream_kerne
 
   BwdPre cur, nxt;
   long long t = t_begin + warp;
-  load_sel(t, cur);
-  load_sel(t + kBwdStreamWarps, nxt);
+  load_sel(t, cur.lb);
+  load_sel(t + kBwdStreamWarps, nxt.lb);
   load_rows(t, cur);
-  uint32_t patched[2] = {0u, 0u};              // rows of my tile that currently hold non-zero data (bit = lane, per k)
+  uint32_t patched[RPL];                       // rows of my tile that currently hold non-zero data (bit = lane, per slot)
+#pragma unroll
+  for (int k = 0; k < RPL; ++k) patched[k] = 0u;
   for (; t < t_end; t += kBwdStreamWarps) {
     const long long row0 = t * kBwdTileRows;
     const int nrows = (int)(rows - row0 < kBwdTileRows ? rows - row0 : kBwdTileRows);
     // read pipeline first (ahead of this iteration's stores): the selected logits rows of the NEXT tile
     // of this warp (its sel arrived an iteration ago), sel of the one after
     load_rows(t + kBwdStreamWarps, nxt);
-    int lb_nn[2];
-    {
-      BwdPre tmp;
-      load_sel(t + 2 * kBwdStreamWarps, tmp);
-      lb_nn[0] = tmp.lb[0];
-      lb_nn[1] = tmp.lb[1];
-    }
+    int lb_nn[RPL];
+    load_sel(t + 2 * kBwdStreamWarps, lb_nn);
     // the previous bulk store of this warp has read the tile: clear what it carried
     bulk_wait_read_all();
     __syncwarp();          // (lane 0 owns the bulk group: nobody touches the tile before its wait returns)
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < RPL; ++k) {
       uint32_t m = patched[k];
       while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
-        float* g = tile + (size_t)(src * 2 + k) * C;
+        float* g = tile + (size_t)(src * RPL + k) * C;
         for (int c = lane; c < C; c += 32) g[c] = 0.f;
       }
+      patched[k] = __ballot_sync(SSDBOX_FULL_MASK, cur.lb[k] >= 0);
     }
-    patched[0] = __ballot_sync(SSDBOX_FULL_MASK, cur.lb[0] >= 0);
-    patched[1] = __ballot_sync(SSDBOX_FULL_MASK, cur.lb[1] >= 0);
     // gradient rows of the selected priors: (softmax - onehot) * grad / N
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (cur.rl[j] >= 0) put_row(cur.rl[j], cur.tl[j], cur.xv[j]);
-    unsigned long long m = cur.rest;           // more than four selected rows in the tile (rare)
-    while (m) {
-      const int bit = __ffsll((long long)m) - 1;
-      m &= m - 1;
-      const int k = bit >> 5, src = bit & 31;
-      const int tl = __shfl_sync(SSDBOX_FULL_MASK, k ? cur.lb[1] : cur.lb[0], src);
-      const int rl = src * 2 + k;
-      const float* x = a.conf + (row0 + rl) * C;
-      float xv[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) xv[u] = lane + 32 * u < C ? x[lane + 32 * u] : -INFINITY;
-      put_row(rl, tl, xv);
+    for (int k = 0; k < RPL; ++k) {
+      uint32_t m = cur.rest[k];                // more than four selected rows in the tile
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int tl = __shfl_sync(SSDBOX_FULL_MASK, cur.lb[k], src);
+        const int rl = src * RPL + k;
+        const float* x = a.conf + (row0 + rl) * C;
+        float xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xv[u] = lane + 32 * u < C ? x[lane + 32 * u] : -INFINITY;
+        put_row(rl, tl, xv);
+      }
     }
     __syncwarp();
     const uint32_t bytes = (uint32_t)nrows * (uint32_t)C * 4u;
@@ -1531,8 +1543,8 @@ __global__ void __launch_bounds__(kBwdStreamWarps * 32, 1) loss_bwd_stream_kerne
     }
     // grad_loc of the tile: zeros, or smooth-L1' for positives
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const long long row = row0 + lane * 2 + k;
+    for (int k = 0; k < RPL; ++k) {
+      const long long row = row0 + lane * RPL + k;
       if (row >= rows) continue;
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
       if (cur.lb[k] > 0) {
@@ -1552,8 +1564,8 @@ __global__ void __launch_bounds__(kBwdStreamWarps * 32, 1) loss_bwd_stream_kerne
       __stcs(reinterpret_cast<float4*>(a.grad_loc + row * 4), g);
     }
     cur = nxt;
-    nxt.lb[0] = lb_nn[0];
-    nxt.lb[1] = lb_nn[1];
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) nxt.lb[k] = lb_nn[k];
   }
   bulk_wait_all();          // the tile must outlive its last bulk store
 }
