@@ -61,7 +61,8 @@ enum {
   SSDBOX_OP_NMS = 4,
   SSDBOX_OP_LSE = 5,
   SSDBOX_OP_MINE = 6,
-  SSDBOX_OP_COMPACT = 7       /* ssdbox_detections_compact: B, C used */
+  SSDBOX_OP_COMPACT = 7,      /* ssdbox_detections_compact: B, C used */
+  SSDBOX_OP_VOC_EVAL = 8      /* ssdbox_voc_eval: P = detection rows, C = classes, gmax = truths (all images) */
 };
 
 SSDBOX_API int ssdbox_abi_version(void);
@@ -298,6 +299,53 @@ SSDBOX_API int ssdbox_detections_compact(const float* det, int32_t B, int32_t C,
                               const float* image_ids, int32_t mode, float* out, int64_t capacity_rows,
                               int32_t* total, int32_t* seg_offsets, void* ws, size_t ws_bytes,
                               ssdbox_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * PASCAL VOC evaluation of the accumulated detections -- replaces the chain
+ * evaluate_detections -> write_voc_results_file -> do_python_eval -> voc_eval -> voc_ap of
+ * lib/datasets/voc_eval.py:58-75, 78-106, 109-242, 244-262 for all classes in one call.
+ *   rows        [num_rows, row_stride] fp32, columns 0..4 = (xmin, ymin, xmax, ymax, score) in pixels:
+ *               the rows ssdbox_detections_compact writes (mode 0 / 1), all images concatenated,
+ *               grouped by (image, class) segments
+ *   seg_offsets int32 [num_images*num_classes + 1] first row of every (image, class) segment
+ *   gt_boxes    [num_gt,4] fp32 pixel boxes as parse_rec yields them (:26-30), 16-byte aligned;
+ *   gt_labels   int32 [num_gt] class index as in the rows' class column (1-based, 0 = background);
+ *   gt_difficult uint8 [num_gt];  gt_offsets int32 [num_images+1] truths of image i
+ * The reference prints every detection to a text file ('{:.3f}' score, '{:.1f}' coordinate + 1) and
+ * parses it back; the same quantisation is applied arithmetically (exact, see voceval.cu).  Scores
+ * must quantise into [0, 1]; *status counts the rows that do not (their bin is clamped).
+ * Outputs (sorted order = by class, then descending quantised score, equal scores in row order --
+ * the stable form of np.argsort(-confidence) :178):
+ *   order       int32 [num_rows]  sorted position -> row index
+ *   cls_offsets int32 [num_classes+1] class c owns sorted positions cls_offsets[c] .. cls_offsets[c+1]-1
+ *   tpfp        uint8 [num_rows]  1 true positive, 2 false positive, 0 neither (matched a difficult truth :208)
+ *   rec, prec   fp64 [num_rows]   :218-223, bit-exact
+ *   ap          fp64 [num_classes] ap[c] for c >= 1; -1 for a class without detections (:238-241);
+ *               11-point metric bit-exact, area metric summed in a fixed tree order (1e-12 relative)
+ *   npos        int32 [num_classes] non-difficult truths per class (:163)
+ * ws: SSDBOX_OP_VOC_EVAL. */
+typedef struct {
+  int32_t num_images, num_classes;
+  int32_t num_rows, row_stride;
+  int32_t num_gt;
+  int32_t use_07_metric;
+  double ovthresh;
+} ssdbox_voc_eval_cfg;
+SSDBOX_API int ssdbox_voc_eval(const ssdbox_voc_eval_cfg* cfg, const float* rows, const int32_t* seg_offsets,
+                    const float* gt_boxes, const int32_t* gt_labels, const uint8_t* gt_difficult,
+                    const int32_t* gt_offsets, int32_t* order, int32_t* cls_offsets, uint8_t* tpfp, double* rec,
+                    double* prec, double* ap, int32_t* npos, int32_t* status, void* ws, size_t ws_bytes,
+                    ssdbox_stream_t stream);
+
+/* The data-parallel part of RandomSampleCrop trials (lib/utils/augmentations.py:13-37 jaccard_numpy,
+ * :250-268), batched over B images x T candidate rects, fp64 like the numpy pipeline (bit-exact).
+ *   boxes       fp64 [box_offsets[B], 4] absolute xyxy truths;  box_offsets int32 [B+1]
+ *   rects       int64 [B,T,4] candidate crops (x1, y1, x2, y2) (:248)
+ *   overlap     fp64, image b holds [T, G_b] at element box_offsets[b]*T (nullable)
+ *   minmax      fp64 [B,T,2] overlap.min(), overlap.max() of the trial (:254); (+inf, -inf) when G_b = 0
+ *   center_mask uint8, same layout as overlap: truth centre strictly inside the rect (:257-268) (nullable) */
+SSDBOX_API int ssdbox_crop_overlaps(const double* boxes, const int32_t* box_offsets, const int64_t* rects, int32_t B,
+                         int32_t T, double* overlap, double* minmax, uint8_t* center_mask, ssdbox_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Head-output layout -- replaces lib/models/ssd_v3.py:114-121

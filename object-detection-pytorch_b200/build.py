@@ -17,7 +17,7 @@ OUT_DIR = os.path.join(HERE, "ssdbox", "lib")
 OUT = os.path.join(OUT_DIR, "libssdbox.so")
 STAMP = OUT + ".stamp"
 
-SOURCES = ["abi.cu", "boxops.cu", "match.cu", "loss.cu", "detect.cu", "evalpost.cu", "heads.cu"]
+SOURCES = ["abi.cu", "boxops.cu", "match.cu", "loss.cu", "detect.cu", "evalpost.cu", "heads.cu", "voceval.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-cudart", "static",

@@ -148,6 +148,7 @@ extern "C" size_t ssdbox_workspace_bytes(int op, int B, int P, int C, int gmax, 
     case SSDBOX_OP_LSE: return 256;
     case SSDBOX_OP_MINE: return mine_ws_bytes(B, P) + 256;
     case SSDBOX_OP_COMPACT: return compact_ws_bytes(B, C) + 256;
+    case SSDBOX_OP_VOC_EVAL: return voc_eval_ws_bytes(P, gmax, C) + 256;
     default: return 0;
   }
 }

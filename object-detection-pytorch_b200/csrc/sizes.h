@@ -65,6 +65,14 @@ static inline size_t compact_ws_bytes(int B, int C) {
   return align_up((size_t)B * C * 4) + align_up(((size_t)B * C + 1) * 4) + 256;
 }
 
+// ---- VOC evaluation (rows = detections, M = truths) -------------------------------------------
+static inline size_t voc_eval_ws_bytes(int rows, int M, int C) {
+  const size_t n = (size_t)rows + 1;
+  const size_t nblk = ((size_t)rows + 4095) / 4096;
+  return align_up(((size_t)M + 1) * 8) + 6 * align_up(n * 4) + align_up((size_t)C * 4) +
+         align_up(256 * (nblk ? nblk : 1) * 4) + 256;
+}
+
 // ---- nms -----------------------------------------------------------------------------------
 static inline size_t nms_ws_bytes(int n, int top_k) {
   (void)top_k;

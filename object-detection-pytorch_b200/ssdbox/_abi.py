@@ -18,7 +18,7 @@ LOSS_SEPARATE_MATCH = 1
 LOSS_GENERIC_MINE = 2
 LOSS_NO_CLUSTER = 4
 LOSS_DEFER_PEER_WAIT = 8
-OP_MATCH, OP_LOSS_FWD, OP_DETECT, OP_NMS, OP_LSE, OP_MINE, OP_COMPACT = 1, 2, 3, 4, 5, 6, 7
+OP_MATCH, OP_LOSS_FWD, OP_DETECT, OP_NMS, OP_LSE, OP_MINE, OP_COMPACT, OP_VOC_EVAL = 1, 2, 3, 4, 5, 6, 7, 8
 MAX_LAYERS, MAX_MIN_SIZES, MAX_RATIOS = 16, 4, 6
 
 # every symbol include/ssdbox.h declares (tests check the library exports exactly these)
@@ -29,7 +29,7 @@ SYMBOLS = [
     "ssdbox_multibox_loss_fwd", "ssdbox_multibox_loss_fwd_peers", "ssdbox_multibox_loss_peer_finish",
     "ssdbox_peer_buffer_bytes",
     "ssdbox_multibox_loss_finalize", "ssdbox_multibox_loss_bwd",
-    "ssdbox_nms", "ssdbox_detect", "ssdbox_detections_compact", "ssdbox_heads_to_rows", "ssdbox_arm_filter", "ssdbox_timers_enable", "ssdbox_timers_read",
+    "ssdbox_nms", "ssdbox_detect", "ssdbox_detections_compact", "ssdbox_heads_to_rows", "ssdbox_voc_eval", "ssdbox_crop_overlaps", "ssdbox_arm_filter", "ssdbox_timers_enable", "ssdbox_timers_read",
 ]
 
 KERNEL_NAMES = ["init", "match", "loss_stream", "mine_reduce", "loss_bwd", "detect_stream", "detect_segment",
@@ -79,6 +79,13 @@ class HeadsCfg(C.Structure):
 
 
 
+class VocEvalCfg(C.Structure):
+    """ssdbox_voc_eval_cfg"""
+    _fields_ = [("num_images", C.c_int32), ("num_classes", C.c_int32), ("num_rows", C.c_int32),
+                ("row_stride", C.c_int32), ("num_gt", C.c_int32), ("use_07_metric", C.c_int32),
+                ("ovthresh", C.c_double)]
+
+
 class PeerGroup(C.Structure):
     """ssdbox_peer_group: every rank's exchange buffer as addressable from this device."""
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("bufs", C.c_void_p * MAX_PEERS)]
@@ -121,6 +128,8 @@ def _declare(lib):
         "ssdbox_arm_filter": [P_, i64, f32, P_, P_],
         "ssdbox_detections_compact": [P_, i32, i32, i32, P_, P_, i32, P_, i64, P_, P_, P_, sz, P_],
         "ssdbox_heads_to_rows": [C.POINTER(HeadsCfg), P_, P_],
+        "ssdbox_voc_eval": [C.POINTER(VocEvalCfg)] + [P_] * 14 + [P_, sz, P_],
+        "ssdbox_crop_overlaps": [P_, P_, P_, i32, i32, P_, P_, P_, P_],
     }
     sigs["ssdbox_timers_enable"] = [C.c_int]
     sigs["ssdbox_timers_read"] = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]

@@ -136,3 +136,83 @@ def load():
     ns.detect = detect
     _REF = ns
     return ns
+
+
+def voc_eval_reference(case, workdir, use_07_metric=True, ovthresh=0.5):
+    """Runs the reference's own write_voc_results_file + voc_eval (lib/datasets/voc_eval.py:58-75,
+    109-242) on a case of ssdbox.synth.gen_voc_eval_case: the annotation cache (annots.pkl, what
+    :143-150 would write after parsing the xml files), the image-set file and the per-class result
+    files are created under `workdir`.  Returns [(rec, prec, ap)] for the classes 1..C-1.
+
+    Shim S5: the module-level `devkit_path` (:9, from the global cfg) is pointed at `workdir` while the
+    result files are written; the `dets == []` test of :65 is a list-vs-ndarray comparison that numpy 2
+    evaluates element-wise, so images without detections keep the reference's own `[]` placeholder and
+    the others go through unchanged."""
+    import pickle
+
+    import numpy as np
+    load()
+    import lib.datasets.voc_eval as ve
+    C, I = int(case["num_classes"]), int(case["num_images"])
+    names = ["%06d" % (i + 1) for i in range(I)]
+    classes = ["cls%02d" % c for c in range(1, C)]
+    recs = {}
+    for i, nm in enumerate(names):
+        objs = []
+        for g in range(int(case["gt_offsets"][i]), int(case["gt_offsets"][i + 1])):
+            objs.append({"name": classes[int(case["gt_labels"][g]) - 1], "pose": "Unspecified", "truncated": 0,
+                         "difficult": int(case["gt_difficult"][g]), "bbox": [int(v) for v in case["gt_boxes"][g]]})
+        recs[nm] = objs
+    cachedir = os.path.join(workdir, "annotations_cache")
+    os.makedirs(cachedir, exist_ok=True)
+    with open(os.path.join(cachedir, "annots.pkl"), "wb") as f:
+        pickle.dump(recs, f)
+    imageset = os.path.join(workdir, "test.txt")
+    with open(imageset, "w") as f:
+        f.write("\n".join(names) + "\n")
+    # EvalVOC.reset_results / post_proc layout (evaluate_utils.py:122-151): results[cls][img] = float32 [n,5] or []
+    seg, rows = case["seg"], case["rows"]
+    all_boxes = [[[] for _ in range(I)] for _ in range(C)]
+    for i in range(I):
+        for c in range(1, C):
+            a, b = int(seg[i * C + c]), int(seg[i * C + c + 1])
+            if b > a:
+                all_boxes[c][i] = rows[a:b, 0:5].astype(np.float32, copy=False)
+    dataset = types.SimpleNamespace(ids=[("VOC2007", nm) for nm in names])
+    saved = (ve.devkit_path, ve.labelmap)
+    ve.devkit_path, ve.labelmap = workdir, classes
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            _write_results(ve, all_boxes, dataset)
+        out = []
+        for cls in classes:
+            detfile = ve.get_voc_results_file_template("test", cls)
+            out.append(ve.voc_eval(detfile, os.path.join(workdir, "%s.xml"), imageset, cls, cachedir,
+                                   ovthresh=ovthresh, use_07_metric=use_07_metric))
+    finally:
+        ve.devkit_path, ve.labelmap = saved
+    return out
+
+
+def _write_results(ve, all_boxes, dataset):
+    """write_voc_results_file (:58-75) unmodified when numpy still accepts its `dets == []` test;
+    otherwise the same per-line format call (:70-74) driven from here."""
+    try:
+        import io
+        import contextlib
+        with contextlib.redirect_stdout(io.StringIO()):
+            ve.write_voc_results_file(all_boxes, dataset, "test")
+        return "reference"
+    except (ValueError, TypeError):
+        for cls_ind, cls in enumerate(ve.labelmap):
+            with open(ve.get_voc_results_file_template("test", cls), "wt") as f:
+                for im_ind, index in enumerate(dataset.ids):
+                    dets = all_boxes[cls_ind + 1][im_ind]
+                    if isinstance(dets, list):
+                        continue
+                    for k in range(dets.shape[0]):
+                        f.write('{:s} {:.3f} {:.1f} {:.1f} {:.1f} {:.1f}\n'.format(
+                            index[1], dets[k, -1], dets[k, 0] + 1, dets[k, 1] + 1, dets[k, 2] + 1, dets[k, 3] + 1))
+        return "format-only"

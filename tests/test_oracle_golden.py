@@ -157,3 +157,43 @@ def test_head_output_layout_golden():
     g = U.golden("heads.npz")
     outs = [torch.tensor(g["loc_in%d" % k]) for k in range(6)]
     assert np.array_equal(O.heads_to_rows(outs, 4).numpy(), g["loc_out"])
+
+
+def test_voc_eval_golden():
+    """oracle voc_eval_rows against rec / prec / ap recorded from the reference's voc_eval
+    (lib/datasets/voc_eval.py:109-242; oracle/make_golden_voc.py), both AP metrics."""
+    from oracle import voc_oracle as V
+    g = U.golden("voceval.npz")
+    I, C = len(g["gt_offsets"]) - 1, 21
+    for tag, use07 in (("07", True), ("area", False)):
+        got, _ = V.voc_eval_rows(g["rows"], g["seg"], I, C, g["gt_boxes"], g["gt_labels"], g["gt_difficult"],
+                                 g["gt_offsets"], 0.5, use07)
+        assert np.array_equal(np.array([m["ap"] for m in got]), g["ap_" + tag])
+    rec = np.concatenate([m["rec"] for m in got if np.ndim(m["rec"])])
+    prec = np.concatenate([m["prec"] for m in got if np.ndim(m["prec"])])
+    assert np.array_equal(rec, g["rec"], equal_nan=True) and np.array_equal(prec, g["prec"])
+    assert [len(m["tp"]) for m in got] == g["count"].tolist()
+
+
+def test_text_round_trip_is_arithmetic():
+    """The CUDA path replaces '{:.3f}' / '{:.1f}' + float() (voc_eval.py:70-74, 170-175) by
+    rint(x * 10^d) / 10^d in float64; the two agree bit for bit on float32 inputs, including exact
+    halves (x * 10^d is exact in float64, rint and the formatter both round half to even)."""
+    rs = np.random.RandomState(0)
+    s = np.concatenate([rs.rand(20000).astype(np.float32), np.float32([0.0005, 0.0015, 0.0025, 0.5, 1.0, 0.9995, 0.0104999]),
+                        (np.arange(0, 2000, dtype=np.float32) + 0.5) / np.float32(1000)])
+    x = np.concatenate([(rs.rand(20000) * 600 - 20).astype(np.float32), np.float32([0.05, 0.15, 0.25, 12.25, 100.75, -0.05, -3.35]),
+                        np.arange(0, 4000, dtype=np.float32) / np.float32(20)])
+    want_s = np.array([float('{:.3f}'.format(v)) for v in s])
+    want_x = np.array([float('{:.1f}'.format(v + 1)) for v in x])
+    assert np.array_equal(np.rint(s.astype(np.float64) * 1000.0) / 1000.0, want_s)
+    assert np.array_equal(np.rint((x + np.float32(1)).astype(np.float64) * 10.0) / 10.0, want_x)
+
+
+def test_crop_overlaps_golden():
+    from oracle import make_golden_voc as MG
+    from oracle import voc_oracle as V
+    g = U.golden("voceval.npz")
+    boxes, rects = MG.crop_inputs()
+    got = np.concatenate([V.jaccard_numpy(bx, rects[b, t]) for b, bx in enumerate(boxes) for t in range(rects.shape[1])])
+    assert np.array_equal(got, g["crop_overlap"])

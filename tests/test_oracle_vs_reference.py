@@ -204,3 +204,46 @@ def test_head_output_layout_bit_exact(ref):
     assert len(outs["loc"]) == 6 and outs["conf"][0].shape == (2, 84, 38, 38)
     assert torch.equal(O.heads_to_rows(outs["loc"], 4), loc)
     assert torch.equal(O.heads_to_rows(outs["conf"], ref_cfg.MODEL.NUM_CLASSES), conf)
+
+
+@pytest.mark.parametrize("use07", [True, False])
+def test_voc_eval_bit_exact(ref, use07, tmp_path):
+    """oracle voc_eval_rows == the reference's write_voc_results_file + voc_eval + voc_ap
+    (lib/datasets/voc_eval.py:58-75, 78-106, 109-242) on result files and an annotation cache written
+    to a temporary directory: rec, prec and ap bit for bit, with the literal (unstable) argsort and --
+    on a tie-free set -- with the canonical stable order the CUDA path implements."""
+    import contextlib
+    import io
+    import numpy as np
+    from oracle import voc_oracle as V
+    for kw, stable in ((dict(seed=3), False), (dict(seed=4, distinct_scores=True), True)):
+        case = synth.gen_voc_eval_case(50, 21, **kw)
+        with contextlib.redirect_stdout(io.StringIO()):
+            want = ref_loader.voc_eval_reference(case, str(tmp_path), use07)
+        got, mean_ap = V.voc_eval_rows(case["rows"], case["seg"], 50, 21, case["gt_boxes"], case["gt_labels"],
+                                       case["gt_difficult"], case["gt_offsets"], 0.5, use07, stable=stable)
+        assert len(want) == len(got) == 20
+        seen = 0
+        for (rec, prec, ap), m in zip(want, got):
+            if np.ndim(rec) == 0:
+                assert rec == prec == ap == -1. and m["ap"] == -1.
+                continue
+            seen += 1
+            assert np.array_equal(rec, m["rec"], equal_nan=True) and np.array_equal(prec, m["prec"])
+            assert ap == m["ap"]
+        assert seen >= 15
+        assert mean_ap == float(np.mean([w[2] for w in want]))
+
+
+def test_crop_overlaps_bit_exact(ref):
+    """oracle jaccard_numpy == lib/utils/augmentations.py:20-37 (float64 truths, int64 rect)."""
+    import numpy as np
+    import lib.utils.augmentations as aug
+    from oracle import voc_oracle as V
+    rs = np.random.RandomState(0)
+    for _ in range(20):
+        G = rs.randint(1, 12)
+        xy = rs.rand(G, 2) * 300
+        boxes = np.concatenate([xy, xy + rs.rand(G, 2) * 150 + 1], 1)
+        rect = np.array([int(rs.uniform(0, 200)), int(rs.uniform(0, 200)), int(rs.uniform(220, 500)), int(rs.uniform(220, 400))])
+        assert np.array_equal(aug.jaccard_numpy(boxes, rect), V.jaccard_numpy(boxes, rect))
