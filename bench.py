@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-voc-eval", action="store_true", help="skip the VOC evaluation side phase")
     ap.add_argument("--dense", action="store_true", help="detect scores with background bias 4 (worst case)")
     return ap.parse_args()
 
@@ -372,6 +373,37 @@ def main():
         heads_equal = bool(torch.equal(ref_rows.view(B, P, C), rows_out))
     del head_outs, rows_out, ref_rows
 
+    # SURVEY 8f rank 4 (reported beside the headline): PASCAL VOC evaluation of an accumulated result set
+    voc_phase = None
+    if rank == 0 and not args.no_voc_eval:
+        from ssdbox import voc_eval as VE
+        n_img = 4952                                   # VOC2007 test
+        case = synth.gen_voc_eval_case(n_img, 21, 11, fp_max=12)
+        vgt = VE.VOCGroundTruth(case["gt_boxes"], case["gt_labels"], case["gt_difficult"], case["gt_offsets"], dev)
+        vrows, vseg = torch.as_tensor(case["rows"]).to(dev), torch.as_tensor(case["seg"]).to(dev)
+        res = VE.voc_eval(vrows, vseg, vgt, 21)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(5):
+            res = VE.voc_eval(vrows, vseg, vgt, 21)
+        ev[1].record()
+        torch.cuda.synchronize()
+        voc_phase = {"note": "ssdbox_voc_eval: write_voc_results_file + voc_eval + voc_ap (lib/datasets/voc_eval.py:58-242) for all 20 classes of a "
+                             "synthetic VOC2007-test sized result set, incl. the host mirror's status read",
+                     "images": n_img, "detections": int(vrows.size(0)), "truths": int(case["gt_boxes"].shape[0]),
+                     "us": 1e3 * ev[0].elapsed_time(ev[1]) / 5, "mean_ap": res.mean_ap}
+        if not args.no_cpu_baseline and n_gpus == 1:
+            from oracle import voc_oracle as _V    # CPU leg only: the reference algorithm's port timed beside the GPU call
+            sub = synth.gen_voc_eval_case(300, 21, 12, fp_max=12)
+            t0 = time.perf_counter()
+            _V.voc_eval_rows(sub["rows"], sub["seg"], 300, 21, sub["gt_boxes"], sub["gt_labels"], sub["gt_difficult"], sub["gt_offsets"])
+            dt = time.perf_counter() - t0
+            voc_phase["cpu_port"] = {"sample": "300 images, %d detections, numpy oracle, 1 thread" % sub["rows"].shape[0],
+                                     "detections_per_s": sub["rows"].shape[0] / dt,
+                                     "extrapolated_s_for_this_set": int(vrows.size(0)) * dt / sub["rows"].shape[0]}
+        del vrows, vseg, vgt, res
+
     log("per-kernel timers done")
     # ---- the timed region: K replays of the captured step (or eager launches) -------------------
     use_graph = not args.no_graph
@@ -532,6 +564,7 @@ def main():
         "head_layout": {"note": "ssdbox_heads_to_rows: conf head outputs NCHW -> [B,P,C] in one launch (ssd_v3.py:114-121) against torch permute().contiguous() + cat",
                         "us": heads_us, "torch_us": heads_torch_us, "bytes_moved": 2 * B * P * C * 4, "identical_to_torch": heads_equal,
                         "hbm_frac": 2 * B * P * C * 4 / (heads_us * 1e-6) / 1e9 / peak},
+        "voc_eval": voc_phase,
         "step_hbm_frac": (bytes_T(P, C, g_avg, B) + bytes_D(P, C, top_k)) * B / (ms_per_step * 1e-3) / 1e9 / peak,
         other + "_kernel": {"avg_launch_us": kernels_us.get(other), "achieved_GBps": dom_bytes / (kernels_us[other] * 1e-6) / 1e9 if other in kernels_us else None,
                             "traffic": traffic.get(other)},
