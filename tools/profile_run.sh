@@ -9,9 +9,9 @@ python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "bench exit 
 python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_reference.json 2> $O/${TAG}_bench_reference.err; echo "reference exit $?"
 CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 --no-graph"
 $CMD > $O/${TAG}_plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_ncu_launches.csv $CMD > $O/${TAG}_ncu_list.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/${TAG}_ncu_launches.csv $CMD > $O/${TAG}_ncu_list.log 2>&1
 echo "ncu list exit $?"
 $CMD > $O/${TAG}_plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k 'regex:loss_stream|detect_stream|mine_reduce|detect_segment|detect_overflow' -s 10 -c 10 -f -o $O/${TAG}_prof $CMD > $O/${TAG}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k 'regex:loss_stream|loss_bwd_stream|detect_stream|mine_reduce|detect_segment|detect_overflow' -s 10 -c 14 -f -o $O/${TAG}_prof $CMD > $O/${TAG}_ncu_full.log 2>&1
 echo "ncu full exit $?"
 ls -la $O | tail -12

@@ -78,7 +78,7 @@ if os.path.isfile(ll):
             nm = r[4].split("(")[0].replace("void ", "")
             agg.setdefault(nm, []).append(float(r[-1]) / 1e3)
     ours = {k: v for k, v in agg.items() if k.startswith("ssdbox::")}
-    fwd = [k for k in ours if not any(s in k for s in ("zero_fill", "loss_bwd", "priorbox", ", 1>", "compact_", "peer_finish", "heads_to_rows"))]
+    fwd = [k for k in ours if not any(s in k for s in ("zero_fill", "loss_bwd", "priorbox", ", 1>", "compact_", "peer_finish", "heads_to_rows", "voc_", "radix_", "crop_"))]
     tot = sum(mean(ours[k]) * (2 if "init_kernel" in k else 1) for k in fwd)
     lines += ["", "## launch list (ncu --metrics gpu__time_duration.sum, cold cache, serialised): share of one step (T fwd + D)", "",
               "| kernel | launches | mean us | share of step |", "|---|---|---|---|"]
