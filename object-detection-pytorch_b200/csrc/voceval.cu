@@ -148,18 +148,21 @@ __global__ void __launch_bounds__(kRadixThreads) radix_hist_kernel(const uint32_
   blockhist[(size_t)threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];    // digit-major
 }
 
-// exclusive scan of blockhist in (digit, block) order, in place (one CTA)
+// exclusive scan of blockhist in (digit, block) order, in place (one CTA): every thread sums a run of
+// consecutive entries, one block scan of the run totals, then the run is rewritten with its prefixes
+// (two barriers in all; the table is a few hundred KB and stays in L2)
 __global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t* blockhist, int total) {
   __shared__ int s_scan[33];
-  int running = 0;
-  for (int base = 0; base < total; base += 1024) {
-    const int i = base + threadIdx.x;
-    const int v = i < total ? (int)blockhist[i] : 0;
-    int sum;
-    const int ex = block_exclusive_scan(v, s_scan, &sum);
-    if (i < total) blockhist[i] = (uint32_t)(running + ex);
-    running += sum;
-    __syncthreads();
+  const int per = (total + 1023) / 1024;
+  const int lo = min(threadIdx.x * per, total), hi = min(lo + per, total);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += (int)blockhist[i];
+  int all;
+  int run = block_exclusive_scan(sum, s_scan, &all);
+  for (int i = lo; i < hi; ++i) {
+    const int v = (int)blockhist[i];
+    blockhist[i] = (uint32_t)run;
+    run += v;
   }
 }
 

@@ -88,9 +88,7 @@ class VOCEvalResult(object):
 
     def __init__(self, order, cls_offsets, tpfp, rec, prec, ap, npos):
         self.order, self.tpfp, self._rec, self._prec = order, tpfp, rec, prec
-        self.cls_offsets = cls_offsets.cpu().numpy()
-        self.ap = ap.cpu().numpy()
-        self.npos = npos.cpu().numpy()
+        self.cls_offsets, self.ap, self.npos = cls_offsets, ap, npos      # host numpy arrays
 
     def _range(self, c):
         return int(self.cls_offsets[c]), int(self.cls_offsets[c + 1])
@@ -131,10 +129,12 @@ def voc_eval(rows, seg, gt, num_classes, ovthresh=0.5, use_07_metric=True):
     tpfp = torch.empty(N, dtype=torch.uint8, device=dev)
     rec = torch.empty(N, dtype=torch.float64, device=dev)
     prec = torch.empty(N, dtype=torch.float64, device=dev)
-    cls_offsets = torch.empty(C + 1, dtype=torch.int32, device=dev)
-    ap = torch.empty(C, dtype=torch.float64, device=dev)
-    npos = torch.empty(C, dtype=torch.int32, device=dev)
-    status = torch.empty(1, dtype=torch.int32, device=dev)
+    # the small outputs share one buffer so that the host needs a single D2H copy:
+    # ap fp64 [C] | cls_offsets int32 [C+1] | npos int32 [C] | status int32 [1]
+    small = torch.empty(8 * C + 4 * (2 * C + 2), dtype=torch.uint8, device=dev)
+    ap = small[:8 * C].view(torch.float64)
+    ints = small[8 * C:].view(torch.int32)
+    cls_offsets, npos, status = ints[:C + 1], ints[C + 1:2 * C + 1], ints[2 * C + 1:]
     cfg = _abi.VocEvalCfg(I, C, N, rows.size(1), M, 1 if use_07_metric else 0, float(ovthresh))
     ws, n = _ws.setdefault(dev, _abi.Workspace()).get(_abi.workspace_bytes(_abi.OP_VOC_EVAL, 0, N, C, M), dev)
     _abi.check(_abi.lib().ssdbox_voc_eval(
@@ -143,10 +143,13 @@ def voc_eval(rows, seg, gt, num_classes, ovthresh=0.5, use_07_metric=True):
         _abi.ptr(gt.difficult, torch.uint8, "gt difficult"), _abi.ptr(gt.offsets, torch.int32, "gt offsets"),
         _abi.ptr(order), _abi.ptr(cls_offsets), _abi.ptr(tpfp), _abi.ptr(rec), _abi.ptr(prec), _abi.ptr(ap),
         _abi.ptr(npos), _abi.ptr(status), ws, n, _abi.stream_ptr(dev)))
-    bad = int(status.item())
+    host = small.cpu()
+    h_ints = host[8 * C:].view(torch.int32).numpy()
+    bad = int(h_ints[2 * C + 1])
     if bad:
         raise ValueError("voc_eval: %d detection scores fall outside [0, 1] after '%%.3f' rounding" % bad)
-    return VOCEvalResult(order, cls_offsets, tpfp, rec, prec, ap, npos)
+    return VOCEvalResult(order, h_ints[:C + 1].copy(), tpfp, rec, prec, host[:8 * C].view(torch.float64).numpy().copy(),
+                         h_ints[C + 1:2 * C + 1].copy())
 
 
 def evaluate_detections(detections, gt, classes, ovthresh=0.5, use_07_metric=True):
