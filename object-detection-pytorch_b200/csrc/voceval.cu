@@ -40,6 +40,7 @@ constexpr int kRadixRounds = 16;                                       // items 
 constexpr int kRadixTile = kRadixThreads * kRadixRounds;               // 4096 items per CTA
 constexpr int kScoreBits = 10;                                         // 1000 - k, k = 0..1000
 constexpr int kCurveThreads = 1024;
+constexpr int kCurveItems = 4;                                         // 4096 positions per block scan: counts fit 16 bits
 
 struct VocArgs {
   const float* rows;
@@ -286,33 +287,52 @@ __global__ void __launch_bounds__(kCurveThreads) voc_curve_kernel(VocArgs a) {
 #pragma unroll
   for (int q = 0; q < 11; ++q) m[q] = 0.0;
   int carry_tp = 0, carry_fp = 0;
-  for (int base = 0; base < n; base += kCurveThreads) {
-    const int p = base + tid;
-    int tp = 0, fp = 0;
-    if (p < n) {
-      const uint32_t row = (uint32_t)a.order[begin + p];
-      const int code = a.code[row];
-      if (code == -2) {
-        fp = 1;
-      } else if (code >= 0) {                                          // :209-214: the first detection in sorted order claims the truth
-        const unsigned long long mine = ((unsigned long long)(a.skey[row] & ((1u << kScoreBits) - 1u)) << 32) | row;
-        if (a.claim[code] == mine) tp = 1; else fp = 1;
+  // kCurveItems consecutive sorted positions per thread: the three dependent gathers (order -> code /
+  // key -> claim) of the items overlap and one block scan serves kCurveItems * 1024 positions
+  for (int base = 0; base < n; base += kCurveThreads * kCurveItems) {
+    const int p0 = base + tid * kCurveItems;
+    uint32_t row[kCurveItems];
+    int code[kCurveItems];
+    uint32_t bin[kCurveItems];
+    int flag[kCurveItems];                                             // (tp << 16) | fp
+#pragma unroll
+    for (int q = 0; q < kCurveItems; ++q) row[q] = p0 + q < n ? (uint32_t)a.order[begin + p0 + q] : 0u;
+#pragma unroll
+    for (int q = 0; q < kCurveItems; ++q) {
+      const bool valid = p0 + q < n;
+      code[q] = valid ? a.code[row[q]] : -1;
+      bin[q] = valid ? a.skey[row[q]] & ((1u << kScoreBits) - 1u) : 0u;
+    }
+    int mine_sum = 0;
+#pragma unroll
+    for (int q = 0; q < kCurveItems; ++q) {
+      int f = 0;
+      if (code[q] == -2) {
+        f = 1;
+      } else if (code[q] >= 0) {                                       // :209-214: the first detection in sorted order claims the truth
+        const unsigned long long key = ((unsigned long long)bin[q] << 32) | row[q];
+        f = a.claim[code[q]] == key ? (1 << 16) : 1;
       }
+      flag[q] = f;
+      mine_sum += f;
     }
     int sum;
-    const int packed = (tp << 16) | fp;
-    const int inc = block_exclusive_scan(packed, s_scan, &sum) + packed;
-    if (p < n) {
-      const double t = (double)(carry_tp + (inc >> 16));               // np.cumsum of 0/1 doubles: exact integers
-      const double f = (double)(carry_fp + (inc & 0xffff));
-      const double r = __ddiv_rn(t, npos);                             // :220
-      const double pr = __ddiv_rn(t, fmax(__dadd_rn(t, f), DBL_EPSILON));   // :223
-      a.rec[begin + p] = r;
-      a.prec[begin + p] = pr;
-      a.tpfp[begin + p] = tp ? 1 : (fp ? 2 : 0);
+    int run = block_exclusive_scan(mine_sum, s_scan, &sum);
 #pragma unroll
-      for (int q = 0; q < 11; ++q)
-        if (r >= __dmul_rn((double)q, 0.1)) m[q] = fmax(m[q], pr);     // np.arange(0., 1.1, 0.1)[q] == q * 0.1
+    for (int q = 0; q < kCurveItems; ++q) {
+      run += flag[q];
+      if (p0 + q < n) {
+        const double t = (double)(carry_tp + (run >> 16));             // np.cumsum of 0/1 doubles: exact integers
+        const double f = (double)(carry_fp + (run & 0xffff));
+        const double r = __ddiv_rn(t, npos);                           // :220
+        const double pr = __ddiv_rn(t, fmax(__dadd_rn(t, f), DBL_EPSILON));   // :223
+        a.rec[begin + p0 + q] = r;
+        a.prec[begin + p0 + q] = pr;
+        a.tpfp[begin + p0 + q] = (flag[q] >> 16) ? 1 : (flag[q] ? 2 : 0);
+#pragma unroll
+        for (int k = 0; k < 11; ++k)
+          if (r >= __dmul_rn((double)k, 0.1)) m[k] = fmax(m[k], pr);   // np.arange(0., 1.1, 0.1)[k] == k * 0.1
+      }
     }
     carry_tp += sum >> 16;
     carry_fp += sum & 0xffff;
