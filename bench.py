@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--loss-flags", type=int, default=0, help="experiments: ssdbox_loss_cfg.flags (1 = matching as its own kernel)")
     ap.add_argument("--no-voc-eval", action="store_true", help="skip the VOC evaluation side phase")
     ap.add_argument("--dense", action="store_true", help="detect scores with background bias 4 (worst case)")
     return ap.parse_args()
@@ -259,6 +260,7 @@ def main():
     gt, offs = gt_h.to(dev), offs_h.to(dev)
 
     crit = ssdbox.MultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, distributed=(world > 1))
+    crit.abi_flags |= args.loss_flags
     det = ssdbox.DetectOut(C, 0, top_k, 0.01, 0.45, VAR)
     det_out = torch.empty(B, C, top_k, 5, dtype=torch.float32, device=dev)
 

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) detect_stream_kernel(DetStrea
     mbar_wait(&rc.full[j], (uint32_t)(ph & 1));
     for (int k = 0; k < KR; ++k) {
       const int r = k * (32 * kRingGroupWarps) + rbase;
-      const long long row = (rc.t0 + it) * R + r;
+      const long long row = (rc.t0 + it * rc.tstep) * R + r;
       const bool valid = (r < R) && (row < a.ring.rows);
       bool kept = true;
       if (valid && a.keep) kept = a.keep[row] != 0;          // RefineDet: filtered anchors score 0

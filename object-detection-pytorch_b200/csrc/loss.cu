@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) loss_stream_kernel(StreamAr
     mbar_wait(&rc.full[j], (uint32_t)(ph & 1));
     for (int k = 0; k < KR; ++k) {
       const int r = k * (32 * kRingGroupWarps) + rbase;
-      const long long row = (rc.t0 + it) * R + r;
+      const long long row = (rc.t0 + it * rc.tstep) * R + r;
       if ((r < R) && (row < a.ring.rows)) {
         const float* rp = rc.stages + (size_t)s * rc.stage_floats + (size_t)r * C;
         const float lse = row_lse<CT>(rp, C);

@@ -39,6 +39,7 @@ struct RingPlan {
   int NS;
   int tiles_per_cta;
   int bulk_ok;
+  int interleave;  // 1: CTA b takes tiles b, b + grid, b + 2*grid ... (all CTAs sweep one moving window)
   int grid;
   size_t smem_bytes;
 };
@@ -72,6 +73,10 @@ static inline int plan_ring(RingPlan* p, const float* src, long long rows, int C
   p->KR = KR;
   p->NS = NS;
   p->tiles = (rows + R - 1) / R;
+  if (const char* e = getenv("SSDBOX_RING_GRID")) {            // experiments only: stream on fewer SMs
+    int cap = atoi(e);
+    if (cap >= 1 && cap < sm_count) sm_count = cap;
+  }
   int grid = (int)(p->tiles < sm_count ? p->tiles : sm_count);
   if (grid < 1) grid = 1;
   p->tiles_per_cta = (int)((p->tiles + grid - 1) / grid);
@@ -79,6 +84,7 @@ static inline int plan_ring(RingPlan* p, const float* src, long long rows, int C
   p->grid = (int)((p->tiles + p->tiles_per_cta - 1) / p->tiles_per_cta);
   if (p->grid < 1) p->grid = 1;
   p->bulk_ok = aligned16(src) ? 1 : 0;
+  p->interleave = getenv("SSDBOX_RING_INTERLEAVE") ? 1 : 0;       // experiments only
   p->smem_bytes = kRingHeaderBytes + (size_t)NS * stage_bytes;
   return SSDBOX_OK;
 }
@@ -89,6 +95,7 @@ struct RingCtx {
   float* stages;
   size_t stage_floats;
   long long t0;
+  long long tstep;   // tile of iteration it = t0 + it * tstep
   int n_local;
 };
 
@@ -98,10 +105,17 @@ __device__ __forceinline__ RingCtx ring_setup(const RingPlan& p, unsigned char* 
   r.empty = r.full + 2 * kRingMaxStages;
   r.stages = reinterpret_cast<float*>(smem_raw + kRingHeaderBytes);
   r.stage_floats = (size_t)p.R * p.C;
-  r.t0 = (long long)blockIdx.x * p.tiles_per_cta;
-  long long t1 = r.t0 + p.tiles_per_cta;
-  if (t1 > p.tiles) t1 = p.tiles;
-  r.n_local = t1 > r.t0 ? (int)(t1 - r.t0) : 0;
+  if (p.interleave) {
+    r.t0 = blockIdx.x;
+    r.tstep = gridDim.x;
+    r.n_local = r.t0 < p.tiles ? (int)((p.tiles - r.t0 + gridDim.x - 1) / gridDim.x) : 0;
+  } else {
+    r.t0 = (long long)blockIdx.x * p.tiles_per_cta;
+    r.tstep = 1;
+    long long t1 = r.t0 + p.tiles_per_cta;
+    if (t1 > p.tiles) t1 = p.tiles;
+    r.n_local = t1 > r.t0 ? (int)(t1 - r.t0) : 0;
+  }
   if (threadIdx.x == 0) {
     for (int j = 0; j < 2 * p.NS; ++j) {
       mbar_init(&r.full[j], 1);
@@ -125,7 +139,7 @@ __device__ __forceinline__ void ring_produce(const RingPlan& p, const RingCtx& r
       mbar_wait(&r.empty[prev % (2 * p.NS)], (uint32_t)((prev / (2 * p.NS)) & 1));
     }
     __syncwarp();
-    long long r0 = (r.t0 + it) * p.R;
+    long long r0 = (r.t0 + it * r.tstep) * p.R;
     long long left = p.rows - r0;
     int nrows = left < p.R ? (int)left : p.R;
     uint32_t bytes = (uint32_t)nrows * (uint32_t)p.C * 4u;
