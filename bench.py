@@ -377,7 +377,7 @@ def main():
 
     # SURVEY 8f rank 4 (reported beside the headline): PASCAL VOC evaluation of an accumulated result set
     voc_phase = None
-    if rank == 0 and not args.no_voc_eval:
+    if n_gpus == 1 and not args.no_voc_eval:      # single-GPU side phase: a rank-asymmetric pause would trip the peers' bounded wait
         from ssdbox import voc_eval as VE
         n_img = 4952                                   # VOC2007 test
         case = synth.gen_voc_eval_case(n_img, 21, 11, fp_max=12)
@@ -395,7 +395,7 @@ def main():
                              "synthetic VOC2007-test sized result set, incl. the host mirror's status read",
                      "images": n_img, "detections": int(vrows.size(0)), "truths": int(case["gt_boxes"].shape[0]),
                      "us": 1e3 * ev[0].elapsed_time(ev[1]) / 5, "mean_ap": res.mean_ap}
-        if not args.no_cpu_baseline and n_gpus == 1:
+        if not args.no_cpu_baseline:
             from oracle import voc_oracle as _V    # CPU leg only: the reference algorithm's port timed beside the GPU call
             sub = synth.gen_voc_eval_case(300, 21, 12, fp_max=12)
             t0 = time.perf_counter()
