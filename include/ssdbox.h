@@ -214,11 +214,14 @@ SSDBOX_API int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float*
  * (bit-identical on every rank) and finalises: `sums` / `losses` then hold the GLOBAL values.
  * There is no separate collective launch.  Like any collective, every rank must issue the same
  * sequence of peer-reduced forwards; a call epoch kept in the buffer makes the call replayable
- * from a CUDA graph.  A peer that never arrives traps the kernel after ~4 s instead of hanging. */
+ * from a CUDA graph.  A peer that never arrives traps the kernel after wait_timeout_ms (wall clock;
+ * 0 = 30 s) instead of hanging: size it for the longest stall a rank may see between two steps
+ * (data loading, checkpointing). */
 #define SSDBOX_MAX_PEERS 16
 typedef struct {
   int32_t rank, world;                 /* 1 <= world <= SSDBOX_MAX_PEERS */
   void* bufs[SSDBOX_MAX_PEERS];        /* bufs[r]: rank r's exchange buffer as addressable from THIS device */
+  int64_t wait_timeout_ms;             /* bound of the wait for the peers' sums; 0 = default (30 000) */
 } ssdbox_peer_group;
 SSDBOX_API size_t ssdbox_peer_buffer_bytes(void);
 /* completes a call made with SSDBOX_LOSS_DEFER_PEER_WAIT: waits for every rank's sums, adds them in

@@ -489,6 +489,7 @@ struct MineArgs {
   float* dbg_keys;
   // multi-GPU: exchange buffers of every rank (world == 0: single GPU)
   int peer_rank, peer_world, peer_defer;
+  long long peer_timeout_ns;
   void* peer_bufs[SSDBOX_MAX_PEERS];
 };
 
@@ -540,16 +541,30 @@ __device__ unsigned long long peer_post(void* const* bufs, int me, int world, do
 
 // one warp: waits for every rank's slot of call `epoch` in MY buffer and adds them in rank order (the
 // same fp64 result on every rank); result valid in lane 0
-__device__ void peer_collect(void* const* bufs, int me, int world, unsigned long long epoch, int lane, double* out) {
+__device__ __forceinline__ unsigned long long wall_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// peers->wait_timeout_ms, 0 = default
+static inline long long peer_timeout_ns(const ssdbox_peer_group* peers) {
+  const long long ms = peers->wait_timeout_ms > 0 ? peers->wait_timeout_ms : 30000;
+  return ms * 1000000ll;
+}
+
+__device__ void peer_collect(void* const* bufs, int me, int world, unsigned long long epoch, int lane, double* out,
+                             long long timeout_ns) {
   const char* mine = static_cast<const char*>(bufs[me]);
   const size_t bank = kPeerHeaderBytes + (size_t)(epoch & 1ull) * world * kPeerSlotBytes;
   double r0 = 0.0, r1 = 0.0, r2 = 0.0;
   if (lane < world) {
     const char* src = mine + bank + (size_t)lane * kPeerSlotBytes;
     const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(src + 24);
-    const long long t0 = clock64();
+    const unsigned long long t0 = wall_ns();
+    unsigned spins = 0;
     while (ld_acquire_sys(flag) != epoch) {
-      if (clock64() - t0 > 8000000000LL) __trap();     // a peer never arrived
+      if ((++spins & 1023u) == 0 && wall_ns() - t0 > (unsigned long long)timeout_ns) __trap();     // a peer never arrived
     }
     const volatile double* q = reinterpret_cast<const volatile double*>(src);
     r0 = q[0];
@@ -575,7 +590,7 @@ __device__ void peer_exchange(const MineArgs& a, double* s, int lane) {
   unsigned long long epoch = peer_post(a.peer_bufs, a.peer_rank, a.peer_world, v0, v1, v2, lane);
   if (a.peer_defer) return;
   double g[3];
-  peer_collect(a.peer_bufs, a.peer_rank, a.peer_world, epoch, lane, g);
+  peer_collect(a.peer_bufs, a.peer_rank, a.peer_world, epoch, lane, g, a.peer_timeout_ns);
   if (lane == 0) {
     s[0] = g[0];
     s[1] = g[1];
@@ -585,6 +600,7 @@ __device__ void peer_exchange(const MineArgs& a, double* s, int lane) {
 
 struct PeerFinishArgs {
   int rank, world;
+  long long timeout_ns;
   void* bufs[SSDBOX_MAX_PEERS];
   double* sums;
   float* losses;
@@ -594,7 +610,7 @@ __global__ void peer_finish_kernel(PeerFinishArgs a) {
   const int lane = threadIdx.x & 31;
   const unsigned long long epoch = *reinterpret_cast<const unsigned long long*>(a.bufs[a.rank]);   // posted by the forward
   double g[3];
-  peer_collect(a.bufs, a.rank, a.world, epoch, lane, g);
+  peer_collect(a.bufs, a.rank, a.world, epoch, lane, g, a.timeout_ns);
   if (lane == 0) {
     a.sums[0] = g[0];
     a.sums[1] = g[1];
@@ -1714,6 +1730,7 @@ extern "C" int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const 
   if (peers) {
     m.peer_rank = peers->rank;
     m.peer_world = peers->world;
+    m.peer_timeout_ns = peer_timeout_ns(peers);
     for (int r = 0; r < peers->world; ++r) m.peer_bufs[r] = peers->bufs[r];
   }
   size_t smem = fixed + (m.uk_in_smem ? (size_t)P * 6 + 16 : 0);
@@ -1789,6 +1806,7 @@ extern "C" int ssdbox_multibox_loss_peer_finish(const ssdbox_peer_group* peers, 
   PeerFinishArgs a{};
   a.rank = peers->rank;
   a.world = peers->world;
+  a.timeout_ns = peer_timeout_ns(peers);
   for (int r = 0; r < peers->world; ++r) a.bufs[r] = peers->bufs[r];
   a.sums = sums;
   a.losses = losses;

@@ -88,7 +88,8 @@ class VocEvalCfg(C.Structure):
 
 class PeerGroup(C.Structure):
     """ssdbox_peer_group: every rank's exchange buffer as addressable from this device."""
-    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("bufs", C.c_void_p * MAX_PEERS)]
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("bufs", C.c_void_p * MAX_PEERS),
+                ("wait_timeout_ms", C.c_int64)]
 
 
 _lib = None

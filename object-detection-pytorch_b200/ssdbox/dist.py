@@ -41,7 +41,10 @@ class PeerExchange(object):
     construct it at the same point.  Raises when symmetric memory / peer access is unavailable --
     MultiBoxLoss then keeps the NCCL all-reduce."""
 
-    def __init__(self, device, group=None):
+    def __init__(self, device, group=None, wait_timeout_s=30.0):
+        """wait_timeout_s: how long a rank waits for its peers' sums before the kernel traps (a rank
+        that stalls longer than this between two steps -- data loading, checkpointing -- kills the
+        job instead of hanging it; raise it for such runs)."""
         import ctypes as C
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -73,6 +76,7 @@ class PeerExchange(object):
         self.group = _abi.PeerGroup()
         self.group.rank = self.rank
         self.group.world = self.world
+        self.group.wait_timeout_ms = int(wait_timeout_s * 1000)
         for r, ptr in enumerate(ptrs):
             self.group.bufs[r] = C.c_void_p(ptr)
 

@@ -53,7 +53,10 @@ def test_version_and_struct_layouts(lib):
     prog = r'''
     #include <stdio.h>
     #include "ssdbox.h"
-    int main(){printf("%zu %zu %zu\n", sizeof(ssdbox_prior_cfg), sizeof(ssdbox_loss_cfg), sizeof(ssdbox_detect_cfg));return 0;}
+    #include <stddef.h>
+    int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ssdbox_prior_cfg), sizeof(ssdbox_loss_cfg), sizeof(ssdbox_detect_cfg),
+                      sizeof(ssdbox_peer_group), offsetof(ssdbox_peer_group, wait_timeout_ms), sizeof(ssdbox_heads_cfg),
+                      sizeof(ssdbox_voc_eval_cfg), offsetof(ssdbox_voc_eval_cfg, ovthresh));return 0;}
     '''
     import tempfile
     with tempfile.TemporaryDirectory() as d:
@@ -62,7 +65,9 @@ def test_version_and_struct_layouts(lib):
         exe = os.path.join(d, "s")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
-    assert sizes == [C.sizeof(_abi.PriorCfg), C.sizeof(_abi.LossCfg), C.sizeof(_abi.DetectCfg)]
+    assert sizes == [C.sizeof(_abi.PriorCfg), C.sizeof(_abi.LossCfg), C.sizeof(_abi.DetectCfg),
+                     C.sizeof(_abi.PeerGroup), _abi.PeerGroup.wait_timeout_ms.offset, C.sizeof(_abi.HeadsCfg),
+                     C.sizeof(_abi.VocEvalCfg), _abi.VocEvalCfg.ovthresh.offset]
 
 
 def test_workspace_query(lib):
@@ -81,6 +86,12 @@ def test_argument_validation_without_gpu(lib):
     rc = lib.ssdbox_multibox_loss_fwd(C.byref(lc), *([None] * 15), None, 0, None)
     assert rc == _abi.ESHAPE
     assert lib.ssdbox_nms(None, None, 5, 0.45, 0, None, None, None, 0, None) == _abi.ESHAPE
+    vc = _abi.VocEvalCfg(1, 2000, 0, 7, 0, 1, 0.5)
+    assert lib.ssdbox_voc_eval(C.byref(vc), *([None] * 14), None, 0, None) == _abi.ESHAPE
+    vc = _abi.VocEvalCfg(1, 3, 0, 4, 0, 1, 0.5)
+    assert lib.ssdbox_voc_eval(C.byref(vc), *([None] * 14), None, 0, None) == _abi.EINVAL
+    assert lib.ssdbox_crop_overlaps(None, None, None, -1, 2, None, None, None, None) == _abi.EINVAL
+    assert _abi.workspace_bytes(_abi.OP_VOC_EVAL, 0, 600000, 21, 17000) > 600000 * 24
     pc = _abi.PriorCfg()
     pc.num_layers = 99
     assert lib.ssdbox_priorbox_count(C.byref(pc)) == _abi.ESHAPE
