@@ -442,6 +442,11 @@ def main():
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if dist is not None:
+        # ranks leave the host-side barrier up to ~0.5 ms apart; without this the rank that leaves first is
+        # charged the others' delay inside its timed region (its first peer wait).  One more untimed step:
+        # its peer exchange lines the GPUs up, and the start event is recorded on the stream right behind it.
+        run_once()
     e0.record()
     for _ in range(args.steps):
         run_once()
