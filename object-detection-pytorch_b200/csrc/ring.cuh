@@ -39,7 +39,8 @@ struct RingPlan {
   int NS;
   int tiles_per_cta;
   int bulk_ok;
-  int interleave;  // 1: CTA b takes tiles b, b + grid, b + 2*grid ... (all CTAs sweep one moving window)
+  int interleave;  // g > 0: groups of g consecutive CTAs share one contiguous run of tiles and take its tiles in turn
+                   // (member m takes tiles m, m + g, m + 2g ... of the run); 0: every CTA has a run of its own
   int grid;
   size_t smem_bytes;
 };
@@ -84,7 +85,11 @@ static inline int plan_ring(RingPlan* p, const float* src, long long rows, int C
   p->grid = (int)((p->tiles + p->tiles_per_cta - 1) / p->tiles_per_cta);
   if (p->grid < 1) p->grid = 1;
   p->bulk_ok = aligned16(src) ? 1 : 0;
-  p->interleave = getenv("SSDBOX_RING_INTERLEAVE") ? 1 : 0;       // experiments only
+  p->interleave = 0;
+  if (const char* e = getenv("SSDBOX_RING_INTERLEAVE")) {         // experiments only
+    int g = atoi(e);
+    p->interleave = g < 1 ? 0 : (g > p->grid ? p->grid : g);
+  }
   p->smem_bytes = kRingHeaderBytes + (size_t)NS * stage_bytes;
   return SSDBOX_OK;
 }
@@ -106,9 +111,15 @@ __device__ __forceinline__ RingCtx ring_setup(const RingPlan& p, unsigned char* 
   r.stages = reinterpret_cast<float*>(smem_raw + kRingHeaderBytes);
   r.stage_floats = (size_t)p.R * p.C;
   if (p.interleave) {
-    r.t0 = blockIdx.x;
-    r.tstep = gridDim.x;
-    r.n_local = r.t0 < p.tiles ? (int)((p.tiles - r.t0 + gridDim.x - 1) / gridDim.x) : 0;
+    const int g = p.interleave;
+    const int group = blockIdx.x / g, member = blockIdx.x % g;
+    const int members = min(g, (int)gridDim.x - group * g);                       // the last group may be short
+    const long long lo = (long long)group * g * p.tiles_per_cta;                  // the members' own runs, pooled
+    long long hi = lo + (long long)members * p.tiles_per_cta;
+    if (hi > p.tiles) hi = p.tiles;
+    r.t0 = lo + member;
+    r.tstep = members;
+    r.n_local = r.t0 < hi ? (int)((hi - r.t0 + members - 1) / members) : 0;
   } else {
     r.t0 = (long long)blockIdx.x * p.tiles_per_cta;
     r.tstep = 1;
