@@ -352,8 +352,7 @@ def main():
 
     # SURVEY 8f rank 3 (reported beside the headline): multibox head outputs (NCHW) -> conf [B,P,C]
     from ssdbox import heads as HD
-    from oracle import ssd_oracle as _O   # only for the per-cell anchor counts of the config (host-side arithmetic)
-    per_cell = _O.num_priors_per_cell(cfg.MODEL)
+    per_cell = ssdbox.PriorBoxSSD(cfg).num_priors     # anchors per cell of every source layer (prior_box.py:46-50)
     with torch.no_grad():
         head_outs = [torch.randn(B, a_ * C, h_, w_, device=dev) for a_, (h_, w_) in zip(per_cell, c["layer_dims"])]
         rows_out = torch.empty(B, P, C, device=dev)
