@@ -15,8 +15,10 @@ from .prior_box import PriorBoxSSD
 _BOX_FUNCS = ["point_form", "center_size", "jaccard", "match", "encode", "decode", "log_sum_exp", "nms"]
 
 
-def install(variance_from_cfg=True):
-    """Patches the reference modules in sys.modules (imports them first if `lib` is importable)."""
+def install(variance_from_cfg=True, patch_eval=False):
+    """Patches the reference modules in sys.modules (imports them first if `lib` is importable).
+    patch_eval=True also swaps the evaluation solvers (lib.utils.evaluate_utils.EvalVOC / EvalCOCO and
+    lib.utils.eval_solver_map, what eval_solver_factory hands out) for the device-resident ones."""
     try:
         import lib.layers  # noqa: F401  (reference tree on sys.path)
     except Exception as e:  # pragma: no cover - reference not importable here
@@ -53,4 +55,14 @@ def install(variance_from_cfg=True):
     if bu is not None:
         for f in _BOX_FUNCS:
             setattr(bu, f, getattr(_bu, f))
+    if patch_eval:
+        from . import evaluate_utils as _eu
+        mod = sys.modules.get("lib.utils.evaluate_utils")
+        if mod is not None:
+            mod.EvalVOC, mod.EvalCOCO, mod.EvalBase = _eu.EvalVOC, _eu.EvalCOCO, _eu.EvalBase
+        utils = sys.modules.get("lib.utils")
+        if utils is not None:
+            utils.EvalVOC, utils.EvalCOCO = _eu.EvalVOC, _eu.EvalCOCO
+            if hasattr(utils, "eval_solver_map"):
+                utils.eval_solver_map.update({'VOC0712': _eu.EvalVOC, 'COCO2014': _eu.EvalCOCO})
     return loss_cls

@@ -175,3 +175,109 @@ def test_crop_overlaps(dev):
             assert mm[b, t, 0] == lo and mm[b, t, 1] == hi
             assert np.array_equal(mask[b][t].cpu().numpy(), m.astype(bool))
     assert np.isinf(mm[-1]).all()
+
+
+def _write_voc_xml(path, objs):
+    rows = "".join(
+        "<object><name>%s</name><pose>Unspecified</pose><truncated>0</truncated><difficult>%d</difficult>"
+        "<bndbox><xmin>%d</xmin><ymin>%d</ymin><xmax>%d</xmax><ymax>%d</ymax></bndbox></object>" % ((o[0], o[1]) + tuple(o[2]))
+        for o in objs)
+    with open(path, "w") as f:
+        f.write("<annotation>%s</annotation>" % rows)
+
+
+def test_eval_solvers_end_to_end(dev, tmp_path):
+    """EvalVOC.validate (lib/utils/evaluate_utils.py:41-78, 114-162) with a stand-in network, data loader
+    and PASCAL VOC annotation files: network outputs -> DetectOut -> result rows -> accumulation ->
+    ssdbox_voc_eval, against the CPU oracle chain (detect, rescale, convert_ssd_result, voc_eval_rows).
+    EvalCOCO's accumulated result rows against the oracle's post_proc rows."""
+    import types
+    import ssdbox
+    from oracle import ssd_oracle as O
+    from ssdbox import configs
+    from ssdbox import evaluate_utils as EU
+    pri = O.prior_boxes(U.SMALL_MODEL, U.SMALL_DIMS)
+    P, C, B, nb = pri.size(0), 21, 3, 2
+    cfg = configs.AttrDict(MODEL=U.SMALL_MODEL)
+    rs = np.random.RandomState(4)
+    batches, outputs, ids, all_det = [], [], [], []
+    (tmp_path / "Annotations").mkdir()
+    gtb, gtl, gtd, goff = [], [], [], [0]
+    for k in range(nb):
+        loc = synth.gen_loc(B, P, 40 + k)
+        sc = synth.gen_detect_scores(B, P, C, 40 + k, bkg_bias=6.0)
+        extra = torch.tensor([[375.0, 500.0], [333.0, 500.0], [480.0, 640.0]])
+        batches.append((torch.zeros(B, 3, 8, 8), None, extra))
+        outputs.append((loc, sc))
+        det = O.detect(loc, sc, pri, C)
+        all_det.append(O.convert_ssd_result(O.rescale_detections(det, extra)).numpy())
+        for b in range(B):
+            name = "%06d" % (k * B + b)
+            ids.append((str(tmp_path), name))
+            # truths: a few of the image's own detections (so that there are true positives) + a difficult one
+            rows = all_det[-1][all_det[-1][:, 5] == b]
+            pick = rows[rs.permutation(len(rows))[:4]] if len(rows) else np.zeros((0, 7))
+            objs = [(EU.VOC_CLASSES[int(r[6]) - 1], int(j == 3), [int(r[0]) + 1, int(r[1]) + 1, int(r[2]) + 2, int(r[3]) + 2]) for j, r in enumerate(pick)]
+            _write_voc_xml(str(tmp_path / "Annotations" / (name + ".xml")), objs)
+            for o in objs:
+                gtb.append([v - 1 for v in o[2]]); gtl.append(EU.VOC_CLASSES.index(o[0]) + 1); gtd.append(o[1])
+            goff.append(len(gtl))
+    dataset = types.SimpleNamespace(name="VOC0712", ids=ids, image_sets=[("2007", "test")],
+                                    _annopath="%s/Annotations/%s.xml")          # voc0712.py:100
+    calls = iter(outputs)
+
+    class Loader(object):
+        def __init__(self):
+            self.dataset = dataset
+
+        def __iter__(self):
+            return iter(batches)
+
+    def net(images, phase="eval"):
+        loc, sc = next(calls)
+        return loc.to(images.device), sc.to(images.device)
+
+    solver = EU.EvalVOC(Loader(), cfg, output_dir=str(tmp_path / "out"))
+    res, maps = solver.validate(net, pri.to(dev))
+    # oracle chain on the same data
+    seg, rows = [0], []
+    for k in range(nb):
+        d = all_det[k]
+        for b in range(B):
+            for c in range(C):
+                r = d[(d[:, 5] == b) & (d[:, 6] == c)]
+                rows.append(r)
+                seg.append(seg[-1] + len(r))
+    rows = np.concatenate(rows, 0)
+    want, want_map = V.voc_eval_rows(rows, np.asarray(seg), nb * B, C, np.float32(gtb).reshape(-1, 4), np.int32(gtl), np.uint8(gtd), np.int32(goff))
+    assert len(res) == 20 and maps == [want_map]
+    hit = 0
+    for (name, ap, prec, rec), w in zip(res, want):
+        assert ap == w["ap"]
+        if w["ap"] != -1.0:
+            hit += 1
+            assert np.array_equal(prec, w["prec"]) and np.array_equal(rec, w["rec"], equal_nan=True)
+    assert hit >= 5 and max(x[1] for x in res) > 0.0
+    import pickle
+    with open(str(tmp_path / "out" / (res[0][0] + "_pr.pkl")), "rb") as f:
+        assert pickle.load(f)["ap"] == res[0][1]
+    # COCO: accumulated result rows
+    coco_ids = [100 + 7 * i for i in range(nb * B)]
+    calls = iter(outputs)
+    cds = types.SimpleNamespace(name="COCO2014", ids=coco_ids, image_sets=None)
+
+    class CLoader(Loader):
+        def __init__(self):
+            self.dataset = cds
+
+    cs = EU.EvalCOCO(CLoader(), configs.AttrDict(MODEL=U.SMALL_MODEL, DATASET=configs.AttrDict(NUM_EVAL_PICS=0)))
+    cs.reset_results()
+    idx = 0
+    for (images, _, extra), (loc, sc) in zip(batches, outputs):
+        det = cs.detector(loc.to(dev), sc.to(dev), pri.to(dev))
+        idx = cs.consume(det, extra.to(dev), idx)
+    got = cs.result_rows().cpu()
+    want_rows = torch.cat([O.coco_post_proc(O.convert_ssd_result(O.rescale_detections(O.detect(loc, sc, pri, C), batches[k][2]),
+                                                                coco_ids=coco_ids[k * B:(k + 1) * B])) for k, (loc, sc) in enumerate(outputs)], 0)
+    assert idx == nb * B and torch.equal(got[:, [0, 5, 6]], want_rows[:, [0, 5, 6]])
+    assert float((got - want_rows).abs().max()) <= 1e-5 * 640

@@ -147,6 +147,15 @@ assert crit.variance == list(cfg.MODEL.VARIANCE)
 pb = PriorBoxSSD(cfg)                                                 # models/__init__.py:28
 assert pb.num_priors == [4, 6, 6, 6, 4, 4]
 det = DetectOut(21, 0, 200, 0.01, 0.45, cfg.MODEL.VARIANCE)           # evaluate_utils.py:16-17
+# the evaluation solvers eval_solver_factory hands out (lib/utils/__init__.py:4-11)
+import lib.utils
+from ssdbox import evaluate_utils as EU
+ssdbox.compat.install(patch_eval=True)
+assert lib.utils.eval_solver_map["VOC0712"] is EU.EvalVOC and lib.utils.eval_solver_map["COCO2014"] is EU.EvalCOCO
+import types
+loader = types.SimpleNamespace(dataset=types.SimpleNamespace(name="VOC0712", ids=[], image_sets=[("2007", "test")]))
+solver = lib.utils.eval_solver_factory(loader, cfg)                   # eval.py:100
+assert isinstance(solver, EU.EvalVOC) and solver.detector.top_k == 200 and solver._classes() == list(lib.datasets.VOC_CLASSES)
 print("ok")
 ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
@@ -247,3 +256,16 @@ def test_crop_overlaps_bit_exact(ref):
         boxes = np.concatenate([xy, xy + rs.rand(G, 2) * 150 + 1], 1)
         rect = np.array([int(rs.uniform(0, 200)), int(rs.uniform(0, 200)), int(rs.uniform(220, 500)), int(rs.uniform(220, 400))])
         assert np.array_equal(aug.jaccard_numpy(boxes, rect), V.jaccard_numpy(boxes, rect))
+
+
+def test_parse_rec_bit_exact(ref, tmp_path):
+    """ssdbox.evaluate_utils.parse_rec == lib/datasets/voc_eval.py:15-33 on a PASCAL VOC annotation file."""
+    import lib.datasets.voc_eval as ve
+    from ssdbox import evaluate_utils as EU
+    xml = """<annotation><folder>VOC2007</folder><filename>000001.jpg</filename><size><width>353</width><height>500</height><depth>3</depth></size>
+<object><name>dog</name><pose>Left</pose><truncated>1</truncated><difficult>0</difficult><bndbox><xmin>48</xmin><ymin>240</ymin><xmax>195</xmax><ymax>371</ymax></bndbox></object>
+<object><name>person</name><pose>Unspecified</pose><truncated>0</truncated><difficult>1</difficult><bndbox><xmin>8</xmin><ymin>12</ymin><xmax>352</xmax><ymax>498</ymax></bndbox></object>
+</annotation>"""
+    f = tmp_path / "000001.xml"
+    f.write_text(xml)
+    assert EU.parse_rec(str(f)) == ve.parse_rec(str(f))
