@@ -495,7 +495,8 @@ struct MineArgs {
 
 #ifdef SSDBOX_PHASE_TIMING
 __device__ long long g_phase[16 * 64];
-#define PHASE_MARK(k) do { __syncthreads(); if (blockIdx.x < 64 && threadIdx.x == 0) g_phase[blockIdx.x * 16 + (k)] = clock64(); } while (0)
+#define PHASE_MARK(k) do { __syncthreads(); if (blockIdx.x < 64 && threadIdx.x == 0) { g_phase[blockIdx.x * 16 + (k)] = clock64(); \
+    if ((k) == 0) g_phase[blockIdx.x * 16 + 14] = (long long)gtimer_ns(); if ((k) == 7) g_phase[blockIdx.x * 16 + 15] = (long long)gtimer_ns(); } } while (0)
 #else
 #define PHASE_MARK(k) do { } while (0)
 #endif
@@ -624,32 +625,27 @@ __global__ void peer_finish_kernel(PeerFinishArgs a) {
 
 // last CTA: fold the per-image partials in image order (bit-reproducible run to run); the loads
 // are spread over the threads (one L2 round trip), the fp64 adds stay sequential in image order
-__device__ void fold_partials(const MineArgs& a, double* s_dscr, int nparts) {
+__device__ void fold_partials(const MineArgs& a, double* s_dscr, double* s_big, int nparts) {
+  // s_big: the (dead by now) level-histogram area, 1024 doubles.  One round trip brings up to kChunk
+  // partials in; three threads then add one quantity each in CTA order (bit-reproducible, the same
+  // association as a sequential loop over the partials).
+  constexpr int kChunk = 336;
   const int tid = threadIdx.x;
-  double sl = 0.0, sc = 0.0, sn = 0.0;
-  for (int base = 0; base < nparts; base += 32) {
+  double acc = 0.0;
+  for (int base = 0; base < nparts; base += kChunk) {
+    const int n = nparts - base < kChunk ? nparts - base : kChunk;
     __syncthreads();
-    if (tid < 96) {
-      int i = base + (tid & 31), f = tid >> 5;
-      s_dscr[f * 32 + (tid & 31)] = i < nparts ? __ldcg(&a.partial[(size_t)i * 3 + f]) : 0.0;
-    }
+    for (int t = tid; t < 3 * n; t += blockDim.x) s_big[t] = __ldcg(&a.partial[(size_t)base * 3 + t]);
     __syncthreads();
-    if (tid == 0) {
-      int n = nparts - base < 32 ? nparts - base : 32;
-      for (int i = 0; i < n; ++i) {
-        sl += s_dscr[i];
-        sc += s_dscr[32 + i];
-        sn += s_dscr[64 + i];
-      }
-    }
+    if (tid < 3)
+      for (int i = 0; i < n; ++i) acc += s_big[i * 3 + tid];
   }
+  __syncthreads();
+  if (tid < 3) s_dscr[tid] = acc;
+  __syncthreads();
+  double sl = s_dscr[0], sc = s_dscr[1], sn = s_dscr[2];
   if (a.peer_world > 0) {     // uniform over the CTA
-    if (tid == 0) {
-      s_dscr[0] = sl;
-      s_dscr[1] = sc;
-      s_dscr[2] = sn;
-    }
-    __syncthreads();
+    __syncthreads();          // every thread has read s_dscr[0..2]
     if (tid < 32) peer_exchange(a, s_dscr, tid);
     __syncthreads();
     sl = s_dscr[0];
@@ -852,7 +848,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  fold_partials(a, s_dscr, a.B);
+  fold_partials(a, s_dscr, reinterpret_cast<double*>(smem_raw), a.B);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1242,7 +1238,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  fold_partials(a, s_dscr, (int)gridDim.x);
+  fold_partials(a, s_dscr, reinterpret_cast<double*>(smem_mine), (int)gridDim.x);
   PHASE_MARK(8);
 }
 

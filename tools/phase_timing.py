@@ -30,6 +30,9 @@ for it in range(4):
     d = np.diff(ph[:, :8], axis=1)
     print("  mine phases (cycles, median over CTAs / max): load %d/%d  forced %d/%d  keys+scan %d/%d  positives %d/%d  select %d/%d  final %d/%d  sum %d/%d ; total med %d max %d; kernel span %d"
           % tuple([x for i in range(7) for x in (int(np.median(d[:, i])), int(d[:, i].max()))] + [int(np.median(ph[:, 7] - ph[:, 0])), int((ph[:, 7] - ph[:, 0]).max()), int(ph[:, :8].max() - ph[:, 0].min())]))
+    gt0, gt1 = ph[:, 14], ph[:, 15]
+    print("  mine CTAs 0..63 (globaltimer): start spread %.1f us, end spread %.1f us, first start -> last end %.1f us, CTA duration med %.1f max %.1f us"
+          % ((gt0.max() - gt0.min()) / 1e3, (gt1.max() - gt1.min()) / 1e3, (gt1.max() - gt0.min()) / 1e3, np.median(gt1 - gt0) / 1e3, (gt1 - gt0).max() / 1e3))
     sb = (C.c_longlong * (8 * 160))()
     _abi.lib().ssdbox_debug_sphases.argtypes = [C.c_void_p]
     _abi.lib().ssdbox_debug_sphases(sb)
