@@ -382,18 +382,22 @@ def main():
         case = synth.gen_voc_eval_case(n_img, 21, 11, fp_max=12)
         vgt = VE.VOCGroundTruth(case["gt_boxes"], case["gt_labels"], case["gt_difficult"], case["gt_offsets"], dev)
         vrows, vseg = torch.as_tensor(case["rows"]).to(dev), torch.as_tensor(case["seg"]).to(dev)
-        res = VE.voc_eval(vrows, vseg, vgt, 21)
-        torch.cuda.synchronize()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        ev[0].record()
-        for _ in range(5):
+        for _ in range(3):                              # warm-up: workspace, allocator blocks of these sizes
             res = VE.voc_eval(vrows, vseg, vgt, 21)
-        ev[1].record()
         torch.cuda.synchronize()
+        voc_us = []
+        for _ in range(9):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
+            res = VE.voc_eval(vrows, vseg, vgt, 21)
+            ev[1].record()
+            torch.cuda.synchronize()
+            voc_us.append(1e3 * ev[0].elapsed_time(ev[1]))
+        voc_us.sort()
         voc_phase = {"note": "ssdbox_voc_eval: write_voc_results_file + voc_eval + voc_ap (lib/datasets/voc_eval.py:58-242) for all 20 classes of a "
-                             "synthetic VOC2007-test sized result set, incl. the host mirror's status read",
+                             "synthetic VOC2007-test sized result set; median per call incl. the host mirror's allocations and its D2H read",
                      "images": n_img, "detections": int(vrows.size(0)), "truths": int(case["gt_boxes"].shape[0]),
-                     "us": 1e3 * ev[0].elapsed_time(ev[1]) / 5, "mean_ap": res.mean_ap}
+                     "us": voc_us[len(voc_us) // 2], "us_min_max": [voc_us[0], voc_us[-1]], "calls": len(voc_us), "mean_ap": res.mean_ap}
         if not args.no_cpu_baseline:
             from oracle import voc_oracle as _V    # CPU leg only: the reference algorithm's port timed beside the GPU call
             sub = synth.gen_voc_eval_case(300, 21, 12, fp_max=12)

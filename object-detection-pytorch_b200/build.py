@@ -28,7 +28,7 @@ def _digest():
     h = hashlib.sha256()
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "ssdbox.h")]
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.relpath(f, ROOT).encode())     # relative: the stamp stays valid when the tree is copied (GPU box)
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
