@@ -95,3 +95,38 @@ class LocalPeerExchange(object):
         self.group.rank = 0
         self.group.world = 1
         self.group.bufs[0] = C.c_void_p(self.buf.data_ptr())
+
+
+def gather_detections(rows, seg, group=None):
+    """Evaluation shards the image set by rank (contiguous ranges, shard_range) and needs ONE exchange before
+    the metric: every rank's result rows.  rows [n_r, ncol] + seg int32 [I_r*C + 1] of this rank's images
+    (ssdbox.voc_eval.VOCDetections.flat()) -> the rows / seg of the whole image set in rank order, on every
+    rank: two all-gathers (row counts and segment counts, then the padded payloads).  The result is what a
+    single process would have accumulated, so ssdbox_voc_eval sees the same file order."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return rows, seg
+    world = dist.get_world_size(group)
+    dev = rows.device
+    seg = seg.to(dev, torch.int32)
+    sizes = torch.tensor([rows.size(0), seg.numel() - 1], dtype=torch.int64, device=dev)
+    all_sizes = [torch.empty_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    n_rows = [int(s[0]) for s in all_sizes]
+    n_segs = [int(s[1]) for s in all_sizes]
+    ncol = rows.size(1)
+    pad_rows = torch.zeros(max(max(n_rows), 1), ncol, dtype=rows.dtype, device=dev)
+    pad_rows[:rows.size(0)] = rows
+    pad_seg = torch.zeros(max(max(n_segs), 1), dtype=torch.int32, device=dev)
+    pad_seg[:seg.numel() - 1] = seg[:-1]
+    got_rows = [torch.empty_like(pad_rows) for _ in range(world)]
+    got_seg = [torch.empty_like(pad_seg) for _ in range(world)]
+    dist.all_gather(got_rows, pad_rows, group=group)
+    dist.all_gather(got_seg, pad_seg, group=group)
+    out_rows, out_seg, base = [], [], 0
+    for r in range(world):
+        out_rows.append(got_rows[r][:n_rows[r]])
+        out_seg.append(got_seg[r][:n_segs[r]] + base)
+        base += n_rows[r]
+    out_seg.append(torch.tensor([base], dtype=torch.int32, device=dev))
+    return torch.cat(out_rows, 0).contiguous(), torch.cat(out_seg).contiguous()

@@ -63,6 +63,50 @@ def test_sharded_loss_equals_full_batch():
     assert float(r0["ll"]) == float(r1["ll"]) and float(r0["lc"]) == float(r1["lc"])
 
 
+def _gather_worker(rank, world, port, outdir):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "object-detection-pytorch_b200"))
+    from ssdbox import dist as sdist
+    from ssdbox import synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    case = synth.gen_voc_eval_case(7, 5, 21, gt_max=3, fp_max=3)
+    C = 5
+    b, e = sdist.shard_range(7, rank, world)                 # 4 + 3 images
+    seg = torch.as_tensor(case["seg"])
+    r0, r1 = int(seg[b * C]), int(seg[e * C])
+    rows = torch.as_tensor(case["rows"])[r0:r1]
+    my_seg = (seg[b * C:e * C + 1] - r0).to(torch.int32)
+    full_rows, full_seg = sdist.gather_detections(rows, my_seg)
+    if rank == 1:
+        rows, my_seg = rows[:0], torch.zeros_like(my_seg)    # a rank without any detection
+    g_rows, g_seg = sdist.gather_detections(rows, my_seg)
+    torch.save({"rows": g_rows, "seg": g_seg, "full_rows": full_rows, "full_seg": full_seg}, os.path.join(outdir, "g%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_detections_rebuilds_the_single_process_layout():
+    """world_size 2 over gloo: the rows / segment offsets of two image shards (one of them empty) gathered in
+    rank order equal what one process would have accumulated."""
+    import numpy as np
+    from ssdbox import synth
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_gather_worker, args=(2, _free_port(), d), nprocs=2, join=True)
+        g0 = torch.load(os.path.join(d, "g0.pt"))
+        g1 = torch.load(os.path.join(d, "g1.pt"))
+    case = synth.gen_voc_eval_case(7, 5, 21, gt_max=3, fp_max=3)
+    n0 = int(case["seg"][4 * 5])                             # rows of rank 0's four images
+    want_seg = np.concatenate([case["seg"][:4 * 5], np.full(3 * 5 + 1, n0, np.int32)])
+    for g in (g0, g1):
+        assert np.array_equal(g["full_rows"].numpy(), case["rows"]) and np.array_equal(g["full_seg"].numpy(), case["seg"])
+        assert np.array_equal(g["rows"].numpy(), case["rows"][:n0])
+        assert np.array_equal(g["seg"].numpy(), want_seg)
+
+
 def test_shard_range_partitions():
     from ssdbox import dist as sdist
     for n in (0, 1, 7, 64, 65):
