@@ -8,7 +8,7 @@
 //                        8 consumer warps  one thread per prior row: lse and the background key
 //                                          lse - x[0]; level-1 mining histogram (top 11 bits of the
 //                                          order-preserving key).  Independent of the class targets.
-//                        1 scheduler warp + 8 match warps: box_utils.match while the consumers wait
+//                        1 scheduler warp + 6 or 8 match warps: box_utils.match while the consumers wait
 //                                          on memory.  Work units (1024 priors of one image) come
 //                                          from a global counter, the unit's truths and priors are
 //                                          staged in shared memory (priors by TMA); 4 consecutive
@@ -54,11 +54,14 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 #define SMARK(k) do { } while (0)
 #endif
 
-constexpr int kMatchWarps = 8;
-constexpr int kMatchTile = kMatchWarps * 128;                      // priors of one matching work unit
+constexpr int kMatchWarpsMax = 8;                                  // the kernel is launched with 6 or 8 match warps:
+// 8 when the matching is the longer half of the kernel (narrow conf rows, C = 21: RFB300-VOC B=256 87 us against
+// 102 us with 6), 6 when the conf stream is (C = 81: 16 warps = 4 per scheduler, 90 us against 93 us with 8;
+// 4 / 5 / 7 warps measured 91.4 / - / 95.0 us).  One work unit = match_warps * 128 priors.
+static inline int match_warps_for(int C) { return C >= 48 ? 6 : 8; }
 constexpr int kSchedWarp = kRingConsumerWarps + 1;                 // warp 8 = conf producer, 9 = unit scheduler
 constexpr int kFirstMatchWarp = kRingConsumerWarps + 2;
-constexpr int kStreamThreads = (kRingConsumerWarps + 2 + kMatchWarps) * 32;
+constexpr int kStreamThreads = (kRingConsumerWarps + 2 + kMatchWarpsMax) * 32;      // launch bound; launched with match_warps
 constexpr int kMatchBarBytes = 64;                                 // mfull[2], mempty[2]
 
 struct StreamArgs {
@@ -70,6 +73,7 @@ struct StreamArgs {
   int P;
   // fused matching (box_utils.py:92-130 on dedicated warps)
   int fuse;
+  int match_warps, match_tile;   // warps doing the matching, priors per work unit (= 128 * match_warps)
   int B;
   const float* gt;
   const int32_t* gt_offsets;
@@ -116,7 +120,7 @@ __device__ __forceinline__ float row_lse(const float* __restrict__ rp, int C) {
 }
 
 // ---- matching on dedicated warps -----------------------------------------------------------------
-// Work unit = kMatchTile consecutive priors of one image.  Units are handed out dynamically (one
+// Work unit = match_tile (128 per match warp) consecutive priors of one image.  Units are handed out dynamically (one
 // global counter, heavy coarse-layer tiles first) so the matching load is balanced over the SMs
 // whatever the truth counts of the images a CTA happens to stream.  The scheduler warp stages a
 // unit in one of two shared-memory buffers: the unit's truths (+area, +label, +CTA-local best-prior
@@ -127,24 +131,24 @@ struct MatchUnit {
 };
 struct UnitBuf {
   MatchUnit* hd;
-  float4* pri;                // [kMatchTile] centre-form priors (or xyxy anchors)
+  float4* pri;                // [match_tile] centre-form priors (or xyxy anchors)
   float4* box;                // [gpad] truth xyxy
   unsigned long long* best;   // [gpad] per-truth best prior over this unit
   float* area;                // [gpad]
   int* lab;                   // [gpad] class target (label + 1)
 };
-__device__ __forceinline__ UnitBuf unit_buf(unsigned char* mbase, int buf, int unit_bytes, int gpad) {
+__device__ __forceinline__ UnitBuf unit_buf(unsigned char* mbase, int buf, int unit_bytes, int gpad, int match_tile) {
   unsigned char* ub = mbase + kMatchBarBytes + (size_t)buf * unit_bytes;
   UnitBuf u;
   u.hd = reinterpret_cast<MatchUnit*>(ub);
   u.pri = reinterpret_cast<float4*>(ub + 16);
-  u.box = u.pri + kMatchTile;
+  u.box = u.pri + match_tile;
   u.best = reinterpret_cast<unsigned long long*>(u.box + gpad);
   u.area = reinterpret_cast<float*>(u.best + gpad);
   u.lab = reinterpret_cast<int*>(u.area + gpad);
   return u;
 }
-static inline int unit_buf_bytes(int gpad) { return (int)align_up((size_t)16 + (size_t)kMatchTile * 16 + (size_t)gpad * 32, 128); }
+static inline int unit_buf_bytes(int gpad, int match_tile) { return (int)align_up((size_t)16 + (size_t)match_tile * 16 + (size_t)gpad * 32, 128); }
 
 // max IoU, lowest prior index on ties (box_utils.py:116); shared-memory copy first: the global
 // atomic happens once per (unit, truth), never inside the truth loop
@@ -157,12 +161,12 @@ __device__ __forceinline__ void best_prior_update(unsigned long long* dst, uint3
 __device__ void match_sched_loop(const StreamArgs& a, unsigned char* mbase, int lane) {
   uint64_t* mfull = reinterpret_cast<uint64_t*>(mbase);
   uint64_t* mempty = mfull + 2;
-  const int ntile = (a.P + kMatchTile - 1) / kMatchTile;
+  const int ntile = (a.P + a.match_tile - 1) / a.match_tile;
   const unsigned nunits = (unsigned)ntile * (unsigned)a.B;
   const float* src_base = a.anchors_xyxy ? a.anchors_xyxy : a.priors;
   for (int k = 0;; ++k) {
     const int buf = k & 1;
-    UnitBuf ub = unit_buf(mbase, buf, a.unit_bytes, a.gpad);
+    UnitBuf ub = unit_buf(mbase, buf, a.unit_bytes, a.gpad, a.match_tile);
     if (k >= 2) {    // the match warps have released the unit staged two rounds ago
       if (lane == 0) mbar_wait(&mempty[buf], (uint32_t)(((k >> 1) - 1) & 1));
       __syncwarp();
@@ -179,8 +183,8 @@ __device__ void match_sched_loop(const StreamArgs& a, unsigned char* mbase, int 
     }
     const int tile = ntile - 1 - (int)(u / (unsigned)a.B);     // coarse layers (most truths per warp) first
     const int b = (int)(u % (unsigned)a.B);
-    const int p0 = tile * kMatchTile;
-    const int nrows = a.P - p0 < kMatchTile ? a.P - p0 : kMatchTile;
+    const int p0 = tile * a.match_tile;
+    const int nrows = a.P - p0 < a.match_tile ? a.P - p0 : a.match_tile;
     const int g0 = a.gt_offsets[b];
     int G = a.gt_offsets[b + 1] - g0;
     G = G < 0 ? 0 : (G > a.gmax ? a.gmax : G);
@@ -217,7 +221,7 @@ __device__ void match_unit_loop(const StreamArgs& a, unsigned char* mbase, int m
 #endif
   for (int k = 0;; ++k) {
     const int buf = k & 1;
-    UnitBuf ub = unit_buf(mbase, buf, a.unit_bytes, a.gpad);
+    UnitBuf ub = unit_buf(mbase, buf, a.unit_bytes, a.gpad, a.match_tile);
 #ifdef SSDBOX_PHASE_TIMING
     long long c0 = clock64();
 #endif
@@ -324,8 +328,8 @@ __device__ void match_unit_loop(const StreamArgs& a, unsigned char* mbase, int m
       }
     }
     // every match warp is done with the unit: publish its per-truth candidates, release the buffer
-    asm volatile("bar.sync 1, %0;" ::"n"(kMatchWarps * 32) : "memory");
-    for (int g = mw * 32 + lane; g < G; g += kMatchWarps * 32) {
+    asm volatile("bar.sync 1, %0;" ::"r"(a.match_warps * 32) : "memory");
+    for (int g = mw * 32 + lane; g < G; g += a.match_warps * 32) {
       unsigned long long v = ub.best[g];
       if (v > kBestInit) atomicMax(&a.gt_best[(size_t)hd.b * a.gpad + g], v);
     }
@@ -358,8 +362,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) loss_stream_kernel(StreamAr
     uint64_t* mfull = reinterpret_cast<uint64_t*>(mbase);
     mbar_init(&mfull[0], 1);
     mbar_init(&mfull[1], 1);
-    mbar_init(&mfull[2], kMatchWarps);
-    mbar_init(&mfull[3], kMatchWarps);
+    mbar_init(&mfull[2], a.match_warps);
+    mbar_init(&mfull[3], a.match_warps);
   }
   if (warp == 0) SMARK(0);
   RingCtx rc = ring_setup(a.ring, smem_ring);   // fences the barrier inits, __syncthreads()
@@ -377,7 +381,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) loss_stream_kernel(StreamAr
     if (warp == kFirstMatchWarp) SMARK(3);
     if (a.fuse) match_unit_loop(a, mbase, warp - kFirstMatchWarp, lane);
     if (warp == kFirstMatchWarp) SMARK(4);
-    if (warp == kFirstMatchWarp + kMatchWarps - 1) SMARK(5);
+    if (warp == kFirstMatchWarp + a.match_warps - 1) SMARK(5);
     return;
   }
   const int wg = warp / kRingGroupWarps;
@@ -413,8 +417,10 @@ static int plan_stream(StreamArgs* a, const float* conf, long long rows, int C, 
                        bool want_fuse, size_t* smem_out) {
   a->fuse = 0;
   a->unit_bytes = 0;
+  a->match_warps = match_warps_for(C);
+  a->match_tile = a->match_warps * 128;
   if (want_fuse) {
-    int ub = unit_buf_bytes(a->gpad);
+    int ub = unit_buf_bytes(a->gpad, a->match_tile);
     size_t need = (size_t)kMatchBarBytes + 2 * (size_t)ub;
     if (need + 65536 < (size_t)max_smem) {
       RingPlan rp;
@@ -443,7 +449,7 @@ static int launch_stream(const StreamArgs& a, size_t smem, cudaStream_t st) {
   SSDBOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     TimerScope ts__(KID_LOSS_STREAM, st);
-    kern<<<a.ring.grid, kStreamThreads, smem, st>>>(a);
+    kern<<<a.ring.grid, (kRingConsumerWarps + 2 + (a.fuse ? a.match_warps : 0)) * 32, smem, st>>>(a);
   }
   SSDBOX_LAUNCH_OK("loss_stream_kernel");
   return SSDBOX_OK;
