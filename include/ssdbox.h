@@ -323,7 +323,8 @@ SSDBOX_API int ssdbox_detections_compact(const float* det, int32_t B, int32_t C,
  *   cls_offsets int32 [num_classes+1] class c owns sorted positions cls_offsets[c] .. cls_offsets[c+1]-1
  *   tpfp        uint8 [num_rows]  1 true positive, 2 false positive, 0 neither (matched a difficult truth :208)
  *   rec, prec   fp64 [num_rows]   :218-223, bit-exact
- *   ap          fp64 [num_classes] ap[c] for c >= 1; -1 for a class without detections (:238-241);
+ *   ap          fp64 [num_classes] ap[c] for c >= 1; -1 for a class without detections (:238-241) and for
+ *               c = 0 (rows of background segments sort in front with tpfp = 0 and are not evaluated);
  *               11-point metric bit-exact, area metric summed in a fixed tree order (1e-12 relative)
  *   npos        int32 [num_classes] non-difficult truths per class (:163)
  * ws: SSDBOX_OP_VOC_EVAL. */

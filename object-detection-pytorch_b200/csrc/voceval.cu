@@ -76,8 +76,15 @@ __global__ void __launch_bounds__(kVocWarps * 32) voc_match_kernel(VocArgs a) {
   const long long s = (long long)blockIdx.x * kVocWarps + warp;
   if (s >= (long long)a.I * a.C) return;
   const int i = (int)(s / a.C), c = (int)(s - (long long)i * a.C);
-  if (c == 0) return;                                                  // background: never evaluated
   const int r0 = a.seg[s], r1 = a.seg[s + 1];
+  if (c == 0) {                                                        // background rows (DetectOut emits none) are never
+    if (lane == 0 && r1 > r0) atomicAdd(&a.cnt[0], r1 - r0);           // evaluated: they sort in front, flagged "neither"
+    for (int r = r0 + lane; r < r1; r += 32) {
+      a.skey[r] = 0u;
+      a.code[r] = -1;
+    }
+    return;
+  }
   const int g0 = a.gt_offsets[i], g1 = a.gt_offsets[i + 1];
   int np = 0;
   for (int g = g0 + lane; g < g1; g += 32) np += (a.gt_labels[g] == c && !a.gt_difficult[g]) ? 1 : 0;
@@ -259,17 +266,16 @@ __global__ void __launch_bounds__(kCurveThreads) voc_curve_kernel(VocArgs a) {
   __shared__ double s_d[33];
   __shared__ double s_m[11][33];
   __shared__ int s_begin, s_n;
-  const int c = blockIdx.x + 1;
+  const int c = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     int off = 0;
-    for (int cc = 1; cc < c; ++cc) off += a.cnt[cc];
+    for (int cc = 0; cc < c; ++cc) off += a.cnt[cc];
     s_begin = off;
     s_n = a.cnt[c];
-    if (c == 1) {                                                      // the first CTA publishes the class offsets
+    if (c == 0) {                                                      // the first CTA publishes the class offsets
       int run = 0;
-      a.cls_offsets[0] = 0;
-      for (int cc = 1; cc < a.C; ++cc) {
+      for (int cc = 0; cc < a.C; ++cc) {
         a.cls_offsets[cc] = run;
         run += a.cnt[cc];
       }
@@ -278,6 +284,15 @@ __global__ void __launch_bounds__(kCurveThreads) voc_curve_kernel(VocArgs a) {
   }
   __syncthreads();
   const int begin = s_begin, n = s_n;
+  if (c == 0) {                                                        // background rows: no curve
+    for (int p = tid; p < n; p += kCurveThreads) {
+      a.rec[begin + p] = 0.0;
+      a.prec[begin + p] = 0.0;
+      a.tpfp[begin + p] = 0;
+    }
+    if (tid == 0) a.ap[0] = -1.0;
+    return;
+  }
   if (n == 0) {
     if (tid == 0) a.ap[c] = -1.0;                                      // :238-241
     return;
@@ -502,12 +517,8 @@ extern "C" int ssdbox_voc_eval(const ssdbox_voc_eval_cfg* cfg, const float* rows
       vin = vout;
     }
   }
-  if (C > 1) {
-    voc_curve_kernel<<<C - 1, kCurveThreads, 0, st>>>(a);
-    SSDBOX_LAUNCH_OK("voc_curve_kernel");
-  } else {
-    SSDBOX_CUDA(cudaMemsetAsync(cls_offsets, 0, 2 * sizeof(int32_t), st));
-  }
+  voc_curve_kernel<<<C, kCurveThreads, 0, st>>>(a);
+  SSDBOX_LAUNCH_OK("voc_curve_kernel");
   return SSDBOX_OK;
 }
 

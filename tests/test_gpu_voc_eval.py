@@ -33,6 +33,7 @@ def _check(case, dev, use07, ovthresh=0.5, rows=None):
                                      case["gt_offsets"], ovthresh, use07, stable=True)
     got = VE.voc_eval(torch.as_tensor(r).to(dev), torch.as_tensor(case["seg"]).to(dev), _gt(case, dev), C, ovthresh, use07)
     assert got.cls_offsets[0] == 0 and got.cls_offsets[C] == r.shape[0]
+    bg = int(got.cls_offsets[1])                                  # rows of background segments sort in front
     for c in range(1, C):
         w = want[c - 1]
         assert int(got.npos[c]) == w["npos"]
@@ -42,6 +43,7 @@ def _check(case, dev, use07, ovthresh=0.5, rows=None):
             assert got.ap[c] == -1.0 and w["ap"] == -1.0
             continue
         assert np.array_equal(got.rows_of(c).cpu().numpy(), w["rows"][w["order"]])       # the sorted order itself
+        assert bg == sum(int(case["seg"][i * C + 1] - case["seg"][i * C]) for i in range(I))
         a, b = got._range(c)
         flags = got.tpfp[a:b].cpu().numpy()
         assert np.array_equal(flags == 1, w["tp"] == 1.0) and np.array_equal(flags == 2, w["fp"] == 1.0)
@@ -113,6 +115,13 @@ def test_voc_eval_edge_cases(dev):
                 gt_difficult=np.uint8([0]), gt_offsets=np.int32([0, 1]))
     got = _check(mini, dev, True)
     assert got.tpfp.cpu().tolist() == [2, 2] and got.ap[1] == 0.0
+    # rows in a background (class 0) segment are carried along but never evaluated
+    seg0 = case["seg"].astype(np.int64).copy()
+    extra_rows = np.float32([[1, 1, 9, 9, 0.7, 0, 0], [2, 2, 8, 8, 0.6, 0, 0]])
+    seg0[1:] += 2                                                 # two rows in (image 0, class 0)
+    with_bg = dict(case, rows=np.concatenate([extra_rows, case["rows"]], 0), seg=seg0.astype(np.int32))
+    got = _check(with_bg, dev, True)
+    assert got.cls_offsets[1] == 2 and got.tpfp[:2].cpu().tolist() == [0, 0] and got.ap[0] == -1.0
     # no detections at all: every class reports -1 (voc_eval.py:238-241)
     empty = dict(case, rows=np.zeros((0, 7), np.float32), seg=np.zeros_like(case["seg"]))
     got = _check(empty, dev, True)
