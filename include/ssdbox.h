@@ -316,7 +316,8 @@ SSDBOX_API int ssdbox_detections_compact(const float* det, int32_t B, int32_t C,
  *   gt_difficult uint8 [num_gt];  gt_offsets int32 [num_images+1] truths of image i
  * The reference prints every detection to a text file ('{:.3f}' score, '{:.1f}' coordinate + 1) and
  * parses it back; the same quantisation is applied arithmetically (exact, see voceval.cu).  Scores
- * must quantise into [0, 1]; *status counts the rows that do not (their bin is clamped).
+ * must quantise into [0, 1]; *status counts the rows that do not (their bin is clamped), plus 2^30 when
+ * seg_offsets does not cover the rows exactly (seg_offsets[num_images*num_classes] != num_rows).
  * Outputs (sorted order = by class, then descending quantised score, equal scores in row order --
  * the stable form of np.argsort(-confidence) :178):
  *   order       int32 [num_rows]  sorted position -> row index

@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(kCurveThreads) voc_curve_kernel(VocArgs a) {
         run += a.cnt[cc];
       }
       a.cls_offsets[a.C] = run;
+      if (run != a.N) atomicAdd(a.status, 1 << 30);                    // the segments do not cover the rows exactly
     }
   }
   __syncthreads();
@@ -489,6 +490,8 @@ extern "C" int ssdbox_voc_eval(const ssdbox_voc_eval_cfg* cfg, const float* rows
   a.npos = npos; a.status = status; a.order = order; a.cls_offsets = cls_offsets; a.tpfp = tpfp;
   a.rec = rec; a.prec = prec; a.ap = ap;
   SSDBOX_CUDA(cudaMemsetAsync(a.claim, 0xff, ((size_t)M + 1) * 8, st));
+  SSDBOX_CUDA(cudaMemsetAsync(a.skey, 0, ((size_t)N + 1) * 4, st));      // rows outside every segment (caller error, reported
+  SSDBOX_CUDA(cudaMemsetAsync(a.code, 0xff, ((size_t)N + 1) * 4, st));   // through *status): class 0, "neither", never dereferenced
   SSDBOX_CUDA(cudaMemsetAsync(a.cnt, 0, (size_t)C * 4, st));
   SSDBOX_CUDA(cudaMemsetAsync(npos, 0, (size_t)C * 4, st));
   SSDBOX_CUDA(cudaMemsetAsync(status, 0, 4, st));

@@ -133,6 +133,9 @@ def test_voc_eval_edge_cases(dev):
         VE.voc_eval(torch.as_tensor(bad).to(dev), torch.as_tensor(case["seg"]).to(dev), _gt(case, dev), 6)
     with pytest.raises(RuntimeError, match="no CPU path"):
         VE.voc_eval(torch.as_tensor(case["rows"]), torch.as_tensor(case["seg"]), _gt(case, dev), 6)
+    # segments that do not cover the rows are reported, not evaluated on uninitialised keys
+    with pytest.raises(ValueError, match="does not cover"):
+        VE.voc_eval(torch.as_tensor(np.concatenate([case["rows"], case["rows"][:3]], 0)).to(dev), torch.as_tensor(case["seg"]).to(dev), _gt(case, dev), 6)
 
 
 def test_voc_eval_after_detect_pipeline(dev):
