@@ -11,8 +11,9 @@ configs[1] (SSD512 VGG16 COCO: P=24564 priors, C=81 classes, B=64 images PER GPU
 image passes through both T and D), timed with CUDA events around K CUDA-graph replays.
 `e2e` = same metric through the public modules (MultiBoxLoss.forward / DetectOut.__call__) with
 pinned HOST inputs: H2D of loc/conf/targets/scores and D2H of the losses and the detection tensor
-inside the timed region.  `--impl reference` times the reference algorithm's CPU path (the oracle
-port: /root/reference itself is Python and not present on the GPU box) on the host cores.
+inside the timed region.  `--impl reference` times the reference's own CPU path on the host cores: the
+unmodified copy of its `lib/` package that oracle/build_ref.py places under oracle/_ref (git-ignored, travels
+to the GPU box), or the in-repo oracle port when that copy is absent.
 """
 import argparse
 import json
@@ -33,6 +34,17 @@ import torch  # noqa: E402
 METRIC = "SSD512 COCO images/s: match+MultiBoxLoss & Detect/NMS, 1/2/4/8 B200"
 WORKLOAD = "ssd512_coco"
 VAR = [0.1, 0.2]
+# kernels launched per step.  plain: T = init, loss_stream, mine_reduce; D = init, detect_stream, segment (warp / CTA),
+# overflow select.  refine: ARM loss (3) + ODM loss (decode, arm_filter + 3) + RefineDetectOut (decode, arm_filter + 5)
+LAUNCHES = {"plain": 8, "refine": 15}
+# BASELINE.json configs; `--workload` selects one (the headline metric is quoted on ssd512_coco)
+DESCR = {
+    "ssd300_voc": "SSD300 VGG16 VOC",
+    "ssd512_coco": "SSD512 VGG16 COCO",
+    "rfb300_voc": "RFBNet300 VGG16 VOC",
+    "fssd300_coco": "FSSD300 VGG COCO",
+    "refinedet320_voc": "RefineDet320 VOC two-step",
+}
 
 
 def parse():
@@ -49,6 +61,7 @@ def parse():
     ap.add_argument("--loss-flags", type=int, default=0, help="experiments: ssdbox_loss_cfg.flags (1 = matching as its own kernel)")
     ap.add_argument("--no-voc-eval", action="store_true", help="skip the VOC evaluation side phase")
     ap.add_argument("--dense", action="store_true", help="detect scores with background bias 4 (worst case)")
+    ap.add_argument("--no-side-phases", action="store_true", help="skip backward / fused softmax / eval post / head layout / VOC eval / dense phases")
     return ap.parse_args()
 
 
@@ -138,19 +151,50 @@ class ClockSampler(object):
 # ----------------------------------------------------------------------------------------------
 # CPU side (oracle port of the reference algorithm) -- the only place bench.py executes oracle/
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_pass(name, C, P, priors_cpu, bt, bd, seed, dense):
+def cpu_impl(name):
+    """(kind, loss_fn, detect_fn): the reference's OWN functions (box_utils.match / MultiBoxLoss.forward /
+    DetectOut.forward / nms, unmodified copy under oracle/_ref placed there by oracle/build_ref.py, run through
+    oracle/ref_loader.py's torch >= 1.x shims) when they are present, else the in-repo restatement
+    (oracle/ssd_oracle.py, proved bit-identical to them by tests/test_oracle_vs_reference.py).  RefineDet has
+    no reference code: always the restatement."""
+    from oracle import ssd_oracle as O
+    if name != "refinedet320_voc":
+        try:
+            from oracle import ref_loader as RL
+            if RL.use_vendored():
+                R = RL.load()
+                return ("reference",
+                        lambda loc, conf, pri, tg, C: R.multibox_loss(C, (loc, conf, pri), tg),
+                        lambda loc, sc, pri, C: R.detect(C, loc, sc, pri))
+        except Exception as e:      # pragma: no cover - e.g. a missing import of the reference's chain
+            sys.stderr.write("bench: reference copy under oracle/_ref unusable (%r); timing the oracle port\n" % (e,))
+    return ("port", lambda loc, conf, pri, tg, C: O.multibox_loss(loc, conf, pri, tg, C),
+            lambda loc, sc, pri, C: O.detect(loc, sc, pri, C))
+
+
+def cpu_reference_pass(name, C, P, priors_cpu, bt, bd, seed, dense, impl=None):
     """times ONE pass: T on `bt` images + D on `bd` images; returns (t_T, t_D) seconds."""
     from oracle import ssd_oracle as O
     from ssdbox import configs, synth
     _, c = configs.get(name)
+    kind, loss_fn, det_fn = impl or cpu_impl(name)
     tg = synth.gen_targets(bt, C, c["gt_max"], seed)
     loc = synth.gen_loc(max(bt, bd), P, seed)
     conf = synth.gen_train_logits(bt, P, C, seed)
     sc = synth.gen_detect_scores(bd, P, C, seed, bkg_bias=4.0 if dense else 10.0)
+    if name == "refinedet320_voc":          # two-step path: ARM loss + ODM loss + refined Detect (own restatement)
+        arm_loc, arm_conf = synth.gen_arm_outputs(max(bt, bd), P, seed)
+        t0 = time.perf_counter()
+        O.refine_multibox_loss(arm_loc[:bt], arm_conf[:bt], loc[:bt], conf, priors_cpu, tg, 2, use_arm=False)
+        O.refine_multibox_loss(arm_loc[:bt], arm_conf[:bt], loc[:bt], conf, priors_cpu, tg, C, use_arm=True)
+        t1 = time.perf_counter()
+        O.refine_detect(arm_loc[:bd], arm_conf[:bd], loc[:bd], sc, priors_cpu, C)
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1
     t0 = time.perf_counter()
-    O.multibox_loss(loc[:bt], conf, priors_cpu, tg, C)
+    loss_fn(loc[:bt], conf, priors_cpu, tg, C)
     t1 = time.perf_counter()
-    O.detect(loc[:bd], sc, priors_cpu, C)
+    det_fn(loc[:bd], sc, priors_cpu, C)
     t2 = time.perf_counter()
     return t1 - t0, t2 - t1
 
@@ -171,25 +215,29 @@ def run_reference(args):
     pri = O.prior_boxes(cfg.MODEL, c["layer_dims"])
     P = pri.size(0)
     bt, bd = 4, 2
+    impl = cpu_impl(args.workload)
     for i in range(args.warmup):
-        cpu_reference_pass(args.workload, C, P, pri, bt, bd, i, args.dense)
+        cpu_reference_pass(args.workload, C, P, pri, bt, bd, i, args.dense, impl)
     tt = td = 0.0
     t_start = time.perf_counter()
     for i in range(args.steps):
-        a, b = cpu_reference_pass(args.workload, C, P, pri, bt, bd, 100 + i, args.dense)
+        a, b = cpu_reference_pass(args.workload, C, P, pri, bt, bd, 100 + i, args.dense, impl)
         tt += a
         td += b
     wall = time.perf_counter() - t_start
     per_img = tt / (args.steps * bt) + td / (args.steps * bd)
     value = 1.0 / per_img
-    sample = "per step: match+MultiBoxLoss fwd on %d images + Detect on %d images (sparse scores), torch CPU, %d threads" % (bt, bd, cores)
+    what = ("the reference's own box_utils.match + MultiBoxLoss.forward / DetectOut.forward + nms (unmodified copy in oracle/_ref)"
+            if impl[0] == "reference" else "the oracle port of the reference algorithm (oracle/ssd_oracle.py)")
+    sample = "per step: match+MultiBoxLoss fwd on %d images + Detect on %d images (%s scores), %s, torch CPU, %d threads" % (
+        bt, bd, "dense" if args.dense else "sparse", what, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (tt + td) / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: P=%d C=%d, CPU sample of the B=%d step" % (args.workload, P, C, c["batch"]),
+        "config": {"workload": "%s: %s box path, P=%d C=%d, CPU sample of the B=%d step" % (args.workload, DESCR.get(args.workload, args.workload), P, C, c["batch"]),
                    "inputs": "synthetic seeded (ssdbox.synth), same generator as the GPU arm"},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": impl[0], "sample": sample},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "phases": {"train_fwd_images_per_s": args.steps * bt / tt, "detect_images_per_s": args.steps * bd / td},
         "wall_s": wall,
@@ -197,99 +245,10 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-# ----------------------------------------------------------------------------------------------
-# GPU arm
-# ----------------------------------------------------------------------------------------------
-def main():
-    T0 = time.perf_counter()
-    args = parse()
-    if args.impl == "reference":
-        run_reference(args)
-        return
-
-    import ssdbox
-    from ssdbox import _abi, configs, synth
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the box path has no CPU fallback); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        # NCCL announces its version on stdout at communicator creation: keep stdout for the ONE JSON line
-        sys.stdout.flush()
-        saved_stdout = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            dist.all_reduce(torch.zeros(1, device=dev))
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved_stdout, 1)
-            os.close(saved_stdout)
-    n_gpus = world
-
-    def log(msg):
-        if rank == 0:
-            sys.stderr.write("bench[%.1fs]: %s\n" % (time.perf_counter() - T0, msg))
-            sys.stderr.flush()
-
-    cfg, c = configs.get(args.workload)
-    C = cfg.MODEL.NUM_CLASSES
-    B = args.batch or c["batch"]
-    top_k = 200
-    priors = ssdbox.PriorBoxSSD(cfg).forward(c["layer_dims"], keep_on_device=True)
-    P = priors.size(0)
-
-    # ---- synthetic inputs: drawn on the CPU (seeded per rank), kept in pinned memory for e2e ----
-    seed = 1000 * rank
-    tg = synth.gen_targets(B, C, c["gt_max"], seed)
-    gt_h, offs_h = synth.pack_targets(tg)
-    gmax = max(int(t.size(0)) for t in tg)
-    g_avg = float(gt_h.size(0)) / B
-    loc_h = synth.gen_loc(B, P, seed).pin_memory()
-    conf_h = synth.gen_train_logits(B, P, C, seed).pin_memory()
-    sc_h = synth.gen_detect_scores(B, P, C, seed, bkg_bias=4.0 if args.dense else 10.0).pin_memory()
-    gt_h, offs_h = gt_h.pin_memory(), offs_h.pin_memory()
-    loc, conf, sc = loc_h.to(dev), conf_h.to(dev), sc_h.to(dev)
-    gt, offs = gt_h.to(dev), offs_h.to(dev)
-
-    crit = ssdbox.MultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, distributed=(world > 1))
-    crit.abi_flags |= args.loss_flags
-    det = ssdbox.DetectOut(C, 0, top_k, 0.01, 0.45, VAR)
-    det_out = torch.empty(B, C, top_k, 5, dtype=torch.float32, device=dev)
-
-    def step():
-        # T, then D, then the (multi-GPU) wait for the other ranks' loss sums: D overlaps that wait
-        with torch.no_grad():
-            pending = crit.forward_packed_deferred(loc, conf, priors, gt, offs, gmax)
-            out = det.forward(loc, sc, priors, out=det_out)
-            ll, lc = pending.wait()
-        return ll, lc, out
-
-    log("inputs ready")
-    # eager warm-up (lazy init, workspace allocation), also the functional sanity of the step
-    for _ in range(2):
-        ll, lc, out = step()
-    torch.cuda.synchronize()
-    sanity = {"loss_l": float(ll), "loss_c": float(lc), "detections": int((out[..., 0] > 0).sum())}
-
-    # ---- per-kernel device times (eager, CUDA events inside the library on the launch stream) ---
-    _abi.timers_enable(True)
-    n_prof = max(3, min(args.steps, 20))
-    for _ in range(n_prof):
-        step()
-    torch.cuda.synchronize()
-    kt = _abi.timers_read()
-    _abi.timers_enable(False)
-    kernels_us = {k: (1e3 * v[0] / v[1]) for k, v in kt.items() if v[1]}
-
-    # forward + backward through the autograd module (reported beside the headline, not part of it)
+def side_phases(args, ssdbox, _abi, synth, crit, det, det_out, cfg, c, loc, conf, sc, priors, gt, offs, gmax, B, P, C, top_k, dev, n_gpus):
+    """phases reported beside the headline (not part of the step): forward + backward, DetectOut on raw logits,
+    eval post-processing, head-output layout, VOC evaluation."""
+    # forward + backward through the autograd module
     loc_g = loc.clone().requires_grad_(True)
     conf_g = conf.clone().requires_grad_(True)
     for i in range(4):
@@ -409,6 +368,129 @@ def main():
                                      "extrapolated_s_for_this_set": int(vrows.size(0)) * dt / sub["rows"].shape[0]}
         del vrows, vseg, vgt, res
 
+    return (bwd_us, fused_us, fused_stream_us, fused_dets, softmax_us, evalpost_us, evalpost_rows, heads_us, heads_torch_us,
+            heads_equal, voc_phase)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def main():
+    T0 = time.perf_counter()
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import ssdbox
+    from ssdbox import _abi, configs, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the box path has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        # NCCL announces its version on stdout at communicator creation: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
+    n_gpus = world
+
+    def log(msg):
+        if rank == 0:
+            sys.stderr.write("bench[%.1fs]: %s\n" % (time.perf_counter() - T0, msg))
+            sys.stderr.flush()
+
+    cfg, c = configs.get(args.workload)
+    C = cfg.MODEL.NUM_CLASSES
+    B = args.batch or c["batch"]
+    top_k = 200
+    priors = ssdbox.PriorBoxSSD(cfg).forward(c["layer_dims"], keep_on_device=True)
+    P = priors.size(0)
+
+    # ---- synthetic inputs: drawn on the CPU (seeded per rank), kept in pinned memory for e2e ----
+    seed = 1000 * rank
+    tg = synth.gen_targets(B, C, c["gt_max"], seed)
+    gt_h, offs_h = synth.pack_targets(tg)
+    gmax = max(int(t.size(0)) for t in tg)
+    g_avg = float(gt_h.size(0)) / B
+    loc_h = synth.gen_loc(B, P, seed).pin_memory()
+    conf_h = synth.gen_train_logits(B, P, C, seed).pin_memory()
+    sc_h = synth.gen_detect_scores(B, P, C, seed, bkg_bias=4.0 if args.dense else 10.0).pin_memory()
+    gt_h, offs_h = gt_h.pin_memory(), offs_h.pin_memory()
+    loc, conf, sc = loc_h.to(dev), conf_h.to(dev), sc_h.to(dev)
+    gt, offs = gt_h.to(dev), offs_h.to(dev)
+
+    refine = args.workload == "refinedet320_voc"
+    crit = ssdbox.MultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, distributed=(world > 1))
+    crit.abi_flags |= args.loss_flags
+    det = ssdbox.DetectOut(C, 0, top_k, 0.01, 0.45, VAR)
+    det_out = torch.empty(B, C, top_k, 5, dtype=torch.float32, device=dev)
+    if refine:
+        # cfg5 is measured as RefineDet: ARM loss (C=2, raw priors) + ODM loss (per-image refined anchors,
+        # negative-anchor filtering) + RefineDetectOut -- SURVEY.md 8a-R, own restatement (parity unpinned)
+        arm_loc_h, arm_conf_h = synth.gen_arm_outputs(B, P, seed)
+        arm_loc_h, arm_conf_h = arm_loc_h.pin_memory(), arm_conf_h.pin_memory()
+        arm_loc, arm_conf = arm_loc_h.to(dev), arm_conf_h.to(dev)
+        arm_crit = ssdbox.RefineMultiBoxLoss(2, 0.5, True, 0, True, 3, 0.5, False, use_ARM=False, distributed=(world > 1))
+        odm_crit = ssdbox.RefineMultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, use_ARM=True, distributed=(world > 1))
+        rdet = ssdbox.RefineDetectOut(C, 0, top_k, 0.01, 0.45, VAR, theta=0.01)
+        crit = odm_crit
+
+        def step():
+            with torch.no_grad():
+                al, ac = arm_crit.forward_packed_two_step(arm_loc, arm_conf, loc, conf, priors, gt, offs, gmax)
+                ol, oc = odm_crit.forward_packed_two_step(arm_loc, arm_conf, loc, conf, priors, gt, offs, gmax)
+                out = rdet.forward(arm_loc, arm_conf, loc, sc, priors, out=det_out)
+            return al + ol, ac + oc, out
+    else:
+        def step():
+            # T, then D, then the (multi-GPU) wait for the other ranks' loss sums: D overlaps that wait
+            with torch.no_grad():
+                pending = crit.forward_packed_deferred(loc, conf, priors, gt, offs, gmax)
+                out = det.forward(loc, sc, priors, out=det_out)
+                ll, lc = pending.wait()
+            return ll, lc, out
+
+    log("inputs ready")
+    # eager warm-up (lazy init, workspace allocation), also the functional sanity of the step
+    for _ in range(2):
+        ll, lc, out = step()
+    torch.cuda.synchronize()
+    sanity = {"loss_l": float(ll), "loss_c": float(lc), "detections": int((out[..., 0] > 0).sum()), "mgpu": None}
+
+    # ---- per-kernel device times (eager, CUDA events inside the library on the launch stream) ---
+    _abi.timers_enable(True)
+    n_prof = max(3, min(args.steps, 20))
+    for _ in range(n_prof):
+        step()
+    torch.cuda.synchronize()
+    kt = _abi.timers_read()
+    _abi.timers_enable(False)
+    kernels_us = {k: (1e3 * v[0] / v[1]) for k, v in kt.items() if v[1]}
+
+    side = not (args.no_side_phases or refine)
+    bwd_us = fused_us = fused_stream_us = softmax_us = evalpost_us = heads_us = heads_torch_us = 0.0
+    fused_dets = evalpost_rows = 0
+    heads_equal = None
+    voc_phase = None
+    if side:
+        (bwd_us, fused_us, fused_stream_us, fused_dets, softmax_us, evalpost_us, evalpost_rows, heads_us, heads_torch_us,
+         heads_equal, voc_phase) = side_phases(args, ssdbox, _abi, synth, crit, det, det_out, cfg, c, loc, conf, sc, priors,
+                                               gt, offs, gmax, B, P, C, top_k, dev, n_gpus)
     log("per-kernel timers done")
     # ---- the timed region: K replays of the captured step (or eager launches) -------------------
     use_graph = not args.no_graph
@@ -485,6 +567,8 @@ def main():
     tg_h = [t.pin_memory() for t in tg]
 
     copy_stream = torch.cuda.Stream()
+    if refine:
+        arm_loc_d, arm_conf_d = torch.empty_like(arm_loc), torch.empty_like(arm_conf)
 
     def e2e_step():
         # H2D on a copy stream, kernels on the current stream: T runs while the scores are still in
@@ -495,17 +579,25 @@ def main():
             with torch.cuda.stream(copy_stream):
                 loc_d.copy_(loc_h, non_blocking=True)
                 conf_d.copy_(conf_h, non_blocking=True)
-                tgd = [t.to(dev, non_blocking=True) for t in tg_h]
+                if refine:
+                    arm_loc_d.copy_(arm_loc_h, non_blocking=True)
+                    arm_conf_d.copy_(arm_conf_h, non_blocking=True)
+                tgd = tg_h                                   # host targets: packed into ONE pinned staging copy by pack_targets
                 ev_t = torch.cuda.Event()
                 ev_t.record(copy_stream)
                 sc_d.copy_(sc_h, non_blocking=True)
                 ev_d = torch.cuda.Event()
                 ev_d.record(copy_stream)
             cur.wait_event(ev_t)
-            ll, lc = crit((loc_d, conf_d, priors), tgd)
+            if refine:
+                al, ac = arm_crit((arm_loc_d, arm_conf_d, loc_d, conf_d, priors), tgd)
+                ol, oc = odm_crit((arm_loc_d, arm_conf_d, loc_d, conf_d, priors), tgd)
+                ll, lc = al + ol, ac + oc
+            else:
+                ll, lc = crit((loc_d, conf_d, priors), tgd)
             loss_h.copy_(torch.stack([ll, lc]), non_blocking=True)
             cur.wait_event(ev_d)
-            o = det(loc_d, sc_d, priors)
+            o = rdet(arm_loc_d, arm_conf_d, loc_d, sc_d, priors) if refine else det(loc_d, sc_d, priors)
             out_h.copy_(o, non_blocking=True)
         torch.cuda.synchronize()
 
@@ -516,17 +608,126 @@ def main():
     for _ in range(args.e2e_steps):
         e2e_step()
     e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    h2d = loc_h.numel() * 4 + conf_h.numel() * 4 + sc_h.numel() * 4 + gt_h.numel() * 4 + offs_h.numel() * 4
+    if refine:
+        h2d += arm_loc_h.numel() * 4 + arm_conf_h.numel() * 4
+    d2h = out_h.numel() * 4 + 8
+    e2e_rank_s = [e2e_s]
     if dist is not None:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    h2d = loc_h.numel() * 4 + conf_h.numel() * 4 + sc_h.numel() * 4 + gt_h.numel() * 4
-    d2h = out_h.numel() * 4 + 8
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        e2e_rank_s = [float(x.item()) for x in allt]
+        e2e_s = max(e2e_rank_s)
+    # a bare pinned H2D copy of the same size on this rank, alone on the link (what PCIe gives one GPU) ...
+    probe = torch.empty(conf_h.numel(), dtype=torch.float32, device=dev)
+    probe.copy_(conf_h, non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    probe.copy_(conf_h, non_blocking=True)
+    torch.cuda.synchronize()
+    solo_gbps = conf_h.numel() * 4 / (time.perf_counter() - t0) / 1e9
+    all_gbps = None
+    if dist is not None:
+        # ... and with every rank copying at once (what the host's memory / PCIe root complexes give N GPUs)
+        dist.barrier()
+        t0 = time.perf_counter()
+        probe.copy_(conf_h, non_blocking=True)
+        torch.cuda.synchronize()
+        mine = conf_h.numel() * 4 / (time.perf_counter() - t0) / 1e9
+        t = torch.tensor([mine], dtype=torch.float64, device=dev)
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        all_gbps = [float(x.item()) for x in allt]
+    del probe
     e2e = {"value": n_gpus * B / e2e_s, "unit": "images/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
-           "api": "ssdbox.MultiBoxLoss.forward + ssdbox.DetectOut.__call__ from pinned host tensors (H2D on a copy stream, kernels overlap the next copy)"}
+           "rank_ms_per_step": [1e3 * x for x in e2e_rank_s],
+           "h2d_gbps_per_rank": [h2d / x / 1e9 for x in e2e_rank_s],
+           "h2d_probe_gbps": {"one_rank_alone_this_rank": solo_gbps, "all_ranks_at_once": all_gbps,
+                              "note": "bare pinned cudaMemcpyAsync of conf (%.0f MB): the PCIe / host-memory ceiling of the e2e number" % (conf_h.numel() * 4 / 1e6)},
+           "api": ("ssdbox.RefineMultiBoxLoss.forward x2 + ssdbox.RefineDetectOut.__call__" if refine else
+                   "ssdbox.MultiBoxLoss.forward + ssdbox.DetectOut.__call__") +
+                  " from pinned host tensors (H2D on a copy stream, kernels overlap the next copy)"}
 
     log("e2e done")
+
+    # ---- N > 1: is the peer-reduced loss the loss of the global batch? (printed in sanity.mgpu) -------------
+    mgpu = None
+    if dist is not None and not refine:
+        with torch.no_grad():
+            local_crit = ssdbox.MultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, distributed=False)
+            local_crit.forward_packed(loc, conf, priors, gt, offs, gmax)
+            local_sums = local_crit._last[0].clone()
+            gl_, gc_, _ = step()
+            global_sums = crit._last[0].clone()         # after PendingLoss.wait(): the GLOBAL {sum_l, sum_c, N}
+            global_losses = torch.stack([gl_, gc_]).double()
+        gathered = [torch.empty_like(local_sums) for _ in range(world)]
+        dist.all_gather(gathered, local_sums)            # NCCL: the ranks' LOCAL sums
+        tot = [0.0, 0.0, 0.0]
+        for r in range(world):                           # rank-ordered fp64 adds on the host, like the kernel does
+            v = gathered[r].cpu().tolist()
+            for k in range(3):
+                tot[k] += v[k]
+        mine = global_sums.cpu().tolist()
+        ok = torch.tensor([1 if all(tot[k] == mine[k] for k in range(3)) else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        same = [torch.empty_like(global_sums) for _ in range(world)]
+        dist.all_gather(same, global_sums)
+        mgpu = {"reduce": crit.reduce_used, "bit_equal": bool(int(ok.item())),
+                "note": "peer-exchanged {sum_l, sum_c, N} == rank-ordered fp64 sum of the NCCL-gathered local sums, on every rank",
+                "identical_on_all_ranks": all(torch.equal(v, same[0]) for v in same),
+                "global_sums": mine, "n_pos_global": int(mine[2])}
+        if world <= 2:
+            # rank 0 recomputes the criterion over the concatenated global batch on its own GPU (the reference
+            # computes it on one device over the gathered batch, train.py:137-142)
+            rel = None
+            if rank == 0:
+                locs, confs, tgs = [loc], [conf], list(tg)
+                for r in range(1, world):
+                    tr = synth.gen_targets(B, C, c["gt_max"], 1000 * r)
+                    tgs += tr
+                    locs.append(synth.gen_loc(B, P, 1000 * r).to(dev))
+                    confs.append(synth.gen_train_logits(B, P, C, 1000 * r).to(dev))
+                g_all, o_all = synth.pack_targets(tgs)
+                with torch.no_grad():
+                    one = ssdbox.MultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, distributed=False)
+                    wl, wc = one.forward_packed(torch.cat(locs), torch.cat(confs), priors, g_all.to(dev), o_all.to(dev),
+                                                max(int(t.size(0)) for t in tgs))
+                want = torch.stack([wl, wc]).double()
+                rel = float(((global_losses - want).abs() / want.abs()).max())
+                mgpu["single_device_losses"] = want.cpu().tolist()
+                mgpu["n_pos_single_device"] = int(one._last[0][2])
+                del locs, confs
+            mgpu["global_batch_on_one_gpu_rel_err"] = rel
+            mgpu["global_batch_ok"] = (rel is not None and rel <= 1e-6 and mgpu["n_pos_single_device"] == mgpu["n_pos_global"]) if rank == 0 else None
+        mgpu["losses"] = global_losses.cpu().tolist()
+        dist.barrier()
+
+    # ---- dense-score regime of Detect (SURVEY 8d "worst case": background bias 4) as a second phase ----------
+    dense_phase = None
+    if side and n_gpus == 1 and not args.dense:
+        sc_dense = synth.gen_detect_scores(B, P, C, seed, bkg_bias=4.0).to(dev)
+        with torch.no_grad():
+            for _ in range(2):
+                det.forward(loc, sc_dense, priors, out=det_out)
+            torch.cuda.synchronize()
+            _abi.timers_enable(True)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
+            for _ in range(5):
+                det.forward(loc, sc_dense, priors, out=det_out)
+            ev[1].record()
+            torch.cuda.synchronize()
+            kd = _abi.timers_read()
+            _abi.timers_enable(False)
+        dense_us = 1e3 * ev[0].elapsed_time(ev[1]) / 5
+        dense_phase = {"note": "DetectOut alone on dense scores (bkg bias 4: ~50 % of the (prior, class) pairs pass 0.01, every class saturates top_k)",
+                       "us": dense_us, "images_per_s": B / (dense_us * 1e-6), "detections": int((det_out[..., 0] > 0).sum()),
+                       "pass_fraction": float((sc_dense[:2, :, 1:] > 0.01).float().mean()),
+                       "kernels_us": {k: 1e3 * v[0] / v[1] for k, v in kd.items() if v[1]},
+                       "hbm_frac": bytes_D(P, C, top_k) * B / (dense_us * 1e-6) / 1e9 / load_peak()[0]}
+        del sc_dense
 
     def teardown():
         # a process group whose collectives were captured in a CUDA graph can block in
@@ -549,22 +750,32 @@ def main():
     t_us = sum(kernels_us.get(k, 0.0) for k in ("init", "match", "loss_stream", "mine_reduce"))
     d_us = sum(kernels_us.get(k, 0.0) for k in ("init", "detect_stream", "detect_segment", "detect_segment_big", "detect_overflow"))
     dom = max(("loss_stream", "detect_stream"), key=lambda k: kernels_us.get(k, 0.0))
+    if refine:
+        dom = "detect_stream"        # the library's loss_stream timer averages the ARM (C=2) and ODM (C=21) launches
+    bT, bD = bytes_T(P, C, g_avg, B), bytes_D(P, C, top_k)
+    if refine:
+        # + ARM loss P*(4*2+16) + 20G, + the re-read of arm_loc / arm_conf (24 B per anchor) by the ODM loss and by Detect
+        bT += P * (4 * 2 + 16) + 20 * g_avg + 24 * P
+        bD += 24 * P
     dom_us = kernels_us[dom]
     dom_bytes = float(B) * P * 4 * C       # the compulsory read of conf / scores [B,P,C] fp32
     achieved = dom_bytes / (dom_us * 1e-6) / 1e9
     roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic.get(dom), "avg_launch_us": dom_us,
+                "frac": achieved / peak, "traffic": traffic.get(dom) if args.workload == WORKLOAD else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/traffic.json), not measured in this run",
+                "avg_launch_us": dom_us,
                 "algorithmic_bytes_per_launch": dom_bytes, "peak_source": peak_src}
     other = "detect_stream" if dom == "loss_stream" else "loss_stream"
     phases = {
-        "step_bytes_model": "T: P*(4C+16)+20G+16P/B per image; D: P*(4C+16)+20*C*top_k per image (SURVEY.md 8d)",
-        "train_fwd": {"kernel_us_sum": t_us, "bytes_per_image": bytes_T(P, C, g_avg, B),
-                      "hbm_frac_of_kernel_sum": bytes_T(P, C, g_avg, B) * B / (t_us * 1e-6) / 1e9 / peak if t_us else None},
+        "step_bytes_model": "T: P*(4C+16)+20G+16P/B per image; D: P*(4C+16)+20*C*top_k per image (SURVEY.md 8d)" +
+                            ("; two-step: T += P*(4*2+16)+20G (ARM loss) + 24P (arm_loc/arm_conf re-read by the ODM loss), D += 24P" if refine else ""),
+        "train_fwd": {"kernel_us_sum": t_us, "bytes_per_image": bT,
+                      "hbm_frac_of_kernel_sum": bT * B / (t_us * 1e-6) / 1e9 / peak if t_us and not refine else None},
         "train_bwd": {"kernel_us_sum": bwd_us, "note": "loss_bwd_stream_kernel: one pass, TMA bulk stores of zero tiles carrying the selected rows; grad_conf/grad_loc fully written",
                       "bytes_written_per_image": P * (4 * C + 16),
                       "hbm_frac": P * (4 * C + 16) * B / (bwd_us * 1e-6) / 1e9 / peak if bwd_us else None},
-        "detect": {"kernel_us_sum": d_us, "bytes_per_image": bytes_D(P, C, top_k),
-                   "hbm_frac_of_kernel_sum": bytes_D(P, C, top_k) * B / (d_us * 1e-6) / 1e9 / peak if d_us else None},
+        "detect": {"kernel_us_sum": d_us, "bytes_per_image": bD,
+                   "hbm_frac_of_kernel_sum": bD * B / (d_us * 1e-6) / 1e9 / peak if d_us else None},
         "detect_fused_softmax": {"note": "DetectOut(conf_is_logits=True): softmax of ssd_v3.py:123-124 fused into the candidate pass (SURVEY 8f rank 2), same detections",
                                  "kernel_us_sum": fused_us, "detect_stream_us": fused_stream_us, "detections": fused_dets,
                                  "unfused_us": softmax_us + d_us, "torch_softmax_us": softmax_us,
@@ -573,9 +784,10 @@ def main():
                       "us": evalpost_us, "rows": evalpost_rows, "bytes_read": B * C * top_k * 5 * 4},
         "head_layout": {"note": "ssdbox_heads_to_rows: conf head outputs NCHW -> [B,P,C] in one launch (ssd_v3.py:114-121) against torch permute().contiguous() + cat",
                         "us": heads_us, "torch_us": heads_torch_us, "bytes_moved": 2 * B * P * C * 4, "identical_to_torch": heads_equal,
-                        "hbm_frac": 2 * B * P * C * 4 / (heads_us * 1e-6) / 1e9 / peak},
+                        "hbm_frac": 2 * B * P * C * 4 / (heads_us * 1e-6) / 1e9 / peak if heads_us else None},
         "voc_eval": voc_phase,
-        "step_hbm_frac": (bytes_T(P, C, g_avg, B) + bytes_D(P, C, top_k)) * B / (ms_per_step * 1e-3) / 1e9 / peak,
+        "dense": dense_phase,
+        "step_hbm_frac": (bT + bD) * B / (ms_per_step * 1e-3) / 1e9 / peak,
         other + "_kernel": {"avg_launch_us": kernels_us.get(other), "achieved_GBps": dom_bytes / (kernels_us[other] * 1e-6) / 1e9 if other in kernels_us else None,
                             "traffic": traffic.get(other)},
         "kernels_us": kernels_us,
@@ -590,26 +802,31 @@ def main():
         torch.set_num_threads(cores)
         pri_cpu = priors.cpu()
         bt, bd, reps = 4, 2, 3
-        cpu_reference_pass(args.workload, C, P, pri_cpu, bt, bd, 7, args.dense)
+        impl = cpu_impl(args.workload)
+        cpu_reference_pass(args.workload, C, P, pri_cpu, bt, bd, 7, args.dense, impl)
         tt = td = 0.0
         for i in range(reps):
-            a, b = cpu_reference_pass(args.workload, C, P, pri_cpu, bt, bd, 50 + i, args.dense)
+            a, b = cpu_reference_pass(args.workload, C, P, pri_cpu, bt, bd, 50 + i, args.dense, impl)
             tt += a
             td += b
         per_img = tt / (reps * bt) + td / (reps * bd)
-        cpu_baseline = {"value": 1.0 / per_img, "unit": "images/s", "cores": cores, "kind": "port",
-                        "sample": "%d reps of (match+MultiBoxLoss fwd on %d images + Detect on %d images) of the same workload, torch CPU oracle, %d threads"
-                                  % (reps, bt, bd, cores),
+        cpu_baseline = {"value": 1.0 / per_img, "unit": "images/s", "cores": cores, "kind": impl[0],
+                        "sample": "%d reps of (match+MultiBoxLoss fwd on %d images + Detect on %d images) of the same workload, %s, torch CPU, %d threads"
+                                  % (reps, bt, bd, "the reference's own functions (unmodified copy in oracle/_ref)" if impl[0] == "reference"
+                                     else "the oracle port (oracle/ssd_oracle.py)", cores),
                         "train_fwd_images_per_s": reps * bt / tt, "detect_images_per_s": reps * bd / td}
 
     # T: init, loss_stream, mine_reduce; D: init, detect_stream, segment (warp / CTA), overflow; N > 1: + the collect kernel
-    launches_per_step = 8 + (1 if n_gpus > 1 else 0)
+    launches_per_step = LAUNCHES["refine" if refine else "plain"] + (1 if n_gpus > 1 and not refine else 0)
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: SSD512 VGG16 COCO box path, P=%d priors, C=%d classes, B=%d images per GPU, "
-                               "step = match+MultiBoxLoss fwd + DetectOut(top_k=200, conf 0.01, nms 0.45)" % (args.workload, P, C, B),
+        "config": {"workload": "%s: %s box path, P=%d priors, C=%d classes, B=%d images per GPU, step = %s" % (
+                       args.workload, DESCR.get(args.workload, args.workload), P, C, B,
+                       "ARM MultiBoxLoss (C=2) + ODM RefineMultiBoxLoss (refined anchors, negative-anchor filtering) fwd + "
+                       "RefineDetectOut(top_k=200, conf 0.01, nms 0.45, theta 0.01)" if refine else
+                       "match+MultiBoxLoss fwd + DetectOut(top_k=200, conf 0.01, nms 0.45)"),
                    "global_batch": n_gpus * B, "detect_scores": "dense (bkg bias 4)" if args.dense else "sparse/realistic (bkg bias 10)",
                    "l2": "inputs larger than L2 (conf and scores are %.0f MB each vs 126 MB L2)" % (conf.numel() * 4 / 1e6),
                    "launch": "CUDA graph replay" if graph is not None else "eager launches",
@@ -619,6 +836,7 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps, "rank_ms_per_step": rank_ms, "clocks": clocks, "phases": phases, "sanity": sanity,
     }
+    sanity["mgpu"] = mgpu
     print(json.dumps(line), flush=True)
     teardown()
 

@@ -214,9 +214,12 @@ SSDBOX_API int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float*
  * (bit-identical on every rank) and finalises: `sums` / `losses` then hold the GLOBAL values.
  * There is no separate collective launch.  Like any collective, every rank must issue the same
  * sequence of peer-reduced forwards; a call epoch kept in the buffer makes the call replayable
- * from a CUDA graph.  A peer that never arrives traps the kernel after wait_timeout_ms (wall clock;
- * 0 = 30 s) instead of hanging: size it for the longest stall a rank may see between two steps
- * (data loading, checkpointing). */
+ * from a CUDA graph.  A rank whose local shard is empty (B == 0: global batch smaller than the world)
+ * still calls: it posts zeros, so the epochs stay in step.  A peer that never arrives does NOT kill the
+ * context: after wait_timeout_ms (wall clock; 0 = 30 s) the waiting rank gives up, its sums / losses of
+ * that call become NaN and the event is counted in 64-bit word 1 of its own exchange buffer (word 0 is
+ * the call epoch); the host mirror reads it (PeerExchange.timeouts()).  After a timeout the ranks are out
+ * of step: rebuild the exchange (zero-fill + rendezvous) before the next call. */
 #define SSDBOX_MAX_PEERS 16
 typedef struct {
   int32_t rank, world;                 /* 1 <= world <= SSDBOX_MAX_PEERS */

@@ -562,27 +562,38 @@ static inline long long peer_timeout_ns(const ssdbox_peer_group* peers) {
 
 __device__ void peer_collect(void* const* bufs, int me, int world, unsigned long long epoch, int lane, double* out,
                              long long timeout_ns) {
-  const char* mine = static_cast<const char*>(bufs[me]);
+  char* mine = static_cast<char*>(bufs[me]);
   const size_t bank = kPeerHeaderBytes + (size_t)(epoch & 1ull) * world * kPeerSlotBytes;
   double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+  bool arrived = true;
   if (lane < world) {
     const char* src = mine + bank + (size_t)lane * kPeerSlotBytes;
     const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(src + 24);
     const unsigned long long t0 = wall_ns();
     unsigned spins = 0;
     while (ld_acquire_sys(flag) != epoch) {
-      if ((++spins & 1023u) == 0 && wall_ns() - t0 > (unsigned long long)timeout_ns) __trap();     // a peer never arrived
+      if ((++spins & 1023u) == 0 && wall_ns() - t0 > (unsigned long long)timeout_ns) {     // a peer never arrived
+        arrived = false;
+        break;
+      }
     }
     const volatile double* q = reinterpret_cast<const volatile double*>(src);
     r0 = q[0];
     r1 = q[1];
     r2 = q[2];
   }
+  // A missing peer does not kill the context: the sums of this call become NaN and the owner's buffer
+  // counts the event (header word 1, read by ssdbox_peer_status / PeerExchange.timeouts()).
+  const bool ok = __all_sync(SSDBOX_FULL_MASK, arrived);
   double t0s = 0.0, t1s = 0.0, t2s = 0.0;
   for (int r = 0; r < world; ++r) {
     t0s += __shfl_sync(SSDBOX_FULL_MASK, r0, r);
     t1s += __shfl_sync(SSDBOX_FULL_MASK, r1, r);
     t2s += __shfl_sync(SSDBOX_FULL_MASK, r2, r);
+  }
+  if (!ok) {
+    t0s = t1s = t2s = __longlong_as_double(0x7ff8000000000000ll);
+    if (lane == 0) reinterpret_cast<unsigned long long*>(mine)[1] += 1ull;
   }
   out[0] = t0s;
   out[1] = t1s;
@@ -623,8 +634,26 @@ __global__ void peer_finish_kernel(PeerFinishArgs a) {
     a.sums[1] = g[1];
     a.sums[2] = g[2];
     if (a.losses) {
-      a.losses[0] = g[2] > 0.0 ? (float)(g[0] / g[2]) : 0.0f;
-      a.losses[1] = g[2] > 0.0 ? (float)(g[1] / g[2]) : 0.0f;
+      a.losses[0] = g[2] == 0.0 ? 0.0f : (float)(g[0] / g[2]);
+      a.losses[1] = g[2] == 0.0 ? 0.0f : (float)(g[1] / g[2]);
+    }
+  }
+}
+
+// a rank whose local shard is empty still takes part in the exchange: it posts {0, 0, 0} for this call
+// (and, unless the wait is deferred, collects and finalises) so that the epochs of all ranks stay in step
+__global__ void peer_empty_kernel(PeerFinishArgs a, int defer, int finalize) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long epoch = peer_post(a.bufs, a.rank, a.world, 0.0, 0.0, 0.0, lane);
+  double g[3] = {0.0, 0.0, 0.0};
+  if (!defer) peer_collect(a.bufs, a.rank, a.world, epoch, lane, g, a.timeout_ns);
+  if (lane == 0) {
+    a.sums[0] = g[0];
+    a.sums[1] = g[1];
+    a.sums[2] = g[2];
+    if (finalize && a.losses) {
+      a.losses[0] = g[2] == 0.0 ? 0.0f : (float)(g[0] / g[2]);
+      a.losses[1] = g[2] == 0.0 ? 0.0f : (float)(g[1] / g[2]);
     }
   }
 }
@@ -663,8 +692,8 @@ __device__ void fold_partials(const MineArgs& a, double* s_dscr, double* s_big, 
     a.sums[1] = sc;
     a.sums[2] = sn;
     if (a.finalize && a.losses) {     // multibox_loss.py:114-116 (N == 0 -> 0 instead of inf/nan)
-      a.losses[0] = sn > 0.0 ? (float)(sl / sn) : 0.0f;
-      a.losses[1] = sn > 0.0 ? (float)(sc / sn) : 0.0f;
+      a.losses[0] = sn == 0.0 ? 0.0f : (float)(sl / sn);
+      a.losses[1] = sn == 0.0 ? 0.0f : (float)(sc / sn);
     }
   }
 }
@@ -976,11 +1005,12 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   // (last truth wins); winners drop their label into a per-prior override array in shared memory
   // that every thread merges into its registers (one 8-byte shared load per quad)
   if (small_g) {
+    const uint32_t gmask = __ballot_sync(SSDBOX_FULL_MASK, tid < G);     // whole warps reach this point together
     if (tid < G) {
       const uint32_t pj = ~(uint32_t)(s_best[tid] & 0xffffffffull);
       bool winner = pj < (uint32_t)P;
       if (G <= 32) {                 // one warp holds every truth: the highest lane with this prior wins
-        const uint32_t same = __match_any_sync(__activemask(), pj);
+        const uint32_t same = __match_any_sync(gmask, pj);
         winner = winner && (31 - __clz(same)) == (int)(tid & 31);
       } else {
         for (int j2 = tid + 1; winner && j2 < G; ++j2)
@@ -1250,8 +1280,8 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
 
 __global__ void finalize_kernel(const double* __restrict__ sums, float* __restrict__ losses) {
   double n = sums[2];
-  losses[0] = n > 0.0 ? (float)(sums[0] / n) : 0.0f;
-  losses[1] = n > 0.0 ? (float)(sums[1] / n) : 0.0f;
+  losses[0] = n == 0.0 ? 0.0f : (float)(sums[0] / n);      // NaN sums (a peer timed out) stay NaN
+  losses[1] = n == 0.0 ? 0.0f : (float)(sums[1] / n);
 }
 
 // stand-alone mining on caller-supplied keys (multibox_loss.py:97-103 in isolation)
@@ -1633,12 +1663,24 @@ extern "C" int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const 
     for (int r = 0; r < peers->world; ++r)
       SSDBOX_REQUIRE(peers->bufs[r] && (reinterpret_cast<uintptr_t>(peers->bufs[r]) & 15u) == 0, SSDBOX_EINVAL,
                      "loss: peer buffer %d is null or misaligned", r);
-    SSDBOX_REQUIRE(cfg->B > 0 && cfg->P > 0, SSDBOX_EINVAL, "loss: a peer-reduced call needs a non-empty local batch");
   }
   const int B = cfg->B, P = cfg->P, C = cfg->C;
   SSDBOX_REQUIRE(sums && ws && gt_offsets, SSDBOX_EINVAL, "loss: null pointer");
   SSDBOX_REQUIRE(!cfg->finalize || losses, SSDBOX_EINVAL, "loss: finalize needs `losses`");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((B == 0 || P == 0) && peers) {
+    // empty local shard (global batch smaller than the world, last batch of an epoch): zeros are posted
+    PeerFinishArgs pa{};
+    pa.rank = peers->rank;
+    pa.world = peers->world;
+    pa.timeout_ns = peer_timeout_ns(peers);
+    for (int r = 0; r < peers->world; ++r) pa.bufs[r] = peers->bufs[r];
+    pa.sums = sums;
+    pa.losses = losses;
+    peer_empty_kernel<<<1, 32, 0, st>>>(pa, (cfg->flags & SSDBOX_LOSS_DEFER_PEER_WAIT) ? 1 : 0, cfg->finalize);
+    SSDBOX_LAUNCH_OK("peer_empty_kernel");
+    return SSDBOX_OK;
+  }
   if (B == 0 || P == 0) {
     SSDBOX_CUDA(cudaMemsetAsync(sums, 0, 3 * sizeof(double), st));
     if (losses) SSDBOX_CUDA(cudaMemsetAsync(losses, 0, 2 * sizeof(float), st));
@@ -1851,7 +1893,11 @@ extern "C" int ssdbox_multibox_loss_bwd(const ssdbox_loss_cfg* cfg, const float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long rows = (long long)a.B * a.P;
   const size_t stream_smem = (size_t)kBwdStreamWarps * kBwdTileRows * a.C * 4;
-  if (a.conf_aligned && a.C <= 128 && stream_smem <= (size_t)dev.max_smem_optin - 1024 && !getenv("SSDBOX_BWD_TWO_PASS")) {
+  if (a.conf_aligned && a.C <= 128 && stream_smem <= (size_t)dev.max_smem_optin - 1024
+#ifdef SSDBOX_EXPERIMENTS
+      && !getenv("SSDBOX_BWD_TWO_PASS")
+#endif
+  ) {
     void (*kern)(BwdArgs) = a.C == 81 ? loss_bwd_stream_kernel<81> : (a.C == 21 ? loss_bwd_stream_kernel<21> : loss_bwd_stream_kernel<0>);
     SSDBOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem));
     long long tiles = (rows + kBwdTileRows - 1) / kBwdTileRows;

@@ -62,10 +62,12 @@ static inline int plan_ring(RingPlan* p, const float* src, long long rows, int C
   size_t stage_bytes = (size_t)R * C * 4;
   int NS = (int)(budget / stage_bytes);
   if (NS > kRingMaxStages) NS = kRingMaxStages;
-  if (const char* e = getenv("SSDBOX_RING_MAX_STAGES")) {      // experiments only
+#ifdef SSDBOX_EXPERIMENTS      // tools/exp_*.sh builds only: the release library reads no environment
+  if (const char* e = getenv("SSDBOX_RING_MAX_STAGES")) {
     int cap = atoi(e);
     if (cap >= 2 && NS > cap) NS = cap;
   }
+#endif
   while (NS > 1 && (2 * NS) % kRingGroups) --NS;     // see the header comment
   p->src = src;
   p->rows = rows;
@@ -74,10 +76,12 @@ static inline int plan_ring(RingPlan* p, const float* src, long long rows, int C
   p->KR = KR;
   p->NS = NS;
   p->tiles = (rows + R - 1) / R;
-  if (const char* e = getenv("SSDBOX_RING_GRID")) {            // experiments only: stream on fewer SMs
+#ifdef SSDBOX_EXPERIMENTS
+  if (const char* e = getenv("SSDBOX_RING_GRID")) {            // stream on fewer SMs
     int cap = atoi(e);
     if (cap >= 1 && cap < sm_count) sm_count = cap;
   }
+#endif
   int grid = (int)(p->tiles < sm_count ? p->tiles : sm_count);
   if (grid < 1) grid = 1;
   p->tiles_per_cta = (int)((p->tiles + grid - 1) / grid);
@@ -86,10 +90,12 @@ static inline int plan_ring(RingPlan* p, const float* src, long long rows, int C
   if (p->grid < 1) p->grid = 1;
   p->bulk_ok = aligned16(src) ? 1 : 0;
   p->interleave = 0;
-  if (const char* e = getenv("SSDBOX_RING_INTERLEAVE")) {         // experiments only
+#ifdef SSDBOX_EXPERIMENTS
+  if (const char* e = getenv("SSDBOX_RING_INTERLEAVE")) {
     int g = atoi(e);
     p->interleave = g < 1 ? 0 : (g > p->grid ? p->grid : g);
   }
+#endif
   p->smem_bytes = kRingHeaderBytes + (size_t)NS * stage_bytes;
   return SSDBOX_OK;
 }

@@ -76,7 +76,14 @@ __global__ void __launch_bounds__(kVocWarps * 32) voc_match_kernel(VocArgs a) {
   const long long s = (long long)blockIdx.x * kVocWarps + warp;
   if (s >= (long long)a.I * a.C) return;
   const int i = (int)(s / a.C), c = (int)(s - (long long)i * a.C);
-  const int r0 = a.seg[s], r1 = a.seg[s + 1];
+  int r0 = a.seg[s], r1 = a.seg[s + 1];
+  // malformed segments (not monotone / beyond the rows) never index out of bounds: they are clamped here and
+  // reported through the status word (same 2^30 flag voc_curve_kernel raises for seg[-1] != num_rows)
+  if (r0 < 0 || r1 < r0 || r1 > a.N) {
+    if (lane == 0) atomicOr(reinterpret_cast<unsigned int*>(a.status), 1u << 30);
+    r0 = r0 < 0 ? 0 : (r0 > a.N ? a.N : r0);
+    r1 = r1 < r0 ? r0 : (r1 > a.N ? a.N : r1);
+  }
   if (c == 0) {                                                        // background rows (DetectOut emits none) are never
     if (lane == 0 && r1 > r0) atomicAdd(&a.cnt[0], r1 - r0);           // evaluated: they sort in front, flagged "neither"
     for (int r = r0 + lane; r < r1; r += 32) {
@@ -280,7 +287,7 @@ __global__ void __launch_bounds__(kCurveThreads) voc_curve_kernel(VocArgs a) {
         run += a.cnt[cc];
       }
       a.cls_offsets[a.C] = run;
-      if (run != a.N) atomicAdd(a.status, 1 << 30);                    // the segments do not cover the rows exactly
+      if (run != a.N) atomicOr(reinterpret_cast<unsigned int*>(a.status), 1u << 30);                   // the segments do not cover the rows exactly
     }
   }
   __syncthreads();

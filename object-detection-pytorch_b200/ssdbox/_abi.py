@@ -203,16 +203,26 @@ def as_f32(t, device=None):
 
 
 class Workspace(object):
-    """Grow-only per-owner scratch buffer (pointer stays stable once large enough: graph-safe)."""
+    """Grow-only scratch buffer, one per (device, stream) that uses the owner: two streams driving the same
+    module never share scratch (the C ABI is re-entrant only with distinct workspaces).  The pointer of a
+    (device, stream) stays stable once large enough: graph-safe."""
 
     def __init__(self):
-        self.buf = None
+        self.bufs = {}
 
     def get(self, nbytes, device):
         nbytes = int(nbytes)
-        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
-            self.buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
-        return C.c_void_p(self.buf.data_ptr()), self.buf.numel()
+        key = (device, torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0)
+        buf = self.bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+            self.bufs[key] = buf
+        return C.c_void_p(buf.data_ptr()), buf.numel()
+
+    @property
+    def buf(self):
+        """the most recently created buffer (tests / introspection)"""
+        return next(reversed(self.bufs.values())) if self.bufs else None
 
 
 def workspace_bytes(op, B=0, P=0, Cn=0, gmax=0, top_k=0):

@@ -32,7 +32,11 @@ class DetectOut(object):
         dev = loc_data.device
         num = loc_data.size(0)
         pri = _abi.as_f32(prior_data, dev)
+        if pri.dim() == 3 and pri.size(0) == 1:               # the reference docstring's [1, num_priors, 4]
+            pri = pri[0]
         per_image = pri.dim() == 3
+        if per_image and pri.size(0) != num:
+            raise ValueError("ssdbox: per-image priors have batch %d, loc_data has %d" % (pri.size(0), num))
         P = pri.size(-2)
         loc = _abi.as_f32(loc_data).view(num, P, 4)
         scores = _abi.as_f32(conf_data, dev).view(num, P, self.num_classes)      # detection.py:38

@@ -42,9 +42,9 @@ class PeerExchange(object):
     MultiBoxLoss then keeps the NCCL all-reduce."""
 
     def __init__(self, device, group=None, wait_timeout_s=30.0):
-        """wait_timeout_s: how long a rank waits for its peers' sums before the kernel traps (a rank
-        that stalls longer than this between two steps -- data loading, checkpointing -- kills the
-        job instead of hanging it; raise it for such runs)."""
+        """wait_timeout_s: how long a rank waits for its peers' sums before it gives up (the losses of
+        that call are NaN and timeouts() counts it; the CUDA context survives).  Size it for the longest
+        stall a rank may see between two steps (data loading, checkpointing)."""
         import ctypes as C
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -79,6 +79,12 @@ class PeerExchange(object):
         self.group.wait_timeout_ms = int(wait_timeout_s * 1000)
         for r, ptr in enumerate(ptrs):
             self.group.bufs[r] = C.c_void_p(ptr)
+
+
+    def timeouts(self):
+        """number of calls in which this rank gave up waiting for a peer (word 1 of its exchange buffer;
+        synchronises the device).  Non-zero: the ranks are out of step -- build a new PeerExchange."""
+        return int(self.buf[1].item())
 
 
 class LocalPeerExchange(object):

@@ -45,6 +45,8 @@ def _compact(detections, extra, image_ids, mode, capacity=None):
         _abi.ptr(det, torch.float32, "detections"), B, Cn, K, _abi.ptr(ex, torch.float32, "extra", True),
         _abi.ptr(ids, torch.float32, "image_ids", True), mode, _abi.ptr(out), cap, _abi.ptr(total), _abi.ptr(seg),
         ws, n, _abi.stream_ptr(dev)))
+    if capacity is not None:
+        seg.clamp_(max=cap)        # rows beyond the capacity were dropped: the segments end with the buffer
     return out, total, seg
 
 

@@ -13,7 +13,9 @@ from . import _abi
 def pack_targets(targets, device):
     """list of B tensors [G_b,5] (or the 1-element sentinel of multibox_loss_v1.py:70) ->
     (gt [sum G,5] f32 on device, offsets int32 [B+1] on device, gmax).  Only shapes are read on
-    the host (no device sync)."""
+    the host (no device sync).  Host targets (the reference's data loader yields CPU tensors,
+    train.py:131-135) travel as ONE pinned staging buffer -- offsets and boxes in a single H2D copy;
+    device targets are gathered by one concatenation."""
     offs = [0]
     rows = []
     gmax = 0
@@ -22,31 +24,45 @@ def pack_targets(targets, device):
         offs.append(offs[-1] + g)
         gmax = max(gmax, g)
         if g:
-            rows.append(t if t.device == device else t.to(device, non_blocking=True))
-    if rows:
-        gt = torch.cat(rows, 0).to(torch.float32).contiguous()
-    else:
-        gt = torch.zeros(1, 5, dtype=torch.float32, device=device)
-    offsets = torch.tensor(offs, dtype=torch.int32).to(device, non_blocking=True)
+            rows.append(t)
+    B1 = len(offs)
+    total = offs[-1]
+    if all(not t.is_cuda for t in rows):
+        # staging layout (4-byte words): [offsets int32 (B+1) | pad to 4 words | gt f32 (total*5)]
+        head = (B1 + 3) // 4 * 4
+        stage = torch.empty(head + max(total, 1) * 5, dtype=torch.float32, pin_memory=torch.cuda.is_available())
+        stage[:B1].view(torch.int32).copy_(torch.tensor(offs, dtype=torch.int32))
+        if rows:
+            torch.cat([r.to(torch.float32) for r in rows], 0, out=stage[head:head + total * 5].view(total, 5))
+        else:
+            stage[head:].zero_()
+        dstage = stage.to(device, non_blocking=True)
+        return dstage[head:].view(-1, 5), dstage[:B1].view(torch.int32), gmax
+    rows = [r if r.device == device else r.to(device, non_blocking=True) for r in rows]
+    gt = torch.cat(rows, 0).to(torch.float32).contiguous()
+    offsets = torch.tensor(offs, dtype=torch.int32, pin_memory=True).to(device, non_blocking=True)
     return gt, offsets, gmax
 
 
 class _State(object):
-    """Per-module reusable buffers (stable pointers: the forward can be captured in a CUDA graph)."""
+    """Per-module reusable buffers, one set per (batch shape, device, stream): stable pointers (the forward can
+    be captured in a CUDA graph) and no sharing between two streams that drive the same module."""
 
     def __init__(self):
         self.ws = _abi.Workspace()
-        self.key = None
+        self.slots = {}
         self.sel = self.tidx = self.sums = self.losses = None
 
     def ensure(self, B, P, device):
-        key = (B, P, device)
-        if self.key != key:
-            self.sel = torch.empty(B, P, dtype=torch.int16, device=device)
-            self.tidx = torch.empty(B, P, dtype=torch.int16, device=device)
-            self.sums = torch.zeros(3, dtype=torch.float64, device=device)
-            self.losses = torch.zeros(2, dtype=torch.float32, device=device)
-            self.key = key
+        key = (B, P, device, torch.cuda.current_stream(device).cuda_stream)
+        slot = self.slots.get(key)
+        if slot is None:
+            slot = (torch.empty(B, P, dtype=torch.int16, device=device),
+                    torch.empty(B, P, dtype=torch.int16, device=device),
+                    torch.zeros(3, dtype=torch.float64, device=device),
+                    torch.zeros(2, dtype=torch.float32, device=device))
+            self.slots[key] = slot
+        self.sel, self.tidx, self.sums, self.losses = slot
 
 
 def loss_forward_raw(state, loc, conf, priors, gt, offsets, gmax, num_classes, threshold, negpos_ratio,
@@ -66,7 +82,13 @@ def loss_forward_raw(state, loc, conf, priors, gt, offsets, gmax, num_classes, t
     else:
         state.ensure(B, P, dev)
         sel, tidx, sums, losses = state.sel, state.tidx, state.sums, state.losses
+    if priors.dim() == 3 and priors.size(0) == 1:          # the reference docstring's [1, num_priors, 4]
+        priors = priors[0]
     per_image = priors.dim() == 3
+    if per_image and priors.size(0) != B:
+        raise ValueError("ssdbox: per-image priors have batch %d, loc_data has %d" % (priors.size(0), B))
+    if priors.size(-2) != P or priors.size(-1) != 4:
+        raise ValueError("ssdbox: priors must be [%d,4] or [%d,%d,4], got %s" % (P, B, P, tuple(priors.shape)))
     cfg = _abi.LossCfg(B, P, int(num_classes), int(gmax), float(threshold), int(negpos_ratio),
                        float(variance[0]), float(variance[1]), 1 if binarize else 0, 1 if finalize else 0,
                        4 * P if per_image else 0, int(flags), 0)
@@ -95,6 +117,8 @@ class _MultiBoxLossFn(torch.autograd.Function):
             peers = mod._peers.group
         else:
             peers = mod._peer_group(loc.device) if distributed else None
+        if peers is not None:
+            mod._check_no_pending()
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         cfg, sums, losses, sel, tidx = loss_forward_raw(
             st, loc, conf, priors, gt, offsets, gmax, mod.num_classes, mod.threshold, mod.negpos_ratio,
@@ -106,6 +130,10 @@ class _MultiBoxLossFn(torch.autograd.Function):
             _abi.check(_abi.lib().ssdbox_multibox_loss_finalize(_abi.ptr(sums), _abi.ptr(losses),
                                                                 _abi.stream_ptr(loc.device)))
         mod._last = (sums, sel, tidx)
+        ctx.grad_mul = 1.0
+        if distributed and mod.ddp_average:
+            import torch.distributed as dist
+            ctx.grad_mul = float(dist.get_world_size(mod.process_group))
         if need_grad:
             ctx.cfg = cfg
             ctx.save_for_backward(loc, conf, priors, gt, offsets, sel, tidx, sums)
@@ -118,6 +146,8 @@ class _MultiBoxLossFn(torch.autograd.Function):
         loc, conf, priors, gt, offsets, sel, tidx, sums = ctx.saved_tensors
         dev = loc.device
         gout = torch.stack([g_l.reshape(()).to(torch.float32), g_c.reshape(()).to(torch.float32)]).contiguous()
+        if ctx.grad_mul != 1.0:
+            gout = gout * ctx.grad_mul
         grad_loc = torch.empty_like(loc)
         grad_conf = torch.empty_like(conf)
         _abi.check(_abi.lib().ssdbox_multibox_loss_bwd(
@@ -131,11 +161,14 @@ class PendingLoss(object):
     """Result of MultiBoxLoss.forward_packed_deferred: wait() enqueues ssdbox_multibox_loss_peer_finish
     on the current stream and returns (loss_l, loss_c) of the GLOBAL batch."""
 
-    def __init__(self, peers, sums, losses, ready):
+    def __init__(self, peers, sums, losses, ready, owner=None):
         self._peers, self._sums, self._losses, self._ready = peers, sums, losses, ready
+        self._owner = owner
 
     def wait(self):
         if self._ready is None:
+            if self._owner is not None:
+                self._owner._pending_unwaited = False
             _abi.check(_abi.lib().ssdbox_multibox_loss_peer_finish(
                 C.byref(self._peers), _abi.ptr(self._sums), _abi.ptr(self._losses),
                 _abi.stream_ptr(self._losses.device)))
@@ -151,11 +184,12 @@ class MultiBoxLoss(nn.Module):
     `distributed=True` (or an initialised default process group with world size > 1) sums the loss
     numerators and the positive count across ranks (images are sharded by rank).  `reduce`:
     "p2p" = inside the mining kernel over NVLink peer memory (ssdbox.dist.PeerExchange), "nccl" = one
-    all-reduce after it, "auto" = p2p when symmetric memory is available, else nccl."""
+    all-reduce after it, "auto" = p2p when symmetric memory is available, else nccl.  `ddp_average`: see
+    the comment in __init__ (set it when the network is wrapped in DistributedDataParallel)."""
 
     def __init__(self, num_classes, overlap_thresh, prior_for_matching, bkg_label, neg_mining, neg_pos,
                  neg_overlap, encode_target, use_gpu=True, variance=(0.1, 0.2), distributed=None,
-                 process_group=None, reduce="auto"):
+                 process_group=None, reduce="auto", ddp_average=False):
         super(MultiBoxLoss, self).__init__()
         self.use_gpu = use_gpu
         self.num_classes = num_classes
@@ -174,6 +208,12 @@ class MultiBoxLoss(nn.Module):
             raise ValueError("reduce must be 'auto', 'p2p' or 'nccl'")
         self.reduce = reduce
         self.reduce_used = None     # "p2p" / "nccl" once the first distributed forward has run
+        # Distributed losses are normalised by the GLOBAL N, so a rank's backward yields its shard's part of the
+        # single-device gradient: parameter gradients must be SUMMED over ranks.  DistributedDataParallel
+        # averages them -- ddp_average=True multiplies the backward by the world size so that DDP's mean
+        # equals the reference's single-device gradient (train.py:137-144); the returned loss values stay global.
+        self.ddp_average = bool(ddp_average)
+        self._pending_unwaited = False
         self._peers = None
         self.abi_flags = 0          # _abi.LOSS_SEPARATE_MATCH: matching as its own kernel
         self._state = _State()
@@ -214,6 +254,15 @@ class MultiBoxLoss(nn.Module):
         self.reduce_used = "p2p" if self._peers else "nccl"
         return self._peers.group if self._peers else None
 
+    def _check_no_pending(self):
+        """The deferred protocol posts in call k and collects in PendingLoss.wait(); a second peer-reduced
+        forward before that wait would advance the epoch and overwrite the slot bank the un-collected call
+        still has to read (two banks by epoch parity).  A dropped PendingLoss therefore raises here instead
+        of silently desynchronising the ranks."""
+        if self._pending_unwaited:
+            raise RuntimeError("ssdbox: the previous forward_packed_deferred() has not been completed -- call "
+                               "PendingLoss.wait() before the next peer-reduced forward")
+
     def use_local_peer_exchange(self, device):
         """tests: run the peer-exchange path with a world of one rank (no process group needed)."""
         from . import dist as sdist
@@ -226,9 +275,11 @@ class MultiBoxLoss(nn.Module):
             raise RuntimeError("ssdbox: MultiBoxLoss runs on CUDA tensors only (no CPU path)")
         dev = loc_data.device
         loc = _abi.as_f32(loc_data)
-        conf = _abi.as_f32(conf_data).view(loc.size(0), loc.size(1), -1)
-        if conf.size(2) != self.num_classes:
-            raise ValueError("conf_data has %d classes, MultiBoxLoss was built for %d" % (conf.size(2), self.num_classes))
+        conf = _abi.as_f32(conf_data)
+        if conf.numel() != loc.size(0) * loc.size(1) * self.num_classes:
+            raise ValueError("conf_data has %d elements, MultiBoxLoss(num_classes=%d) expects %d x %d x %d"
+                             % (conf.numel(), self.num_classes, loc.size(0), loc.size(1), self.num_classes))
+        conf = conf.view(loc.size(0), loc.size(1), self.num_classes)       # (an empty shard has no -1 to infer)
         pri = _abi.as_f32(priors, dev)[:loc.size(1), :].contiguous()        # multibox_loss.py:62
         gt, offsets, gmax = pack_targets(targets, dev)
         return self.forward_packed(loc, conf, pri, gt, offsets, gmax)
@@ -251,12 +302,14 @@ class MultiBoxLoss(nn.Module):
             if peers is None:
                 ll, lc = self.forward_packed(loc, conf, priors, gt, offsets, gmax)
                 return PendingLoss(None, None, None, (ll, lc))
+            self._check_no_pending()
             cfg, sums, losses, sel, tidx = loss_forward_raw(
                 self._state, loc, conf, priors, gt, offsets, gmax, self.num_classes, self.threshold,
                 self.negpos_ratio, self.variance, None, None, self.binarize_labels, finalize=True,
                 debug=None, fresh=False, flags=self.abi_flags | _abi.LOSS_DEFER_PEER_WAIT, peers=peers)
             self._last = (sums, sel, tidx)
-            return PendingLoss(peers, sums, losses, None)
+            self._pending_unwaited = True
+            return PendingLoss(peers, sums, losses, None, owner=self)
 
     def intermediates(self, predictions, targets):
         """Runs the forward and also materialises the reference's intermediates

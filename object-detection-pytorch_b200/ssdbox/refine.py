@@ -59,14 +59,19 @@ class RefineMultiBoxLoss(MultiBoxLoss):
         P = arm_loc.size(1)
         pri = _abi.as_f32(priors, dev)[:P].contiguous()
         gt, offsets, gmax = pack_targets(targets, dev)
+        return self.forward_packed_two_step(arm_loc, arm_conf, odm_loc, odm_conf, pri, gt, offsets, gmax)
+
+    def forward_packed_two_step(self, arm_loc, arm_conf, odm_loc, odm_conf, pri, gt, offsets, gmax):
+        """forward with the targets already in the C-ABI layout (no host work: CUDA-graph capturable)."""
+        P = arm_loc.size(1)
         if not self.use_ARM:
             loc = _abi.as_f32(arm_loc)
-            conf = _abi.as_f32(arm_conf).view(loc.size(0), P, -1)
+            conf = _abi.as_f32(arm_conf).view(loc.size(0), P, 2)
             return self.forward_packed(loc, conf, pri, gt, offsets, gmax)
         xy, cf = refine_anchors(arm_loc, pri, self.variance)
         pool = arm_filter(arm_conf, self.theta)
         loc = _abi.as_f32(odm_loc)
-        conf = _abi.as_f32(odm_conf).view(loc.size(0), P, -1)
+        conf = _abi.as_f32(odm_conf).view(loc.size(0), P, self.num_classes)
         return self.forward_packed(loc, conf, cf, gt, offsets, gmax, anchors_xyxy=xy, pool=pool)
 
 
@@ -77,9 +82,9 @@ class RefineDetectOut(DetectOut):
         super(RefineDetectOut, self).__init__(num_classes, bkg_label, top_k, conf_thresh, nms_thresh, variance)
         self.theta = theta
 
-    def forward(self, arm_loc, arm_conf, odm_loc, odm_scores, prior_data):
+    def forward(self, arm_loc, arm_conf, odm_loc, odm_scores, prior_data, out=None):
         _, cf = refine_anchors(arm_loc, prior_data, self.variance)
         keep = arm_filter(arm_conf, self.theta)
-        return DetectOut.forward(self, odm_loc, odm_scores, cf, score_keep=keep)
+        return DetectOut.forward(self, odm_loc, odm_scores, cf, score_keep=keep, out=out)
 
     __call__ = forward

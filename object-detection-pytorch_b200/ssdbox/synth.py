@@ -41,6 +41,17 @@ def gen_detect_scores(batch, num_priors, num_classes, seed, bkg_bias=10.0):
     return torch.softmax(x, -1)
 
 
+def gen_arm_outputs(batch, num_priors, seed):
+    """RefineDet ARM head outputs: arm_loc = 0.2 * N(0,1) (a refinement, smaller than
+    a regression from scratch) and binary objectness logits 2.5 * N(0,1) with a background bias of 2 --
+    roughly a quarter of the anchors fall below theta = 0.01 and are filtered."""
+    g = torch.Generator().manual_seed(seed + 5000)
+    arm_loc = torch.randn(batch, num_priors, 4, generator=g) * 0.2
+    arm_conf = torch.randn(batch, num_priors, 2, generator=g) * 2.5
+    arm_conf[..., 0] += 2.0
+    return arm_loc, arm_conf
+
+
 def pack_targets(targets):
     """list of [G_b,5] -> (flat [sum G,5] float32, offsets int32 [B+1]) -- the C-ABI layout."""
     offs = [0]

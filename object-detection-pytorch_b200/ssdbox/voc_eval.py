@@ -146,7 +146,7 @@ def voc_eval(rows, seg, gt, num_classes, ovthresh=0.5, use_07_metric=True):
     host = small.cpu()
     h_ints = host[8 * C:].view(torch.int32).numpy()
     bad = int(h_ints[2 * C + 1])
-    if bad >= (1 << 30):
+    if bad & (1 << 30):
         raise ValueError("voc_eval: seg does not cover the %d rows exactly (seg[-1] must equal the row count)" % N)
     if bad:
         raise ValueError("voc_eval: %d detection scores fall outside [0, 1] after '%%.3f' rounding" % bad)

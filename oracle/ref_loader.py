@@ -29,11 +29,36 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("SSDBOX_REFERENCE_ROOT", "/root/reference")
+VENDORED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")     # oracle/build_ref.py
+
+
+def _has_lib(root):
+    return os.path.isfile(os.path.join(root, "lib", "layers", "box_utils.py"))
+
+
+def _pick_root():
+    """SSDBOX_REFERENCE_ROOT if set; else the read-only mount of the build container; else the unmodified copy
+    oracle/build_ref.py left under oracle/_ref (what travels to the GPU box)."""
+    env = os.environ.get("SSDBOX_REFERENCE_ROOT")
+    if env:
+        return env
+    return "/root/reference" if _has_lib("/root/reference") else VENDORED_ROOT
+
+
+REFERENCE_ROOT = _pick_root()
+
+
+def use_vendored():
+    """bench.py: always time the copy under oracle/_ref (never reads /root/reference at run time)."""
+    global REFERENCE_ROOT
+    if _REF is not None and REFERENCE_ROOT != VENDORED_ROOT:
+        raise RuntimeError("reference already loaded from %s" % REFERENCE_ROOT)
+    REFERENCE_ROOT = VENDORED_ROOT
+    return available()
 
 
 def available():
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "lib", "layers", "box_utils.py"))
+    return _has_lib(REFERENCE_ROOT)
 
 
 def _install_stubs():

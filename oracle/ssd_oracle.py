@@ -328,7 +328,7 @@ def arm_objectness(arm_conf):
 
 def refine_multibox_loss(arm_loc, arm_conf, odm_loc, odm_conf, priors, targets, num_classes,
                          threshold=0.5, negpos_ratio=3, variances=(0.1, 0.2), theta=0.01,
-                         use_arm=False, stable=True, detail=False):
+                         use_arm=False, stable=True, detail=False, anchors=None, pool=None):
     """use_arm=False: ARM loss  = MultiBoxLoss with binarised labels (C=2) on the raw priors.
     use_arm=True : ODM loss  = match against per-image refined anchors, anchors whose ARM
                    objectness <= theta leave the positives and the mining pool, then a6."""
@@ -338,7 +338,9 @@ def refine_multibox_loss(arm_loc, arm_conf, odm_loc, odm_conf, priors, targets, 
         bt = [torch.cat([t[:, :4], torch.zeros_like(t[:, 4:5])], 1) for t in targets]
         return multibox_loss(arm_loc, arm_conf, priors, bt, 2, threshold, negpos_ratio, variances,
                              stable=stable, detail=detail)
-    xy, cf = refine_anchors(arm_loc.detach(), priors, variances)
+    # `anchors` = (xyxy, centre form) and `pool` override the refinement / the ARM filter (tests feed the same
+    # refined anchors to the CUDA path and to this function, so that only the ODM logic is compared)
+    xy, cf = anchors if anchors is not None else refine_anchors(arm_loc.detach(), priors, variances)
     loc_t = torch.zeros(B, P, 4)
     conf_t = torch.zeros(B, P, dtype=torch.int64)
     for b in range(B):
@@ -346,7 +348,8 @@ def refine_multibox_loss(arm_loc, arm_conf, odm_loc, odm_conf, priors, targets, 
         m = match_image(threshold, t[:, :4], cf[b], variances, t[:, 4], anchors_xyxy=xy[b])
         loc_t[b] = m["loc"]
         conf_t[b] = m["conf"]
-    pool = arm_objectness(arm_conf.detach()) > theta
+    if pool is None:
+        pool = arm_objectness(arm_conf.detach()) > theta
     pos = (conf_t > 0) & pool
     sel4 = pos.unsqueeze(2).expand_as(odm_loc)
     loss_l = F.smooth_l1_loss(odm_loc[sel4].view(-1, 4), loc_t[sel4].view(-1, 4), reduction="sum")
@@ -359,8 +362,10 @@ def refine_multibox_loss(arm_loc, arm_conf, odm_loc, odm_conf, priors, targets, 
                              conf_eff[chosen], reduction="sum")
     n = pos.long().sum()
     if detail:
+        mk = keys.detach().clone()
+        mk[pos] = 0
         return dict(loss_l=loss_l / n, loss_c=loss_c / n, sum_l=loss_l, sum_c=loss_c, n=n,
-                    loc_t=loc_t, conf_t=conf_eff, pos=pos, neg=neg, pool=pool)
+                    loc_t=loc_t, conf_t=conf_eff, conf_t_raw=conf_t, pos=pos, neg=neg, pool=pool, mining_keys=mk)
     return loss_l / n, loss_c / n
 
 

@@ -59,6 +59,52 @@ def main():
         dl, dc = pend.wait()
     assert abs(float(dl) - res["p2p"][0]) <= 1e-7 * abs(res["p2p"][0]) and abs(float(dc) - res["p2p"][1]) <= 1e-7 * abs(res["p2p"][1])
     assert torch.equal(crit._last[0], res["p2p"][2])
+    # (a) global batch smaller than the world: the last rank's shard is EMPTY, it still takes part (posts zeros)
+    Bs = world - 1
+    xs = U.seeded_inputs("ssd300_voc", max(Bs, 1), 33)
+    sl, sc_, st = sdist.shard_batch(xs["loc"][:Bs], xs["conf"][:Bs], xs["targets"][:Bs], rank, world)
+    fulls = ssdbox.MultiBoxLoss(xs["C"], 0.5, True, 0, True, 3, 0.5, False, distributed=False)
+    with torch.no_grad():
+        wl, wc = fulls((xs["loc"][:Bs].to(dev), xs["conf"][:Bs].to(dev), pri), [t.to(dev) for t in xs["targets"][:Bs]])
+    for mode in ("p2p", "nccl"):
+        crit = ssdbox.MultiBoxLoss(xs["C"], 0.5, True, 0, True, 3, 0.5, False, distributed=True, reduce=mode)
+        for it in range(2):
+            with torch.no_grad():
+                el, ec = crit((sl.to(dev), sc_.to(dev), pri), [t.to(dev) for t in st])
+        assert abs(float(el) - float(wl)) <= 1e-6 * abs(float(wl)) and abs(float(ec) - float(wc)) <= 1e-6 * abs(float(wc)), \
+            ("empty shard", mode, rank, float(el), float(ec), float(wl), float(wc))
+        if mode == "p2p":
+            assert crit._peers.timeouts() == 0
+    # (b) DistributedDataParallel averages parameter gradients; with ddp_average=True the result equals the
+    # single-device gradient of the reference's criterion over the gathered batch (train.py:137-144)
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    F_ = 6
+
+    class Heads(torch.nn.Module):
+        def __init__(self, C):
+            super().__init__()
+            self.loc = torch.nn.Linear(F_, 4)
+            self.conf = torch.nn.Linear(F_, C)
+
+        def forward(self, f):
+            return self.loc(f), self.conf(f)
+
+    torch.manual_seed(7)
+    heads = Heads(x["C"]).to(dev)
+    single = Heads(x["C"]).to(dev)
+    single.load_state_dict(heads.state_dict())
+    feat = torch.randn(B, x["P"], F_, generator=torch.Generator().manual_seed(9))
+    ddp = DDP(heads, device_ids=[local])
+    crit = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False, distributed=True, ddp_average=True)
+    lo, co = ddp(feat[b:e].to(dev))
+    ll, lc = crit((lo, co, pri), tgd)
+    (ll + lc).backward()
+    lo, co = single(feat.to(dev))
+    fl2, fc2 = full((lo, co, pri), [t.to(dev) for t in x["targets"]])
+    (fl2 + fc2).backward()
+    assert abs(float(ll) - float(fl2)) <= 1e-6 * abs(float(fl2))
+    for (n1, p1), (n2, p2) in zip(heads.named_parameters(), single.named_parameters()):
+        U.assert_close_rel(p1.grad, p2.grad, 1e-4, 1e-7, "DDP grad " + n1)
     # every rank holds bit-identical global sums (rank-ordered fp64 adds)
     mine = res["p2p"][2]
     allv = [torch.empty_like(mine) for _ in range(world)]

@@ -1,0 +1,315 @@
+"""GPU parity, second set: the shapes and semantics the first round left untested.
+
+* backward at the headline shape (SSD512-COCO, B=64) and full batches of cfg4 / cfg5,
+* RefineDet split into (a) the refinement arithmetic (1e-5) and (b) the ODM logic on the ORACLE's refined
+  anchors / ARM mask (class targets, negative sets, keep-lists bit-exact),
+* zero-area truths in the matching, 3-D priors, empty shards in the peer exchange, the deferred-wait guard,
+  one module driven from two streams.
+Bars as in test_gpu_parity.py: indices / labels / sets / keep-lists bit-exact, floats 1e-5 relative.
+"""
+import pytest
+import torch
+
+import ssdbox
+from oracle import ssd_oracle as O
+from ssdbox import box_utils as BU
+from ssdbox import configs, synth
+from tests import _util as U
+from tests.test_gpu_parity import _check_neg_sets, _compare_detect, _gpu_targets
+
+pytestmark = pytest.mark.gpu
+VAR = [0.1, 0.2]
+REL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+# ------------------------------------------------------------------------------------------------
+# a11 at the headline shape: loss_bwd_stream_kernel<81> with 148 persistent CTAs, many tiles per warp
+# ------------------------------------------------------------------------------------------------
+def test_full_size_ssd512_coco_backward(dev):
+    cfg, c = configs.get("ssd512_coco")
+    B, P, C = 64, 24564, 81
+    pri = U.oracle_priors("ssd512_coco")
+    tg = synth.gen_targets(B, C, 32, 0)
+    loc_h = synth.gen_loc(B, P, 0)
+    conf_h = synth.gen_train_logits(B, P, C, 0)
+    loc = loc_h.to(dev).requires_grad_(True)
+    conf = conf_h.to(dev).requires_grad_(True)
+    crit = ssdbox.MultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False)
+    ll, lc = crit((loc, conf, pri.to(dev)), _gpu_targets(tg, dev))
+    (ll + lc).backward()
+    sums, sel, _ = crit._last
+    n_full = float(sums[2])
+    chosen = sel >= 0
+    # rows outside pos U neg carry exactly zero gradient (multibox_loss.py:106-110 never reads them)
+    gc = conf.grad
+    assert float(gc[~chosen].abs().max()) == 0.0
+    assert float(loc.grad[sel <= 0].abs().max()) == 0.0
+    # every selected row: softmax - onehot sums to ~0 and is non-zero
+    rs = gc[chosen]
+    assert float(rs.sum(-1).abs().max()) < 1e-6 and bool((rs.abs().sum(-1) > 0).all())
+    # oracle autograd on a 3-image subset; per-image gradients only differ by the normaliser N
+    sub = [0, 31, 63]
+    r = O.multibox_loss(loc_h[sub], conf_h[sub], pri, [tg[i] for i in sub], C, detail=True)
+    n_sub = float(r["n"])
+    gl, gcr = O.multibox_loss_grads(loc_h[sub], conf_h[sub], pri, [tg[i] for i in sub], C)
+    same = torch.equal((sel[sub] >= 0).cpu(), r["pos"] | r["neg"])
+    scale = n_full / n_sub
+    U.assert_close_rel(loc.grad[sub].cpu() * scale, gl, REL, 1e-8, "grad_loc subset")      # 1e-5 relative
+    if same:
+        U.assert_close_rel(gc[sub].cpu() * scale, gcr, REL, 1e-8, "grad_conf subset")      # 1e-5 relative
+    else:       # a mining key within 2e-6 of the threshold flipped: compare the rows both selected
+        both = ((sel[sub] >= 0).cpu() & (r["pos"] | r["neg"]))
+        U.assert_close_rel((gc[sub].cpu() * scale)[both], gcr[both], REL, 1e-8, "grad_conf subset (common rows)")
+    # the last image's last tile (ragged tail of the persistent partition) is covered by `sub`
+
+
+@pytest.mark.parametrize("name,B,seed", [("fssd300_coco", 32, 40), ("refinedet320_voc", 32, 41), ("ssd300_voc", 32, 42)])
+def test_full_batch_small_configs(dev, name, B, seed):
+    """cfg1 / cfg4 / cfg5 at their full batch (the multi-tile / persistent paths change with B)."""
+    x = U.seeded_inputs(name, B, seed)
+    loc = x["loc"].to(dev).requires_grad_(True)
+    conf = x["conf"].to(dev).requires_grad_(True)
+    crit = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False)
+    d = crit.intermediates((loc, conf, x["priors"].to(dev)), _gpu_targets(x["targets"], dev))
+    r = O.multibox_loss(x["loc"], x["conf"], x["priors"], x["targets"], x["C"], detail=True)
+    n_diff = _check_neg_sets(d, r, x["P"])
+    U.assert_close_rel(d["loss_l"], r["loss_l"], REL, 0, "loss_l")
+    U.assert_close_rel(d["loss_c"], r["loss_c"], REL, 0, "loss_c")
+    U.assert_close_rel(d["loc_t"], r["loc_t"], REL, 1e-6, "loc_t")
+    (d["loss_l"] + d["loss_c"]).backward()
+    gl, gc = O.multibox_loss_grads(x["loc"], x["conf"], x["priors"], x["targets"], x["C"])
+    U.assert_close_rel(loc.grad, gl, REL, 1e-8, "grad_loc")
+    if n_diff == 0:
+        U.assert_close_rel(conf.grad, gc, REL, 1e-8, "grad_conf")
+    out = ssdbox.DetectOut(x["C"], 0, 200, 0.01, 0.45, VAR)(x["loc"].to(dev), x["scores"].to(dev), x["priors"].to(dev))
+    sub = [0, B // 2, B - 1]
+    _compare_detect(out[sub].cpu(), O.detect(x["loc"][sub], x["scores"][sub], x["priors"], x["C"]), name + " detect subset")
+
+
+# ------------------------------------------------------------------------------------------------
+# a-R RefineDet, split: refinement arithmetic (1e-5) | ODM logic on the oracle's anchors (bit-exact)
+# ------------------------------------------------------------------------------------------------
+def _refine_case(B, seed):
+    pri = U.oracle_priors("refinedet320_voc")
+    P, C = pri.size(0), 21
+    tg = synth.gen_targets(B, C, 16, seed)
+    arm_loc, arm_conf = synth.gen_arm_outputs(B, P, seed)
+    odm_loc = synth.gen_loc(B, P, seed + 1)
+    odm_conf = synth.gen_train_logits(B, P, C, seed + 2)
+    sc = synth.gen_detect_scores(B, P, C, seed + 3, bkg_bias=8.0)
+    return pri, P, C, tg, arm_loc, arm_conf, odm_loc, odm_conf, sc
+
+
+def test_refine_anchor_arithmetic(dev):
+    """The only floating-point step of the two-step path that is not shared with SSD: decode(arm_loc, priors)
+    -> xyxy and centre form (1e-5 relative), objectness softmax(arm_conf)[:,1] > theta (flips only where the
+    objectness is within 1e-6 relative of theta: expf ulp)."""
+    pri, P, C, tg, arm_loc, arm_conf, *_ = _refine_case(8, 50)
+    xy, cf = ssdbox.refine_anchors(arm_loc.to(dev), pri.to(dev))
+    oxy, ocf = O.refine_anchors(arm_loc, pri)
+    U.assert_close_rel(xy, oxy, REL, 1e-6, "refined xyxy")
+    U.assert_close_rel(cf, ocf, REL, 1e-6, "refined centre form")
+    keep = ssdbox.arm_filter(arm_conf.to(dev), 0.01).cpu().bool()
+    obj = O.arm_objectness(arm_conf)
+    flips = keep != (obj > 0.01)
+    assert float(((obj[flips] - 0.01).abs() / 0.01).max()) < 1e-6 if bool(flips.any()) else True
+    assert 0.05 < float((~keep).float().mean()) < 0.6          # the filter is exercised
+
+
+@pytest.mark.parametrize("B,seed", [(6, 60), (32, 61)])
+def test_refinedet_odm_logic_bit_exact_on_oracle_anchors(dev, B, seed):
+    """ODM loss and RefineDetectOut fed with the ORACLE's refined anchors and ARM mask: what is left is the
+    reference's own match / mining / NMS logic (box_utils.py:92-133, multibox_loss.py:97-103, box_utils.py:279-343
+    with per-image anchors and a pool), so class targets, matched truths, negative sets and keep-lists must
+    be bit-exact and the losses within 1e-5."""
+    pri, P, C, tg, arm_loc, arm_conf, odm_loc, odm_conf, sc = _refine_case(B, seed)
+    oxy, ocf = O.refine_anchors(arm_loc, pri)
+    pool = O.arm_objectness(arm_conf) > 0.01
+    r = O.refine_multibox_loss(arm_loc, arm_conf, odm_loc, odm_conf, pri, tg, C, use_arm=True, detail=True,
+                               anchors=(oxy, ocf), pool=pool)
+    crit = ssdbox.RefineMultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, use_ARM=True)
+    gt, offs, gmax = ssdbox.pack_targets(_gpu_targets(tg, dev), dev)
+    crit._debug = dict(conf_t=torch.empty(B, P, dtype=torch.int64, device=dev),
+                       loc_t=torch.empty(B, P, 4, dtype=torch.float32, device=dev),
+                       neg=torch.empty(B, P, dtype=torch.uint8, device=dev),
+                       keys=torch.empty(B, P, dtype=torch.float32, device=dev))
+    ll, lc = crit.forward_packed(odm_loc.to(dev), odm_conf.to(dev), ocf.to(dev), gt, offs, gmax,
+                                 anchors_xyxy=oxy.to(dev), pool=pool.to(torch.uint8).to(dev))
+    d = crit._debug
+    crit._debug = None
+    sums, sel, tidx = crit._last
+    assert torch.equal(d["conf_t"].cpu(), r["conf_t_raw"])                      # match labels: bit-exact
+    pos_gpu = (sel > 0).cpu()
+    assert torch.equal(pos_gpu, r["pos"])                                      # positives inside the pool: bit-exact
+    assert torch.equal(sel.cpu().long()[pos_gpu], r["conf_t"][pos_gpu])
+    n_diff = _check_neg_sets(dict(conf_t=r["conf_t_raw"], neg=d["neg"]), dict(conf_t=r["conf_t_raw"], neg=r["neg"], mining_keys=
+                             torch.where(pool, r["mining_keys"], torch.full_like(r["mining_keys"], float("-inf")))), P)
+    assert not bool((d["neg"].cpu().bool() & ~pool).any())                     # filtered anchors are never mined
+    assert int(sums[2]) == int(r["n"])
+    U.assert_close_rel(d["loc_t"].cpu()[r["pos"]], r["loc_t"][r["pos"]], REL, 1e-6, "ODM loc_t")   # 1e-5 relative
+    U.assert_close_rel(ll, r["loss_l"], REL, 0, "ODM loss_l")                  # 1e-5 relative
+    U.assert_close_rel(lc, r["loss_c"], REL, 0, "ODM loss_c")
+    # inference on the same anchors / mask: keep-lists bit-exact
+    det = ssdbox.DetectOut(C, 0, 200, 0.01, 0.45, VAR)
+    out = det.forward(odm_loc.to(dev), sc.to(dev), ocf.to(dev), score_keep=pool.to(torch.uint8).to(dev)).cpu()
+    ref = O.detect(odm_loc, sc, pri, C, score_mask=pool, anchors_center=ocf)
+    _compare_detect(out, ref, "RefineDetectOut on oracle anchors")
+    assert int((out[..., 0] > 0).sum()) > 0
+
+
+def test_refinedet_end_to_end_modules(dev):
+    """The public two-step modules (their own refinement on the GPU) against the oracle end to end: losses
+    within 5e-5 (the refined anchors differ by expf ulps, which moves IoUs at the 1e-7 level), at most a handful
+    of detections differ."""
+    B = 8
+    pri, P, C, tg, arm_loc, arm_conf, odm_loc, odm_conf, sc = _refine_case(B, 70)
+    preds = tuple(t.to(dev) for t in (arm_loc, arm_conf, odm_loc, odm_conf, pri))
+    gtg = _gpu_targets(tg, dev)
+    arm = ssdbox.RefineMultiBoxLoss(2, 0.5, True, 0, True, 3, 0.5, False, use_ARM=False)
+    ll, lc = arm(preds, gtg)
+    rl, rc = O.refine_multibox_loss(arm_loc, arm_conf, odm_loc, odm_conf, pri, tg, 2, use_arm=False)
+    U.assert_close_rel(ll, rl, REL, 0, "ARM loss_l")
+    U.assert_close_rel(lc, rc, REL, 0, "ARM loss_c")
+    odm = ssdbox.RefineMultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, use_ARM=True)
+    ll, lc = odm(preds, gtg)
+    rl, rc = O.refine_multibox_loss(arm_loc, arm_conf, odm_loc, odm_conf, pri, tg, C, use_arm=True)
+    U.assert_close_rel(ll, rl, 5e-5, 0, "ODM loss_l")
+    U.assert_close_rel(lc, rc, 5e-5, 0, "ODM loss_c")
+    det = ssdbox.RefineDetectOut(C, 0, 200, 0.01, 0.45, VAR, theta=0.01)
+    out = det(arm_loc.to(dev), arm_conf.to(dev), odm_loc.to(dev), sc.to(dev), pri.to(dev)).cpu()
+    ref = O.refine_detect(arm_loc, arm_conf, odm_loc, sc, pri, C)
+    assert int((out[..., 0] != ref[..., 0]).sum()) <= 4
+    # backward of the ODM loss reaches odm_loc / odm_conf only
+    ol = odm_loc.to(dev).requires_grad_(True)
+    oc = odm_conf.to(dev).requires_grad_(True)
+    ll, lc = odm((arm_loc.to(dev), arm_conf.to(dev), ol, oc, pri.to(dev)), gtg)
+    (ll + lc).backward()
+    assert float(ol.grad.abs().sum()) > 0 and float(oc.grad.abs().sum()) > 0
+
+
+# ------------------------------------------------------------------------------------------------
+# semantics at the edges
+# ------------------------------------------------------------------------------------------------
+def test_match_zero_area_truths(dev):
+    """A truth with zero width / height has IoU 0 with every (positive-area) prior (box_utils.py:63-70: 0 / area):
+    its best prior is index 0 (first maximum, :116) and is force-matched (:123-127).  Bit-exact with the oracle.
+    (0/0 = NaN needs a zero-area PRIOR under a zero-area truth; PriorBoxSSD never emits one -- the kernels define
+    IoU := 0 there, documented in DESIGN.md.)"""
+    pri = U.oracle_priors("ssd300_voc")
+    tg = [torch.tensor([[0.30, 0.30, 0.30, 0.60, 4.0], [0.1, 0.1, 0.5, 0.6, 2.0]]),      # zero width + a normal truth
+          torch.tensor([[0.5, 0.5, 0.5, 0.5, 9.0]]),                                      # a point
+          torch.tensor([[0.2, 0.7, 0.6, 0.7, 1.0], [0.2, 0.7, 0.6, 0.7, 3.0], [0.25, 0.2, 0.7, 0.8, 5.0]])]
+    gt, offs = synth.pack_targets(tg)
+    loc_t, conf_t, midx, ov = BU.match_batch(0.5, gt.to(dev), offs.to(dev), 3, pri.to(dev), VAR, want_overlap=True)
+    for b, t in enumerate(tg):
+        m = O.match_image(0.5, t[:, :4], pri, VAR, t[:, 4])
+        assert torch.equal(conf_t[b].cpu(), m["conf"]), b
+        assert torch.equal(midx[b].cpu().long(), m["truth_idx"]), b
+        assert torch.equal(ov[b].cpu(), m["overlap"]), b
+    assert int(conf_t[1, 0]) == 10 and int((conf_t[1] > 0).sum()) == 1      # the point truth claims prior 0 only
+    # the fused path (matching inside loss_stream) agrees
+    loc = synth.gen_loc(3, pri.size(0), 1)
+    conf = synth.gen_train_logits(3, pri.size(0), 21, 1)
+    crit = ssdbox.MultiBoxLoss(21, 0.5, True, 0, True, 3, 0.5, False)
+    d = crit.intermediates((loc.to(dev), conf.to(dev), pri.to(dev)), _gpu_targets(tg, dev))
+    assert torch.equal(d["conf_t"], conf_t)
+
+
+def test_priors_3d_shapes(dev):
+    x = U.seeded_inputs("ssd300_voc", 2, 3)
+    loc, conf, pri, sc = x["loc"].to(dev), x["conf"].to(dev), x["priors"].to(dev), x["scores"].to(dev)
+    crit = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False)
+    gt, offs, gmax = ssdbox.pack_targets(_gpu_targets(x["targets"], dev), dev)
+    a = crit.forward_packed(loc, conf, pri, gt, offs, gmax)
+    b = crit.forward_packed(loc, conf, pri.unsqueeze(0), gt, offs, gmax)                  # [1,P,4] as the reference docstring says
+    c = crit.forward_packed(loc, conf, pri.unsqueeze(0).expand(2, -1, -1).contiguous(), gt, offs, gmax)   # per-image priors
+    assert float(a[0]) == float(b[0]) == float(c[0]) and float(a[1]) == float(b[1]) == float(c[1])
+    with pytest.raises(ValueError):
+        crit.forward_packed(loc, conf, pri.unsqueeze(0).expand(3, -1, -1).contiguous(), gt, offs, gmax)
+    det = ssdbox.DetectOut(x["C"], 0, 200, 0.01, 0.45, VAR)
+    o1 = det(loc, sc, pri).clone()
+    assert torch.equal(det(loc, sc, pri.unsqueeze(0)), o1)
+    with pytest.raises(ValueError):
+        det(loc, sc, pri.unsqueeze(0).expand(3, -1, -1).contiguous())
+
+
+def test_pack_targets_host_and_device(dev):
+    """host targets travel as one pinned staging copy, device targets as one gather: same packed layout."""
+    tg = synth.gen_targets(5, 21, 9, 3)
+    tg[2] = torch.tensor([-1.0])                           # multibox_loss_v1.py:70 sentinel
+    g1, o1, m1 = ssdbox.pack_targets(tg, dev)
+    g2, o2, m2 = ssdbox.pack_targets([t.to(dev) for t in tg], dev)
+    assert m1 == m2 and torch.equal(o1, o2) and torch.equal(g1[:int(o1[-1])], g2[:int(o2[-1])])
+    assert g1.data_ptr() % 16 == 0 and o1.dtype == torch.int32
+    ref, roffs = synth.pack_targets([t if t.dim() == 2 else torch.zeros(0, 5) for t in tg])
+    assert torch.equal(g1[:ref.size(0)].cpu(), ref) and torch.equal(o1.cpu(), roffs)
+
+
+def test_peer_exchange_empty_shard_and_pending_guard(dev):
+    """(1) a rank whose local shard is empty (global batch < world) still posts zeros and keeps its epoch in
+    step; (2) a second deferred forward before PendingLoss.wait() raises instead of desynchronising the banks."""
+    x = U.seeded_inputs("ssd300_voc", 2, 5)
+    crit = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False)
+    crit.use_local_peer_exchange(dev)
+    pri = x["priors"].to(dev)
+    P, C = x["P"], x["C"]
+    e_loc = torch.zeros(0, P, 4, device=dev)
+    e_conf = torch.zeros(0, P, C, device=dev)
+    gt0 = torch.zeros(1, 5, device=dev)
+    offs0 = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.no_grad():
+        ll, lc = crit.forward_packed(e_loc, e_conf, pri, gt0, offs0, 0)
+    assert float(ll) == 0.0 and float(lc) == 0.0 and int(crit._peers.buf[0]) == 1
+    pend = crit.forward_packed_deferred(e_loc, e_conf, pri, gt0, offs0, 0)
+    a, b = pend.wait()
+    assert float(a) == 0.0 and float(b) == 0.0 and int(crit._peers.buf[0]) == 2
+    # a non-empty call afterwards still matches the plain module (epochs in step)
+    plain = ssdbox.MultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False)
+    gt, offs, gmax = ssdbox.pack_targets(_gpu_targets(x["targets"], dev), dev)
+    with torch.no_grad():
+        want = plain.forward_packed(x["loc"].to(dev), x["conf"].to(dev), pri, gt, offs, gmax)
+        got = crit.forward_packed(x["loc"].to(dev), x["conf"].to(dev), pri, gt, offs, gmax)
+    assert float(want[0]) == float(got[0]) and float(want[1]) == float(got[1])
+    # guard
+    pend = crit.forward_packed_deferred(x["loc"].to(dev), x["conf"].to(dev), pri, gt, offs, gmax)
+    with pytest.raises(RuntimeError):
+        crit.forward_packed_deferred(x["loc"].to(dev), x["conf"].to(dev), pri, gt, offs, gmax)
+    with pytest.raises(RuntimeError):
+        with torch.no_grad():
+            crit.forward_packed(x["loc"].to(dev), x["conf"].to(dev), pri, gt, offs, gmax)
+    dl, dc = pend.wait()
+    assert float(dl) == float(want[0]) and float(dc) == float(want[1])
+    assert crit._peers.timeouts() == 0 if hasattr(crit._peers, "timeouts") else True
+
+
+def test_one_module_two_streams(dev):
+    """Per-(device, stream) workspaces: the same DetectOut / MultiBoxLoss objects driven from two streams at once
+    give the single-stream results."""
+    xa = U.seeded_inputs("ssd300_voc", 4, 80)
+    xb = U.seeded_inputs("ssd300_voc", 4, 81)
+    det = ssdbox.DetectOut(xa["C"], 0, 200, 0.01, 0.45, VAR)
+    crit = ssdbox.MultiBoxLoss(xa["C"], 0.5, True, 0, True, 3, 0.5, False)
+    ins = []
+    for x in (xa, xb):
+        gt, offs, gmax = ssdbox.pack_targets(_gpu_targets(x["targets"], dev), dev)
+        ins.append((x["loc"].to(dev), x["scores"].to(dev), x["conf"].to(dev), x["priors"].to(dev), gt, offs, gmax))
+    want = []
+    with torch.no_grad():
+        for loc, sc, conf, pri, gt, offs, gmax in ins:
+            want.append((det(loc, sc, pri).clone(), torch.stack(crit.forward_packed(loc, conf, pri, gt, offs, gmax)).clone()))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for rep in range(5):
+        got = []
+        for s, (loc, sc, conf, pri, gt, offs, gmax) in zip(streams, ins):
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s), torch.no_grad():
+                got.append((det(loc, sc, pri), torch.stack(crit.forward_packed(loc, conf, pri, gt, offs, gmax))))
+        torch.cuda.synchronize()
+        for (o, l), (wo, wl) in zip(got, want):
+            assert torch.equal(o, wo) and torch.equal(l, wl)

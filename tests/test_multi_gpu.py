@@ -1,6 +1,7 @@
 """N > 1 on real GPUs (skipped on a box with fewer than two): the sharded MultiBoxLoss with the
 NVLink peer-memory reduction and with the NCCL all-reduce against the single-GPU result."""
 import os
+import socket
 import subprocess
 import sys
 
@@ -14,8 +15,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_sharded_loss_two_gpus():
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
-    n = min(torch.cuda.device_count(), 4)
+    n = min(torch.cuda.device_count(), 8)
+    with socket.socket() as sk:                       # a free port instead of a fixed one
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
-           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "_mgpu_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT)
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "_mgpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=400, cwd=ROOT)
+    log = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(log):                            # evidence that survives the box: copied to profiles/ by the builder
+        with open(os.path.join(log, "mgpu_pytest_%dgpu.log" % n), "w") as f:
+            f.write("$ %s\nexit %d\n--- stdout\n%s\n--- stderr (tail)\n%s\n" % (" ".join(cmd), r.returncode, r.stdout, r.stderr[-6000:]))
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
