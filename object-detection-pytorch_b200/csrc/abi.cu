@@ -50,6 +50,18 @@ int get_dev_info(DevInfo* out) {
   return SSDBOX_OK;
 }
 
+int smem_carveout_pct() {
+#ifdef SSDBOX_EXPERIMENTS
+  static int v = [] {
+    const char* e = getenv("SSDBOX_CARVEOUT");
+    return e ? atoi(e) : -1;
+  }();
+  return v;
+#else
+  return -1;
+#endif
+}
+
 // ---- opt-in kernel timers ---------------------------------------------------------------------
 struct TimerSlot {
   std::vector<cudaEvent_t> start, stop;   // pending pairs

@@ -23,6 +23,11 @@ struct DevInfo {
 // attributes of the current device (cached per device id)
 int get_dev_info(DevInfo* out);
 
+// Preferred shared-memory carve-out (percent) applied to every kernel of a step, or -1 to leave the driver's
+// heuristic alone.  Consecutive kernels that ask for different carve-outs make every SM drain and re-partition
+// its L1 / shared memory between them; one common value removes that from the kernel boundaries.
+int smem_carveout_pct();
+
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -64,6 +69,12 @@ struct Carver {
   do {                                                               \
     cudaError_t e__ = (call);                                        \
     if (e__ != cudaSuccess) return ::ssdbox::cuda_fail(e__, #call);  \
+  } while (0)
+
+#define SSDBOX_CARVE(kern)                                                                              \
+  do {                                                                                                  \
+    int pct__ = ::ssdbox::smem_carveout_pct();                                                          \
+    if (pct__ >= 0) SSDBOX_CUDA(cudaFuncSetAttribute((kern), cudaFuncAttributePreferredSharedMemoryCarveout, pct__)); \
   } while (0)
 
 #define SSDBOX_LAUNCH_OK(name)                                        \

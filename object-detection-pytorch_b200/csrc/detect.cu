@@ -835,6 +835,7 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
     if (C == 81) kern = logits ? detect_stream_kernel<81, true> : detect_stream_kernel<81, false>;
     else if (C == 21) kern = logits ? detect_stream_kernel<21, true> : detect_stream_kernel<21, false>;
     SSDBOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa.ring.smem_bytes));
+    SSDBOX_CARVE(kern);
 {
     TimerScope ts__(KID_DET_STREAM, st);
     kern<<<sa.ring.grid, kRingThreads, sa.ring.smem_bytes, st>>>(sa);
@@ -849,6 +850,7 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
   g.loc = loc; g.scores = scores; g.priors = priors; g.keep = score_keep;
   g.cnt = cnt; g.cand = cand; g.ovf_count = cnt + (size_t)B * C; g.ovf_list = ovf_list; g.big_count = cnt + (size_t)B * C + 1; g.big_list = big_list; g.scratch = scratch; g.out = out; g.counts = counts;
   g.row_m = logits ? row_m : nullptr; g.row_s = logits ? row_s : nullptr;
+  SSDBOX_CARVE(detect_segment_small_kernel);
   {
     TimerScope ts__(KID_DET_SEGMENT, st);
     int per = kSmallThreads / 32;
@@ -862,6 +864,7 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
   if (top_k <= 256 && cap == 1024 && chunk_smem <= (size_t)dev.max_smem_optin - 1024) {
     // chunked dense path: (image, 8 classes) work items, reads each score sector once per pass
     SSDBOX_CUDA(cudaFuncSetAttribute(detect_overflow_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chunk_smem));
+    SSDBOX_CARVE(detect_overflow_chunk_kernel);
     const int items = B * ((C - 1 + kOvfClasses - 1) / kOvfClasses);
     if (ovf_grid > items) ovf_grid = items;
     if (ovf_grid > 0) {
@@ -879,6 +882,7 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
 
   size_t seg_smem = (size_t)cap * 8 + nms_smem_bytes(top_k);
   SSDBOX_CUDA(cudaFuncSetAttribute(detect_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem));
+  SSDBOX_CARVE(detect_segment_kernel);
   {
     TimerScope ts__(KID_DET_SEGMENT_BIG, st);
     int big_grid = dev.sm_count * 4 < B * C ? dev.sm_count * 4 : B * C;

@@ -447,6 +447,7 @@ static int launch_stream(const StreamArgs& a, size_t smem, cudaStream_t st) {
   else if (C == 21) kern = loss_stream_kernel<21>;
   else if (C == 2) kern = loss_stream_kernel<2>;
   SSDBOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SSDBOX_CARVE(kern);
   {
     TimerScope ts__(KID_LOSS_STREAM, st);
     kern<<<a.ring.grid, (kRingConsumerWarps + 2 + (a.fuse ? a.match_warps : 0)) * 32, smem, st>>>(a);
@@ -1793,6 +1794,7 @@ extern "C" int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const 
            (size_t)P * 2 + 16;      // ... + positives list + forced-label override array
     if (pair) {
       SSDBOX_CUDA(cudaFuncSetAttribute(mkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SSDBOX_CARVE(mkern);
       cudaLaunchConfig_t lc = {};
       lc.gridDim = dim3(2 * B);
       lc.blockDim = dim3(kMineThreads);
@@ -1814,6 +1816,7 @@ extern "C" int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const 
   }
   if (!launched) {
     SSDBOX_CUDA(cudaFuncSetAttribute(mkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SSDBOX_CARVE(mkern);
     TimerScope ts__(KID_MINE, st);
     mkern<<<B, kMineThreads, smem, st>>>(m);
   }

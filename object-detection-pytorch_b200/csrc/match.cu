@@ -36,7 +36,8 @@ int launch_init(unsigned long long* best, size_t nbest, uint32_t* z0, size_t n0,
   if (m == 0) return SSDBOX_OK;
   int blocks = (int)((m + 255) / 256);
   if (blocks > 592) blocks = 592;
-{
+  SSDBOX_CARVE(init_kernel);
+  {
     TimerScope ts__(KID_INIT, st);
     init_kernel<<<blocks, 256, 0, st>>>(best, nbest, z0, n0, z1, n1, z2, n2);
   }
