@@ -5,8 +5,8 @@
 
 One "step" = one pass of the hot path over one batch of synthetic input of BASELINE.json
 configs[1] (SSD512 VGG16 COCO: P=24564 priors, C=81 classes, B=64 images PER GPU):
-    T  match + MultiBoxLoss forward  (init, match, loss_stream, mine_reduce kernels)
-    D  DetectOut: threshold, top-200, NMS (init, detect_stream, detect_segment small/big, detect_overflow)
+    T  match + MultiBoxLoss forward  (loss_stream with the matching on dedicated warps, mine_reduce)
+    D  DetectOut: threshold, top-200, NMS (detect_stream, detect_segments, overflow select + rewritten lists)
 `value` = images/s with inputs resident in HBM (whole job: N * B / max-over-ranks step time; every
 image passes through both T and D), timed with CUDA events around K CUDA-graph replays.
 `e2e` = same metric through the public modules (MultiBoxLoss.forward / DetectOut.__call__) with
@@ -34,9 +34,10 @@ import torch  # noqa: E402
 METRIC = "SSD512 COCO images/s: match+MultiBoxLoss & Detect/NMS, 1/2/4/8 B200"
 WORKLOAD = "ssd512_coco"
 VAR = [0.1, 0.2]
-# kernels launched per step.  plain: T = init, loss_stream, mine_reduce; D = init, detect_stream, segment (warp / CTA),
-# overflow select.  refine: ARM loss (3) + ODM loss (decode, arm_filter + 3) + RefineDetectOut (decode, arm_filter + 5)
-LAUNCHES = {"plain": 8, "refine": 15}
+# kernels launched per step (the init launches are gone from the second call on: self-cleaning workspaces).
+# plain: T = loss_stream, mine_reduce; D = detect_stream, segments, overflow select, rewritten lists.
+# refine: ARM loss (2) + ODM loss (decode, arm_filter + 2) + RefineDetectOut (decode, arm_filter + 4)
+LAUNCHES = {"plain": 6, "refine": 12}
 # BASELINE.json configs; `--workload` selects one (the headline metric is quoted on ssd512_coco)
 DESCR = {
     "ssd300_voc": "SSD300 VGG16 VOC",
@@ -501,9 +502,12 @@ def main():
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 step()
+                step()
             torch.cuda.current_stream().wait_stream(s)
+            # captured on the warm-up stream: the modules' per-stream workspaces already exist there and are in their
+            # clean state, so the captured step carries no init launch (SSDBOX_*_WS_CLEAN)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=s):
                 step()
         except Exception as e:  # e.g. NCCL capture unsupported
             sys.stderr.write("bench: CUDA-graph capture failed (%r); timing eager launches\n" % (e,))
@@ -620,7 +624,7 @@ def main():
         e2e_rank_s = [float(x.item()) for x in allt]
         e2e_s = max(e2e_rank_s)
     # a bare pinned H2D copy of the same size on this rank, alone on the link (what PCIe gives one GPU) ...
-    probe = torch.empty(conf_h.numel(), dtype=torch.float32, device=dev)
+    probe = torch.empty_like(conf_h, device=dev)
     probe.copy_(conf_h, non_blocking=True)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -816,7 +820,7 @@ def main():
                                      else "the oracle port (oracle/ssd_oracle.py)", cores),
                         "train_fwd_images_per_s": reps * bt / tt, "detect_images_per_s": reps * bd / td}
 
-    # T: init, loss_stream, mine_reduce; D: init, detect_stream, segment (warp / CTA), overflow; N > 1: + the collect kernel
+    # N > 1: + the collect kernel
     launches_per_step = LAUNCHES["refine" if refine else "plain"] + (1 if n_gpus > 1 and not refine else 0)
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": n_gpus, "steps": args.steps,

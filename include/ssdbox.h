@@ -186,6 +186,13 @@ typedef struct {
  * the same stream.  Work enqueued in between (e.g. DetectOut of the same step) overlaps the wait, so
  * rank skew no longer stalls the step. */
 #define SSDBOX_LOSS_DEFER_PEER_WAIT 8
+/* Workspace state is clean: skip the init launch.  The op keeps per-truth best-prior keys, per-image mining
+ * histograms and work tickets in `ws`; every call hands them back initialised (the mining CTA of an image resets
+ * what it has read, the last CTA the tickets).  A caller may set this flag iff the previous work on this `ws` was
+ * a COMPLETED ssdbox_multibox_loss_fwd[_peers] call with the same (B, P, C, gmax) and the same flags.  Without the
+ * flag nothing is assumed about the workspace contents.  The host mirror (MultiBoxLoss) sets it from the second
+ * call on. */
+#define SSDBOX_LOSS_WS_CLEAN 16
 
 /* forward.
  *   loc [B,P,4], conf [B,P,C] raw logits, priors, anchors_xyxy (nullable), gt/gt_offsets
@@ -281,6 +288,12 @@ typedef struct {
  * softmax kernel's read + write of conf (2 x 4*B*P*C bytes).  Scores then agree with
  * torch.softmax to fp32 rounding (<= 1e-6 relative) instead of bit for bit. */
 #define SSDBOX_DETECT_LOGITS 1
+/* Workspace state is clean: skip the init launch.  The op keeps a few counters in `ws`; every call hands them
+ * back zeroed (each list's counter is reset by the kernel that finishes the list).  A caller may therefore set
+ * this flag iff the previous work on this `ws` was a COMPLETED ssdbox_detect call with the same (B, P, C, top_k)
+ * on the same stream order (or the state region was just zero-filled).  Without the flag nothing is assumed
+ * about the workspace contents.  The host mirror (DetectOut) sets it from the second call on. */
+#define SSDBOX_DETECT_WS_CLEAN 2
 
 SSDBOX_API int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, const float* scores,
                   const float* priors, const uint8_t* score_keep, float* out, int32_t* counts, void* ws,

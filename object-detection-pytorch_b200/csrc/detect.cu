@@ -1,7 +1,6 @@
 // DetectOut.forward (lib/layers/functions/detection.py:25-64) and nms (box_utils.py:279-343).
 //
-// Detect = 5 launches on the caller's stream:
-//   init_kernel            candidate counters := 0
+// Detect = 4 launches on the caller's stream (5 the first time a workspace is used: + init_kernel):
 //   detect_stream_kernel   THE HBM-bound kernel: scores [B*P, C] streamed once through the TMA
 //                          bulk-copy ring; one thread per prior row takes the row maximum over the
 //                          foreground classes; the few rows with a hit are re-scanned by the warp
@@ -10,17 +9,18 @@
 //                          raw logits (SSDBOX_DETECT_LOGITS) the softmax is fused in.  The transposed
 //                          [C,P] view of detection.py:38-39 is never materialised; decode runs only
 //                          on candidates.
-//   detect_segment_small_kernel  one WARP per (image, class) with <= 32 candidates (the normal case):
-//                          shuffle bitonic sort, decode, NMS and output rows entirely in registers;
-//                          larger lists are queued
+//   detect_segments_kernel every list that fits the capacity: one WARP per (image, class) finishes lists of
+//                          <= 32 candidates (the normal case) entirely in registers -- shuffle bitonic sort,
+//                          decode, NMS, output rows; longer lists go to a CTA-local queue and are finished by
+//                          the whole CTA (bitonic sort by (score desc, prior desc) = the reference's visiting
+//                          order, top_k cut, decode of the survivors, upper-triangular suppression bit-matrix
+//                          built with warp ballots in shared memory, one-warp greedy sweep)
 //   detect_overflow_chunk_kernel  only for lists that exceeded the candidate capacity (dense scores):
 //                          per (image, 8 classes) a range-adaptive radix select straight from
 //                          `scores` rewrites each list with the <= 1024 best keys and queues it
-//   detect_segment_kernel  one CTA per queued (image, class): bitonic sort by (score desc, prior desc)
-//                          = the reference's visiting order, top_k cut, decode of the survivors,
-//                          upper-triangular suppression bit-matrix built with warp ballots in shared
-//                          memory, one-warp greedy sweep, zero-padded output rows.
+//   detect_segment_kernel  one CTA per rewritten list; both exit on one load when nothing overflowed.
 // (top_k > 256: detect_overflow_kernel, one CTA per overflowed list, exact column select + NMS.)
+// Every kernel resets the counters of the lists it finishes: the workspace state is clean after the call.
 #include "ops.h"
 #include "ring.cuh"
 #include "select.cuh"
@@ -292,8 +292,9 @@ struct DetSegArgs {
   unsigned long long* cand;
   uint32_t* ovf_count; // [1] number of (image, class) lists that overflowed
   int32_t* ovf_list;   // [B*C] their segment ids
-  uint32_t* big_count; // [1] number of lists with 32 < n <= cap
+  uint32_t* big_count; // [1] number of lists rewritten by the overflow select (<= cap candidates each)
   int32_t* big_list;   // [B*C]
+  uint32_t* tail_ticket; // [1] CTAs of detect_segment_kernel that are done (the last one resets the bookkeeping)
   uint32_t* scratch;   // [kOverflowSlots, P]
   const float* row_m;  // logits mode (nullptr otherwise): softmax row max / denominator from the stream pass
   const float* row_s;
@@ -341,7 +342,8 @@ __device__ void segment_finish(const DetSegArgs& a, int b, int seg, unsigned lon
 // shuffle bitonic sort, decode, suppression bits via broadcast + ballot sweep.  Larger ones are
 // queued for the CTA-wide kernel (<= capacity) or the overflow kernel (> capacity).
 // ------------------------------------------------------------------------------------------------
-constexpr int kSmallThreads = 128;
+constexpr int kSmallThreads = 256;       // 8 warps = 8 (image, class) segments per CTA
+constexpr int kSmallSegs = kSmallThreads / 32;
 
 __device__ __forceinline__ void warp_zero_rows(float* o, int nfloat, int lane) {
   if ((reinterpret_cast<uintptr_t>(o) & 15u) == 0 && (nfloat & 3) == 0) {
@@ -352,95 +354,145 @@ __device__ __forceinline__ void warp_zero_rows(float* o, int nfloat, int lane) {
   }
 }
 
-__global__ void __launch_bounds__(kSmallThreads) detect_segment_small_kernel(DetSegArgs a) {
+// One launch finishes every list that fits the candidate capacity:
+//   phase 1  one warp per (image, class): lists of <= 32 candidates entirely in registers (the normal case);
+//            longer lists are noted in a CTA-local queue, overflowed ones (> capacity, dense scores) in the
+//            global overflow list for detect_overflow_chunk_kernel
+//   phase 2  the CTA works off its own queue (sort in shared memory, decode, bit-matrix NMS)
+// The kernel also leaves the workspace state clean for the next call: the counter of every list it finishes
+// goes back to zero (SSDBOX_DETECT_WS_CLEAN, include/ssdbox.h).
+__global__ void __launch_bounds__(kSmallThreads) detect_segments_kernel(DetSegArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_seg[];
+  __shared__ int s_q[kSmallSegs], s_qn[kSmallSegs], s_nq;
   const int lane = threadIdx.x & 31;
-  const int seg = blockIdx.x * (kSmallThreads / 32) + (threadIdx.x >> 5);
-  if (seg >= a.B * a.C) return;
-  const int b = seg / a.C, c = seg - b * a.C;
-  const uint32_t total = c == 0 ? 0u : a.cnt[seg];
-  if (total > 32u) {                       // queue for the CTA-wide kernels
-    if (lane == 0) {
-      if (total > (uint32_t)a.cap) a.ovf_list[atomicAdd(a.ovf_count, 1u)] = seg;
-      else a.big_list[atomicAdd(a.big_count, 1u)] = seg;
-    }
-    return;
-  }
-  float* o = a.out + (size_t)seg * a.top_k * 5;
-  warp_zero_rows(o, a.top_k * 5, lane);    // background plane / no candidate: zeros (detection.py:37,50-51)
-  if (total == 0u) {
-    if (lane == 0 && a.counts) a.counts[seg] = 0;
-    return;
-  }
-  const int n = (int)total;
-  unsigned long long key = lane < n ? a.cand[(size_t)seg * a.cap + lane] : 0ull;
-  // bitonic sort, descending (= visiting order: score desc, higher prior first); padding sinks
+  if (threadIdx.x == 0) s_nq = 0;
+  __syncthreads();
+  const int seg = blockIdx.x * kSmallSegs + (threadIdx.x >> 5);
+  if (seg < a.B * a.C) {
+    const int b = seg / a.C, c = seg - b * a.C;
+    const uint32_t total = c == 0 ? 0u : a.cnt[seg];
+    if (total > 32u) {
+      if (lane == 0) {
+        if (total > (uint32_t)a.cap) {
+          a.ovf_list[atomicAdd(a.ovf_count, 1u)] = seg;      // its counter stays: the overflow kernels read it
+        } else {
+          const int q = atomicAdd(&s_nq, 1);
+          s_q[q] = seg;
+          s_qn[q] = (int)total;
+          a.cnt[seg] = 0u;
+        }
+      }
+    } else {
+      float* o = a.out + (size_t)seg * a.top_k * 5;
+      warp_zero_rows(o, a.top_k * 5, lane);    // background plane / no candidate: zeros (detection.py:37,50-51)
+      if (total == 0u) {
+        if (lane == 0 && a.counts) a.counts[seg] = 0;
+      } else {
+        if (lane == 0) a.cnt[seg] = 0u;
+        const int n = (int)total;
+        unsigned long long key = lane < n ? a.cand[(size_t)seg * a.cap + lane] : 0ull;
+        // bitonic sort, descending (= visiting order: score desc, higher prior first); padding sinks
 #pragma unroll
-  for (int k = 2; k <= 32; k <<= 1) {
+        for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      unsigned long long other = __shfl_xor_sync(SSDBOX_FULL_MASK, key, j);
-      bool desc = (lane & k) == 0;
-      bool lower = (lane & j) == 0;
-      bool keep_max = lower == desc;
-      key = keep_max ? (key > other ? key : other) : (key < other ? key : other);
+          for (int j = k >> 1; j > 0; j >>= 1) {
+            unsigned long long other = __shfl_xor_sync(SSDBOX_FULL_MASK, key, j);
+            bool desc = (lane & k) == 0;
+            bool lower = (lane & j) == 0;
+            bool keep_max = lower == desc;
+            key = keep_max ? (key > other ? key : other) : (key < other ? key : other);
+          }
+        }
+        const int m = n < a.top_k ? n : a.top_k;           // box_utils.py:301 idx[-top_k:]
+        Box me;
+        me.x1 = me.y1 = me.x2 = me.y2 = 0.f;
+        if (lane < m) {
+          uint32_t p = (uint32_t)(key & 0xffffffffull);
+          me = decode_box(*reinterpret_cast<const float4*>(a.loc + ((size_t)b * a.P + p) * 4),
+                          *reinterpret_cast<const float4*>(a.priors + (size_t)b * (size_t)a.prior_stride + (size_t)p * 4),
+                          a.var0, a.var1);
+        }
+        const float my_area = box_area(me);
+        uint32_t supp_by = 0u;                              // bit i: box i (earlier in the order) suppresses me
+        for (int i = 0; i + 1 < m; ++i) {
+          Box bi;
+          bi.x1 = __shfl_sync(SSDBOX_FULL_MASK, me.x1, i);
+          bi.y1 = __shfl_sync(SSDBOX_FULL_MASK, me.y1, i);
+          bi.x2 = __shfl_sync(SSDBOX_FULL_MASK, me.x2, i);
+          bi.y2 = __shfl_sync(SSDBOX_FULL_MASK, me.y2, i);
+          float ai = __shfl_sync(SSDBOX_FULL_MASK, my_area, i);
+          if (lane > i && lane < m && !(iou_nms(bi, ai, me, my_area) <= a.nms_thr)) supp_by |= 1u << i;
+        }
+        uint32_t removed = 0u, kept = 0u;
+        for (int i = 0; i < m; ++i) {
+          uint32_t col = __ballot_sync(SSDBOX_FULL_MASK, (supp_by >> i) & 1u);
+          if (!((removed >> i) & 1u)) {
+            kept |= 1u << i;
+            removed |= col;
+          }
+        }
+        __syncwarp();                                        // orders the zero fill before the row writes
+        if (lane < m && ((kept >> lane) & 1u)) {
+          float* r = o + __popc(kept & ((1u << lane) - 1u)) * 5;
+          r[0] = ord2f((uint32_t)(key >> 32));
+          r[1] = me.x1; r[2] = me.y1; r[3] = me.x2; r[4] = me.y2;
+        }
+        if (lane == 0 && a.counts) a.counts[seg] = __popc(kept);
+      }
     }
   }
-  const int m = n < a.top_k ? n : a.top_k;           // box_utils.py:301 idx[-top_k:]
-  Box me;
-  me.x1 = me.y1 = me.x2 = me.y2 = 0.f;
-  if (lane < m) {
-    uint32_t p = (uint32_t)(key & 0xffffffffull);
-    me = decode_box(*reinterpret_cast<const float4*>(a.loc + ((size_t)b * a.P + p) * 4),
-                    *reinterpret_cast<const float4*>(a.priors + (size_t)b * (size_t)a.prior_stride + (size_t)p * 4),
-                    a.var0, a.var1);
+  __syncthreads();
+  const int nq = s_nq;
+  if (nq == 0) return;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_seg);
+  NmsSmem ns = carve_nms(smem_seg + (size_t)a.cap * 8, a.top_k);
+  for (int q = 0; q < nq; ++q) {
+    const int sg = s_q[q], n = s_qn[q];                    // 32 < n <= cap
+    int npad = 64;
+    while (npad < n) npad <<= 1;
+    const unsigned long long* src = a.cand + (size_t)sg * a.cap;
+    for (int i = threadIdx.x; i < npad; i += kSmallThreads) keys[i] = i < n ? src[i] : 0ull;
+    __syncthreads();
+    segment_finish(a, sg / a.C, sg, keys, n, npad, ns);
+    __syncthreads();
   }
-  const float my_area = box_area(me);
-  uint32_t supp_by = 0u;                              // bit i: box i (earlier in the order) suppresses me
-  for (int i = 0; i + 1 < m; ++i) {
-    Box bi;
-    bi.x1 = __shfl_sync(SSDBOX_FULL_MASK, me.x1, i);
-    bi.y1 = __shfl_sync(SSDBOX_FULL_MASK, me.y1, i);
-    bi.x2 = __shfl_sync(SSDBOX_FULL_MASK, me.x2, i);
-    bi.y2 = __shfl_sync(SSDBOX_FULL_MASK, me.y2, i);
-    float ai = __shfl_sync(SSDBOX_FULL_MASK, my_area, i);
-    if (lane > i && lane < m && !(iou_nms(bi, ai, me, my_area) <= a.nms_thr)) supp_by |= 1u << i;
-  }
-  uint32_t removed = 0u, kept = 0u;
-  for (int i = 0; i < m; ++i) {
-    uint32_t col = __ballot_sync(SSDBOX_FULL_MASK, (supp_by >> i) & 1u);
-    if (!((removed >> i) & 1u)) {
-      kept |= 1u << i;
-      removed |= col;
-    }
-  }
-  __syncwarp();                                        // orders the zero fill before the row writes
-  if (lane < m && ((kept >> lane) & 1u)) {
-    float* r = o + __popc(kept & ((1u << lane) - 1u)) * 5;
-    r[0] = ord2f((uint32_t)(key >> 32));
-    r[1] = me.x1; r[2] = me.y1; r[3] = me.x2; r[4] = me.y2;
-  }
-  if (lane == 0 && a.counts) a.counts[seg] = __popc(kept);
 }
 
 constexpr int kSegThreads = 256;
 
+// Lists rewritten by the overflow select (dense scores).  Exits at once when nothing overflowed -- the normal case;
+// otherwise the CTA that finishes last resets the overflow bookkeeping (the workspace state is clean again).
 __global__ void __launch_bounds__(kSegThreads) detect_segment_kernel(DetSegArgs a) {
   extern __shared__ __align__(16) unsigned char smem_seg[];
+  __shared__ int s_last;
+  if (*a.ovf_count == 0u) return;                     // written by detect_segments_kernel; nothing to do, nothing to clean
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_seg);
   NmsSmem ns = carve_nms(smem_seg + (size_t)a.cap * 8, a.top_k);
   const int tid = threadIdx.x;
-  const int nbig = (int)*a.big_count;                 // written by detect_segment_small_kernel
+  const int nbig = (int)*a.big_count;                 // written by detect_overflow_chunk_kernel
   for (int w = blockIdx.x; w < nbig; w += gridDim.x) {
     const int seg = a.big_list[w];
     const int b = seg / a.C;
-    const int n = (int)a.cnt[seg];                    // 32 < n <= cap
+    const int n = (int)a.cnt[seg];                    // <= cap
     int npad = 64;
     while (npad < n) npad <<= 1;
     const unsigned long long* src = a.cand + (size_t)seg * a.cap;
     for (int i = tid; i < npad; i += kSegThreads) keys[i] = i < n ? src[i] : 0ull;
     __syncthreads();
+    if (tid == 0) a.cnt[seg] = 0u;
     segment_finish(a, b, seg, keys, n, npad, ns);
     __syncthreads();
+  }
+  if (tid == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(a.tail_ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && tid == 0) {
+    *a.ovf_count = 0u;
+    *a.big_count = 0u;
+    *a.tail_ticket = 0u;
   }
 }
 
@@ -489,6 +541,7 @@ __global__ void __launch_bounds__(kOvfThreads, 1) detect_overflow_kernel(DetSegA
     for (int i = n + tid; i < npad; i += kOvfThreads) keys[i] = 0ull;
     __syncthreads();
     segment_finish(a, b, seg, keys, n, npad, ns);
+    if (tid == 0) a.cnt[seg] = 0u;
     __syncthreads();
   }
 }
@@ -589,6 +642,7 @@ __device__ void overflow_column_segment(const DetSegArgs& a, int b, int c, int s
   for (int i = n + tid; i < npad; i += kOvfThreads) keys[i] = 0ull;
   __syncthreads();
   segment_finish(a, b, seg, keys, n, npad, ns);
+  if (tid == 0) a.cnt[seg] = 0u;
   __syncthreads();
 }
 
@@ -807,7 +861,7 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
   if (rc) return rc;
   const int cap = detect_cand_cap(top_k);
   Carver cv(ws);
-  uint32_t* cnt = cv.take<uint32_t>((size_t)B * C + 2);   // [B*C] counters + overflow / big counts
+  uint32_t* cnt = cv.take<uint32_t>((size_t)B * C + 4);   // [B*C] counters + overflow count / rewritten-list count / tail ticket
   int32_t* ovf_list = cv.take<int32_t>((size_t)B * C);
   int32_t* big_list = cv.take<int32_t>((size_t)B * C);
   unsigned long long* cand = cv.take<unsigned long long>((size_t)B * C * cap);
@@ -816,8 +870,12 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
   float* row_s = cv.take<float>((size_t)B * P);
   const bool logits = (cfg->flags & SSDBOX_DETECT_LOGITS) != 0;
 
-  rc = launch_init(nullptr, 0, cnt, (size_t)B * C + 2, nullptr, 0, nullptr, 0, st);
-  if (rc) return rc;
+  // State = the counters.  Every call hands them back zeroed (each list's counter is reset by the kernel that
+  // finishes the list), so a caller that reuses the workspace for the same shape may skip the init launch.
+  if (!(cfg->flags & SSDBOX_DETECT_WS_CLEAN)) {
+    rc = launch_init(nullptr, 0, cnt, (size_t)B * C + 4, nullptr, 0, nullptr, 0, st);
+    if (rc) return rc;
+  }
 
   if (P > 0) {
     DetStreamArgs sa{};
@@ -848,15 +906,17 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
   g.nms_thr = cfg->nms_thresh; g.conf_thr = cfg->conf_thresh; g.var0 = cfg->var0; g.var1 = cfg->var1;
   g.prior_stride = (long long)cfg->prior_batch_stride;
   g.loc = loc; g.scores = scores; g.priors = priors; g.keep = score_keep;
-  g.cnt = cnt; g.cand = cand; g.ovf_count = cnt + (size_t)B * C; g.ovf_list = ovf_list; g.big_count = cnt + (size_t)B * C + 1; g.big_list = big_list; g.scratch = scratch; g.out = out; g.counts = counts;
+  g.cnt = cnt; g.cand = cand; g.ovf_count = cnt + (size_t)B * C; g.ovf_list = ovf_list; g.big_count = cnt + (size_t)B * C + 1;
+  g.tail_ticket = cnt + (size_t)B * C + 2; g.big_list = big_list; g.scratch = scratch; g.out = out; g.counts = counts;
   g.row_m = logits ? row_m : nullptr; g.row_s = logits ? row_s : nullptr;
-  SSDBOX_CARVE(detect_segment_small_kernel);
+  const size_t seg_smem = (size_t)cap * 8 + nms_smem_bytes(top_k);
+  SSDBOX_CUDA(cudaFuncSetAttribute(detect_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem));
+  SSDBOX_CARVE(detect_segments_kernel);
   {
     TimerScope ts__(KID_DET_SEGMENT, st);
-    int per = kSmallThreads / 32;
-    detect_segment_small_kernel<<<(B * C + per - 1) / per, kSmallThreads, 0, st>>>(g);
+    detect_segments_kernel<<<(B * C + kSmallSegs - 1) / kSmallSegs, kSmallThreads, seg_smem, st>>>(g);
   }
-  SSDBOX_LAUNCH_OK("detect_segment_small_kernel");
+  SSDBOX_LAUNCH_OK("detect_segments_kernel");
   // overflowed lists first: the chunked kernel only SELECTS (it rewrites the list with <= 1024 keys and
   // queues the segment for the CTA-wide kernel below)
   int ovf_grid = dev.sm_count < kOverflowSlots ? dev.sm_count : kOverflowSlots;
@@ -880,7 +940,6 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
   }
   SSDBOX_LAUNCH_OK("detect_overflow_kernel");
 
-  size_t seg_smem = (size_t)cap * 8 + nms_smem_bytes(top_k);
   SSDBOX_CUDA(cudaFuncSetAttribute(detect_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem));
   SSDBOX_CARVE(detect_segment_kernel);
   {

@@ -1,7 +1,9 @@
 // MultiBoxLoss forward / backward: lib/layers/modules/multibox_loss.py:48-117 (+ autograd).
 //
-// Forward = 3 launches on the caller's stream (CUDA-graph capturable, no host sync):
-//   init_kernel        per-truth best-prior keys := (0, prior 0); tickets / histograms := 0
+// Forward = 2 launches on the caller's stream (CUDA-graph capturable, no host sync), 3 the first time a workspace
+// is used:
+//   init_kernel        per-truth best-prior keys := (0, prior 0); tickets / histograms := 0.  Skipped with
+//                      SSDBOX_LOSS_WS_CLEAN: every call hands this state back initialised
 //   loss_stream_kernel THE HBM-bound kernel, warp-specialised, one persistent CTA per SM:
 //                        1 producer warp   streams conf [B*P, C] through a ring of TMA bulk-copy
 //                                          stages (cp.async.bulk + mbarrier)
@@ -483,6 +485,7 @@ struct MineArgs {
   int fuse;
   int gmax, gpad, binarize;
   const unsigned long long* gt_best;
+  unsigned long long* gt_best_w;   // same array: the mining CTA of an image hands it back initialised
   int16_t* lab_w;
   int16_t* tidx_w;
   uint32_t* ukey_global;   // used when the ordered keys do not fit in shared memory
@@ -689,6 +692,8 @@ __device__ void fold_partials(const MineArgs& a, double* s_dscr, double* s_big, 
     sn = s_dscr[2];
   }
   if (tid == 0) {
+    a.ticket[0] = 0u;      // mining ticket and matching work-unit counter: clean for the next call
+    a.ticket[1] = 0u;
     a.sums[0] = sl;
     a.sums[1] = sc;
     a.sums[2] = sn;
@@ -768,6 +773,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
       }
     }
     __syncthreads();
+    for (int j = tid; j < G; j += kMineThreads) a.gt_best_w[(size_t)b * a.gpad + j] = kBestInit;   // state handed back clean
   }
 
   // pass A: positives (count, CE, smooth-L1) and the ordered mining keys
@@ -833,6 +839,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
   uint32_t Tu = 0xffffffffu;
   if (K > 0) Tu = cta_select_threshold<false, VEC>(uk, P, K, a.hist + (size_t)b * kHistBins, s_hist, s_iscr, s_res);
   __syncthreads();
+  for (int i = tid; i < kHistBins; i += kMineThreads) a.hist[(size_t)b * kHistBins + i] = 0u;     // state handed back clean
   PHASE_MARK(3);
 
   // final pass: neg = rank < num_neg (:103); CE over pos U neg (:106-110).  The CE of a selected
@@ -1000,6 +1007,14 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   if (small_g && tid < G) s_best[tid] = my_best;
   if (gt_cached && tid < 5 * G) s_gt[tid] = my_gt;
   sync_all();          // cluster: the peer's histogram copy is in place before it receives remote updates
+  // every CTA of the image has read its streamed histogram and best-prior keys: hand them back initialised
+  // (the workspace state is clean again after the call, SSDBOX_LOSS_WS_CLEAN)
+  if (rank == 0) {
+    a.hist[(size_t)b * kHistBins + tid] = 0u;
+    a.hist[(size_t)b * kHistBins + 1024 + tid] = 0u;
+    if (a.fuse)
+      for (int j = tid; j < G; j += kMineThreads) a.gt_best_w[(size_t)b * a.gpad + j] = kBestInit;
+  }
 
   PHASE_MARK(1);
   // (2) forced assignment: truth j keeps its best prior unless a later truth claims the same prior
@@ -1712,9 +1727,13 @@ extern "C" int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const 
 
   w.lse = c.take<float>((size_t)B * P);
 
-  rc = launch_init(w.m.gt_best, (size_t)(B + 1) * gt_pad(cfg->gmax), w.m.done, (size_t)B + 1, w.hist,
-                   (size_t)B * kHistBins, w.ticket, 2, st);
-  if (rc) return rc;
+  // State = per-truth best-prior keys, image tickets, mining histograms, work tickets.  Every call hands it back
+  // initialised, so a caller that reuses the workspace for the same shape may skip this launch.
+  if (!(cfg->flags & SSDBOX_LOSS_WS_CLEAN)) {
+    rc = launch_init(w.m.gt_best, (size_t)(B + 1) * gt_pad(cfg->gmax), w.m.done, (size_t)B + 1, w.hist,
+                     (size_t)B * kHistBins, w.ticket, 2, st);
+    if (rc) return rc;
+  }
 
   // Matching runs on dedicated warps of the streaming kernel unless the caller asked for the
   // separate kernel or the truths of a CTA's images do not fit in shared memory beside the ring.
@@ -1764,7 +1783,7 @@ extern "C" int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const 
   m.loc = loc; m.priors = priors; m.gt = gt; m.gt_offsets = gt_offsets; m.pool = pool;
   m.keys = w.keys; m.lse = w.lse; m.conf = conf; m.lab = w.m.lab; m.tidx = tidx; m.hist = w.hist;
   m.fuse = sa.fuse; m.gmax = cfg->gmax; m.gpad = sa.gpad; m.binarize = cfg->binarize_labels;
-  m.gt_best = w.m.gt_best; m.lab_w = w.m.lab; m.tidx_w = tidx;
+  m.gt_best = w.m.gt_best; m.gt_best_w = w.m.gt_best; m.lab_w = w.m.lab; m.tidx_w = tidx;
   m.ukey_global = w.ukey;
   size_t fixed = kMineFixedSmem;
   m.uk_in_smem = (fixed + (size_t)P * 6 + 16 <= (size_t)dev.max_smem_optin - 1024) ? 1 : 0;

@@ -188,7 +188,11 @@ match_kernel(MatchArgs a, unsigned long long* __restrict__ gt_best, uint32_t* __
   __threadfence();
 
   // forced assignment, box_utils.py:123-127: overlap := 2, truth := j, sequentially (last j wins)
-  for (int g = tid; g < G; g += kMatchThreads) s_best[g] = __ldcg(&gt_best[(size_t)b * gpad + g]);
+  for (int g = tid; g < G; g += kMatchThreads) {
+    s_best[g] = __ldcg(&gt_best[(size_t)b * gpad + g]);
+    gt_best[(size_t)b * gpad + g] = kBestInit;          // the image's state is handed back initialised
+  }
+  if (tid == 0) done[b] = 0u;
   __syncthreads();
   for (int j = tid; j < G; j += kMatchThreads) {
     uint32_t pj = ~(uint32_t)(s_best[j] & 0xffffffffull);

@@ -55,7 +55,7 @@ static inline size_t mine_ws_bytes(int B, int P) { return align_up((size_t)B * P
 constexpr int kOverflowSlots = 160;    // >= SM count: one ordered-score scratch row per resident CTA
 static inline int detect_cand_cap(int top_k) { return top_k <= 512 ? 1024 : 2048; }
 static inline size_t detect_ws_bytes(int B, int P, int C, int top_k) {
-  return align_up((size_t)B * C * 4 + 8) + 2 * align_up((size_t)B * C * 4) +
+  return align_up((size_t)B * C * 4 + 16) + 2 * align_up((size_t)B * C * 4) +
          align_up((size_t)B * C * detect_cand_cap(top_k) * 8) +
          align_up((size_t)kOverflowSlots * P * 4) + 2 * align_up((size_t)B * P * 4);   // + softmax row max / sum (logits mode)
 }

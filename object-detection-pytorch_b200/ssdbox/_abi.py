@@ -18,6 +18,7 @@ LOSS_SEPARATE_MATCH = 1
 LOSS_GENERIC_MINE = 2
 LOSS_NO_CLUSTER = 4
 LOSS_DEFER_PEER_WAIT = 8
+LOSS_WS_CLEAN = 16
 OP_MATCH, OP_LOSS_FWD, OP_DETECT, OP_NMS, OP_LSE, OP_MINE, OP_COMPACT, OP_VOC_EVAL = 1, 2, 3, 4, 5, 6, 7, 8
 MAX_LAYERS, MAX_MIN_SIZES, MAX_RATIOS = 16, 4, 6
 
@@ -68,6 +69,7 @@ class DetectCfg(C.Structure):
 
 
 DETECT_LOGITS = 1
+DETECT_WS_CLEAN = 2
 MAX_PEERS = 16
 MAX_HEADS = 16
 
@@ -205,19 +207,43 @@ def as_f32(t, device=None):
 class Workspace(object):
     """Grow-only scratch buffer, one per (device, stream) that uses the owner: two streams driving the same
     module never share scratch (the C ABI is re-entrant only with distinct workspaces).  The pointer of a
-    (device, stream) stays stable once large enough: graph-safe."""
+    (device, stream) stays stable once large enough: graph-safe.
+
+    The loss and Detect ops keep a little state in their workspace and hand it back clean after every call
+    (SSDBOX_LOSS_WS_CLEAN / SSDBOX_DETECT_WS_CLEAN in include/ssdbox.h).  acquire() / commit() track that: acquire
+    reports `clean` when the last COMPLETED call on this buffer carried the same tag (op + shape); the caller
+    then sets the flag and the library skips its init launch."""
 
     def __init__(self):
         self.bufs = {}
+        self.tags = {}
+        self._pending = None
+
+    def _key(self, device):
+        return (device, torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0)
 
     def get(self, nbytes, device):
+        ptr, n, _ = self.acquire(nbytes, device, None)
+        return ptr, n
+
+    def acquire(self, nbytes, device, tag):
         nbytes = int(nbytes)
-        key = (device, torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0)
+        key = self._key(device)
         buf = self.bufs.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
             self.bufs[key] = buf
-        return C.c_void_p(buf.data_ptr()), buf.numel()
+            self.tags[key] = None
+        clean = tag is not None and self.tags.get(key) == tag
+        self.tags[key] = None                 # unknown until the call has been enqueued without an error
+        self._pending = (key, tag)
+        return C.c_void_p(buf.data_ptr()), buf.numel(), clean
+
+    def commit(self):
+        if self._pending is not None:
+            key, tag = self._pending
+            self.tags[key] = tag
+            self._pending = None
 
     @property
     def buf(self):

@@ -43,15 +43,18 @@ class DetectOut(object):
         if out is None:
             out = torch.empty(num, self.num_classes, self.top_k, 5, dtype=torch.float32, device=dev)
         counts = torch.empty(num, self.num_classes, dtype=torch.int32, device=dev)
+        ws, n, clean = self._ws.acquire(_abi.workspace_bytes(_abi.OP_DETECT, num, P, self.num_classes, 0, self.top_k), dev,
+                                        ("detect", num, P, self.num_classes, int(self.top_k)))
         cfg = _abi.DetectCfg(num, P, self.num_classes, int(self.top_k), float(self.conf_thresh),
                              float(self.nms_thresh), float(self.variance[0]), float(self.variance[1]),
-                             4 * P if per_image else 0, _abi.DETECT_LOGITS if self.conf_is_logits else 0, 0)
-        ws, n = self._ws.get(_abi.workspace_bytes(_abi.OP_DETECT, num, P, self.num_classes, 0, self.top_k), dev)
+                             4 * P if per_image else 0,
+                             (_abi.DETECT_LOGITS if self.conf_is_logits else 0) | (_abi.DETECT_WS_CLEAN if clean else 0), 0)
         keep = score_keep.to(dev).to(torch.uint8).contiguous() if score_keep is not None else None
         _abi.check(_abi.lib().ssdbox_detect(
             C.byref(cfg), _abi.ptr(loc, torch.float32, "loc_data"), _abi.ptr(scores, torch.float32, "conf_data"),
             _abi.ptr(pri, torch.float32, "prior_data"), _abi.ptr(keep, torch.uint8, "score_keep", True),
             _abi.ptr(out, torch.float32, "out"), _abi.ptr(counts), ws, n, _abi.stream_ptr(dev)))
+        self._ws.commit()
         self.last_counts = counts
         return out
 

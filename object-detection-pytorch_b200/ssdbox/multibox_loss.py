@@ -89,10 +89,18 @@ def loss_forward_raw(state, loc, conf, priors, gt, offsets, gmax, num_classes, t
         raise ValueError("ssdbox: per-image priors have batch %d, loc_data has %d" % (priors.size(0), B))
     if priors.size(-2) != P or priors.size(-1) != 4:
         raise ValueError("ssdbox: priors must be [%d,4] or [%d,%d,4], got %s" % (P, B, P, tuple(priors.shape)))
-    cfg = _abi.LossCfg(B, P, int(num_classes), int(gmax), float(threshold), int(negpos_ratio),
+    # gmax is an upper bound of the truths per image: rounded up to a power of two (>= 8) the workspace layout --
+    # and with it the "clean" state the previous call left behind -- stays the same from batch to batch
+    gmax = int(gmax)
+    gq = 8
+    while gq < gmax:
+        gq *= 2
+    gmax = gq if gmax > 0 else 0
+    ws, n, clean = state.ws.acquire(_abi.workspace_bytes(_abi.OP_LOSS_FWD, B, P, num_classes, gmax), dev,
+                                    ("loss", B, P, int(num_classes), gmax))
+    cfg = _abi.LossCfg(B, P, int(num_classes), gmax, float(threshold), int(negpos_ratio),
                        float(variance[0]), float(variance[1]), 1 if binarize else 0, 1 if finalize else 0,
-                       4 * P if per_image else 0, int(flags), 0)
-    ws, n = state.ws.get(_abi.workspace_bytes(_abi.OP_LOSS_FWD, B, P, num_classes, gmax), dev)
+                       4 * P if per_image else 0, int(flags) | (_abi.LOSS_WS_CLEAN if clean else 0), 0)
     dbg = debug or {}
     _abi.check(_abi.lib().ssdbox_multibox_loss_fwd_peers(
         C.byref(cfg), _abi.ptr(loc, torch.float32, "loc_data"), _abi.ptr(conf, torch.float32, "conf_data"),
@@ -103,6 +111,7 @@ def loss_forward_raw(state, loc, conf, priors, gt, offsets, gmax, num_classes, t
         _abi.ptr(dbg.get("loc_t"), torch.float32, "loc_t", True), _abi.ptr(dbg.get("neg"), torch.uint8, "neg", True),
         _abi.ptr(dbg.get("keys"), torch.float32, "keys", True),
         C.byref(peers) if peers is not None else None, ws, n, _abi.stream_ptr(dev)))
+    state.ws.commit()
     return cfg, sums, losses, sel, tidx
 
 

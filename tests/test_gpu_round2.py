@@ -313,3 +313,58 @@ def test_one_module_two_streams(dev):
         torch.cuda.synchronize()
         for (o, l), (wo, wl) in zip(got, want):
             assert torch.equal(o, wo) and torch.equal(l, wl)
+
+
+# ------------------------------------------------------------------------------------------------
+# self-cleaning workspaces (SSDBOX_LOSS_WS_CLEAN / SSDBOX_DETECT_WS_CLEAN): from the second call on a module
+# skips its init launch; every call must therefore leave the state exactly as the init kernel would
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flags", [0, 1, 2, 4, 3])       # fused / separate matching, generic mining, no cluster
+def test_loss_workspace_clean_after_every_call(dev, flags):
+    from ssdbox import _abi
+    name, B = "ssd300_voc", 5
+    pri = U.oracle_priors(name).to(dev)
+    C = 21
+    reused = ssdbox.MultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False)
+    reused.abi_flags = flags
+    for it, (seed, gtm) in enumerate([(1, 16), (2, 16), (3, 9), (4, 16), (5, 150), (6, 16)]):
+        tg = synth.gen_targets(B, C, gtm, seed, gt_min=max(1, gtm // 2))
+        if it == 3:
+            tg[1] = torch.zeros(0, 5)                      # an image without truths
+            tg[2] = torch.cat([tg[2], tg[2][:1]], 0)       # duplicate truth (shared best prior)
+        loc = synth.gen_loc(B, 8732, seed).to(dev)
+        conf = synth.gen_train_logits(B, 8732, C, seed).to(dev)
+        fresh = ssdbox.MultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False)
+        fresh.abi_flags = flags
+        want = fresh.intermediates((loc, conf, pri), _gpu_targets(tg, dev))
+        got = reused.intermediates((loc, conf, pri), _gpu_targets(tg, dev))
+        for k in ("conf_t", "neg", "sel", "tidx", "keys", "sums", "loc_t"):
+            assert torch.equal(want[k], got[k]), (it, k)
+    tags = [t for t in reused._state.ws.tags.values() if t is not None]
+    assert tags and tags[0][0] == "loss"
+
+
+def test_detect_workspace_clean_after_every_call(dev):
+    name = "ssd300_voc"
+    pri = U.oracle_priors(name).to(dev)
+    P, C, B = 8732, 21, 2
+    reused = ssdbox.DetectOut(C, 0, 200, 0.01, 0.45, VAR)
+    reused_lg = ssdbox.DetectOut(C, 0, 200, 0.01, 0.45, VAR, conf_is_logits=True)
+    g = torch.Generator().manual_seed(5)
+    for it, bias in enumerate([10.0, 1.0, 10.0, 6.0, 1.0, 9.0, 10.0]):     # sparse, dense (overflow), sparse, CTA-wide lists, ...
+        logits = torch.randn(B, P, C, generator=g)
+        logits[..., 0] += bias
+        if it == 3:
+            logits[..., 5] += 5.0                         # one class overflows while the others stay sparse
+        sc = torch.softmax(logits, -1).to(dev)
+        loc = synth.gen_loc(B, P, it).to(dev)
+        want = ssdbox.DetectOut(C, 0, 200, 0.01, 0.45, VAR)(loc, sc, pri)
+        got = reused(loc, sc, pri)
+        assert torch.equal(want, got), it
+        want = ssdbox.DetectOut(C, 0, 200, 0.01, 0.45, VAR, conf_is_logits=True)(loc, logits.to(dev), pri)
+        got = reused_lg(loc, logits.to(dev), pri)
+        assert torch.equal(want, got), ("logits", it)
+    # the counters really are zero after a call (what SSDBOX_DETECT_WS_CLEAN promises)
+    torch.cuda.synchronize()
+    ws = reused._ws.buf
+    assert int(ws[:(B * C + 4) * 4].view(torch.int32).abs().sum()) == 0
