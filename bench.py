@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--loss-flags", type=int, default=0, help="experiments: ssdbox_loss_cfg.flags (1 = matching as its own kernel)")
     ap.add_argument("--no-voc-eval", action="store_true", help="skip the VOC evaluation side phase")
     ap.add_argument("--dense", action="store_true", help="detect scores with background bias 4 (worst case)")
+    ap.add_argument("--only", default="", choices=["", "T", "D"], help="experiments: time only the loss half (T) or the Detect half (D) of the step")
     ap.add_argument("--no-side-phases", action="store_true", help="skip backward / fused softmax / eval post / head layout / VOC eval / dense phases")
     return ap.parse_args()
 
@@ -458,11 +459,15 @@ def main():
                 out = rdet.forward(arm_loc, arm_conf, loc, sc, priors, out=det_out)
             return al + ol, ac + oc, out
     else:
+        zero = torch.zeros((), device=dev)
+
         def step():
             # T, then D, then the (multi-GPU) wait for the other ranks' loss sums: D overlaps that wait
             with torch.no_grad():
+                if args.only == "D":
+                    return zero, zero, det.forward(loc, sc, priors, out=det_out)
                 pending = crit.forward_packed_deferred(loc, conf, priors, gt, offs, gmax)
-                out = det.forward(loc, sc, priors, out=det_out)
+                out = det.forward(loc, sc, priors, out=det_out) if args.only != "T" else det_out
                 ll, lc = pending.wait()
             return ll, lc, out
 
@@ -831,7 +836,7 @@ def main():
                        "ARM MultiBoxLoss (C=2) + ODM RefineMultiBoxLoss (refined anchors, negative-anchor filtering) fwd + "
                        "RefineDetectOut(top_k=200, conf 0.01, nms 0.45, theta 0.01)" if refine else
                        "match+MultiBoxLoss fwd + DetectOut(top_k=200, conf 0.01, nms 0.45)"),
-                   "global_batch": n_gpus * B, "detect_scores": "dense (bkg bias 4)" if args.dense else "sparse/realistic (bkg bias 10)",
+                   "only": args.only or None, "global_batch": n_gpus * B, "detect_scores": "dense (bkg bias 4)" if args.dense else "sparse/realistic (bkg bias 10)",
                    "l2": "inputs larger than L2 (conf and scores are %.0f MB each vs 126 MB L2)" % (conf.numel() * 4 / 1e6),
                    "launch": "CUDA graph replay" if graph is not None else "eager launches",
                    "parallelism": ("images sharded by rank; {sum_l, sum_c, N_pos} reduced per step: %s" % (

@@ -94,7 +94,11 @@ struct StreamArgs {
 };
 
 // log-sum-exp of one row with the row maximum (box_utils.py:273 uses one global maximum; same value
-// up to fp32 rounding).  4 independent accumulators; ex2.approx on (x - m) * log2(e).
+// up to fp32 rounding).  Compile-time class counts: the row sits in registers, the maximum is a tree of
+// three-input max (FMNMX3) and the exponentials are fed / summed two at a time with packed fp32x2 FMA / ADD
+// (FFMA2 / FADD2) on four independent accumulator pairs: ~300 issue slots per row of 81 classes instead of
+// ~430 with scalar instructions (the consumer warps share their SM sub-partitions with the match warps).
+// ex2.approx on (x - m) * log2(e).
 template <int CT>
 __device__ __forceinline__ float row_lse(const float* __restrict__ rp, int C) {
   float m, s;
@@ -104,13 +108,23 @@ __device__ __forceinline__ float row_lse(const float* __restrict__ rp, int C) {
     for (int c = 0; c < CT; ++c) v[c] = rp[c];
     float m4[4] = {v[0], v[0], v[0], v[0]};
 #pragma unroll
-    for (int c = 1; c < CT; ++c) m4[c & 3] = fmaxf(m4[c & 3], v[c]);
-    m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-    float nml = -m * kLog2e;
-    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 1; c + 1 < CT; c += 2) m4[(c >> 1) & 3] = fmax3(m4[(c >> 1) & 3], v[c], v[c + 1]);
+    if ((CT & 1) == 0) m4[0] = fmaxf(m4[0], v[CT - 1]);          // elements 1 .. CT-1: an odd count leaves one over
+    m = fmax3(m4[0], m4[1], fmaxf(m4[2], m4[3]));
+    const float nml = -m * kLog2e;
+    const unsigned long long l2 = pack_f32x2(kLog2e, kLog2e), n2 = pack_f32x2(nml, nml);
+    unsigned long long s2[4] = {0ull, 0ull, 0ull, 0ull};         // four pairs of +0.0f
 #pragma unroll
-    for (int c = 0; c < CT; ++c) s4[c & 3] += ex2_approx(fmaf(v[c], kLog2e, nml));
-    s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    for (int c = 0; c + 1 < CT; c += 2) {
+      float a, b;
+      unpack_f32x2(fma_f32x2(pack_f32x2(v[c], v[c + 1]), l2, n2), a, b);
+      s2[(c >> 1) & 3] = add_f32x2(s2[(c >> 1) & 3], pack_f32x2(ex2_approx(a), ex2_approx(b)));
+    }
+    float a0, b0, a1, b1;
+    unpack_f32x2(add_f32x2(add_f32x2(s2[0], s2[1]), add_f32x2(s2[2], s2[3])), a0, b0);
+    s = a0 + b0;
+    if (CT & 1) s += ex2_approx(fmaf(v[CT - 1], kLog2e, nml));
+    (void)a1; (void)b1;
   } else {
     m = rp[0];
     for (int c = 1; c < C; ++c) m = fmaxf(m, rp[c]);
@@ -403,7 +417,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) loss_stream_kernel(StreamAr
         a.key0[row] = k0;
         if (!a.pool || a.pool[row]) {
           uint32_t b = (uint32_t)row / (uint32_t)a.P;
-          atomicAdd(&a.hist[(size_t)b * kHistBins + (f2ord(k0) >> 21)], 1u);
+          atomicAdd(&a.hist[(size_t)b * kHistBins + mine_bin(f2ord(k0))], 1u);
         }
       }
     }
@@ -711,13 +725,10 @@ __device__ __forceinline__ uint32_t mine_visit(const MineArgs& a, size_t i, int 
   if (!inpool) return 0u;
   if (lb > 0) {
     ++npos;
-    // CE of a positive = lse - x[target] (multibox_loss.py:94,110); it leaves its streamed bin
-    // and ranks as 0 (multibox_loss.py:97)
+    // CE of a positive = lse - x[target] (multibox_loss.py:94,110); it ranks as 0 (multibox_loss.py:97)
     float cep = a.lse[i] - a.conf[i * (size_t)a.C + lb];
     if (a.dbg_keys) a.dbg_keys[i] = cep;
     ce += (double)cep;
-    atomicSub(&a.hist[(size_t)b * kHistBins + (f2ord(key) >> 21)], 1u);
-    atomicAdd(&a.hist[(size_t)b * kHistBins + (f2ord(0.0f) >> 21)], 1u);
     const float* row = a.gt + (size_t)(g0 + a.tidx[i]) * 5;
     Box m;
     m.x1 = row[0]; m.y1 = row[1]; m.x2 = row[2]; m.y2 = row[3];
@@ -837,7 +848,9 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
   if (kk > P - 1) kk = P - 1;
   const int K = (int)kk;
   uint32_t Tu = 0xffffffffu;
-  if (K > 0) Tu = cta_select_threshold<false, VEC>(uk, P, K, a.hist + (size_t)b * kHistBins, s_hist, s_iscr, s_res);
+  // (the generic kernel builds its own radix histograms; the streamed one -- fine bins, see mine_bin -- is only
+  // handed back clean below)
+  if (K > 0) Tu = cta_select_threshold<false, VEC>(uk, P, K, nullptr, s_hist, s_iscr, s_res);
   __syncthreads();
   for (int i = tid; i < kHistBins; i += kMineThreads) a.hist[(size_t)b * kHistBins + i] = 0u;     // state handed back clean
   PHASE_MARK(3);
@@ -907,6 +920,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
 // ------------------------------------------------------------------------------------------------
 constexpr int kMineQ = 6;
 constexpr int kForceListMax = 128;
+constexpr int kRankCap = 1024;      // members of the threshold bin ranked by counting (more: radix fallback)
 
 __device__ __forceinline__ int reg_find(const uint32_t* s_hist, int nbins, int K, int* s_iscr, int* s_res, int* above) {
   find_digit(s_hist, nbins, K, s_iscr, s_res);
@@ -926,6 +940,9 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   float* s_gt = reinterpret_cast<float*>(s_best + 2 * kForceListMax);               // kForceListMax x 5 (+3 pad)
   uint32_t* s_list = reinterpret_cast<uint32_t*>(s_gt + 5 * kForceListMax + 8);     // P / CL + 4: prior | class << 16
   int16_t* s_ovr = reinterpret_cast<int16_t*>(s_list + ((a.P >> 2) + CL - 1) / CL * 4 + 4);   // forced label of a prior of this CTA, -1 = none
+  __shared__ __align__(8) unsigned long long s_cand[kRankCap];      // members of the bin that holds the K-th key
+  __shared__ unsigned long long s_x[1];
+  __shared__ uint32_t s_ncand[1];
   __shared__ int s_last;
   __shared__ uint32_t s_xch[4];      // [0..1] positives per CTA of the cluster, [2..3] tie counts
 
@@ -1074,11 +1091,11 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
         u = uk[j][e];
         if (lb[e] > 0) {
           ++mypos;
-          atomicSub(&s_hist[u >> 21], 1u);
-          atomicAdd(&s_hist[zero_ord >> 21], 1u);
+          atomicSub(&s_hist[mine_bin(u)], 1u);
+          atomicAdd(&s_hist[0], 1u);                       // mine_bin(zero_ord) == 0
           if (CL > 1) {
-            peer_red_add(rhist + (u >> 21) * 4u, 0xffffffffu);
-            peer_red_add(rhist + (zero_ord >> 21) * 4u, 1u);
+            peer_red_add(rhist + mine_bin(u) * 4u, 0xffffffffu);
+            peer_red_add(rhist, 1u);
           }
           u = zero_ord;
         }
@@ -1136,20 +1153,51 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   if (kk64 > P - 1) kk64 = P - 1;
   const int K = (int)kk64;
 
-  // (4) radix select of the K-th largest ordered key, 11 + 11 + 10 bits, keys in registers
-  uint32_t Tu = 0xffffffffu;
+  // (4) the K-th largest ranked key.  X = (ordered key << 32 | ~prior) of the last selected element in the order
+  // "key descending, prior ascending" (a stable descending sort, multibox_loss.py:99-103): an element is selected
+  // iff its own packed value is >= X.  The streamed histogram has fine bins (mine_bin): the bin of the K-th key
+  // usually has a handful of members, which are gathered into a shared list (both CTAs of a cluster push to both
+  // lists) and ranked by counting -- two barriers instead of two more radix levels.  A crowded bin (tied keys)
+  // falls back to the exact 11 + 11 + 10 bit radix select on the registers.
+  unsigned long long X = ~0ull;
   if (K > 0) {
     int above;
-    int d1 = reg_find(s_hist, kHistBins, K, s_iscr, s_res, &above);
+    const int d1 = reg_find(s_hist, kHistBins, K, s_iscr, s_res, &above);
     if (d1 < 0) {
-      Tu = 1u;      // fewer than K ranked elements: take them all
+      X = 1ull << 32;      // fewer than K ranked elements: take them all (ranked keys are >= 1)
     } else {
-      int K2 = K - above;
-      int n1 = (int)s_hist[d1];
+      const int need = K - above;              // 1 <= need <= n1
+      const int n1 = (int)s_hist[d1];
       __syncthreads();
-      if (K2 == n1) {
-        Tu = ((uint32_t)d1 << 21) ? ((uint32_t)d1 << 21) : 1u;
+      if (n1 <= kRankCap) {
+        if (tid == 0) *s_ncand = 0u;
+        sync_all();
+        const uint32_t rcnt = CL > 1 ? peer_smem(s_ncand, (uint32_t)(rank ^ 1)) : 0u;
+        const uint32_t rcand = CL > 1 ? peer_smem(s_cand, (uint32_t)(rank ^ 1)) : 0u;
+#pragma unroll
+        for (int j = 0; j < Q; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t u = uk[j][e];
+            if (u && (int)mine_bin(u) == d1) {
+              const uint32_t p = (uint32_t)((q0 + tid + j * kMineThreads) * 4 + e);
+              const unsigned long long v = ((unsigned long long)u << 32) | (unsigned long long)(uint32_t)(~p);
+              s_cand[atomicAdd(s_ncand, 1u)] = v;
+              if (CL > 1) peer_st_u64(rcand + peer_atom_add(rcnt, 1u) * 8u, v);
+            }
+          }
+        sync_all();
+        for (int t = tid; t < n1; t += kMineThreads) {     // distinct values: exactly one has `need - 1` larger ones
+          const unsigned long long x = s_cand[t];
+          int larger = 0;
+          for (int i = 0; i < n1; ++i) larger += s_cand[i] > x ? 1 : 0;
+          if (larger == need - 1) *s_x = x;
+        }
+        __syncthreads();
+        X = *s_x;
       } else {
+        // crowded bin: exact radix select, level 1 rebuilt from the registers (top 11 bits of the ordered key)
+        uint32_t Tu;
         s_hist[tid] = 0u;
         s_hist[1024 + tid] = 0u;
         sync_all();
@@ -1158,75 +1206,98 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             uint32_t u = uk[j][e];
-            if (u && (int)(u >> 21) == d1) {
-              atomicAdd(&s_hist[(u >> 10) & 2047u], 1u);
-              if (CL > 1) peer_red_add(rhist + ((u >> 10) & 2047u) * 4u, 1u);
+            if (u) {
+              atomicAdd(&s_hist[u >> 21], 1u);
+              if (CL > 1) peer_red_add(rhist + (u >> 21) * 4u, 1u);
             }
           }
         sync_all();
-        int d2 = reg_find(s_hist, 2048, K2, s_iscr, s_res, &above);
-        int K3 = K2 - above;
-        int n2 = (int)s_hist[d2];
+        const int r1 = reg_find(s_hist, kHistBins, K, s_iscr, s_res, &above);      // >= K ranked elements exist: r1 >= 0
+        int K2 = K - above;
+        int n1r = (int)s_hist[r1];
         __syncthreads();
-        const uint32_t pre2 = ((uint32_t)d1 << 11) | (uint32_t)d2;
-        if (K3 == n2) {
-          Tu = (pre2 << 10) ? (pre2 << 10) : 1u;
+        if (K2 == n1r) {
+          Tu = ((uint32_t)r1 << 21) ? ((uint32_t)r1 << 21) : 1u;
         } else {
           s_hist[tid] = 0u;
+          s_hist[1024 + tid] = 0u;
           sync_all();
 #pragma unroll
           for (int j = 0; j < Q; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               uint32_t u = uk[j][e];
-              if (u && (u >> 10) == pre2) {
-                atomicAdd(&s_hist[u & 1023u], 1u);
-                if (CL > 1) peer_red_add(rhist + (u & 1023u) * 4u, 1u);
+              if (u && (int)(u >> 21) == r1) {
+                atomicAdd(&s_hist[(u >> 10) & 2047u], 1u);
+                if (CL > 1) peer_red_add(rhist + ((u >> 10) & 2047u) * 4u, 1u);
               }
             }
           sync_all();
-          int d3 = reg_find(s_hist, 1024, K3, s_iscr, s_res, &above);
-          int need = K3 - above;
-          int n3 = (int)s_hist[d3];
+          int d2 = reg_find(s_hist, 2048, K2, s_iscr, s_res, &above);
+          int K3 = K2 - above;
+          int n2 = (int)s_hist[d2];
           __syncthreads();
-          Tu = (pre2 << 10) | (uint32_t)d3;
-          if (need != n3) {
-            // ties straddle the cut: equal keys win in ascending prior order (stable descending sort)
-            int running = 0;
-            if (CL > 1) {         // the lower half of the priors (CTA 0) ranks first
-              int mine_ties = 0;
+          const uint32_t pre2 = ((uint32_t)r1 << 11) | (uint32_t)d2;
+          if (K3 == n2) {
+            Tu = (pre2 << 10) ? (pre2 << 10) : 1u;
+          } else {
+            s_hist[tid] = 0u;
+            sync_all();
 #pragma unroll
-              for (int j = 0; j < Q; ++j)
+            for (int j = 0; j < Q; ++j)
 #pragma unroll
-                for (int e = 0; e < 4; ++e) mine_ties += uk[j][e] == Tu ? 1 : 0;
-              int total_ties;
-              block_exclusive_scan(mine_ties, s_iscr, &total_ties);
-              if (tid == 0) {
-                s_xch[2 + rank] = (uint32_t)total_ties;
-                peer_st_u32(peer_smem(&s_xch[2 + rank], (uint32_t)(rank ^ 1)), (uint32_t)total_ties);
-              }
-              cluster_sync_all();
-              running = rank == 0 ? 0 : (int)s_xch[2];
-            }
-#pragma unroll
-            for (int j = 0; j < Q; ++j) {
-              int cnt = 0;
-#pragma unroll
-              for (int e = 0; e < 4; ++e) cnt += uk[j][e] == Tu ? 1 : 0;
-              int total;
-              int ex = block_exclusive_scan(cnt, s_iscr, &total);
-              int rank = running + ex;
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (uk[j][e] == Tu) {
-                  if (rank >= need) uk[j][e] = Tu - 1u;
-                  ++rank;
+              for (int e = 0; e < 4; ++e) {
+                uint32_t u = uk[j][e];
+                if (u && (u >> 10) == pre2) {
+                  atomicAdd(&s_hist[u & 1023u], 1u);
+                  if (CL > 1) peer_red_add(rhist + (u & 1023u) * 4u, 1u);
                 }
-              running += total;
-              __syncthreads();
+              }
+            sync_all();
+            int d3 = reg_find(s_hist, 1024, K3, s_iscr, s_res, &above);
+            int need3 = K3 - above;
+            int n3 = (int)s_hist[d3];
+            __syncthreads();
+            Tu = (pre2 << 10) | (uint32_t)d3;
+            if (need3 != n3) {
+              // ties straddle the cut: equal keys win in ascending prior order (stable descending sort)
+              int running = 0;
+              if (CL > 1) {         // the lower half of the priors (CTA 0) ranks first
+                int mine_ties = 0;
+#pragma unroll
+                for (int j = 0; j < Q; ++j)
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) mine_ties += uk[j][e] == Tu ? 1 : 0;
+                int total_ties;
+                block_exclusive_scan(mine_ties, s_iscr, &total_ties);
+                if (tid == 0) {
+                  s_xch[2 + rank] = (uint32_t)total_ties;
+                  peer_st_u32(peer_smem(&s_xch[2 + rank], (uint32_t)(rank ^ 1)), (uint32_t)total_ties);
+                }
+                cluster_sync_all();
+                running = rank == 0 ? 0 : (int)s_xch[2];
+              }
+#pragma unroll
+              for (int j = 0; j < Q; ++j) {
+                int cnt = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) cnt += uk[j][e] == Tu ? 1 : 0;
+                int total;
+                int ex = block_exclusive_scan(cnt, s_iscr, &total);
+                int rk = running + ex;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (uk[j][e] == Tu) {
+                    if (rk >= need3) uk[j][e] = Tu - 1u;
+                    ++rk;
+                  }
+                running += total;
+                __syncthreads();
+              }
             }
           }
         }
+        X = (unsigned long long)Tu << 32;      // tie losers were demoted below Tu: selected <=> key >= Tu
       }
     }
   }
@@ -1265,7 +1336,8 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
       const uint32_t u = uk[j][e];
       const bool inpool = u != 0u;
       const bool is_pos = inpool && lb[e] > 0;
-      const bool negsel = K > 0 && inpool && u >= Tu;
+      const uint32_t pidx = (uint32_t)(q * 4 + e);
+      const bool negsel = K > 0 && inpool && (((unsigned long long)u << 32) | (unsigned long long)(uint32_t)(~pidx)) >= X;
       if (negsel && !is_pos) ce_neg += (double)ord2f(u);
       so[e] = is_pos ? (int16_t)lb[e] : (negsel ? (int16_t)0 : (int16_t)-1);
       ng[e] = negsel ? 1 : 0;

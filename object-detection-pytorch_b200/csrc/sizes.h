@@ -8,7 +8,7 @@
 namespace ssdbox {
 
 constexpr int kGmaxLimit = 4096;       // truths per image (smem + int16 truth index)
-constexpr int kHistBins = 2048;        // level-1 mining histogram: top 11 bits of the ordered key
+constexpr int kHistBins = 2048;        // level-1 mining histogram: mine_bin() of the ordered key (128 bins per octave)
 constexpr int kTopKLimit = 1024;       // NMS sweep keeps one removed-word per lane
 constexpr int kClassLimit = 32766;     // labels travel as int16 (label + 1)
 
