@@ -63,6 +63,7 @@ def parse():
     ap.add_argument("--no-voc-eval", action="store_true", help="skip the VOC evaluation side phase")
     ap.add_argument("--dense", action="store_true", help="detect scores with background bias 4 (worst case)")
     ap.add_argument("--only", default="", choices=["", "T", "D"], help="experiments: time only the loss half (T) or the Detect half (D) of the step")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not pin the rank to the CPUs / memory next to its GPU")
     ap.add_argument("--no-side-phases", action="store_true", help="skip backward / fused softmax / eval post / head layout / VOC eval / dense phases")
     return ap.parse_args()
 
@@ -394,6 +395,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the box path has no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from ssdbox import dist as sdist
+    numa = sdist.bind_to_local_numa(local_rank) if (world > 1 and not args.no_numa_bind) else {"bound": False, "note": "single process: not bound"}
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -467,7 +470,8 @@ def main():
                 if args.only == "D":
                     return zero, zero, det.forward(loc, sc, priors, out=det_out)
                 pending = crit.forward_packed_deferred(loc, conf, priors, gt, offs, gmax)
-                out = det.forward(loc, sc, priors, out=det_out) if args.only != "T" else det_out
+                # N > 1: the wait for the other ranks' sums rides on the last Detect kernel (ssdbox_detect_peers)
+                out = det.forward(loc, sc, priors, out=det_out, pending=pending) if args.only != "T" else det_out
                 ll, lc = pending.wait()
             return ll, lc, out
 
@@ -652,7 +656,7 @@ def main():
     e2e = {"value": n_gpus * B / e2e_s, "unit": "images/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
            "rank_ms_per_step": [1e3 * x for x in e2e_rank_s],
-           "h2d_gbps_per_rank": [h2d / x / 1e9 for x in e2e_rank_s],
+           "h2d_gbps_per_rank": [h2d / x / 1e9 for x in e2e_rank_s], "numa": numa,
            "h2d_probe_gbps": {"one_rank_alone_this_rank": solo_gbps, "all_ranks_at_once": all_gbps,
                               "note": "bare pinned cudaMemcpyAsync of conf (%.0f MB): the PCIe / host-memory ceiling of the e2e number" % (conf_h.numel() * 4 / 1e6)},
            "api": ("ssdbox.RefineMultiBoxLoss.forward x2 + ssdbox.RefineDetectOut.__call__" if refine else
@@ -825,8 +829,7 @@ def main():
                                      else "the oracle port (oracle/ssd_oracle.py)", cores),
                         "train_fwd_images_per_s": reps * bt / tt, "detect_images_per_s": reps * bd / td}
 
-    # N > 1: + the collect kernel
-    launches_per_step = LAUNCHES["refine" if refine else "plain"] + (1 if n_gpus > 1 and not refine else 0)
+    launches_per_step = LAUNCHES["refine" if refine else "plain"]
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -840,7 +843,7 @@ def main():
                    "l2": "inputs larger than L2 (conf and scores are %.0f MB each vs 126 MB L2)" % (conf.numel() * 4 / 1e6),
                    "launch": "CUDA graph replay" if graph is not None else "eager launches",
                    "parallelism": ("images sharded by rank; {sum_l, sum_c, N_pos} reduced per step: %s" % (
-                       "posted over NVLink peer memory by the mining kernel, collected by a 1-warp kernel after DetectOut (no NCCL launch)" if crit.reduce_used == "p2p"
+                       "posted over NVLink peer memory by the mining kernel (six self-validating 8-byte words per peer, no fence), collected by one warp of the last Detect kernel (no NCCL launch, no extra kernel)" if crit.reduce_used == "p2p"
                        else "one NCCL all-reduce")) if n_gpus > 1 else "single GPU"},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps, "rank_ms_per_step": rank_ms, "clocks": clocks, "phases": phases, "sanity": sanity,

@@ -298,6 +298,14 @@ typedef struct {
 SSDBOX_API int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, const float* scores,
                   const float* priors, const uint8_t* score_keep, float* out, int32_t* counts, void* ws,
                   size_t ws_bytes, ssdbox_stream_t stream);
+/* ssdbox_detect that also completes a loss forward made with SSDBOX_LOSS_DEFER_PEER_WAIT on the same stream (what
+ * ssdbox_multibox_loss_peer_finish does, without a launch of its own): one warp of the last Detect kernel waits for
+ * every rank's sums and writes the global loss_sums[3] / losses[2] (nullable).  In a step "loss forward, then
+ * DetectOut" the Detect kernels run while the other ranks' sums arrive.  peers == NULL: plain ssdbox_detect. */
+SSDBOX_API int ssdbox_detect_peers(const ssdbox_detect_cfg* cfg, const float* loc, const float* scores,
+                  const float* priors, const uint8_t* score_keep, float* out, int32_t* counts,
+                  const ssdbox_peer_group* peers, double* loss_sums, float* losses, void* ws, size_t ws_bytes,
+                  ssdbox_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Eval post-processing right after DetectOut -- replaces

@@ -22,6 +22,7 @@
 // (top_k > 256: detect_overflow_kernel, one CTA per overflowed list, exact column select + NMS.)
 // Every kernel resets the counters of the lists it finishes: the workspace state is clean after the call.
 #include "ops.h"
+#include "peer.cuh"
 #include "ring.cuh"
 #include "select.cuh"
 #include "ssdbox_dev.cuh"
@@ -295,6 +296,8 @@ struct DetSegArgs {
   uint32_t* big_count; // [1] number of lists rewritten by the overflow select (<= cap candidates each)
   int32_t* big_list;   // [B*C]
   uint32_t* tail_ticket; // [1] CTAs of detect_segment_kernel that are done (the last one resets the bookkeeping)
+  int has_fin;           // ssdbox_detect_peers: block 0 of the last launch also completes a deferred loss reduction
+  PeerFinishArgs fin;
   uint32_t* scratch;   // [kOverflowSlots, P]
   const float* row_m;  // logits mode (nullptr otherwise): softmax row max / denominator from the stream pass
   const float* row_s;
@@ -465,6 +468,9 @@ constexpr int kSegThreads = 256;
 __global__ void __launch_bounds__(kSegThreads) detect_segment_kernel(DetSegArgs a) {
   extern __shared__ __align__(16) unsigned char smem_seg[];
   __shared__ int s_last;
+  // multi-GPU step: the wait for the other ranks' loss sums (posted by the mining kernel long before) rides on this
+  // launch instead of a kernel of its own (ssdbox_detect_peers)
+  if (a.has_fin && blockIdx.x == 0 && threadIdx.x < 32) peer_finish_warp(a.fin, threadIdx.x);
   if (*a.ovf_count == 0u) return;                     // written by detect_segments_kernel; nothing to do, nothing to clean
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_seg);
   NmsSmem ns = carve_nms(smem_seg + (size_t)a.cap * 8, a.top_k);
@@ -842,7 +848,19 @@ using namespace ssdbox;
 extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, const float* scores, const float* priors,
                              const uint8_t* score_keep, float* out, int32_t* counts, void* ws, size_t ws_bytes,
                              ssdbox_stream_t stream) {
+  return ssdbox_detect_peers(cfg, loc, scores, priors, score_keep, out, counts, nullptr, nullptr, nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" int ssdbox_detect_peers(const ssdbox_detect_cfg* cfg, const float* loc, const float* scores, const float* priors,
+                                   const uint8_t* score_keep, float* out, int32_t* counts, const ssdbox_peer_group* peers,
+                                   double* loss_sums, float* losses, void* ws, size_t ws_bytes, ssdbox_stream_t stream) {
   SSDBOX_REQUIRE(cfg, SSDBOX_EINVAL, "detect: null cfg");
+  if (peers) {
+    SSDBOX_REQUIRE(peers->world >= 1 && peers->world <= SSDBOX_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world && loss_sums,
+                   SSDBOX_EINVAL, "detect: bad peer group / null loss_sums");
+    if (cfg->B == 0)     // nothing to launch here: complete the reduction with the stand-alone kernel
+      return ssdbox_multibox_loss_peer_finish(peers, loss_sums, losses, stream);
+  }
   SSDBOX_REQUIRE(cfg->nms_thresh > 0.0f, SSDBOX_EINVAL, "nms_threshold must be non negative.");  // detection.py:19-20
   const int B = cfg->B, P = cfg->P, C = cfg->C, top_k = cfg->top_k;
   SSDBOX_REQUIRE(B >= 0 && P >= 0 && C >= 1, SSDBOX_EINVAL, "detect: negative size");
@@ -909,6 +927,15 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
   g.cnt = cnt; g.cand = cand; g.ovf_count = cnt + (size_t)B * C; g.ovf_list = ovf_list; g.big_count = cnt + (size_t)B * C + 1;
   g.tail_ticket = cnt + (size_t)B * C + 2; g.big_list = big_list; g.scratch = scratch; g.out = out; g.counts = counts;
   g.row_m = logits ? row_m : nullptr; g.row_s = logits ? row_s : nullptr;
+  if (peers) {
+    g.has_fin = 1;
+    g.fin.rank = peers->rank;
+    g.fin.world = peers->world;
+    g.fin.timeout_ns = peer_timeout_ns(peers);
+    for (int r = 0; r < peers->world; ++r) g.fin.bufs[r] = peers->bufs[r];
+    g.fin.sums = loss_sums;
+    g.fin.losses = losses;
+  }
   const size_t seg_smem = (size_t)cap * 8 + nms_smem_bytes(top_k);
   SSDBOX_CUDA(cudaFuncSetAttribute(detect_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem));
   SSDBOX_CARVE(detect_segments_kernel);

@@ -31,6 +31,7 @@
 #include <cstdlib>
 
 #include "ops.h"
+#include "peer.cuh"
 #include "ring.cuh"
 #include "select.cuh"
 #include "ssdbox_dev.cuh"
@@ -525,99 +526,6 @@ __device__ long long g_phase[16 * 64];
 #define PHASE_MARK(k) do { } while (0)
 #endif
 
-// ---- NVLink peer-memory reduction of {sum smooth-L1, sum CE, N} (see ssdbox_peer_group) ----------
-// Exchange buffer of a rank: [0] call epoch (u64, touched by the owner only), then at byte 64 two
-// banks (epoch parity) of `world` 32-byte slots { double s[3]; u64 epoch }.  Slot (parity, r) of
-// rank q's buffer is written by rank r only.  A rank can run at most one call ahead of a peer's
-// reads (it needs that peer's slot of the current call to finish), so two banks are enough.
-constexpr int kPeerHeaderBytes = 64;
-constexpr int kPeerSlotBytes = 32;
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// one warp: this rank's sums -> slot `me` of every rank's buffer (peer stores over NVLink; own buffer
-// for lane == me).  Returns the call epoch (advanced here, kept in the owner's buffer).
-__device__ unsigned long long peer_post(void* const* bufs, int me, int world, double v0, double v1, double v2, int lane) {
-  unsigned long long* mine = reinterpret_cast<unsigned long long*>(bufs[me]);
-  unsigned long long epoch = 0;
-  if (lane == 0) {
-    epoch = mine[0] + 1ull;
-    mine[0] = epoch;
-  }
-  epoch = __shfl_sync(SSDBOX_FULL_MASK, epoch, 0);
-  const size_t bank = kPeerHeaderBytes + (size_t)(epoch & 1ull) * world * kPeerSlotBytes;
-  if (lane < world) {
-    char* dst = static_cast<char*>(bufs[lane]) + bank + (size_t)me * kPeerSlotBytes;
-    volatile double* d = reinterpret_cast<volatile double*>(dst);
-    d[0] = v0;
-    d[1] = v1;
-    d[2] = v2;
-    st_release_sys(reinterpret_cast<unsigned long long*>(dst + 24), epoch);
-  }
-  return epoch;
-}
-
-// one warp: waits for every rank's slot of call `epoch` in MY buffer and adds them in rank order (the
-// same fp64 result on every rank); result valid in lane 0
-__device__ __forceinline__ unsigned long long wall_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
-// peers->wait_timeout_ms, 0 = default
-static inline long long peer_timeout_ns(const ssdbox_peer_group* peers) {
-  const long long ms = peers->wait_timeout_ms > 0 ? peers->wait_timeout_ms : 30000;
-  return ms * 1000000ll;
-}
-
-__device__ void peer_collect(void* const* bufs, int me, int world, unsigned long long epoch, int lane, double* out,
-                             long long timeout_ns) {
-  char* mine = static_cast<char*>(bufs[me]);
-  const size_t bank = kPeerHeaderBytes + (size_t)(epoch & 1ull) * world * kPeerSlotBytes;
-  double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-  bool arrived = true;
-  if (lane < world) {
-    const char* src = mine + bank + (size_t)lane * kPeerSlotBytes;
-    const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(src + 24);
-    const unsigned long long t0 = wall_ns();
-    unsigned spins = 0;
-    while (ld_acquire_sys(flag) != epoch) {
-      if ((++spins & 1023u) == 0 && wall_ns() - t0 > (unsigned long long)timeout_ns) {     // a peer never arrived
-        arrived = false;
-        break;
-      }
-    }
-    const volatile double* q = reinterpret_cast<const volatile double*>(src);
-    r0 = q[0];
-    r1 = q[1];
-    r2 = q[2];
-  }
-  // A missing peer does not kill the context: the sums of this call become NaN and the owner's buffer
-  // counts the event (header word 1, read by ssdbox_peer_status / PeerExchange.timeouts()).
-  const bool ok = __all_sync(SSDBOX_FULL_MASK, arrived);
-  double t0s = 0.0, t1s = 0.0, t2s = 0.0;
-  for (int r = 0; r < world; ++r) {
-    t0s += __shfl_sync(SSDBOX_FULL_MASK, r0, r);
-    t1s += __shfl_sync(SSDBOX_FULL_MASK, r1, r);
-    t2s += __shfl_sync(SSDBOX_FULL_MASK, r2, r);
-  }
-  if (!ok) {
-    t0s = t1s = t2s = __longlong_as_double(0x7ff8000000000000ll);
-    if (lane == 0) reinterpret_cast<unsigned long long*>(mine)[1] += 1ull;
-  }
-  out[0] = t0s;
-  out[1] = t1s;
-  out[2] = t2s;
-}
-
 // one warp; s[0..2] in shared memory holds this rank's sums on entry and (unless the wait is
 // deferred to ssdbox_multibox_loss_peer_finish) the global sums on exit
 __device__ void peer_exchange(const MineArgs& a, double* s, int lane) {
@@ -634,29 +542,7 @@ __device__ void peer_exchange(const MineArgs& a, double* s, int lane) {
   }
 }
 
-struct PeerFinishArgs {
-  int rank, world;
-  long long timeout_ns;
-  void* bufs[SSDBOX_MAX_PEERS];
-  double* sums;
-  float* losses;
-};
-
-__global__ void peer_finish_kernel(PeerFinishArgs a) {
-  const int lane = threadIdx.x & 31;
-  const unsigned long long epoch = *reinterpret_cast<const unsigned long long*>(a.bufs[a.rank]);   // posted by the forward
-  double g[3];
-  peer_collect(a.bufs, a.rank, a.world, epoch, lane, g, a.timeout_ns);
-  if (lane == 0) {
-    a.sums[0] = g[0];
-    a.sums[1] = g[1];
-    a.sums[2] = g[2];
-    if (a.losses) {
-      a.losses[0] = g[2] == 0.0 ? 0.0f : (float)(g[0] / g[2]);
-      a.losses[1] = g[2] == 0.0 ? 0.0f : (float)(g[1] / g[2]);
-    }
-  }
-}
+__global__ void peer_finish_kernel(PeerFinishArgs a) { peer_finish_warp(a, threadIdx.x & 31); }
 
 // a rank whose local shard is empty still takes part in the exchange: it posts {0, 0, 0} for this call
 // (and, unless the wait is deferred, collects and finalises) so that the epochs of all ranks stay in step

@@ -30,7 +30,7 @@ SYMBOLS = [
     "ssdbox_multibox_loss_fwd", "ssdbox_multibox_loss_fwd_peers", "ssdbox_multibox_loss_peer_finish",
     "ssdbox_peer_buffer_bytes",
     "ssdbox_multibox_loss_finalize", "ssdbox_multibox_loss_bwd",
-    "ssdbox_nms", "ssdbox_detect", "ssdbox_detections_compact", "ssdbox_heads_to_rows", "ssdbox_voc_eval", "ssdbox_crop_overlaps", "ssdbox_arm_filter", "ssdbox_timers_enable", "ssdbox_timers_read",
+    "ssdbox_nms", "ssdbox_detect", "ssdbox_detect_peers", "ssdbox_detections_compact", "ssdbox_heads_to_rows", "ssdbox_voc_eval", "ssdbox_crop_overlaps", "ssdbox_arm_filter", "ssdbox_timers_enable", "ssdbox_timers_read",
 ]
 
 KERNEL_NAMES = ["init", "match", "loss_stream", "mine_reduce", "loss_bwd", "detect_stream", "detect_segment",
@@ -128,6 +128,7 @@ def _declare(lib):
         "ssdbox_multibox_loss_bwd": [C.POINTER(LossCfg)] + [P_] * 11 + [P_],
         "ssdbox_nms": [P_, P_, i32, f32, i32, P_, P_, P_, sz, P_],
         "ssdbox_detect": [C.POINTER(DetectCfg), P_, P_, P_, P_, P_, P_, P_, sz, P_],
+        "ssdbox_detect_peers": [C.POINTER(DetectCfg), P_, P_, P_, P_, P_, P_, C.POINTER(PeerGroup), P_, P_, P_, sz, P_],
         "ssdbox_arm_filter": [P_, i64, f32, P_, P_],
         "ssdbox_detections_compact": [P_, i32, i32, i32, P_, P_, i32, P_, i64, P_, P_, P_, sz, P_],
         "ssdbox_heads_to_rows": [C.POINTER(HeadsCfg), P_, P_],

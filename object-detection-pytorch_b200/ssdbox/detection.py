@@ -26,7 +26,10 @@ class DetectOut(object):
         self._ws = _abi.Workspace()
         self.last_counts = None
 
-    def forward(self, loc_data, conf_data, prior_data, score_keep=None, out=None):
+    def forward(self, loc_data, conf_data, prior_data, score_keep=None, out=None, pending=None):
+        """`pending` (extension): a PendingLoss of MultiBoxLoss.forward_packed_deferred made on the same stream -- its
+        cross-rank wait rides on the last Detect kernel (ssdbox_detect_peers) instead of a launch of its own; call
+        pending.wait() afterwards as usual (it then only hands out the results)."""
         if not loc_data.is_cuda:
             raise RuntimeError("ssdbox: DetectOut runs on CUDA tensors only (no CPU path)")
         dev = loc_data.device
@@ -50,10 +53,20 @@ class DetectOut(object):
                              4 * P if per_image else 0,
                              (_abi.DETECT_LOGITS if self.conf_is_logits else 0) | (_abi.DETECT_WS_CLEAN if clean else 0), 0)
         keep = score_keep.to(dev).to(torch.uint8).contiguous() if score_keep is not None else None
-        _abi.check(_abi.lib().ssdbox_detect(
-            C.byref(cfg), _abi.ptr(loc, torch.float32, "loc_data"), _abi.ptr(scores, torch.float32, "conf_data"),
-            _abi.ptr(pri, torch.float32, "prior_data"), _abi.ptr(keep, torch.uint8, "score_keep", True),
-            _abi.ptr(out, torch.float32, "out"), _abi.ptr(counts), ws, n, _abi.stream_ptr(dev)))
+        fin = pending._detect_tail_args() if pending is not None else None
+        if fin is None:
+            _abi.check(_abi.lib().ssdbox_detect(
+                C.byref(cfg), _abi.ptr(loc, torch.float32, "loc_data"), _abi.ptr(scores, torch.float32, "conf_data"),
+                _abi.ptr(pri, torch.float32, "prior_data"), _abi.ptr(keep, torch.uint8, "score_keep", True),
+                _abi.ptr(out, torch.float32, "out"), _abi.ptr(counts), ws, n, _abi.stream_ptr(dev)))
+        else:
+            peers, sums, losses = fin
+            _abi.check(_abi.lib().ssdbox_detect_peers(
+                C.byref(cfg), _abi.ptr(loc, torch.float32, "loc_data"), _abi.ptr(scores, torch.float32, "conf_data"),
+                _abi.ptr(pri, torch.float32, "prior_data"), _abi.ptr(keep, torch.uint8, "score_keep", True),
+                _abi.ptr(out, torch.float32, "out"), _abi.ptr(counts), C.byref(peers), _abi.ptr(sums), _abi.ptr(losses),
+                ws, n, _abi.stream_ptr(dev)))
+            pending._completed_by_detect()
         self._ws.commit()
         self.last_counts = counts
         return out

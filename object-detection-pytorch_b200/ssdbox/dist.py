@@ -17,6 +17,47 @@ def shard_batch(loc, conf, targets, rank, world):
     return loc[b:e], conf[b:e], targets[b:e]
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        else:
+            cpus.add(int(part))
+    return cpus
+
+
+def bind_to_local_numa(device_index):
+    """Pins this process to the CPUs next to GPU `device_index` (its PCIe root complex's NUMA node), so that pinned
+    host buffers allocated afterwards are first-touched -- and therefore placed -- in the memory of that node.  With
+    one process per GPU this keeps every rank's host-to-device copies off the inter-socket link; without it all
+    ranks' staging buffers can end up on one node and share its memory controllers and one socket's PCIe uplinks.
+    Returns a dict describing what was done (for logs), never raises."""
+    import os
+    info = {"bound": False}
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        with open(base + "/numa_node") as f:
+            info["numa_node"] = int(f.read().strip())
+        with open(base + "/local_cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        cpus = cpus & allowed if cpus & allowed else set()
+        info["pci"] = bdf
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            info["bound"] = True
+        info["cpus"] = len(cpus) if cpus else len(allowed)
+    except Exception as e:          # no sysfs in the container, exotic topology, ...
+        info["error"] = repr(e)
+    return info
+
+
 def allreduce_loss_sums(sums, group=None):
     """sums: fp64 [3] = {sum smooth-L1, sum CE, N_pos} of the local shard -> global sums (in place)."""
     import torch.distributed as dist

@@ -173,8 +173,23 @@ class PendingLoss(object):
     def __init__(self, peers, sums, losses, ready, owner=None):
         self._peers, self._sums, self._losses, self._ready = peers, sums, losses, ready
         self._owner = owner
+        self._collected = False
+
+    def _detect_tail_args(self):
+        """(peer group, sums, losses) for ssdbox_detect_peers, or None when there is nothing left to collect."""
+        if self._ready is not None or self._collected:
+            return None
+        return self._peers, self._sums, self._losses
+
+    def _completed_by_detect(self):
+        self._collected = True
+        if self._owner is not None:
+            self._owner._pending_unwaited = False
 
     def wait(self):
+        if self._ready is None and self._collected:
+            out = self._losses.clone()
+            self._ready = (out[0], out[1])
         if self._ready is None:
             if self._owner is not None:
                 self._owner._pending_unwaited = False

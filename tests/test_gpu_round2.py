@@ -368,3 +368,45 @@ def test_detect_workspace_clean_after_every_call(dev):
     torch.cuda.synchronize()
     ws = reused._ws.buf
     assert int(ws[:(B * C + 4) * 4].view(torch.int32).abs().sum()) == 0
+
+
+def test_deferred_loss_completed_by_detect(dev):
+    """ssdbox_detect_peers: the cross-rank wait of a deferred loss forward rides on the last Detect kernel (world of
+    one rank here; tests/_mgpu_worker.py runs it across GPUs).  Same losses as the plain module, same detections,
+    over several steps (both slot banks) and under CUDA-graph replay."""
+    x = U.seeded_inputs("ssd300_voc", 4, 90)
+    loc, conf, pri, sc = x["loc"].to(dev), x["conf"].to(dev), x["priors"].to(dev), x["scores"].to(dev)
+    gt, offs, gmax = ssdbox.pack_targets(_gpu_targets(x["targets"], dev), dev)
+    plain = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False)
+    with torch.no_grad():
+        wl, wc = plain.forward_packed(loc, conf, pri, gt, offs, gmax)
+    det = ssdbox.DetectOut(x["C"], 0, 200, 0.01, 0.45, VAR)
+    want = det(loc, sc, pri).clone()
+    crit = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False)
+    crit.use_local_peer_exchange(dev)
+
+    def step():
+        with torch.no_grad():
+            pend = crit.forward_packed_deferred(loc, conf, pri, gt, offs, gmax)
+            out = det.forward(loc, sc, pri, pending=pend)
+            ll, lc = pend.wait()
+        return ll, lc, out
+    for it in range(3):
+        ll, lc, out = step()
+        assert float(ll) == float(wl) and float(lc) == float(wc), it
+        assert torch.equal(out, want)
+    assert int(crit._peers.buf[0]) == 3
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        step()
+        step()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        ll, lc, out = step()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert float(ll) == float(wl) and float(lc) == float(wc) and torch.equal(out, want)
+    assert int(crit._peers.buf[0]) == 9
