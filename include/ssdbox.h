@@ -193,9 +193,6 @@ typedef struct {
  * flag nothing is assumed about the workspace contents.  The host mirror (MultiBoxLoss) sets it from the second
  * call on. */
 #define SSDBOX_LOSS_WS_CLEAN 16
-/* ssdbox_multibox_loss_bwd only: use the TMA bulk-store variant of the one-pass backward kernel (tiles leave with
- * cp.async.bulk from shared memory) instead of the default plain-store variant; same results, for comparison. */
-#define SSDBOX_LOSS_BWD_TMA 32
 
 /* forward.
  *   loc [B,P,4], conf [B,P,C] raw logits, priors, anchors_xyxy (nullable), gt/gt_offsets

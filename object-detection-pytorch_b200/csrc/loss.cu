@@ -1592,149 +1592,6 @@ __global__ void __launch_bounds__(kBwdStreamWarps * 32, 1) loss_bwd_stream_kerne
   bulk_wait_all();          // the tile must outlive its last bulk store
 }
 
-// ---- backward, plain-store variant of the one-pass kernel ------------------------------------------------
-// Same tile logic as loss_bwd_stream_kernel (a warp owns a 32-row tile in shared memory that is all zeros except
-// for the gradient rows of the tile's selected priors; sel two tiles ahead, the selected logits rows one tile
-// ahead), but the tile leaves through the LSU: 16-byte streaming stores, straight from a zero register for the
-// ~60 % of the tiles without a selected row and from the shared tile otherwise.  Nothing is written twice and no
-// warp ever waits for a bulk-copy engine to drain its tile, so the kernel runs at the rate of a flat zero fill.
-constexpr int kBwdFillWarps = 4;
-
-template <int CT>
-__global__ void __launch_bounds__(kBwdFillWarps * 32) loss_bwd_fill_kernel(BwdArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_bwd[];
-  const int C = CT > 0 ? CT : a.C;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* tile = reinterpret_cast<float*>(smem_bwd) + (size_t)warp * 32 * C;
-  const long long rows = (long long)a.B * a.P;
-  const long long tiles = (rows + 31) / 32;
-  const long long nw = (long long)gridDim.x * kBwdFillWarps;
-  const double n = a.sums[2];
-  const float scale_l = n > 0.0 ? (float)((double)a.grad_out[0] / n) : 0.0f;
-  const float scale_c = n > 0.0 ? (float)((double)a.grad_out[1] / n) : 0.0f;
-  for (int i = lane; i < 32 * C; i += 32) tile[i] = 0.f;
-  __syncwarp();
-
-  auto load_sel = [&](long long t) -> int {
-    const long long r = t * 32 + lane;
-    return (t < tiles && r < rows) ? (int)a.sel[r] : -1;
-  };
-  struct Pre {
-    int lb;
-    int rl[4], tl[4];
-    float xv[4][4];
-    uint32_t rest;
-  };
-  auto load_rows = [&](long long t, Pre& p) {
-    const long long row0 = t * 32;
-    uint32_t m = __ballot_sync(SSDBOX_FULL_MASK, p.lb >= 0);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      p.rl[j] = -1;
-      if (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        p.rl[j] = src;
-        p.tl[j] = __shfl_sync(SSDBOX_FULL_MASK, p.lb, src);
-        const float* x = a.conf + (row0 + src) * C;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) p.xv[j][u] = lane + 32 * u < C ? x[lane + 32 * u] : -INFINITY;
-      }
-    }
-    p.rest = m;
-  };
-  auto put_row = [&](int rl, int tl, const float (&xv)[4]) {
-    float mx = fmaxf(fmaxf(xv[0], xv[1]), fmaxf(xv[2], xv[3]));
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(SSDBOX_FULL_MASK, mx, d));
-    float e[4], sum = 0.f;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      e[u] = lane + 32 * u < C ? expf(xv[u] - mx) : 0.f;
-      sum += e[u];
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(SSDBOX_FULL_MASK, sum, d);
-    const float inv = 1.0f / sum;
-    float* g = tile + (size_t)rl * C;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int c = lane + 32 * u;
-      if (c < C) g[c] = scale_c * (e[u] * inv - (c == tl ? 1.0f : 0.0f));
-    }
-  };
-
-  Pre cur, nxt;
-  long long t = (long long)blockIdx.x * kBwdFillWarps + warp;
-  cur.lb = load_sel(t);
-  nxt.lb = load_sel(t + nw);
-  load_rows(t, cur);
-  for (; t < tiles; t += nw) {
-    const long long row0 = t * 32;
-    const int nrows = (int)(rows - row0 < 32 ? rows - row0 : 32);
-    load_rows(t + nw, nxt);                       // read pipeline first, ahead of this iteration's stores
-    const int lb_nn = load_sel(t + 2 * nw);
-    const uint32_t selmask = __ballot_sync(SSDBOX_FULL_MASK, cur.lb >= 0);
-    float* dst = a.grad_conf + row0 * C;          // 16-byte aligned: row0 * C * 4 = t * 128 * C bytes
-    const int nfl = nrows * C, nchunk = nfl >> 2;
-    if (selmask == 0u) {
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int k = lane; k < nchunk; k += 32) __stcs(reinterpret_cast<float4*>(dst) + k, z);
-      for (int i = (nchunk << 2) + lane; i < nfl; i += 32) dst[i] = 0.f;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (cur.rl[j] >= 0) put_row(cur.rl[j], cur.tl[j], cur.xv[j]);
-      uint32_t m = cur.rest;                      // more than four selected rows in the tile
-      while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const int tl = __shfl_sync(SSDBOX_FULL_MASK, cur.lb, src);
-        const float* x = a.conf + (row0 + src) * C;
-        float xv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) xv[u] = lane + 32 * u < C ? x[lane + 32 * u] : -INFINITY;
-        put_row(src, tl, xv);
-      }
-      __syncwarp();
-      const float4* t4 = reinterpret_cast<const float4*>(tile);
-      for (int k = lane; k < nchunk; k += 32) __stcs(reinterpret_cast<float4*>(dst) + k, t4[k]);
-      for (int i = (nchunk << 2) + lane; i < nfl; i += 32) dst[i] = tile[i];
-      __syncwarp();
-      m = selmask;                                // the tile is all zeros again
-      while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        float* g = tile + (size_t)src * C;
-        for (int c = lane; c < C; c += 32) g[c] = 0.f;
-      }
-      __syncwarp();
-    }
-    // grad_loc of the tile: zeros, or smooth-L1' for positives
-    const long long row = row0 + lane;
-    if (row < rows) {
-      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (cur.lb > 0) {
-        const int b = (int)((uint32_t)row / (uint32_t)a.P);
-        const int pi = (int)((uint32_t)row - (uint32_t)b * (uint32_t)a.P);
-        const float4 l = *reinterpret_cast<const float4*>(a.loc + row * 4);
-        const float4 pr = *reinterpret_cast<const float4*>(a.priors + (size_t)b * (size_t)a.prior_stride + (size_t)pi * 4);
-        const float* tr = a.gt + (size_t)(a.gt_offsets[b] + a.tidx[row]) * 5;
-        Box mbox;
-        mbox.x1 = tr[0]; mbox.y1 = tr[1]; mbox.x2 = tr[2]; mbox.y2 = tr[3];
-        float4 tt = encode_box(mbox, pr, a.var0, a.var1);
-        g.x = scale_l * fminf(fmaxf(l.x - tt.x, -1.f), 1.f);     // smooth-L1': d for |d|<1, sign(d) otherwise
-        g.y = scale_l * fminf(fmaxf(l.y - tt.y, -1.f), 1.f);
-        g.z = scale_l * fminf(fmaxf(l.z - tt.z, -1.f), 1.f);
-        g.w = scale_l * fminf(fmaxf(l.w - tt.w, -1.f), 1.f);
-      }
-      __stcs(reinterpret_cast<float4*>(a.grad_loc + row * 4), g);
-    }
-    cur = nxt;
-    nxt.lb = lb_nn;
-  }
-}
-
 }  // namespace ssdbox
 
 using namespace ssdbox;
@@ -2016,21 +1873,7 @@ extern "C" int ssdbox_multibox_loss_bwd(const ssdbox_loss_cfg* cfg, const float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long rows = (long long)a.B * a.P;
   const size_t stream_smem = (size_t)kBwdStreamWarps * kBwdTileRows * a.C * 4;
-  const size_t fill_smem = (size_t)kBwdFillWarps * 32 * a.C * 4;
-  if (a.conf_aligned && a.C <= 128 && !(cfg->flags & SSDBOX_LOSS_BWD_TMA)) {
-    // plain-store one-pass kernel: as many CTAs as fit (4 warps x one 32-row tile each)
-    void (*kern)(BwdArgs) = a.C == 81 ? loss_bwd_fill_kernel<81> : (a.C == 21 ? loss_bwd_fill_kernel<21> : loss_bwd_fill_kernel<0>);
-    SSDBOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
-    int per_sm = 0;
-    SSDBOX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBwdFillWarps * 32, fill_smem));
-    if (per_sm < 1) per_sm = 1;
-    long long tiles = (rows + 31) / 32;
-    long long want = (tiles + kBwdFillWarps - 1) / kBwdFillWarps;
-    long long grid = (long long)dev.sm_count * per_sm;
-    if (grid > want) grid = want;
-    TimerScope ts__(KID_LOSS_BWD, st);
-    kern<<<(int)grid, kBwdFillWarps * 32, fill_smem, st>>>(a);
-  } else if (a.conf_aligned && a.C <= 128 && stream_smem <= (size_t)dev.max_smem_optin - 1024
+  if (a.conf_aligned && a.C <= 128 && stream_smem <= (size_t)dev.max_smem_optin - 1024
 #ifdef SSDBOX_EXPERIMENTS
       && !getenv("SSDBOX_BWD_TWO_PASS")
 #endif
