@@ -636,12 +636,22 @@ def main():
     probe = torch.empty_like(conf_h, device=dev)
     probe.copy_(conf_h, non_blocking=True)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    probe.copy_(conf_h, non_blocking=True)
-    torch.cuda.synchronize()
-    solo_gbps = conf_h.numel() * 4 / (time.perf_counter() - t0) / 1e9
+    solo_gbps = None
+    for r in range(world):                           # the ranks take turns: each copy has the host side to itself
+        if dist is not None:
+            dist.barrier()
+        if r == rank:
+            t0 = time.perf_counter()
+            probe.copy_(conf_h, non_blocking=True)
+            torch.cuda.synchronize()
+            solo_gbps = conf_h.numel() * 4 / (time.perf_counter() - t0) / 1e9
     all_gbps = None
+    solo_all = None
     if dist is not None:
+        t = torch.tensor([solo_gbps], dtype=torch.float64, device=dev)
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        solo_all = [float(x.item()) for x in allt]
         # ... and with every rank copying at once (what the host's memory / PCIe root complexes give N GPUs)
         dist.barrier()
         t0 = time.perf_counter()
@@ -657,7 +667,7 @@ def main():
            "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
            "rank_ms_per_step": [1e3 * x for x in e2e_rank_s],
            "h2d_gbps_per_rank": [h2d / x / 1e9 for x in e2e_rank_s], "numa": numa,
-           "h2d_probe_gbps": {"one_rank_alone_this_rank": solo_gbps, "all_ranks_at_once": all_gbps,
+           "h2d_probe_gbps": {"one_rank_alone_this_rank": solo_gbps, "one_rank_alone_every_rank": solo_all, "all_ranks_at_once": all_gbps,
                               "note": "bare pinned cudaMemcpyAsync of conf (%.0f MB): the PCIe / host-memory ceiling of the e2e number" % (conf_h.numel() * 4 / 1e6)},
            "api": ("ssdbox.RefineMultiBoxLoss.forward x2 + ssdbox.RefineDetectOut.__call__" if refine else
                    "ssdbox.MultiBoxLoss.forward + ssdbox.DetectOut.__call__") +
