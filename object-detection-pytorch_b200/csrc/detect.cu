@@ -320,7 +320,7 @@ struct DetSegArgs {
   uint32_t* big_count; // [1] number of lists rewritten by the overflow select (<= cap candidates each)
   int32_t* big_list;   // [B*C]
   uint32_t* tail_ticket; // [1] CTAs of detect_segment_kernel that are done (the last one resets the bookkeeping)
-  int has_fin;           // ssdbox_detect_peers: block 0 of the last launch also completes a deferred loss reduction
+  int has_fin;           // ssdbox_detect_peers: block 0 of detect_segments_kernel also completes a deferred loss reduction
   PeerFinishArgs fin;
   uint32_t* scratch;   // [kOverflowSlots, P]
   const float* row_m;  // logits mode (nullptr otherwise): softmax row max / denominator from the stream pass
@@ -393,6 +393,9 @@ __global__ void __launch_bounds__(kSmallThreads) detect_segments_kernel(DetSegAr
   __shared__ int s_q[kSmallSegs], s_qn[kSmallSegs], s_nq;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) s_nq = 0;
+  // multi-GPU step: the wait for the other ranks' loss sums (posted by the mining kernel a whole detect_stream
+  // ago) rides on this launch instead of a kernel of its own (ssdbox_detect_peers)
+  if (a.has_fin && blockIdx.x == 0 && threadIdx.x < 32) peer_finish_warp(a.fin, threadIdx.x);
   __syncthreads();
   const int seg = blockIdx.x * kSmallSegs + (threadIdx.x >> 5);
   if (seg < a.B * a.C) {
@@ -492,9 +495,6 @@ constexpr int kSegThreads = 256;
 __global__ void __launch_bounds__(kSegThreads) detect_segment_kernel(DetSegArgs a) {
   extern __shared__ __align__(16) unsigned char smem_seg[];
   __shared__ int s_last;
-  // multi-GPU step: the wait for the other ranks' loss sums (posted by the mining kernel long before) rides on this
-  // launch instead of a kernel of its own (ssdbox_detect_peers)
-  if (a.has_fin && blockIdx.x == 0 && threadIdx.x < 32) peer_finish_warp(a.fin, threadIdx.x);
   if (*a.ovf_count == 0u) return;                     // written by detect_segments_kernel; nothing to do, nothing to clean
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_seg);
   NmsSmem ns = carve_nms(smem_seg + (size_t)a.cap * 8, a.top_k);
@@ -577,24 +577,25 @@ __global__ void __launch_bounds__(kOvfThreads, 1) detect_overflow_kernel(DetSegA
 }
 
 // ------------------------------------------------------------------------------------------------
-// Dense scores: the top_k cut of box_utils.py:299-301 for lists that overflowed the candidate capacity, in ONE
-// pass over the scores.  Work item = (image, 8 consecutive classes): the 8 classes share the sectors of every
-// score row.  A group of 4 warps owns one class and keeps a running candidate list of (ordered score << 32 |
-// prior) keys in shared memory (2048 entries).  The CTA walks the image's rows 1024 at a time; every candidate at
-// or above the class's current admission score is appended; a list that passes 1024 entries is PRUNED by its
-// group to exactly its top_k largest keys (MSB radix select on the 64-bit keys -- distinct, because they carry the
-// prior -- then an in-place compaction), and the score of the top_k-th key becomes the new admission bound: a
-// streaming top-k.  Later priors with an equal score are still admitted (the reference visits equal scores
-// higher index first), so ties need no special path at all.  With dense random scores a class is pruned two or
-// three times per image.  The surviving <= top_k keys replace the class's list and are queued for
-// detect_segment_kernel (sort 256 keys, decode, NMS).
-// (Previous version: range-adaptive radix select with three to five passes over the scores, 604 us at
-// SSD512-COCO B=64 dense; the passes are DRAM-sector bound.)
+// Dense scores, chunked: one work item = (image, 8 consecutive classes).  The per-(image, class)
+// kernel above reads a strided score column per segment (24564 sectors for 24564 floats); here the 8
+// classes of a chunk share the sectors of every row, their radix-select histograms are built in the
+// same passes (8 x 2048 bins in shared memory, one warp per class finds the digit), and all
+// keys >= the class threshold are collected and sorted: the sort order (score desc, prior desc) IS
+// the reference's visiting order, so ties at the cut need no special handling as long as they fit the
+// 1024-entry list; a class whose ties do not fit (e.g. all scores equal) takes the column path.
 // ------------------------------------------------------------------------------------------------
 constexpr int kOvfClasses = 8;
-constexpr int kOvfGroup = kOvfThreads / kOvfClasses;      // 128 threads = 4 warps per class
-constexpr int kOvfListCap = 2048;                         // running list per class
-constexpr int kOvfPruneAt = 1024;                         // prune a list that holds more than this after a block of rows
+
+__device__ __forceinline__ float ovf_score(const DetSegArgs& a, size_t row, int c) {
+  float v = a.scores[row * a.C + c];
+  if (a.row_s) {           // logits: the same expression as the candidate pass
+    const float sden = a.row_s[row];
+    v = sden > 0.0f ? __fdiv_rn(expf(v - a.row_m[row]), sden) : 0.0f;
+  }
+  if (a.keep && !a.keep[row]) v = 0.0f;
+  return v;
+}
 
 // the scores of classes c0 .. c0+7 of one row: all loads issued together, row-wise state read once
 __device__ __forceinline__ void ovf_row_scores(const DetSegArgs& a, size_t row, int c0, float (&v)[kOvfClasses]) {
@@ -644,145 +645,169 @@ __device__ __forceinline__ void warp_find_digit(const uint32_t* hist, int nbins,
   *above_out = __shfl_sync(SSDBOX_FULL_MASK, above, src);
 }
 
-__device__ __forceinline__ void group_sync(int grp) {
-  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(kOvfGroup) : "memory");
-}
-
-// One group (4 warps): keeps exactly the K largest of the n distinct 64-bit keys (K < n <= kOvfListCap), compacted
-// to the front of `keys`.  MSB radix select, digits of 11 / 11 / 10 bits over the score and then over the prior
-// half; it stops at the first level whose bin holds exactly the keys still needed (normally the second or third).
-// Returns the K-th largest key.
-__device__ unsigned long long group_prune(unsigned long long* keys, int n, int K, uint32_t* hist, int* s_sel, int* s_scan,
-                                          int grp, int gt) {
-  const int lane = gt & 31, gw = gt >> 5;
-  unsigned long long prefix = 0ull, pmask = 0ull;
-  int need = K;
-  const int shifts[6] = {53, 42, 32, 21, 10, 0};
-  const int nbits[6] = {11, 11, 10, 11, 11, 10};
-  for (int level = 0; level < 6; ++level) {
-    const int shift = shifts[level], nb = 1 << nbits[level];
-    for (int i = gt; i < nb; i += kOvfGroup) hist[i] = 0u;
-    group_sync(grp);
-    for (int i = gt; i < n; i += kOvfGroup) {
-      const unsigned long long key = keys[i];
-      if ((key & pmask) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & (uint32_t)(nb - 1)], 1u);
+// the per-segment column path (any tie pattern): ordered scores -> scratch, exact select, collect
+__device__ void overflow_column_segment(const DetSegArgs& a, int b, int c, int seg, unsigned long long* keys,
+                                        uint32_t* s_hist, int* s_iscr, int* s_res, const NmsSmem& ns, uint32_t* uk) {
+  const int tid = threadIdx.x;
+  for (int p = tid; p < a.P; p += kOvfThreads) {
+    float v = ovf_score(a, (size_t)b * a.P + p, c);
+    uk[p] = v > a.conf_thr ? f2ord(v) : 0u;
+  }
+  if (tid == 0) s_res[4] = 0;
+  __syncthreads();
+  uint32_t Tu = cta_select_threshold<true>(uk, a.P, a.top_k, nullptr, s_hist, s_iscr, s_res);
+  __syncthreads();
+  for (int p = tid; p < a.P; p += kOvfThreads) {
+    uint32_t u = uk[p];
+    if (u != 0u && u >= Tu) {
+      int slot = atomicAdd(&s_res[4], 1);
+      if (slot < 1024) keys[slot] = ((unsigned long long)u << 32) | (uint32_t)p;
     }
-    group_sync(grp);
-    if (gw == 0) {
-      int d, above;
-      warp_find_digit(hist, nb, need, lane, &d, &above);
-      if (lane == 0) {
-        s_sel[0] = d;
-        s_sel[1] = above;
-        s_sel[2] = (int)hist[d < 0 ? 0 : d];
-      }
-    }
-    group_sync(grp);
-    const int d = s_sel[0];            // >= 0: at least `need` keys carry the prefix
-    need -= s_sel[1];
-    prefix |= (unsigned long long)(uint32_t)d << shift;
-    pmask |= (unsigned long long)(uint32_t)(nb - 1) << shift;
-    const bool done = s_sel[2] == need;          // the whole bin is wanted: every key >= prefix is selected
-    group_sync(grp);                             // s_sel / hist are reused by the next level
-    if (done) break;
   }
-  // compaction: every thread takes a contiguous slice into registers, then the survivors move to the front
-  constexpr int kPer = kOvfListCap / kOvfGroup;      // 16
-  unsigned long long mine[kPer];
-  int cnt = 0;
-#pragma unroll
-  for (int e = 0; e < kPer; ++e) {
-    const int i = gt * kPer + e;
-    mine[e] = i < n ? keys[i] : 0ull;
-    cnt += (i < n && mine[e] >= prefix) ? 1 : 0;
-  }
-  const int incl = warp_inclusive_scan(cnt, lane);
-  if (lane == 31) s_scan[gw] = incl;
-  group_sync(grp);                                   // all slices are in registers, the warp totals are posted
-  int off = incl - cnt;
-  for (int w2 = 0; w2 < gw; ++w2) off += s_scan[w2];
-#pragma unroll
-  for (int e = 0; e < kPer; ++e) {
-    const int i = gt * kPer + e;
-    if (i < n && mine[e] >= prefix) keys[off++] = mine[e];
-  }
-  group_sync(grp);
-  return prefix;
+  __syncthreads();
+  int n = s_res[4];
+  if (n > 1024) n = 1024;
+  int npad = 32;
+  while (npad < n) npad <<= 1;
+  for (int i = n + tid; i < npad; i += kOvfThreads) keys[i] = 0ull;
+  __syncthreads();
+  segment_finish(a, b, seg, keys, n, npad, ns);
+  if (tid == 0) a.cnt[seg] = 0u;
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(kOvfThreads, 1) detect_overflow_chunk_kernel(DetSegArgs a) {
   extern __shared__ __align__(16) unsigned char smem_ovc[];
-  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_ovc);                          // [8][2048]
-  uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_ovc + (size_t)kOvfClasses * kOvfListCap * 8);      // [8][2048]
-  int* s_misc = reinterpret_cast<int*>(smem_ovc + (size_t)kOvfClasses * kOvfListCap * 12);
-  int* s_act = s_misc;                                            // [8]
-  int* s_n = s_misc + 8;                                          // [8] entries of the running list
-  uint32_t* s_lo = reinterpret_cast<uint32_t*>(s_misc + 16);      // [8] admission bound (ordered score)
-  int* s_sel = s_misc + 24;                                       // [8][4]
-  int* s_scan = s_misc + 56;                                      // [8][4]
-  const int tid = threadIdx.x;
-  const int grp = tid / kOvfGroup, gt = tid % kOvfGroup;
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_ovc);                                   // [8][2048]
+  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_ovc + 65536);         // [8][1024]
+  int* s_iscr = reinterpret_cast<int*>(smem_ovc + 131072);                                      // 64
+  int* s_res = s_iscr + 64;                                                                     // 8
+  int* s_cls = s_res + 8;                                                                       // 8 x {active, K left, range lo, n collected, range size - 1, shift}
+  NmsSmem ns = carve_nms(smem_ovc + 131072 + 288 + 192, a.top_k);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nchunk = (a.C - 1 + kOvfClasses - 1) / kOvfClasses;
-  if (*a.ovf_count == 0u) return;       // no list overflowed (the normal case): written by detect_segments_kernel
+  int* s_act = s_cls;
+  int* s_kleft = s_cls + 8;
+  uint32_t* s_pre = reinterpret_cast<uint32_t*>(s_cls + 16);     // key prefix fixed so far, finally the threshold key
+  int* s_n = s_cls + 24;
+  uint32_t* s_spanm1 = reinterpret_cast<uint32_t*>(s_cls + 32);   // current range size - 1 (0: the threshold key is s_pre)
+  int* s_shift = s_cls + 40;
+  uint32_t* uk = a.scratch + (size_t)blockIdx.x * a.P;
+  if (*a.ovf_count == 0u) return;       // no list overflowed (the normal case): written by detect_segment_small_kernel
   for (int item = blockIdx.x; item < a.B * nchunk; item += gridDim.x) {
     const int b = item / nchunk, c0 = 1 + (item - b * nchunk) * kOvfClasses;
     __syncthreads();
     if (tid < kOvfClasses) {
       const int c = c0 + tid;
       s_act[tid] = (c < a.C && a.cnt[(size_t)b * a.C + c] > (uint32_t)a.cap) ? 1 : 0;
+      s_kleft[tid] = a.top_k;
+      const uint32_t lo = f2ord(a.conf_thr), one = f2ord(1.0f);
+      const uint32_t nominal = one > lo ? one - lo : 0u;       // keys of the scores in (conf_thr, 1]
+      const int bits = nominal ? 32 - __clz(nominal) : 0;
+      s_pre[tid] = lo;
+      s_spanm1[tid] = 0xffffffffu - lo;                        // first level: everything above the threshold
+      s_shift[tid] = bits > 11 ? bits - 11 : 0;                // (nominal >> shift) <= 2047: the last bin also catches keys above 1.0
       s_n[tid] = 0;
-      s_lo[tid] = 0u;
     }
     __syncthreads();
     int actmask = 0;
 #pragma unroll
     for (int k = 0; k < kOvfClasses; ++k) actmask |= s_act[k] << k;
     if (actmask == 0) continue;
-    unsigned long long* gkeys = s_keys + (size_t)grp * kOvfListCap;
-    uint32_t* ghist = s_hist + (size_t)grp * kOvfListCap;
-    for (int p0 = 0; p0 < a.P; p0 += kOvfThreads) {
-      uint32_t lo_r[kOvfClasses];
+
+    // Range-adaptive radix select, all active classes per pass: a level buckets the keys of the current
+    // range [lo, lo + span) into 2048 bins of 2^shift keys.  The first range is (key(conf_thr), key(1.0)]
+    // -- softmax scores -- with the last bin catching anything above, so the bins are spread over the
+    // scores' log-range (bucketing the top key bits would put every score in ~30 bins and serialise the
+    // shared-memory atomics).  Three levels in the normal case, at most five.
+    for (int level = 0; level < 5; ++level) {
+      if (level > 0) {
+        int pending = 0;
 #pragma unroll
-      for (int k = 0; k < kOvfClasses; ++k) lo_r[k] = s_lo[k];
-      const int p = p0 + tid;
-      if (p < a.P) {
+        for (int k = 0; k < kOvfClasses; ++k) pending |= ((actmask >> k) & 1) && s_spanm1[k] != 0u;
+        if (!pending) break;                      // uniform: shared state read after a barrier
+      }
+      for (int i = tid; i < kOvfClasses * 2048; i += kOvfThreads) s_hist[i] = 0u;
+      __syncthreads();
+      uint32_t lo_r[kOvfClasses], spanm1_r[kOvfClasses];
+      int shift_r[kOvfClasses];
+#pragma unroll
+      for (int k = 0; k < kOvfClasses; ++k) {
+        lo_r[k] = s_pre[k];
+        spanm1_r[k] = ((actmask >> k) & 1) ? s_spanm1[k] : 0u;     // 0: class inactive or already resolved
+        shift_r[k] = s_shift[k];
+      }
+      for (int p = tid; p < a.P; p += kOvfThreads) {
         float v[kOvfClasses];
         ovf_row_scores(a, (size_t)b * a.P + p, c0, v);
 #pragma unroll
         for (int k = 0; k < kOvfClasses; ++k) {
           const uint32_t u = f2ord(v[k]);
-          if (((actmask >> k) & 1) && v[k] > a.conf_thr && u >= lo_r[k]) {      // detection.py:48 strict >
-            const int slot = atomicAdd(&s_n[k], 1);     // <= 1024 before the block + <= 1024 rows: always < 2048
-            s_keys[(size_t)k * kOvfListCap + slot] = ((unsigned long long)u << 32) | (uint32_t)p;
+          const uint32_t off = u - lo_r[k];
+          if (spanm1_r[k] != 0u && v[k] > a.conf_thr && u >= lo_r[k] && off <= spanm1_r[k]) {
+            const uint32_t bin = off >> shift_r[k];
+            atomicAdd(&s_hist[k * 2048 + (bin < 2047u ? bin : 2047u)], 1u);
           }
         }
       }
       __syncthreads();
-      const int n = s_n[grp];
-      if (n > kOvfPruneAt) {                          // uniform over the group
-        const unsigned long long kth = group_prune(gkeys, n, a.top_k, ghist, s_sel + grp * 4, s_scan + grp * 4, grp, gt);
-        if (gt == 0) {
-          s_n[grp] = a.top_k;
-          s_lo[grp] = (uint32_t)(kth >> 32);
+      if (warp < kOvfClasses && ((actmask >> warp) & 1) && s_spanm1[warp] != 0u) {
+        int d, above;
+        warp_find_digit(s_hist + warp * 2048, 2048, s_kleft[warp], lane, &d, &above);
+        if (lane == 0) {
+          if (d < 0) {               // cannot happen for an overflowed list (more than cap > top_k candidates)
+            d = 0;
+            above = 0;
+          }
+          s_kleft[warp] -= above;
+          const int sh = s_shift[warp];
+          const uint32_t lo = s_pre[warp] + ((uint32_t)d << sh);
+          // bin 2047 of the first level is open-ended; every other bin holds exactly 2^shift keys
+          uint32_t spanm1 = (level == 0 && d == 2047) ? (0xffffffffu - lo) : ((1u << sh) - 1u);
+          // everything above the bin plus the whole bin fits the list: stop refining, the sort of
+          // segment_finish orders the bin and keeps the first top_k
+          if ((a.top_k - s_kleft[warp]) + (int)s_hist[warp * 2048 + d] <= 1024) spanm1 = 0u;
+          int bits = spanm1 ? 32 - __clz(spanm1) : 0;
+          s_pre[warp] = lo;
+          s_spanm1[warp] = spanm1;
+          s_shift[warp] = bits > 11 ? bits - 11 : 0;
         }
       }
       __syncthreads();
     }
-    const int n = s_n[grp];
-    if (n > a.top_k) {                                // final cut (box_utils.py:301 idx[-top_k:])
-      group_prune(gkeys, n, a.top_k, ghist, s_sel + grp * 4, s_scan + grp * 4, grp, gt);
-      if (gt == 0) s_n[grp] = a.top_k;
+    // s_pre[k] is now a key <= the top_k-th largest score with at most 1024 keys >= it (or the exact
+    // key of the top_k-th largest score): collect every key >= it
+    uint32_t thr_r[kOvfClasses];
+#pragma unroll
+    for (int k = 0; k < kOvfClasses; ++k) thr_r[k] = ((actmask >> k) & 1) ? s_pre[k] : 0xffffffffu;
+    for (int p = tid; p < a.P; p += kOvfThreads) {
+      float v[kOvfClasses];
+      ovf_row_scores(a, (size_t)b * a.P + p, c0, v);
+#pragma unroll
+      for (int k = 0; k < kOvfClasses; ++k) {
+        const uint32_t u = f2ord(v[k]);
+        if (v[k] > a.conf_thr && u >= thr_r[k] && thr_r[k] != 0xffffffffu) {
+          const int slot = atomicAdd(&s_n[k], 1);
+          if (slot < 1024) s_keys[k * 1024 + slot] = ((unsigned long long)u << 32) | (uint32_t)p;
+        }
+      }
     }
     __syncthreads();
-    // hand the selected keys to detect_segment_kernel (next launch): several of its small CTAs share an
-    // SM, so the serial NMS sweep of one segment overlaps the IoU matrix of others
-    if ((actmask >> grp) & 1) {
-      const int c = c0 + grp, seg = b * a.C + c;
-      const int m = s_n[grp];
+    for (int k = 0; k < kOvfClasses; ++k) {
+      if (!((actmask >> k) & 1)) continue;
+      const int c = c0 + k, seg = b * a.C + c;
+      const int n = s_n[k];
+      if (n > 1024) {              // ties at the cut do not fit: exact index-ordered selection on the column
+        overflow_column_segment(a, b, c, seg, s_keys + k * 1024, s_hist, s_iscr, s_res, ns, uk);
+        continue;
+      }
+      // hand the selected keys to detect_segment_kernel (next launch): several of its small CTAs share an
+      // SM, so the serial NMS sweep of one segment overlaps the IoU matrix of others
+      const unsigned long long* keys = s_keys + k * 1024;
       unsigned long long* dst = a.cand + (size_t)seg * a.cap;
-      for (int i = gt; i < m; i += kOvfGroup) dst[i] = gkeys[i];
-      if (gt == 0) {
-        a.cnt[seg] = (uint32_t)m;
+      for (int i = tid; i < n; i += kOvfThreads) dst[i] = keys[i];
+      if (tid == 0) {
+        a.cnt[seg] = (uint32_t)n;
         a.big_list[atomicAdd(a.big_count, 1u)] = seg;
       }
     }
@@ -943,34 +968,33 @@ extern "C" int ssdbox_detect_peers(const ssdbox_detect_cfg* cfg, const float* lo
     detect_segments_kernel<<<(B * C + kSmallSegs - 1) / kSmallSegs, kSmallThreads, seg_smem, st>>>(g);
   }
   SSDBOX_LAUNCH_OK("detect_segments_kernel");
-  // overflowed lists first: the chunked kernel only SELECTS (it rewrites the list with <= 1024 keys and
-  // queues the segment for the CTA-wide kernel below)
+  // overflowed lists: the chunked kernel only SELECTS (it rewrites the list with <= 1024 keys and queues the
+  // segment for the CTA-wide kernel that follows)
   int ovf_grid = dev.sm_count < kOverflowSlots ? dev.sm_count : kOverflowSlots;
-  const size_t chunk_smem = (size_t)kOvfClasses * kOvfListCap * 12 + 512;
-  if (top_k <= 256 && cap == 1024 && chunk_smem <= (size_t)dev.max_smem_optin - 1024) {
-    // chunked dense path: (image, 8 classes) work items, reads each score sector once per pass
-    SSDBOX_CUDA(cudaFuncSetAttribute(detect_overflow_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chunk_smem));
-    SSDBOX_CARVE(detect_overflow_chunk_kernel);
+  const size_t chunk_smem = 131072 + 288 + 192 + nms_smem_bytes(top_k);
+  const bool chunked = top_k <= 256 && cap == 1024 && chunk_smem <= (size_t)dev.max_smem_optin - 1024;
+  void (*ovf_kern)(DetSegArgs) = chunked ? detect_overflow_chunk_kernel : detect_overflow_kernel;
+  const size_t ovf_smem = chunked ? chunk_smem : (size_t)16384 + 288 + nms_smem_bytes(top_k);
+  const int ovf_threads = kOvfThreads;
+  if (chunked) {
     const int items = B * ((C - 1 + kOvfClasses - 1) / kOvfClasses);
     if (ovf_grid > items) ovf_grid = items;
-    if (ovf_grid > 0) {
-      TimerScope ts__(KID_DET_OVERFLOW, st);
-      detect_overflow_chunk_kernel<<<ovf_grid, kOvfThreads, chunk_smem, st>>>(g);
-    }
-  } else {
-    size_t ovf_smem = 16384 + 288 + nms_smem_bytes(top_k);
-    SSDBOX_CUDA(cudaFuncSetAttribute(detect_overflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ovf_smem));
-    if (ovf_grid > B * C) ovf_grid = B * C;
-    TimerScope ts__(KID_DET_OVERFLOW, st);
-    detect_overflow_kernel<<<ovf_grid, kOvfThreads, ovf_smem, st>>>(g);
+  } else if (ovf_grid > B * C) {
+    ovf_grid = B * C;
   }
-  SSDBOX_LAUNCH_OK("detect_overflow_kernel");
-
+  if (ovf_grid < 1) ovf_grid = 1;
+  SSDBOX_CUDA(cudaFuncSetAttribute(ovf_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ovf_smem));
+  SSDBOX_CARVE(ovf_kern);
   SSDBOX_CUDA(cudaFuncSetAttribute(detect_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem));
   SSDBOX_CARVE(detect_segment_kernel);
+  const int big_grid = dev.sm_count * 8 < B * C ? dev.sm_count * 8 : B * C;
+  {
+    TimerScope ts__(KID_DET_OVERFLOW, st);
+    ovf_kern<<<ovf_grid, ovf_threads, ovf_smem, st>>>(g);
+  }
+  SSDBOX_LAUNCH_OK("detect_overflow_kernel");
   {
     TimerScope ts__(KID_DET_SEGMENT_BIG, st);
-    int big_grid = dev.sm_count * 8 < B * C ? dev.sm_count * 8 : B * C;
     detect_segment_kernel<<<big_grid, kSegThreads, seg_smem, st>>>(g);
   }
   SSDBOX_LAUNCH_OK("detect_segment_kernel");

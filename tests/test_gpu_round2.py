@@ -410,3 +410,43 @@ def test_deferred_loss_completed_by_detect(dev):
     torch.cuda.synchronize()
     assert float(ll) == float(wl) and float(lc) == float(wc) and torch.equal(out, want)
     assert int(crit._peers.buf[0]) == 8          # 3 eager + 2 warm-up + 3 replays (the capture itself does not run)
+
+
+def test_detect_graph_replay_sparse_dense_sparse(dev):
+    """One captured DetectOut graph replayed on sparse scores (the overflow kernels exit on one load), on dense scores
+    (streaming top-k select + rewritten lists) and on sparse scores again: always the eager results, and the
+    workspace state is clean after every replay."""
+    name, B = "ssd300_voc", 2
+    pri = U.oracle_priors(name).to(dev)
+    P, C = 8732, 21
+    g = torch.Generator().manual_seed(11)
+    loc = synth.gen_loc(B, P, 3).to(dev)
+    cases = []
+    for bias in (10.0, 1.0, 9.0, 1.5):
+        logits = torch.randn(B, P, C, generator=g)
+        logits[..., 0] += bias
+        cases.append(torch.softmax(logits, -1).to(dev))
+    eager = ssdbox.DetectOut(C, 0, 200, 0.01, 0.45, VAR)
+    want = [eager(loc, sc, pri).clone() for sc in cases]
+    assert int((want[1][..., 0] > 0).sum()) > 10 * int((want[0][..., 0] > 0).sum())      # the dense case really is dense
+    det = ssdbox.DetectOut(C, 0, 200, 0.01, 0.45, VAR)
+    buf = cases[0].clone()
+    out = torch.empty(B, C, 200, 5, device=dev)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        det.forward(loc, buf, pri, out=out)
+        det.forward(loc, buf, pri, out=out)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s):
+        det.forward(loc, buf, pri, out=out)
+    for rep in range(2):
+        for sc, w in zip(cases, want):
+            buf.copy_(sc)
+            graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(out, w), rep
+    # the eager module (always-launched overflow kernels) and the replayed graph leave the same clean workspace state
+    ws = det._ws.buf
+    assert int(ws[:(B * C + 4) * 4].view(torch.int32).abs().sum()) == 0
