@@ -257,7 +257,7 @@ __device__ __forceinline__ int nms_sweep(const NmsSmem& s, int m, float thr) {
         const float4 bj = s.box[j];
         Box J;
         J.x1 = bj.x; J.y1 = bj.y; J.x2 = bj.z; J.y2 = bj.w;
-        bit = !(iou_nms(I, ai, J, s.area[j]) <= thr);     // :342 keeps IoU <= overlap
+        bit = nms_suppresses(I, ai, J, s.area[j], thr);   // :342 keeps IoU <= overlap
       }
       const uint32_t word = __ballot_sync(SSDBOX_FULL_MASK, bit);
       if (lane == 0) s.mask[i * W + wd] = word;

@@ -71,7 +71,6 @@ struct StreamArgs {
   RingPlan ring;       // conf [B*P, C]
   const uint8_t* pool;
   float* key0;         // [B*P]  lse - x[0]   (mining key of a non-positive prior, multibox_loss.py:94)
-  float* lse;          // [B*P]  log-sum-exp of the row
   uint32_t* hist;
   int P;
   // fused matching (box_utils.py:92-130 on dedicated warps)
@@ -414,8 +413,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) loss_stream_kernel(StreamAr
         const float* rp = rc.stages + (size_t)s * rc.stage_floats + (size_t)r * C;
         const float lse = row_lse<CT>(rp, C);
         const float k0 = lse - rp[0];                        // multibox_loss.py:94 with conf_t = 0
-        a.lse[row] = lse;
-        a.key0[row] = k0;
+        a.key0[row] = k0;                                    // (a positive's lse is recovered as key0 + x[0]: no second array)
         if (!a.pool || a.pool[row]) {
           uint32_t b = (uint32_t)row / (uint32_t)a.P;
           atomicAdd(&a.hist[(size_t)b * kHistBins + mine_bin(f2ord(k0))], 1u);
@@ -491,8 +489,7 @@ struct MineArgs {
   const int32_t* gt_offsets;
   const uint8_t* pool;
   const float* keys;       // key0 = lse - x[0] from the stream kernel
-  const float* lse;
-  const float* conf;       // gathered once per positive: x[target]
+  const float* conf;       // gathered per positive: x[target] and x[0] (lse = key0 + x[0])
   const int16_t* lab;
   const int16_t* tidx;
   uint32_t* hist;          // level-1 histogram; positives are moved to the zero bin here
@@ -612,7 +609,7 @@ __device__ __forceinline__ uint32_t mine_visit(const MineArgs& a, size_t i, int 
   if (lb > 0) {
     ++npos;
     // CE of a positive = lse - x[target] (multibox_loss.py:94,110); it ranks as 0 (multibox_loss.py:97)
-    float cep = a.lse[i] - a.conf[i * (size_t)a.C + lb];
+    float cep = (key + a.conf[i * (size_t)a.C]) - a.conf[i * (size_t)a.C + lb];
     if (a.dbg_keys) a.dbg_keys[i] = cep;
     ce += (double)cep;
     const float* row = a.gt + (size_t)(g0 + a.tidx[i]) * 5;
@@ -1026,7 +1023,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
     p_p = (int)(ent & 0xffffu);
     const int lb = (int)(ent >> 16);
     const size_t i = off + p_p;
-    p_lse = a.lse[i];
+    p_lse = a.keys[i] + a.conf[i * (size_t)a.C];       // lse = key0 + x[0]
     p_xt = a.conf[i * (size_t)a.C + lb];
     p_t = a.tidx[i];
     p_l = *reinterpret_cast<const float4*>(a.loc + i * 4);
@@ -1205,7 +1202,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
     const uint32_t ent = s_list[sidx];
     const int p = (int)(ent & 0xffffu), lb = (int)(ent >> 16);
     const size_t i = off + p;
-    positive(i, p, a.lse[i], a.conf[i * (size_t)a.C + lb], a.tidx[i], *reinterpret_cast<const float4*>(a.loc + i * 4),
+    positive(i, p, a.keys[i] + a.conf[i * (size_t)a.C], a.conf[i * (size_t)a.C + lb], a.tidx[i], *reinterpret_cast<const float4*>(a.loc + i * 4),
              *reinterpret_cast<const float4*>(pri + (size_t)p * 4));
   }
   // (5) neg = rank < num_neg (:103); CE over pos U neg (:106-110); the CE of a selected negative is
@@ -1683,8 +1680,6 @@ extern "C" int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const 
   w.partial = c.take<double>((size_t)B * 6);     // {l1, ce, npos} per mining CTA (two per image when clustered)
   w.ticket = c.take<uint32_t>(2);      // [0] mine_reduce ticket, [1] next matching unit
 
-  w.lse = c.take<float>((size_t)B * P);
-
   // State = per-truth best-prior keys, image tickets, mining histograms, work tickets.  Every call hands it back
   // initialised, so a caller that reuses the workspace for the same shape may skip this launch.
   if (!(cfg->flags & SSDBOX_LOSS_WS_CLEAN)) {
@@ -1700,7 +1695,6 @@ extern "C" int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const 
   StreamArgs sa{};
   sa.pool = pool;
   sa.key0 = w.keys;
-  sa.lse = w.lse;
   sa.hist = w.hist;
   sa.P = P;
   sa.B = B;
@@ -1739,7 +1733,7 @@ extern "C" int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const 
   m.finalize = cfg->finalize;
   m.prior_stride = (long long)cfg->prior_batch_stride;
   m.loc = loc; m.priors = priors; m.gt = gt; m.gt_offsets = gt_offsets; m.pool = pool;
-  m.keys = w.keys; m.lse = w.lse; m.conf = conf; m.lab = w.m.lab; m.tidx = tidx; m.hist = w.hist;
+  m.keys = w.keys; m.conf = conf; m.lab = w.m.lab; m.tidx = tidx; m.hist = w.hist;
   m.fuse = sa.fuse; m.gmax = cfg->gmax; m.gpad = sa.gpad; m.binarize = cfg->binarize_labels;
   m.gt_best = w.m.gt_best; m.gt_best_w = w.m.gt_best; m.lab_w = w.m.lab; m.tidx_w = tidx;
   m.ukey_global = w.ukey;

@@ -36,7 +36,6 @@ static inline void carve_match_core(Carver& c, int B, int gmax, MatchWs* w) {
 struct LossWs {
   MatchWs m;
   float* keys;        // [B,P]  lse - x[0]
-  float* lse;         // [B,P]
   uint32_t* hist;     // [B, kHistBins]
   uint32_t* ukey;     // [B,P]  ordered mining keys (only used when they do not fit in smem)
   double* partial;    // [2B,3]
@@ -44,7 +43,7 @@ struct LossWs {
 };
 static inline size_t loss_ws_bytes(int B, int P, int C, int gmax) {
   (void)C;
-  return match_core_bytes(B, gmax) + align_up((size_t)B * P * 2) + align_up((size_t)B * P * 4) * 3 +
+  return match_core_bytes(B, gmax) + align_up((size_t)B * P * 2) + align_up((size_t)B * P * 4) * 2 +
          align_up((size_t)B * kHistBins * 4) + align_up((size_t)B * 6 * 8) + 256;
 }
 
