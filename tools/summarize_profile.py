@@ -78,14 +78,14 @@ if os.path.isfile(ll):
             nm = r[4].split("(")[0].replace("void ", "")
             agg.setdefault(nm, []).append(float(r[-1]) / 1e3)
     ours = {k: v for k, v in agg.items() if k.startswith("ssdbox::")}
-    fwd = [k for k in ours if not any(s in k for s in ("zero_fill", "loss_bwd", "priorbox", ", 1>", "compact_", "peer_finish", "heads_to_rows", "voc_", "radix_", "crop_"))]
-    tot = sum(mean(ours[k]) * (2 if "init_kernel" in k else 1) for k in fwd)
+    fwd = [k for k in ours if not any(s in k for s in ("zero_fill", "loss_bwd", "priorbox", ", 1>", "compact_", "peer_finish", "heads_to_rows", "voc_", "radix_", "crop_", "init_kernel"))]
+    tot = sum(mean(ours[k]) for k in fwd)      # (init_kernel runs once per workspace: not part of a step any more)
     lines += ["", "## launch list (ncu --metrics gpu__time_duration.sum, cold cache, serialised): share of one step (T fwd + D)", "",
               "| kernel | launches | mean us | share of step |", "|---|---|---|---|"]
     for k in ours:
         m = mean(ours[k])
-        mult = 2 if "init_kernel" in k else 1
-        share = "%.1f%%" % (100 * m * mult / tot) if k in fwd else "(backward / setup / side phases of bench.py, not in the step)"
+        mult = 1
+        share = "%.1f%%" % (100 * m * mult / tot) if k in fwd else "(first-call init / backward / setup / side phases of bench.py, not in the step)"
         lines.append("| %s%s | %d | %.1f | %s |" % (k, " (x2 per step)" if mult == 2 else "", len(ours[k]), m, share))
     lines.append("| sum over one step | | %.1f | |" % tot)
 
