@@ -401,6 +401,8 @@ __global__ void __launch_bounds__(kSmallThreads) detect_segments_kernel(DetSegAr
   if (seg < a.B * a.C) {
     const int b = seg / a.C, c = seg - b * a.C;
     const uint32_t total = c == 0 ? 0u : a.cnt[seg];
+    // the first 32 candidates are requested together with the counter (one round trip instead of two)
+    const unsigned long long key_first = a.cand[(size_t)seg * a.cap + lane];
     if (total > 32u) {
       if (lane == 0) {
         if (total > (uint32_t)a.cap) {
@@ -420,7 +422,7 @@ __global__ void __launch_bounds__(kSmallThreads) detect_segments_kernel(DetSegAr
       } else {
         if (lane == 0) a.cnt[seg] = 0u;
         const int n = (int)total;
-        unsigned long long key = lane < n ? a.cand[(size_t)seg * a.cap + lane] : 0ull;
+        unsigned long long key = lane < n ? key_first : 0ull;
         // bitonic sort, descending (= visiting order: score desc, higher prior first); padding sinks
 #pragma unroll
         for (int k = 2; k <= 32; k <<= 1) {

@@ -845,12 +845,8 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   const bool small_g = a.fuse && G <= kForceListMax;
 
   PHASE_MARK(0);
-  // (1) everything this CTA needs from memory, requested together
-  unsigned long long my_best = 0ull;
-  if (small_g && tid < G) my_best = __ldcg(&a.gt_best[(size_t)b * a.gpad + tid]);
-  const bool gt_cached = G <= kForceListMax;
-  float my_gt = 0.f;
-  if (gt_cached && tid < 5 * G) my_gt = a.gt[(size_t)g0 * 5 + tid];
+  // (1) everything this CTA needs from memory, requested together.  The loads that do not depend on the image's
+  // truth count go first: a warp issues in order, and the truth offsets take a round trip of their own.
   uint32_t h0 = a.hist[(size_t)b * kHistBins + tid], h1 = a.hist[(size_t)b * kHistBins + 1024 + tid];
   uint32_t uk[Q][4];     // ordered mining keys (0 = outside the ranking)
   short4 ll[Q];
@@ -873,6 +869,11 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
     }
     uk[j][0] = f2ord(kv.x); uk[j][1] = f2ord(kv.y); uk[j][2] = f2ord(kv.z); uk[j][3] = f2ord(kv.w);
   }
+  unsigned long long my_best = 0ull;
+  if (small_g && tid < G) my_best = __ldcg(&a.gt_best[(size_t)b * a.gpad + tid]);
+  const bool gt_cached = G <= kForceListMax;
+  float my_gt = 0.f;
+  if (gt_cached && tid < 5 * G) my_gt = a.gt[(size_t)g0 * 5 + tid];
   if (a.fuse && !small_g) {
     // many truths: replay the forced assignment through global memory first (box_utils.py:123-130)
     const unsigned long long* best = a.gt_best + (size_t)b * a.gpad;
