@@ -824,7 +824,7 @@ def main():
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         pri_cpu = priors.cpu()
-        bt, bd, reps = 4, 2, 3
+        bt, bd, reps = 16, 8, 10          # a bounded sample: ~10 s of CPU work incl. the generation of its inputs
         impl = cpu_impl(args.workload)
         cpu_reference_pass(args.workload, C, P, pri_cpu, bt, bd, 7, args.dense, impl)
         tt = td = 0.0
