@@ -245,6 +245,32 @@ SSDBOX_API int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const 
                              int16_t* sel, int16_t* tidx, int64_t* dbg_conf_t, float* dbg_loc_t,
                              uint8_t* dbg_neg, float* dbg_keys, const ssdbox_peer_group* peers, void* ws, size_t ws_bytes,
                              ssdbox_stream_t stream);
+/* ---- RefineDet, fused two-step path (arXiv 1711.06897; SURVEY.md 8a-R -- no reference code, parity unpinned) ----
+ * The ODM loss and the refined DetectOut take the ARM head's outputs as they are: an anchor of image b is
+ * decode(arm_loc[b,p], priors[p]) (box_utils.py:238-243), recomputed inside the kernels that need it (the match
+ * warps of the streaming kernel, the positives of the mining / backward kernels, the candidates of Detect), and
+ * an anchor whose objectness softmax(arm_conf[b,p])[1] is <= theta leaves the positives, the hard-negative pool
+ * and the detections.  No refined-anchor tensors ([B,P,4] xyxy + centre form) and no [B,P] mask are
+ * materialised, and there is no extra launch.  Bit-identical to the materialised path (ssdbox_decode with
+ * out_center + ssdbox_arm_filter feeding anchors_xyxy / pool / score_keep).  `priors` is the shared [P,4]
+ * centre-form tensor (cfg->prior_batch_stride must be 0). */
+typedef struct {
+  const float* arm_loc;   /* [B,P,4] ARM regression offsets, 16-byte aligned */
+  const float* arm_conf;  /* [B,P,2] ARM objectness logits, 16-byte aligned; NULL: no filtering */
+  float theta;            /* objectness threshold (0.01) */
+  int32_t reserved;
+} ssdbox_refine;
+SSDBOX_API int ssdbox_multibox_loss_fwd_refine(const ssdbox_loss_cfg* cfg, const float* loc, const float* conf,
+                             const float* priors, const ssdbox_refine* refine,
+                             const float* gt, const int32_t* gt_offsets, double* sums, float* losses,
+                             int16_t* sel, int16_t* tidx, int64_t* dbg_conf_t, float* dbg_loc_t,
+                             uint8_t* dbg_neg, float* dbg_keys, const ssdbox_peer_group* peers, void* ws, size_t ws_bytes,
+                             ssdbox_stream_t stream);
+SSDBOX_API int ssdbox_multibox_loss_bwd_refine(const ssdbox_loss_cfg* cfg, const float* loc, const float* conf,
+                             const float* priors, const ssdbox_refine* refine, const float* gt, const int32_t* gt_offsets,
+                             const int16_t* sel, const int16_t* tidx, const double* sums,
+                             const float* grad_out, float* grad_loc, float* grad_conf,
+                             ssdbox_stream_t stream);
 /* losses = sums[0..1] / sums[2]  (after the caller all-reduced `sums` across ranks) */
 SSDBOX_API int ssdbox_multibox_loss_finalize(const double* sums, float* losses, ssdbox_stream_t stream);
 /* backward: grad_loc [B,P,4], grad_conf [B,P,C] (both fully written);
@@ -302,6 +328,11 @@ SSDBOX_API int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
  * ssdbox_multibox_loss_peer_finish does, without a launch of its own): one warp of the last Detect kernel waits for
  * every rank's sums and writes the global loss_sums[3] / losses[2] (nullable).  In a step "loss forward, then
  * DetectOut" the Detect kernels run while the other ranks' sums arrive.  peers == NULL: plain ssdbox_detect. */
+/* RefineDet inference: decode(odm_loc, refined anchors), scores of anchors with ARM objectness <= theta count as 0
+ * (see ssdbox_refine above; `priors` shared [P,4], prior_batch_stride 0). */
+SSDBOX_API int ssdbox_detect_refine(const ssdbox_detect_cfg* cfg, const float* loc, const float* scores,
+                  const float* priors, const ssdbox_refine* refine, float* out, int32_t* counts, void* ws,
+                  size_t ws_bytes, ssdbox_stream_t stream);
 SSDBOX_API int ssdbox_detect_peers(const ssdbox_detect_cfg* cfg, const float* loc, const float* scores,
                   const float* priors, const uint8_t* score_keep, float* out, int32_t* counts,
                   const ssdbox_peer_group* peers, double* loss_sums, float* losses, void* ws, size_t ws_bytes,

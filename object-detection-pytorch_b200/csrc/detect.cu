@@ -35,6 +35,7 @@ namespace ssdbox {
 struct DetStreamArgs {
   RingPlan ring;            // scores [B*P, C]
   const uint8_t* keep;      // [B*P] nullable
+  RefineArgs rf;            // RefineDet fused: the score mask is the ARM objectness
   uint32_t* cnt;            // [B*C]
   unsigned long long* cand; // [B*C, cap]
   int P;
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(kRingThreads, 1) detect_stream_kernel(DetStrea
       const long long row = (rc.t0 + it * rc.tstep) * R + r;
       const bool valid = (r < R) && (row < a.ring.rows);
       bool kept = true;
-      if (valid && a.keep) kept = a.keep[row] != 0;          // RefineDet: filtered anchors score 0
+      if (valid && (a.keep || a.rf.arm_conf)) kept = refine_member(a.rf, a.keep, (size_t)row);   // RefineDet: filtered anchors score 0
       const float* rp = st + (size_t)r * C;
       float m = -INFINITY;        // scores: max over the foreground classes; logits: max over all classes
       bool hit = false;
@@ -313,6 +314,7 @@ struct DetSegArgs {
   const float* scores;
   const float* priors;
   const uint8_t* keep;
+  RefineArgs rf;         // RefineDet fused: boxes are decoded against anchors refined on the fly, scores masked by the ARM objectness
   uint32_t* cnt;
   unsigned long long* cand;
   uint32_t* ovf_count; // [1] number of (image, class) lists that overflowed
@@ -340,7 +342,8 @@ __device__ void segment_finish(const DetSegArgs& a, int b, int seg, unsigned lon
   for (int i = tid; i < m; i += blockDim.x) {
     uint32_t p = (uint32_t)(keys[i] & 0xffffffffull);
     Box bx = decode_box(*reinterpret_cast<const float4*>(a.loc + ((size_t)b * a.P + p) * 4),
-                        *reinterpret_cast<const float4*>(pri + (size_t)p * 4), a.var0, a.var1);   // detection.py:43
+                        refine_center(a.rf, *reinterpret_cast<const float4*>(pri + (size_t)p * 4), (size_t)b * a.P + p),
+                        a.var0, a.var1);   // detection.py:43
     ns.box[i] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
     ns.area[i] = box_area(bx);                                                                    // box_utils.py:298
   }
@@ -441,7 +444,8 @@ __global__ void __launch_bounds__(kSmallThreads) detect_segments_kernel(DetSegAr
         if (lane < m) {
           uint32_t p = (uint32_t)(key & 0xffffffffull);
           me = decode_box(*reinterpret_cast<const float4*>(a.loc + ((size_t)b * a.P + p) * 4),
-                          *reinterpret_cast<const float4*>(a.priors + (size_t)b * (size_t)a.prior_stride + (size_t)p * 4),
+                          refine_center(a.rf, *reinterpret_cast<const float4*>(a.priors + (size_t)b * (size_t)a.prior_stride + (size_t)p * 4),
+                                        (size_t)b * a.P + p),
                           a.var0, a.var1);
         }
         const float my_area = box_area(me);
@@ -551,7 +555,7 @@ __global__ void __launch_bounds__(kOvfThreads, 1) detect_overflow_kernel(DetSegA
         const float sden = a.row_s[row];
         v = sden > 0.0f ? __fdiv_rn(expf(v - a.row_m[row]), sden) : 0.0f;
       }
-      if (a.keep && !a.keep[row]) v = 0.0f;
+      if (!refine_member(a.rf, a.keep, row)) v = 0.0f;
       uk[p] = v > a.conf_thr ? f2ord(v) : 0u;
     }
     if (tid == 0) s_res[4] = 0;
@@ -595,7 +599,7 @@ __device__ __forceinline__ float ovf_score(const DetSegArgs& a, size_t row, int 
     const float sden = a.row_s[row];
     v = sden > 0.0f ? __fdiv_rn(expf(v - a.row_m[row]), sden) : 0.0f;
   }
-  if (a.keep && !a.keep[row]) v = 0.0f;
+  if (!refine_member(a.rf, a.keep, row)) v = 0.0f;
   return v;
 }
 
@@ -604,7 +608,7 @@ __device__ __forceinline__ void ovf_row_scores(const DetSegArgs& a, size_t row, 
   const float* x = a.scores + row * a.C + c0;
 #pragma unroll
   for (int k = 0; k < kOvfClasses; ++k) v[k] = c0 + k < a.C ? x[k] : 0.0f;
-  const bool kept = !a.keep || a.keep[row];
+  const bool kept = refine_member(a.rf, a.keep, row);
   if (a.row_s) {           // logits: the same expression as the candidate pass
     const float sden = a.row_s[row], m = a.row_m[row];
 #pragma unroll
@@ -877,10 +881,40 @@ extern "C" int ssdbox_detect(const ssdbox_detect_cfg* cfg, const float* loc, con
   return ssdbox_detect_peers(cfg, loc, scores, priors, score_keep, out, counts, nullptr, nullptr, nullptr, ws, ws_bytes, stream);
 }
 
+static int detect_impl(const ssdbox_detect_cfg* cfg, const float* loc, const float* scores, const float* priors,
+                       const uint8_t* score_keep, const ssdbox_refine* refine, float* out, int32_t* counts,
+                       const ssdbox_peer_group* peers, double* loss_sums, float* losses, void* ws, size_t ws_bytes,
+                       ssdbox_stream_t stream);
+
 extern "C" int ssdbox_detect_peers(const ssdbox_detect_cfg* cfg, const float* loc, const float* scores, const float* priors,
                                    const uint8_t* score_keep, float* out, int32_t* counts, const ssdbox_peer_group* peers,
                                    double* loss_sums, float* losses, void* ws, size_t ws_bytes, ssdbox_stream_t stream) {
+  return detect_impl(cfg, loc, scores, priors, score_keep, nullptr, out, counts, peers, loss_sums, losses, ws, ws_bytes, stream);
+}
+
+extern "C" int ssdbox_detect_refine(const ssdbox_detect_cfg* cfg, const float* loc, const float* scores, const float* priors,
+                                    const ssdbox_refine* refine, float* out, int32_t* counts, void* ws, size_t ws_bytes,
+                                    ssdbox_stream_t stream) {
+  SSDBOX_REQUIRE(refine, SSDBOX_EINVAL, "detect: null refine descriptor");
+  return detect_impl(cfg, loc, scores, priors, nullptr, refine, out, counts, nullptr, nullptr, nullptr, ws, ws_bytes, stream);
+}
+
+static int detect_impl(const ssdbox_detect_cfg* cfg, const float* loc, const float* scores, const float* priors,
+                       const uint8_t* score_keep, const ssdbox_refine* refine, float* out, int32_t* counts,
+                       const ssdbox_peer_group* peers, double* loss_sums, float* losses, void* ws, size_t ws_bytes,
+                       ssdbox_stream_t stream) {
   SSDBOX_REQUIRE(cfg, SSDBOX_EINVAL, "detect: null cfg");
+  RefineArgs rf{};
+  if (refine) {
+    SSDBOX_REQUIRE(cfg->prior_batch_stride == 0, SSDBOX_EINVAL, "refine: priors must be the shared [P,4] tensor (prior_batch_stride 0)");
+    SSDBOX_REQUIRE((cfg->B == 0 || cfg->P == 0 || refine->arm_loc) && aligned16(refine->arm_loc) && aligned16(refine->arm_conf),
+                   SSDBOX_EINVAL, "refine: arm_loc null / arm tensors not 16-byte aligned");
+    rf.arm_loc = refine->arm_loc;
+    rf.arm_conf = refine->arm_conf;
+    rf.theta = refine->theta;
+    rf.var0 = cfg->var0;
+    rf.var1 = cfg->var1;
+  }
   if (peers) {
     SSDBOX_REQUIRE(peers->world >= 1 && peers->world <= SSDBOX_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world && loss_sums,
                    SSDBOX_EINVAL, "detect: bad peer group / null loss_sums");
@@ -926,6 +960,7 @@ extern "C" int ssdbox_detect_peers(const ssdbox_detect_cfg* cfg, const float* lo
     rc = plan_ring(&sa.ring, scores, (long long)B * P, C, dev.sm_count, dev.max_smem_optin);
     if (rc) return rc;
     sa.keep = score_keep;
+    sa.rf = rf;
     sa.cnt = cnt;
     sa.cand = cand;
     sa.P = P;
@@ -949,7 +984,7 @@ extern "C" int ssdbox_detect_peers(const ssdbox_detect_cfg* cfg, const float* lo
   g.B = B; g.P = P; g.C = C; g.top_k = top_k; g.cap = cap;
   g.nms_thr = cfg->nms_thresh; g.conf_thr = cfg->conf_thresh; g.var0 = cfg->var0; g.var1 = cfg->var1;
   g.prior_stride = (long long)cfg->prior_batch_stride;
-  g.loc = loc; g.scores = scores; g.priors = priors; g.keep = score_keep;
+  g.loc = loc; g.scores = scores; g.priors = priors; g.keep = score_keep; g.rf = rf;
   g.cnt = cnt; g.cand = cand; g.ovf_count = cnt + (size_t)B * C; g.ovf_list = ovf_list; g.big_count = cnt + (size_t)B * C + 1;
   g.tail_ticket = cnt + (size_t)B * C + 2; g.big_list = big_list; g.scratch = scratch; g.out = out; g.counts = counts;
   g.row_m = logits ? row_m : nullptr; g.row_s = logits ? row_s : nullptr;

@@ -83,6 +83,7 @@ struct StreamArgs {
   const float* priors;
   long long prior_stride;
   const float* anchors_xyxy;
+  RefineArgs rf;            // RefineDet fused: anchors decoded from arm_loc in the match warps, pool = ARM objectness
   float threshold;
   int binarize;
   unsigned long long* gt_best;
@@ -152,6 +153,7 @@ struct UnitBuf {
   unsigned long long* best;   // [gpad] per-truth best prior over this unit
   float* area;                // [gpad]
   int* lab;                   // [gpad] class target (label + 1)
+  float4* arm;                // [match_tile] RefineDet fused: the unit's ARM offsets (behind the rest; only then allocated)
 };
 __device__ __forceinline__ UnitBuf unit_buf(unsigned char* mbase, int buf, int unit_bytes, int gpad, int match_tile) {
   unsigned char* ub = mbase + kMatchBarBytes + (size_t)buf * unit_bytes;
@@ -162,9 +164,12 @@ __device__ __forceinline__ UnitBuf unit_buf(unsigned char* mbase, int buf, int u
   u.best = reinterpret_cast<unsigned long long*>(u.box + gpad);
   u.area = reinterpret_cast<float*>(u.best + gpad);
   u.lab = reinterpret_cast<int*>(u.area + gpad);
+  u.arm = reinterpret_cast<float4*>(u.lab + gpad);       // 16-byte aligned: gpad is even
   return u;
 }
-static inline int unit_buf_bytes(int gpad, int match_tile) { return (int)align_up((size_t)16 + (size_t)match_tile * 16 + (size_t)gpad * 32, 128); }
+static inline int unit_buf_bytes(int gpad, int match_tile, bool refine) {
+  return (int)align_up((size_t)16 + (size_t)match_tile * 16 + (size_t)gpad * 32 + (refine ? (size_t)match_tile * 16 : 0), 128);
+}
 
 // max IoU, lowest prior index on ties (box_utils.py:116); shared-memory copy first: the global
 // atomic happens once per (unit, truth), never inside the truth loop
@@ -216,9 +221,15 @@ __device__ void match_sched_loop(const StreamArgs& a, unsigned char* mbase, int 
     if (lane == 0) *ub.hd = MatchUnit{b, p0, nrows, G};
     __syncwarp();
     if (lane == 0) {
-      const float* src = src_base + (size_t)b * (size_t)a.prior_stride + (size_t)p0 * 4;
-      mbar_arrive_expect_tx(&mfull[buf], (uint32_t)nrows * 16u);
-      bulk_g2s_plain(ub.pri, src, (uint32_t)nrows * 16u, &mfull[buf]);
+      if (a.rf.arm_loc) {      // the shared priors of the unit and the image's ARM offsets: decoded by the match warps
+        mbar_arrive_expect_tx(&mfull[buf], (uint32_t)nrows * 32u);
+        bulk_g2s_plain(ub.pri, a.priors + (size_t)p0 * 4, (uint32_t)nrows * 16u, &mfull[buf]);
+        bulk_g2s_plain(ub.arm, a.rf.arm_loc + ((size_t)b * (size_t)a.P + (size_t)p0) * 4, (uint32_t)nrows * 16u, &mfull[buf]);
+      } else {
+        const float* src = src_base + (size_t)b * (size_t)a.prior_stride + (size_t)p0 * 4;
+        mbar_arrive_expect_tx(&mfull[buf], (uint32_t)nrows * 16u);
+        bulk_g2s_plain(ub.pri, src, (uint32_t)nrows * 16u, &mfull[buf]);
+      }
     }
   }
 }
@@ -261,7 +272,9 @@ __device__ void match_unit_loop(const StreamArgs& a, unsigned char* mbase, int m
       box[q].x1 = box[q].y1 = box[q].x2 = box[q].y2 = 0.f;
       if (valid[q]) {
         float4 v = ub.pri[r0 + q];
-        if (a.anchors_xyxy) {
+        if (a.rf.arm_loc) {
+          box[q] = decode_box(ub.arm[r0 + q], v, a.rf.var0, a.rf.var1);     // refined anchor, xyxy
+        } else if (a.anchors_xyxy) {
           box[q].x1 = v.x; box[q].y1 = v.y; box[q].x2 = v.z; box[q].y2 = v.w;
         } else {
           box[q] = point_form(v);
@@ -414,7 +427,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) loss_stream_kernel(StreamAr
         const float lse = row_lse<CT>(rp, C);
         const float k0 = lse - rp[0];                        // multibox_loss.py:94 with conf_t = 0
         a.key0[row] = k0;                                    // (a positive's lse is recovered as key0 + x[0]: no second array)
-        if (!a.pool || a.pool[row]) {
+        if (refine_member(a.rf, a.pool, (size_t)row)) {
           uint32_t b = (uint32_t)row / (uint32_t)a.P;
           atomicAdd(&a.hist[(size_t)b * kHistBins + mine_bin(f2ord(k0))], 1u);
         }
@@ -435,7 +448,7 @@ static int plan_stream(StreamArgs* a, const float* conf, long long rows, int C, 
   a->match_warps = match_warps_for(C);
   a->match_tile = a->match_warps * 128;
   if (want_fuse) {
-    int ub = unit_buf_bytes(a->gpad, a->match_tile);
+    int ub = unit_buf_bytes(a->gpad, a->match_tile, a->rf.arm_loc != nullptr);
     size_t need = (size_t)kMatchBarBytes + 2 * (size_t)ub;
     if (need + 65536 < (size_t)max_smem) {
       RingPlan rp;
@@ -488,6 +501,7 @@ struct MineArgs {
   const float* gt;
   const int32_t* gt_offsets;
   const uint8_t* pool;
+  RefineArgs rf;           // RefineDet fused: pool = ARM objectness, anchors decoded from arm_loc for the positives
   const float* keys;       // key0 = lse - x[0] from the stream kernel
   const float* conf;       // gathered per positive: x[target] and x[0] (lse = key0 + x[0])
   const int16_t* lab;
@@ -615,7 +629,7 @@ __device__ __forceinline__ uint32_t mine_visit(const MineArgs& a, size_t i, int 
     const float* row = a.gt + (size_t)(g0 + a.tidx[i]) * 5;
     Box m;
     m.x1 = row[0]; m.y1 = row[1]; m.x2 = row[2]; m.y2 = row[3];
-    float4 t = encode_box(m, *reinterpret_cast<const float4*>(pri + (size_t)p * 4), a.var0, a.var1);
+    float4 t = encode_box(m, refine_center(a.rf, *reinterpret_cast<const float4*>(pri + (size_t)p * 4), i), a.var0, a.var1);
     float4 l = *reinterpret_cast<const float4*>(a.loc + i * 4);
     l1 += (double)(smooth_l1(l.x, t.x) + smooth_l1(l.y, t.y) + smooth_l1(l.z, t.z) + smooth_l1(l.w, t.w));
     return f2ord(0.0f);
@@ -693,6 +707,11 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
           kk[u] = k4[q];
           ll[u] = l4[q];
           if (p4) pp[u] = p4[q];
+          if (a.rf.arm_conf) {
+            const size_t r0 = off + (size_t)q * 4;
+            pp[u] = make_uchar4(refine_keeps(a.rf.arm_conf, r0, a.rf.theta), refine_keeps(a.rf.arm_conf, r0 + 1, a.rf.theta),
+                                refine_keeps(a.rf.arm_conf, r0 + 2, a.rf.theta), refine_keeps(a.rf.arm_conf, r0 + 3, a.rf.theta));
+          }
         }
       }
 #pragma unroll
@@ -715,7 +734,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_kernel(MineArgs a
       size_t i = off + p;
       float key = a.keys[i];
       int lb = a.lab[i];
-      int inpool = a.pool ? a.pool[i] : 1;
+      int inpool = refine_member(a.rf, a.pool, i) ? 1 : 0;
       uk[p] = mine_visit(a, i, p, b, g0, pri, key, lb, inpool, npos, ce, l1);
       if (in_smem) s_lab[p] = (int16_t)lb;
     }
@@ -864,6 +883,15 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
       if (p4) {
         uchar4 pv = p4[q];
         m = (pv.x ? 1u : 0u) | (pv.y ? 2u : 0u) | (pv.z ? 4u : 0u) | (pv.w ? 8u : 0u);
+      }
+      if (a.rf.arm_conf) {       // RefineDet fused: the ARM objectness of the quad's four anchors (two 16-byte loads)
+        const float4* c4 = reinterpret_cast<const float4*>(a.rf.arm_conf + (off + (size_t)q * 4) * 2);
+        const float4 ca = c4[0], cb = c4[1];
+        const float o0 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(__fsub_rn(ca.x, ca.y))));
+        const float o1 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(__fsub_rn(ca.z, ca.w))));
+        const float o2 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(__fsub_rn(cb.x, cb.y))));
+        const float o3 = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(__fsub_rn(cb.z, cb.w))));
+        m = (o0 > a.rf.theta ? 1u : 0u) | (o1 > a.rf.theta ? 2u : 0u) | (o2 > a.rf.theta ? 4u : 0u) | (o3 > a.rf.theta ? 8u : 0u);
       }
       poolmask |= m << (4 * j);
     }
@@ -1028,7 +1056,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
     p_xt = a.conf[i * (size_t)a.C + lb];
     p_t = a.tidx[i];
     p_l = *reinterpret_cast<const float4*>(a.loc + i * 4);
-    p_pr = *reinterpret_cast<const float4*>(pri + (size_t)p_p * 4);
+    p_pr = refine_center(a.rf, *reinterpret_cast<const float4*>(pri + (size_t)p_p * 4), i);
   }
 
   PHASE_MARK(4);
@@ -1204,7 +1232,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
     const int p = (int)(ent & 0xffffu), lb = (int)(ent >> 16);
     const size_t i = off + p;
     positive(i, p, a.keys[i] + a.conf[i * (size_t)a.C], a.conf[i * (size_t)a.C + lb], a.tidx[i], *reinterpret_cast<const float4*>(a.loc + i * 4),
-             *reinterpret_cast<const float4*>(pri + (size_t)p * 4));
+             refine_center(a.rf, *reinterpret_cast<const float4*>(pri + (size_t)p * 4), i));
   }
   // (5) neg = rank < num_neg (:103); CE over pos U neg (:106-110); the CE of a selected negative is
   // its mining key, recovered exactly from the ordered key
@@ -1314,6 +1342,7 @@ struct BwdArgs {
   float* grad_loc;
   float* grad_conf;
   int conf_aligned;
+  RefineArgs rf;           // RefineDet fused: the positives' anchors are decoded from arm_loc
 };
 
 // (1) grad_conf := 0 at full store bandwidth (only ~4*num_pos rows per image are ever non-zero)
@@ -1361,7 +1390,7 @@ __global__ void __launch_bounds__(kBwdThreads) loss_bwd_kernel(BwdArgs a) {
         const float* tr = a.gt + (size_t)(a.gt_offsets[b] + a.tidx[row]) * 5;
         Box m;
         m.x1 = tr[0]; m.y1 = tr[1]; m.x2 = tr[2]; m.y2 = tr[3];
-        float4 t = encode_box(m, *reinterpret_cast<const float4*>(a.priors + (size_t)b * (size_t)a.prior_stride + (size_t)p * 4),
+        float4 t = encode_box(m, refine_center(a.rf, *reinterpret_cast<const float4*>(a.priors + (size_t)b * (size_t)a.prior_stride + (size_t)p * 4), (size_t)row),
                               a.var0, a.var1);
         float4 l = *reinterpret_cast<const float4*>(a.loc + row * 4);
         g.x = scale_l * fminf(fmaxf(l.x - t.x, -1.f), 1.f);     // smooth-L1': d for |d|<1, sign(d) otherwise
@@ -1571,7 +1600,7 @@ __global__ void __launch_bounds__(kBwdStreamWarps * 32, 1) loss_bwd_stream_kerne
         const int b = (int)((uint32_t)row / (uint32_t)a.P);
         const int pi = (int)((uint32_t)row - (uint32_t)b * (uint32_t)a.P);
         const float4 l = *reinterpret_cast<const float4*>(a.loc + row * 4);
-        const float4 pr = *reinterpret_cast<const float4*>(a.priors + (size_t)b * (size_t)a.prior_stride + (size_t)pi * 4);
+        const float4 pr = refine_center(a.rf, *reinterpret_cast<const float4*>(a.priors + (size_t)b * (size_t)a.prior_stride + (size_t)pi * 4), (size_t)row);
         const float* tr = a.gt + (size_t)(a.gt_offsets[b] + a.tidx[row]) * 5;
         Box mbox;
         mbox.x1 = tr[0]; mbox.y1 = tr[1]; mbox.x2 = tr[2]; mbox.y2 = tr[3];
@@ -1621,13 +1650,59 @@ extern "C" int ssdbox_multibox_loss_fwd(const ssdbox_loss_cfg* cfg, const float*
                                         tidx, dbg_conf_t, dbg_loc_t, dbg_neg, dbg_keys, nullptr, ws, ws_bytes, stream);
 }
 
+static int loss_fwd_impl(const ssdbox_loss_cfg* cfg, const float* loc, const float* conf, const float* priors,
+                         const float* anchors_xyxy, const uint8_t* pool, const ssdbox_refine* refine, const float* gt,
+                         const int32_t* gt_offsets, double* sums, float* losses, int16_t* sel, int16_t* tidx,
+                         int64_t* dbg_conf_t, float* dbg_loc_t, uint8_t* dbg_neg, float* dbg_keys,
+                         const ssdbox_peer_group* peers, void* ws, size_t ws_bytes, ssdbox_stream_t stream);
+
 extern "C" int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const float* loc, const float* conf,
                                               const float* priors, const float* anchors_xyxy, const uint8_t* pool,
                                               const float* gt, const int32_t* gt_offsets, double* sums, float* losses,
                                               int16_t* sel, int16_t* tidx, int64_t* dbg_conf_t, float* dbg_loc_t,
                                               uint8_t* dbg_neg, float* dbg_keys, const ssdbox_peer_group* peers,
                                               void* ws, size_t ws_bytes, ssdbox_stream_t stream) {
+  return loss_fwd_impl(cfg, loc, conf, priors, anchors_xyxy, pool, nullptr, gt, gt_offsets, sums, losses, sel, tidx, dbg_conf_t,
+                       dbg_loc_t, dbg_neg, dbg_keys, peers, ws, ws_bytes, stream);
+}
+
+extern "C" int ssdbox_multibox_loss_fwd_refine(const ssdbox_loss_cfg* cfg, const float* loc, const float* conf,
+                                               const float* priors, const ssdbox_refine* refine, const float* gt,
+                                               const int32_t* gt_offsets, double* sums, float* losses, int16_t* sel,
+                                               int16_t* tidx, int64_t* dbg_conf_t, float* dbg_loc_t, uint8_t* dbg_neg,
+                                               float* dbg_keys, const ssdbox_peer_group* peers, void* ws, size_t ws_bytes,
+                                               ssdbox_stream_t stream) {
+  SSDBOX_REQUIRE(refine, SSDBOX_EINVAL, "loss: null refine descriptor");
+  return loss_fwd_impl(cfg, loc, conf, priors, nullptr, nullptr, refine, gt, gt_offsets, sums, losses, sel, tidx, dbg_conf_t,
+                       dbg_loc_t, dbg_neg, dbg_keys, peers, ws, ws_bytes, stream);
+}
+
+// fills the kernels' RefineArgs from the ABI descriptor (validated); nullptr -> all zero
+static int make_refine(const ssdbox_refine* refine, float var0, float var1, long long prior_batch_stride, int nonempty, RefineArgs* out) {
+  RefineArgs r{};
+  if (refine) {
+    SSDBOX_REQUIRE(prior_batch_stride == 0, SSDBOX_EINVAL, "refine: priors must be the shared [P,4] tensor (prior_batch_stride 0)");
+    SSDBOX_REQUIRE(!nonempty || refine->arm_loc, SSDBOX_EINVAL, "refine: null arm_loc");
+    SSDBOX_REQUIRE(aligned16(refine->arm_loc) && aligned16(refine->arm_conf), SSDBOX_EALIGN, "refine: arm_loc / arm_conf must be 16-byte aligned");
+    r.arm_loc = refine->arm_loc;
+    r.arm_conf = refine->arm_conf;
+    r.theta = refine->theta;
+    r.var0 = var0;
+    r.var1 = var1;
+  }
+  *out = r;
+  return SSDBOX_OK;
+}
+
+static int loss_fwd_impl(const ssdbox_loss_cfg* cfg, const float* loc, const float* conf, const float* priors,
+                         const float* anchors_xyxy, const uint8_t* pool, const ssdbox_refine* refine, const float* gt,
+                         const int32_t* gt_offsets, double* sums, float* losses, int16_t* sel, int16_t* tidx,
+                         int64_t* dbg_conf_t, float* dbg_loc_t, uint8_t* dbg_neg, float* dbg_keys,
+                         const ssdbox_peer_group* peers, void* ws, size_t ws_bytes, ssdbox_stream_t stream) {
   int rc = check_loss_cfg(cfg);
+  if (rc) return rc;
+  RefineArgs rf;
+  rc = make_refine(refine, cfg->var0, cfg->var1, cfg->prior_batch_stride, cfg->B > 0 && cfg->P > 0, &rf);
   if (rc) return rc;
   if (peers) {
     SSDBOX_REQUIRE(peers->world >= 1 && peers->world <= SSDBOX_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world,
@@ -1692,8 +1767,9 @@ extern "C" int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const 
   // Matching runs on dedicated warps of the streaming kernel unless the caller asked for the
   // separate kernel or the truths of a CTA's images do not fit in shared memory beside the ring.
   MatchArgs ma{gt, gt_offsets, cfg->gmax, priors, (long long)cfg->prior_batch_stride, anchors_xyxy, B, P,
-               cfg->threshold, cfg->binarize_labels};
+               cfg->threshold, cfg->binarize_labels, rf};
   StreamArgs sa{};
+  sa.rf = rf;
   sa.pool = pool;
   sa.key0 = w.keys;
   sa.hist = w.hist;
@@ -1733,7 +1809,7 @@ extern "C" int ssdbox_multibox_loss_fwd_peers(const ssdbox_loss_cfg* cfg, const 
   m.var0 = cfg->var0; m.var1 = cfg->var1;
   m.finalize = cfg->finalize;
   m.prior_stride = (long long)cfg->prior_batch_stride;
-  m.loc = loc; m.priors = priors; m.gt = gt; m.gt_offsets = gt_offsets; m.pool = pool;
+  m.loc = loc; m.priors = priors; m.gt = gt; m.gt_offsets = gt_offsets; m.pool = pool; m.rf = rf;
   m.keys = w.keys; m.conf = conf; m.lab = w.m.lab; m.tidx = tidx; m.hist = w.hist;
   m.fuse = sa.fuse; m.gmax = cfg->gmax; m.gpad = sa.gpad; m.binarize = cfg->binarize_labels;
   m.gt_best = w.m.gt_best; m.gt_best_w = w.m.gt_best; m.lab_w = w.m.lab; m.tidx_w = tidx;
@@ -1846,7 +1922,19 @@ extern "C" int ssdbox_multibox_loss_bwd(const ssdbox_loss_cfg* cfg, const float*
                                         const int16_t* sel, const int16_t* tidx, const double* sums,
                                         const float* grad_out, float* grad_loc, float* grad_conf,
                                         ssdbox_stream_t stream) {
+  return ssdbox_multibox_loss_bwd_refine(cfg, loc, conf, priors, nullptr, gt, gt_offsets, sel, tidx, sums, grad_out, grad_loc,
+                                         grad_conf, stream);
+}
+
+extern "C" int ssdbox_multibox_loss_bwd_refine(const ssdbox_loss_cfg* cfg, const float* loc, const float* conf,
+                                               const float* priors, const ssdbox_refine* refine, const float* gt,
+                                               const int32_t* gt_offsets, const int16_t* sel, const int16_t* tidx,
+                                               const double* sums, const float* grad_out, float* grad_loc,
+                                               float* grad_conf, ssdbox_stream_t stream) {
   int rc = check_loss_cfg(cfg);
+  if (rc) return rc;
+  RefineArgs rf;
+  rc = make_refine(refine, cfg->var0, cfg->var1, cfg->prior_batch_stride, cfg->B > 0 && cfg->P > 0, &rf);
   if (rc) return rc;
   if (cfg->B == 0 || cfg->P == 0) return SSDBOX_OK;
   SSDBOX_REQUIRE(loc && conf && priors && gt_offsets && sel && tidx && sums && grad_out && grad_loc && grad_conf,
@@ -1864,6 +1952,7 @@ extern "C" int ssdbox_multibox_loss_bwd(const ssdbox_loss_cfg* cfg, const float*
   a.loc = loc; a.conf = conf; a.priors = priors; a.gt = gt; a.gt_offsets = gt_offsets;
   a.sel = sel; a.tidx = tidx; a.sums = sums; a.grad_out = grad_out;
   a.grad_loc = grad_loc; a.grad_conf = grad_conf;
+  a.rf = rf;
   a.conf_aligned = aligned16(grad_conf) ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long rows = (long long)a.B * a.P;

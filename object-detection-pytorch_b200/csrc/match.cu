@@ -100,7 +100,10 @@ match_kernel(MatchArgs a, unsigned long long* __restrict__ gt_best, uint32_t* __
     pidx[k] = p;
     valid[k] = p < a.P;
     if (valid[k]) {
-      if (anc) {
+      if (a.rf.arm_loc) {
+        box[k] = decode_box(*reinterpret_cast<const float4*>(a.rf.arm_loc + (img_off + (size_t)p) * 4),
+                            *reinterpret_cast<const float4*>(pri + (size_t)p * 4), a.rf.var0, a.rf.var1);
+      } else if (anc) {
         float4 v = *reinterpret_cast<const float4*>(anc + (size_t)p * 4);
         box[k].x1 = v.x; box[k].y1 = v.y; box[k].x2 = v.z; box[k].y2 = v.w;
       } else {
@@ -246,7 +249,7 @@ __global__ void materialize_kernel(MatchArgs a, float var0, float var1, const in
         const float* row = a.gt + (size_t)(g0 + t) * 5;
         Box m;
         m.x1 = row[0]; m.y1 = row[1]; m.x2 = row[2]; m.y2 = row[3];
-        float4 pr = *reinterpret_cast<const float4*>(a.priors + (size_t)b * (size_t)a.prior_stride + (size_t)p * 4);
+        float4 pr = refine_center(a.rf, *reinterpret_cast<const float4*>(a.priors + (size_t)b * (size_t)a.prior_stride + (size_t)p * 4), i);
         r = encode_box(m, pr, var0, var1);
       }
       *reinterpret_cast<float4*>(loc_t + i * 4) = r;

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.h"
 #include "sizes.h"
+#include "ssdbox_dev.cuh"
 
 namespace ssdbox {
 
@@ -17,6 +18,7 @@ struct MatchArgs {
   int B, P;
   float threshold;
   int binarize;
+  RefineArgs rf;           // RefineDet fused: anchors decoded from arm_loc on the fly (anchors_xyxy / prior_stride unused)
 };
 
 // fills `best` with kBestInit and zeroes up to three uint32 ranges (one launch)

@@ -30,6 +30,7 @@ SYMBOLS = [
     "ssdbox_multibox_loss_fwd", "ssdbox_multibox_loss_fwd_peers", "ssdbox_multibox_loss_peer_finish",
     "ssdbox_peer_buffer_bytes",
     "ssdbox_multibox_loss_finalize", "ssdbox_multibox_loss_bwd",
+    "ssdbox_multibox_loss_fwd_refine", "ssdbox_multibox_loss_bwd_refine", "ssdbox_detect_refine",
     "ssdbox_nms", "ssdbox_detect", "ssdbox_detect_peers", "ssdbox_detections_compact", "ssdbox_heads_to_rows", "ssdbox_voc_eval", "ssdbox_crop_overlaps", "ssdbox_arm_filter", "ssdbox_timers_enable", "ssdbox_timers_read",
 ]
 
@@ -88,6 +89,11 @@ class VocEvalCfg(C.Structure):
                 ("ovthresh", C.c_double)]
 
 
+class Refine(C.Structure):
+    """ssdbox_refine: the ARM head's outputs for the fused RefineDet path."""
+    _fields_ = [("arm_loc", C.c_void_p), ("arm_conf", C.c_void_p), ("theta", C.c_float), ("reserved", C.c_int32)]
+
+
 class PeerGroup(C.Structure):
     """ssdbox_peer_group: every rank's exchange buffer as addressable from this device."""
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("bufs", C.c_void_p * MAX_PEERS),
@@ -123,6 +129,9 @@ def _declare(lib):
         "ssdbox_hard_negative_mine": [P_, P_, P_, i32, i32, i32, P_, P_, sz, P_],
         "ssdbox_multibox_loss_fwd": [C.POINTER(LossCfg)] + [P_] * 15 + [P_, sz, P_],
         "ssdbox_multibox_loss_fwd_peers": [C.POINTER(LossCfg)] + [P_] * 15 + [C.POINTER(PeerGroup), P_, sz, P_],
+        "ssdbox_multibox_loss_fwd_refine": [C.POINTER(LossCfg), P_, P_, P_, C.POINTER(Refine)] + [P_] * 10 + [C.POINTER(PeerGroup), P_, sz, P_],
+        "ssdbox_multibox_loss_bwd_refine": [C.POINTER(LossCfg), P_, P_, P_, C.POINTER(Refine)] + [P_] * 8 + [P_],
+        "ssdbox_detect_refine": [C.POINTER(DetectCfg), P_, P_, P_, C.POINTER(Refine), P_, P_, P_, sz, P_],
         "ssdbox_multibox_loss_finalize": [P_, P_, P_],
         "ssdbox_multibox_loss_peer_finish": [C.POINTER(PeerGroup), P_, P_, P_],
         "ssdbox_multibox_loss_bwd": [C.POINTER(LossCfg)] + [P_] * 11 + [P_],

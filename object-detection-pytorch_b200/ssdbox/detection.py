@@ -26,7 +26,7 @@ class DetectOut(object):
         self._ws = _abi.Workspace()
         self.last_counts = None
 
-    def forward(self, loc_data, conf_data, prior_data, score_keep=None, out=None, pending=None):
+    def forward(self, loc_data, conf_data, prior_data, score_keep=None, out=None, pending=None, refine=None):
         """`pending` (extension): a PendingLoss of MultiBoxLoss.forward_packed_deferred made on the same stream -- its
         cross-rank wait rides on the last Detect kernel (ssdbox_detect_peers) instead of a launch of its own; call
         pending.wait() afterwards as usual (it then only hands out the results)."""
@@ -54,7 +54,16 @@ class DetectOut(object):
                              (_abi.DETECT_LOGITS if self.conf_is_logits else 0) | (_abi.DETECT_WS_CLEAN if clean else 0), 0)
         keep = score_keep.to(dev).to(torch.uint8).contiguous() if score_keep is not None else None
         fin = pending._detect_tail_args() if pending is not None else None
-        if fin is None:
+        if refine is not None:        # RefineDet fused (ssdbox_detect_refine): anchors refined / filtered inside the kernels
+            from .multibox_loss import make_refine
+            if per_image or keep is not None:
+                raise ValueError("ssdbox: refine= needs the shared [P,4] priors and no score_keep")
+            rf, keepalive = make_refine(refine)
+            _abi.check(_abi.lib().ssdbox_detect_refine(
+                C.byref(cfg), _abi.ptr(loc, torch.float32, "loc_data"), _abi.ptr(scores, torch.float32, "conf_data"),
+                _abi.ptr(pri, torch.float32, "prior_data"), C.byref(rf), _abi.ptr(out, torch.float32, "out"), _abi.ptr(counts),
+                ws, n, _abi.stream_ptr(dev)))
+        elif fin is None:
             _abi.check(_abi.lib().ssdbox_detect(
                 C.byref(cfg), _abi.ptr(loc, torch.float32, "loc_data"), _abi.ptr(scores, torch.float32, "conf_data"),
                 _abi.ptr(pri, torch.float32, "prior_data"), _abi.ptr(keep, torch.uint8, "score_keep", True),

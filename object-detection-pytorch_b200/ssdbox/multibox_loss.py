@@ -65,9 +65,18 @@ class _State(object):
         self.sel, self.tidx, self.sums, self.losses = slot
 
 
+def make_refine(refine):
+    """(arm_loc [B,P,4], arm_conf [B,P,2] | None, theta) -> (ctypes ssdbox_refine, the tensors it points to)"""
+    arm_loc, arm_conf, theta = refine
+    arm_loc = _abi.as_f32(arm_loc.detach())
+    arm_conf = _abi.as_f32(arm_conf.detach()) if arm_conf is not None else None
+    r = _abi.Refine(_abi.ptr(arm_loc, torch.float32, "arm_loc"), _abi.ptr(arm_conf, torch.float32, "arm_conf", True), float(theta), 0)
+    return r, (arm_loc, arm_conf)
+
+
 def loss_forward_raw(state, loc, conf, priors, gt, offsets, gmax, num_classes, threshold, negpos_ratio,
                      variance, anchors_xyxy=None, pool=None, binarize=False, finalize=True, debug=None,
-                     fresh=False, flags=0, peers=None):
+                     fresh=False, flags=0, peers=None, refine=None):
     """One call of ssdbox_multibox_loss_fwd on validated CUDA tensors.  Returns
     (cfg, sums[3] f64, losses[2] f32, sel[B,P] i16, tidx[B,P] i16).  With fresh=False the outputs are
     the module's persistent buffers (overwritten by the next call); fresh=True allocates new ones
@@ -102,6 +111,18 @@ def loss_forward_raw(state, loc, conf, priors, gt, offsets, gmax, num_classes, t
                        float(variance[0]), float(variance[1]), 1 if binarize else 0, 1 if finalize else 0,
                        4 * P if per_image else 0, int(flags) | (_abi.LOSS_WS_CLEAN if clean else 0), 0)
     dbg = debug or {}
+    if refine is not None:       # RefineDet fused: the ARM outputs go to the kernels as they are
+        rf, keepalive = make_refine(refine)
+        _abi.check(_abi.lib().ssdbox_multibox_loss_fwd_refine(
+            C.byref(cfg), _abi.ptr(loc, torch.float32, "loc_data"), _abi.ptr(conf, torch.float32, "conf_data"),
+            _abi.ptr(priors, torch.float32, "priors"), C.byref(rf), _abi.ptr(gt, torch.float32, "gt"),
+            _abi.ptr(offsets, torch.int32, "gt_offsets"), _abi.ptr(sums), _abi.ptr(losses),
+            _abi.ptr(sel), _abi.ptr(tidx), _abi.ptr(dbg.get("conf_t"), torch.int64, "conf_t", True),
+            _abi.ptr(dbg.get("loc_t"), torch.float32, "loc_t", True), _abi.ptr(dbg.get("neg"), torch.uint8, "neg", True),
+            _abi.ptr(dbg.get("keys"), torch.float32, "keys", True),
+            C.byref(peers) if peers is not None else None, ws, n, _abi.stream_ptr(dev)))
+        state.ws.commit()
+        return cfg, sums, losses, sel, tidx
     _abi.check(_abi.lib().ssdbox_multibox_loss_fwd_peers(
         C.byref(cfg), _abi.ptr(loc, torch.float32, "loc_data"), _abi.ptr(conf, torch.float32, "conf_data"),
         _abi.ptr(priors, torch.float32, "priors"), _abi.ptr(anchors_xyxy, torch.float32, "anchors", True),
@@ -117,7 +138,7 @@ def loss_forward_raw(state, loc, conf, priors, gt, offsets, gmax, num_classes, t
 
 class _MultiBoxLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, loc, conf, priors, gt, offsets, anchors_xyxy, pool, mod, gmax):
+    def forward(ctx, loc, conf, priors, gt, offsets, anchors_xyxy, pool, mod, gmax, refine=None):
         st = mod._state
         distributed = mod._is_distributed()
         # the only collective of the path: {sum smooth-L1, sum CE, N_pos} summed over ranks.  Preferred:
@@ -132,7 +153,7 @@ class _MultiBoxLossFn(torch.autograd.Function):
         cfg, sums, losses, sel, tidx = loss_forward_raw(
             st, loc, conf, priors, gt, offsets, gmax, mod.num_classes, mod.threshold, mod.negpos_ratio,
             mod.variance, anchors_xyxy, pool, mod.binarize_labels, finalize=(not distributed) or peers is not None,
-            debug=mod._debug, fresh=need_grad, flags=mod.abi_flags, peers=peers)
+            debug=mod._debug, fresh=need_grad, flags=mod.abi_flags, peers=peers, refine=refine)
         if distributed and peers is None:
             import torch.distributed as dist
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=mod.process_group)
@@ -145,6 +166,7 @@ class _MultiBoxLossFn(torch.autograd.Function):
             ctx.grad_mul = float(dist.get_world_size(mod.process_group))
         if need_grad:
             ctx.cfg = cfg
+            ctx.refine = refine
             ctx.save_for_backward(loc, conf, priors, gt, offsets, sel, tidx, sums)
             return losses[0], losses[1]
         out = losses.clone()
@@ -159,11 +181,18 @@ class _MultiBoxLossFn(torch.autograd.Function):
             gout = gout * ctx.grad_mul
         grad_loc = torch.empty_like(loc)
         grad_conf = torch.empty_like(conf)
+        if ctx.refine is not None:
+            rf, keepalive = make_refine(ctx.refine)
+            _abi.check(_abi.lib().ssdbox_multibox_loss_bwd_refine(
+                C.byref(ctx.cfg), _abi.ptr(loc), _abi.ptr(conf), _abi.ptr(priors), C.byref(rf), _abi.ptr(gt), _abi.ptr(offsets),
+                _abi.ptr(sel), _abi.ptr(tidx), _abi.ptr(sums), _abi.ptr(gout), _abi.ptr(grad_loc), _abi.ptr(grad_conf),
+                _abi.stream_ptr(dev)))
+            return grad_loc, grad_conf, None, None, None, None, None, None, None, None
         _abi.check(_abi.lib().ssdbox_multibox_loss_bwd(
             C.byref(ctx.cfg), _abi.ptr(loc), _abi.ptr(conf), _abi.ptr(priors), _abi.ptr(gt), _abi.ptr(offsets),
             _abi.ptr(sel), _abi.ptr(tidx), _abi.ptr(sums), _abi.ptr(gout), _abi.ptr(grad_loc), _abi.ptr(grad_conf),
             _abi.stream_ptr(dev)))
-        return grad_loc, grad_conf, None, None, None, None, None, None, None
+        return grad_loc, grad_conf, None, None, None, None, None, None, None, None
 
 
 class PendingLoss(object):
@@ -308,9 +337,10 @@ class MultiBoxLoss(nn.Module):
         gt, offsets, gmax = pack_targets(targets, dev)
         return self.forward_packed(loc, conf, pri, gt, offsets, gmax)
 
-    def forward_packed(self, loc, conf, priors, gt, offsets, gmax, anchors_xyxy=None, pool=None):
-        """Same as forward with the targets already in the C-ABI layout (no host work: capturable)."""
-        return _MultiBoxLossFn.apply(loc, conf, priors, gt, offsets, anchors_xyxy, pool, self, int(gmax))
+    def forward_packed(self, loc, conf, priors, gt, offsets, gmax, anchors_xyxy=None, pool=None, refine=None):
+        """Same as forward with the targets already in the C-ABI layout (no host work: capturable).
+        `refine` = (arm_loc, arm_conf | None, theta): RefineDet fused (anchors refined and filtered inside the kernels)."""
+        return _MultiBoxLossFn.apply(loc, conf, priors, gt, offsets, anchors_xyxy, pool, self, int(gmax), refine)
 
     def forward_packed_deferred(self, loc, conf, priors, gt, offsets, gmax):
         """Inference-style (no autograd) forward whose cross-rank wait is deferred: returns a
@@ -338,7 +368,7 @@ class MultiBoxLoss(nn.Module):
     def intermediates(self, predictions, targets):
         """Runs the forward and also materialises the reference's intermediates
         (conf_t, loc_t, neg mask, mining keys) -- used by the parity tests."""
-        loc_data, conf_data, priors = predictions
+        loc_data = predictions[0]            # (loc, conf, priors) or RefineDet's (arm_loc, arm_conf, odm_loc, odm_conf, priors)
         dev = loc_data.device
         B, P = loc_data.size(0), loc_data.size(1)
         self._debug = dict(conf_t=torch.empty(B, P, dtype=torch.int64, device=dev),

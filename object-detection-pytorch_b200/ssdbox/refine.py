@@ -45,13 +45,17 @@ class RefineMultiBoxLoss(MultiBoxLoss):
 
     def __init__(self, num_classes, overlap_thresh, prior_for_matching, bkg_label, neg_mining, neg_pos,
                  neg_overlap, encode_target, use_gpu=True, theta=0.01, use_ARM=False, variance=(0.1, 0.2),
-                 distributed=None, process_group=None):
+                 distributed=None, process_group=None, fused=True):
         super(RefineMultiBoxLoss, self).__init__(num_classes, overlap_thresh, prior_for_matching, bkg_label,
                                                  neg_mining, neg_pos, neg_overlap, encode_target, use_gpu, variance,
                                                  distributed, process_group)
         self.theta = theta
         self.use_ARM = use_ARM
         self.binarize_labels = not use_ARM
+        # fused (default): arm_loc / arm_conf go to the loss kernels as they are (ssdbox_multibox_loss_fwd_refine): no
+        # refined-anchor tensors, no mask, no extra launch.  fused=False materialises them first (refine_anchors +
+        # arm_filter, two small kernels) -- same results bit for bit, kept for comparison.
+        self.fused = bool(fused)
 
     def forward(self, predictions, targets):
         arm_loc, arm_conf, odm_loc, odm_conf, priors = predictions
@@ -68,21 +72,26 @@ class RefineMultiBoxLoss(MultiBoxLoss):
             loc = _abi.as_f32(arm_loc)
             conf = _abi.as_f32(arm_conf).view(loc.size(0), P, 2)
             return self.forward_packed(loc, conf, pri, gt, offsets, gmax)
-        xy, cf = refine_anchors(arm_loc, pri, self.variance)
-        pool = arm_filter(arm_conf, self.theta)
         loc = _abi.as_f32(odm_loc)
         conf = _abi.as_f32(odm_conf).view(loc.size(0), P, self.num_classes)
+        if self.fused:
+            return self.forward_packed(loc, conf, pri, gt, offsets, gmax, refine=(arm_loc, arm_conf, self.theta))
+        xy, cf = refine_anchors(arm_loc, pri, self.variance)
+        pool = arm_filter(arm_conf, self.theta)
         return self.forward_packed(loc, conf, cf, gt, offsets, gmax, anchors_xyxy=xy, pool=pool)
 
 
 class RefineDetectOut(DetectOut):
     """detector(arm_loc, arm_conf, odm_loc, odm_scores, priors) -> [B,C,top_k,5]."""
 
-    def __init__(self, num_classes, bkg_label, top_k, conf_thresh, nms_thresh, variance, theta=0.01):
+    def __init__(self, num_classes, bkg_label, top_k, conf_thresh, nms_thresh, variance, theta=0.01, fused=True):
         super(RefineDetectOut, self).__init__(num_classes, bkg_label, top_k, conf_thresh, nms_thresh, variance)
         self.theta = theta
+        self.fused = bool(fused)      # see RefineMultiBoxLoss
 
     def forward(self, arm_loc, arm_conf, odm_loc, odm_scores, prior_data, out=None):
+        if self.fused:
+            return DetectOut.forward(self, odm_loc, odm_scores, prior_data, out=out, refine=(arm_loc, arm_conf, self.theta))
         _, cf = refine_anchors(arm_loc, prior_data, self.variance)
         keep = arm_filter(arm_conf, self.theta)
         return DetectOut.forward(self, odm_loc, odm_scores, cf, score_keep=keep, out=out)

@@ -450,3 +450,40 @@ def test_detect_graph_replay_sparse_dense_sparse(dev):
     # the eager module (always-launched overflow kernels) and the replayed graph leave the same clean workspace state
     ws = det._ws.buf
     assert int(ws[:(B * C + 4) * 4].view(torch.int32).abs().sum()) == 0
+
+
+@pytest.mark.parametrize("B,seed,flags", [(5, 100, 0), (32, 101, 0), (5, 102, 1), (5, 103, 2), (5, 104, 4)])
+def test_refinedet_fused_equals_materialised(dev, B, seed, flags):
+    """The fused two-step path (arm_loc / arm_conf handed to the kernels: ssdbox_multibox_loss_fwd_refine / _bwd_refine /
+    ssdbox_detect_refine) against the materialised one (refine_anchors + arm_filter feeding anchors_xyxy / pool /
+    score_keep): same arithmetic, so every target, set, sum, gradient and detection row must be bit-identical -- for the
+    fused and the separate matching kernel, the register-resident and the generic mining kernel."""
+    pri, P, C, tg, arm_loc, arm_conf, odm_loc, odm_conf, sc = _refine_case(B, seed)
+    if B == 5:
+        tg[1] = torch.zeros(0, 5)                      # an image without truths
+    gtg = _gpu_targets(tg, dev)
+    res = []
+    for fused in (True, False):
+        crit = ssdbox.RefineMultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, use_ARM=True, fused=fused)
+        crit.abi_flags = flags
+        ol = odm_loc.to(dev).requires_grad_(True)
+        oc = odm_conf.to(dev).requires_grad_(True)
+        d = crit.intermediates((arm_loc.to(dev), arm_conf.to(dev), ol, oc, pri.to(dev)), gtg)
+        (d["loss_l"] + 2.0 * d["loss_c"]).backward()
+        d["grad_loc"], d["grad_conf"] = ol.grad.clone(), oc.grad.clone()
+        res.append(d)
+    a, b = res
+    for k in ("conf_t", "neg", "sel", "tidx", "keys", "sums", "loc_t", "grad_loc", "grad_conf"):
+        assert torch.equal(a[k], b[k]), k
+    assert float(a["loss_l"]) == float(b["loss_l"]) and float(a["loss_c"]) == float(b["loss_c"])
+    assert int((a["sel"] > 0).sum()) > 0 and int(a["neg"].sum()) > 0
+    args = tuple(t.to(dev) for t in (arm_loc, arm_conf, odm_loc, sc, pri))
+    o_f = ssdbox.RefineDetectOut(C, 0, 200, 0.01, 0.45, VAR, theta=0.01, fused=True)(*args)
+    o_m = ssdbox.RefineDetectOut(C, 0, 200, 0.01, 0.45, VAR, theta=0.01, fused=False)(*args)
+    assert torch.equal(o_f, o_m) and int((o_f[..., 0] > 0).sum()) > 0
+    # dense scores: the overflow kernels read the ARM objectness as well
+    dense = synth.gen_detect_scores(min(B, 2), P, C, seed, bkg_bias=1.0).to(dev)
+    args = tuple(t[:min(B, 2)].to(dev) for t in (arm_loc, arm_conf, odm_loc)) + (dense, pri.to(dev))
+    o_f = ssdbox.RefineDetectOut(C, 0, 200, 0.01, 0.45, VAR, theta=0.01, fused=True)(*args)
+    o_m = ssdbox.RefineDetectOut(C, 0, 200, 0.01, 0.45, VAR, theta=0.01, fused=False)(*args)
+    assert torch.equal(o_f, o_m)
