@@ -63,6 +63,7 @@ def parse():
     ap.add_argument("--no-voc-eval", action="store_true", help="skip the VOC evaluation side phase")
     ap.add_argument("--dense", action="store_true", help="detect scores with background bias 4 (worst case)")
     ap.add_argument("--only", default="", choices=["", "T", "D"], help="experiments: time only the loss half (T) or the Detect half (D) of the step")
+    ap.add_argument("--serial", action="store_true", help="run T and D back to back on ONE stream (default: D on a second stream, its tail overlaps T's conf pass)")
     ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not pin the rank to the CPUs / memory next to its GPU")
     ap.add_argument("--no-side-phases", action="store_true", help="skip backward / fused softmax / eval post / head layout / VOC eval / dense phases")
     return ap.parse_args()
@@ -463,16 +464,27 @@ def main():
             return al + ol, ac + oc, out
     else:
         zero = torch.zeros((), device=dev)
+        two_streams = ssdbox.TwoStreamStep(dev)
 
         def step():
-            # T, then D, then the (multi-GPU) wait for the other ranks' loss sums: D overlaps that wait
             with torch.no_grad():
                 if args.only == "D":
                     return zero, zero, det.forward(loc, sc, priors, out=det_out)
-                pending = crit.forward_packed_deferred(loc, conf, priors, gt, offs, gmax)
-                # N > 1: the wait for the other ranks' sums rides on the last Detect kernel (ssdbox_detect_peers)
-                out = det.forward(loc, sc, priors, out=det_out, pending=pending) if args.only != "T" else det_out
-                ll, lc = pending.wait()
+                if args.only == "T":
+                    return crit.forward_packed_deferred(loc, conf, priors, gt, offs, gmax).wait() + (det_out,)
+                if args.serial:
+                    # T, then D on one stream; N > 1: the wait for the other ranks' sums rides on a Detect kernel
+                    pending = crit.forward_packed_deferred(loc, conf, priors, gt, offs, gmax)
+                    out = det.forward(loc, sc, priors, out=det_out, pending=pending)
+                    ll, lc = pending.wait()
+                    return ll, lc, out
+                # T and D are independent ops on the same batch: D goes to a second stream (submitted first).  Its
+                # HBM-bound candidate pass and T's conf pass still run one after the other (each fills every SM), but
+                # D's latency-bound tail (segments + the overflow kernels, ~11 us) now runs UNDER T's conf pass.
+                # (N > 1: the mining kernel is the last kernel of the step here, so its last CTA posts AND collects the
+                # ranks' sums itself -- nothing is left to overlap a deferred wait with)
+                (ll, lc), out = two_streams(lambda: crit.forward_packed(loc, conf, priors, gt, offs, gmax),
+                                            lambda: det.forward(loc, sc, priors, out=det_out))
             return ll, lc, out
 
     log("inputs ready")
@@ -851,9 +863,11 @@ def main():
                        "match+MultiBoxLoss fwd + DetectOut(top_k=200, conf 0.01, nms 0.45)"),
                    "only": args.only or None, "global_batch": n_gpus * B, "detect_scores": "dense (bkg bias 4)" if args.dense else "sparse/realistic (bkg bias 10)",
                    "l2": "inputs larger than L2 (conf and scores are %.0f MB each vs 126 MB L2)" % (conf.numel() * 4 / 1e6),
-                   "launch": "CUDA graph replay" if graph is not None else "eager launches",
+                   "launch": ("CUDA graph replay" if graph is not None else "eager launches") +
+                             ("" if (args.serial or refine or args.only) else "; two streams inside the step: DetectOut on a side stream (submitted first), its tail kernels overlap MultiBoxLoss's conf pass"),
                    "parallelism": ("images sharded by rank; {sum_l, sum_c, N_pos} reduced per step: %s" % (
-                       "posted over NVLink peer memory by the mining kernel (six self-validating 8-byte words per peer, no fence), collected by one warp of the last Detect kernel (no NCCL launch, no extra kernel)" if crit.reduce_used == "p2p"
+                       ("posted over NVLink peer memory by the mining kernel (six self-validating 8-byte words per peer, no fence) and collected by " +
+                        ("one warp of a Detect kernel" if args.serial else "the same kernel's last CTA") + " (no NCCL launch, no extra kernel)") if crit.reduce_used == "p2p"
                        else "one NCCL all-reduce")) if n_gpus > 1 else "single GPU"},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps, "rank_ms_per_step": rank_ms, "clocks": clocks, "phases": phases, "sanity": sanity,

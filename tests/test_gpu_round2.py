@@ -487,3 +487,42 @@ def test_refinedet_fused_equals_materialised(dev, B, seed, flags):
     o_f = ssdbox.RefineDetectOut(C, 0, 200, 0.01, 0.45, VAR, theta=0.01, fused=True)(*args)
     o_m = ssdbox.RefineDetectOut(C, 0, 200, 0.01, 0.45, VAR, theta=0.01, fused=False)(*args)
     assert torch.equal(o_f, o_m)
+
+
+def test_two_stream_step_equals_serial(dev):
+    """ssdbox.TwoStreamStep (DetectOut on a side stream, submitted first; MultiBoxLoss on the current stream): same
+    losses and detections as the two ops back to back, eagerly and under CUDA-graph replay."""
+    x = U.seeded_inputs("ssd300_voc", 6, 120)
+    loc, conf, pri, sc = x["loc"].to(dev), x["conf"].to(dev), x["priors"].to(dev), x["scores"].to(dev)
+    gt, offs, gmax = ssdbox.pack_targets(_gpu_targets(x["targets"], dev), dev)
+    crit = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False)
+    det = ssdbox.DetectOut(x["C"], 0, 200, 0.01, 0.45, VAR)
+    with torch.no_grad():
+        wl, wc = crit.forward_packed(loc, conf, pri, gt, offs, gmax)
+        want = det(loc, sc, pri).clone()
+    step = ssdbox.TwoStreamStep(dev)
+    out_buf = torch.empty_like(want)
+
+    def run():
+        with torch.no_grad():
+            (ll, lc), out = step(lambda: crit.forward_packed(loc, conf, pri, gt, offs, gmax),
+                                 lambda: det.forward(loc, sc, pri, out=out_buf))
+        return ll, lc, out
+    for _ in range(3):
+        ll, lc, out = run()
+        torch.cuda.synchronize()
+        assert float(ll) == float(wl) and float(lc) == float(wc) and torch.equal(out, want)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        run()
+        run()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        ll, lc, out = run()
+    out_buf.zero_()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert float(ll) == float(wl) and float(lc) == float(wc) and torch.equal(out, want)
