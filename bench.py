@@ -8,7 +8,9 @@ configs[1] (SSD512 VGG16 COCO: P=24564 priors, C=81 classes, B=64 images PER GPU
     T  match + MultiBoxLoss forward  (loss_stream with the matching on dedicated warps, mine_reduce)
     D  DetectOut: threshold, top-200, NMS (detect_stream, detect_segments, overflow select + rewritten lists)
 `value` = images/s with inputs resident in HBM (whole job: N * B / max-over-ranks step time; every
-image passes through both T and D), timed with CUDA events around K CUDA-graph replays.
+image passes through both T and D), timed with CUDA events around K CUDA-graph replays.  T and D are independent
+ops on the same batch: by default D is submitted to a side stream first (ssdbox.TwoStreamStep), so that its
+latency-bound tail kernels run under T's HBM-bound conf pass; `--serial` runs the six kernels back to back.
 `e2e` = same metric through the public modules (MultiBoxLoss.forward / DetectOut.__call__) with
 pinned HOST inputs: H2D of loc/conf/targets/scores and D2H of the losses and the detection tensor
 inside the timed region.  `--impl reference` times the reference's own CPU path on the host cores: the
@@ -456,11 +458,19 @@ def main():
         rdet = ssdbox.RefineDetectOut(C, 0, top_k, 0.01, 0.45, VAR, theta=0.01)
         crit = odm_crit
 
+        three_streams = ssdbox.MultiStreamStep(3, dev)
+
         def step():
             with torch.no_grad():
-                al, ac = arm_crit.forward_packed_two_step(arm_loc, arm_conf, loc, conf, priors, gt, offs, gmax)
-                ol, oc = odm_crit.forward_packed_two_step(arm_loc, arm_conf, loc, conf, priors, gt, offs, gmax)
-                out = rdet.forward(arm_loc, arm_conf, loc, sc, priors, out=det_out)
+                if args.serial or world > 1:
+                    al, ac = arm_crit.forward_packed_two_step(arm_loc, arm_conf, loc, conf, priors, gt, offs, gmax)
+                    ol, oc = odm_crit.forward_packed_two_step(arm_loc, arm_conf, loc, conf, priors, gt, offs, gmax)
+                    out = rdet.forward(arm_loc, arm_conf, loc, sc, priors, out=det_out)
+                else:      # the three ops are independent: RefineDetectOut and the ODM loss on side streams, the ARM loss here
+                    (al, ac), out, (ol, oc) = three_streams([
+                        lambda: arm_crit.forward_packed_two_step(arm_loc, arm_conf, loc, conf, priors, gt, offs, gmax),
+                        lambda: rdet.forward(arm_loc, arm_conf, loc, sc, priors, out=det_out),
+                        lambda: odm_crit.forward_packed_two_step(arm_loc, arm_conf, loc, conf, priors, gt, offs, gmax)])
             return al + ol, ac + oc, out
     else:
         zero = torch.zeros((), device=dev)
@@ -495,11 +505,19 @@ def main():
     sanity = {"loss_l": float(ll), "loss_c": float(lc), "detections": int((out[..., 0] > 0).sum()), "mgpu": None}
 
     # ---- per-kernel device times (eager, CUDA events inside the library on the launch stream) ---
+    # measured with the ops back to back on ONE stream: in the two-stream step the kernels of T and D overlap, and
+    # an event pair around one of them would also time its neighbours
+    was_serial = args.serial
+    args.serial = True
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
     _abi.timers_enable(True)
     n_prof = max(3, min(args.steps, 20))
     for _ in range(n_prof):
         step()
     torch.cuda.synchronize()
+    args.serial = was_serial
     kt = _abi.timers_read()
     _abi.timers_enable(False)
     kernels_us = {k: (1e3 * v[0] / v[1]) for k, v in kt.items() if v[1]}
@@ -799,6 +817,7 @@ def main():
                 "frac": achieved / peak, "traffic": traffic.get(dom) if args.workload == WORKLOAD else None,
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/traffic.json), not measured in this run",
                 "avg_launch_us": dom_us,
+                "avg_launch_us_source": "CUDA events recorded by the library around each launch on the launch stream, in an eager pass with the ops back to back on ONE stream (in the two-stream timed region the kernels of T and D overlap)",
                 "algorithmic_bytes_per_launch": dom_bytes, "peak_source": peak_src}
     other = "detect_stream" if dom == "loss_stream" else "loss_stream"
     phases = {
@@ -864,7 +883,9 @@ def main():
                    "only": args.only or None, "global_batch": n_gpus * B, "detect_scores": "dense (bkg bias 4)" if args.dense else "sparse/realistic (bkg bias 10)",
                    "l2": "inputs larger than L2 (conf and scores are %.0f MB each vs 126 MB L2)" % (conf.numel() * 4 / 1e6),
                    "launch": ("CUDA graph replay" if graph is not None else "eager launches") +
-                             ("" if (args.serial or refine or args.only) else "; two streams inside the step: DetectOut on a side stream (submitted first), its tail kernels overlap MultiBoxLoss's conf pass"),
+                             ("" if (args.serial or args.only or (refine and world > 1)) else
+                              ("; three streams inside the step (RefineDetectOut, ODM loss, ARM loss)" if refine else
+                               "; two streams inside the step: DetectOut on a side stream (submitted first), its tail kernels overlap MultiBoxLoss's conf pass")),
                    "parallelism": ("images sharded by rank; {sum_l, sum_c, N_pos} reduced per step: %s" % (
                        ("posted over NVLink peer memory by the mining kernel (six self-validating 8-byte words per peer, no fence) and collected by " +
                         ("one warp of a Detect kernel" if args.serial else "the same kernel's last CTA") + " (no NCCL launch, no extra kernel)") if crit.reduce_used == "p2p"

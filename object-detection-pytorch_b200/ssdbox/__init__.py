@@ -8,7 +8,7 @@ from .detection import DetectOut                        # noqa: F401
 from .multibox_loss import MultiBoxLoss, pack_targets   # noqa: F401
 from .prior_box import PriorBoxSSD                      # noqa: F401
 from .refine import RefineDetectOut, RefineMultiBoxLoss, arm_filter, refine_anchors  # noqa: F401
-from .overlap import TwoStreamStep                      # noqa: F401
+from .overlap import MultiStreamStep, TwoStreamStep     # noqa: F401
 
-__all__ = ["PriorBoxSSD", "DetectOut", "MultiBoxLoss", "RefineMultiBoxLoss", "RefineDetectOut", "TwoStreamStep",
+__all__ = ["PriorBoxSSD", "DetectOut", "MultiBoxLoss", "RefineMultiBoxLoss", "RefineDetectOut", "TwoStreamStep", "MultiStreamStep",
            "box_utils", "configs", "synth"]

@@ -33,3 +33,25 @@ class TwoStreamStep(object):
         loss = loss_call()
         cur.wait_stream(self.side)
         return loss, det
+
+
+class MultiStreamStep(object):
+    """The same idea for any number of independent ops (e.g. RefineDet's ARM loss, ODM loss and RefineDetectOut of one
+    batch): calls[1:] go to side streams in the order given (first submitted, first served by the SMs), calls[0] to
+    the current stream, which then waits for all of them.  Returns the list of results."""
+
+    def __init__(self, n, device=None):
+        self.sides = [torch.cuda.Stream(device=device) for _ in range(max(n - 1, 0))]
+
+    def __call__(self, calls):
+        dev = self.sides[0].device if self.sides else None
+        cur = torch.cuda.current_stream(dev)
+        res = [None] * len(calls)
+        for i, s in enumerate(self.sides[:len(calls) - 1], start=1):
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                res[i] = calls[i]()
+        res[0] = calls[0]()
+        for s in self.sides[:len(calls) - 1]:
+            cur.wait_stream(s)
+        return res
