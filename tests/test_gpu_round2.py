@@ -526,3 +526,39 @@ def test_two_stream_step_equals_serial(dev):
         g.replay()
     torch.cuda.synchronize()
     assert float(ll) == float(wl) and float(lc) == float(wc) and torch.equal(out, want)
+
+
+# ------------------------------------------------------------------------------------------------
+# head layout through the TMA ring (layers with H*W % 4 == 0, >= 64 positions, 32..576 channels) and through the
+# generic tile kernel (everything else), mixed in one call -- pure data movement, bit-exact against torch
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,shapes", [
+    (2, [(324, 64, 64), (486, 32, 32), (486, 16, 16), (486, 8, 8), (486, 4, 4), (324, 2, 2), (324, 1, 1)]),   # SSD512-COCO conf heads
+    (3, [(40, 10, 10), (35, 7, 5), (576, 8, 8), (577, 8, 8), (33, 9, 12), (256, 6, 12), (257, 12, 6)]),     # ragged position tiles, 1 / 2 / 3 boxes, odd layers
+    (1, [(84, 38, 38), (126, 19, 19), (126, 10, 10), (126, 5, 5), (84, 3, 3), (84, 1, 1)]),                 # SSD300-VOC conf heads
+    (5, [(64, 40, 40), (64, 20, 20)]),
+])
+def test_head_layout_tma_and_generic_layers(dev, B, shapes):
+    from ssdbox import heads as H
+    gen = torch.Generator().manual_seed(11)
+    outs = [torch.randn(B, ch, h, w, generator=gen).to(dev) for ch, h, w in shapes]
+    want = torch.cat([o.permute(0, 2, 3, 1).contiguous().view(B, -1) for o in outs], 1)
+    got = H.heads_to_rows(outs, 1)
+    assert torch.equal(got.view(B, -1), want)
+    # a second call into a poisoned output: every element is written
+    out = torch.full_like(got, float("nan"))
+    H.heads_to_rows(outs, 1, out=out)
+    assert torch.equal(out.view(B, -1), want)
+
+
+@pytest.mark.gpu
+def test_head_layout_unaligned_source_falls_back(dev):
+    """a source that is not 16-byte aligned cannot be described by a tensor map: the generic kernel takes it"""
+    from ssdbox import heads as H
+    gen = torch.Generator().manual_seed(12)
+    big = torch.randn(2 * 64 * 16 * 16 + 1, generator=gen).to(dev)
+    o = big[1:].view(2, 64, 16, 16)
+    assert o.data_ptr() % 16 != 0
+    want = o.permute(0, 2, 3, 1).contiguous().view(2, -1)
+    assert torch.equal(H.heads_to_rows([o], 64).view(2, -1), want)

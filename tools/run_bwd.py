@@ -3,6 +3,9 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "object-detection-pytorch_b200"))
 import torch
+from ssdbox import _abi
+if os.environ.get("SSDBOX_EXP"):
+    _abi.LIB_PATH = os.path.join(ROOT, "tools", os.environ["SSDBOX_EXP"] if os.environ["SSDBOX_EXP"].endswith(".so") else "libssdbox_exp.so")
 import ssdbox
 from ssdbox import configs, synth
 flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0
@@ -15,9 +18,16 @@ loc = (torch.randn(B, P, 4, device=dev) * 0.5).requires_grad_(True)
 conf = torch.randn(B, P, C, device=dev); conf[..., 0] += 4; conf.requires_grad_(True)
 crit = ssdbox.MultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False)
 crit.abi_flags = flags
-for it in range(4):
+from ssdbox import _abi as A
+ts = []
+for it in range(8):
     a, b = crit.forward_packed(loc, conf, pri, gt, offs, 32)
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(); (a + b).backward(); e1.record(); torch.cuda.synchronize()
-    print("backward %.1f us" % (1e3 * e0.elapsed_time(e1)))
+    torch.cuda.synchronize()
+    A.timers_enable(True)
+    (a + b).backward()
+    torch.cuda.synchronize()
+    k = A.timers_read(); A.timers_enable(False)
+    ts.append(1e3 * k["loss_bwd"][0] / max(k["loss_bwd"][1], 1))
     loc.grad = None; conf.grad = None
+ts = sorted(ts[2:])
+print("loss_bwd kernel: median %.1f us  min %.1f us  [%s]" % (ts[len(ts) // 2], ts[0], " ".join("%s=%s" % kv for kv in os.environ.items() if kv[0].startswith("SSDBOX_"))))
