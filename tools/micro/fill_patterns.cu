@@ -73,14 +73,26 @@ __global__ void bulk_fill(char* d, size_t bytes, int tile_bytes, int wait_each, 
 // The loaded values only feed a store that never happens.
 __global__ void bulk_fill_reads(char* d, size_t bytes, int tile_bytes, const short* sel, const float* rowsrc, int reads, int* sink) {
   extern __shared__ __align__(128) char z[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
-  char* mine = z + (size_t)warp * tile_bytes;
-  for (int i = lane; i < tile_bytes / 4; i += 32) reinterpret_cast<float*>(mine)[i] = 0.f;
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncwarp();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int wpc = blockDim.x >> 5;
+  char* mine = z + (size_t)(warp % 20) * tile_bytes;
   const size_t nt = (bytes + tile_bytes - 1) / tile_bytes;
   const size_t per = (nt + gridDim.x - 1) / gridDim.x;
   const size_t t1 = (blockIdx.x + 1) * per < nt ? (blockIdx.x + 1) * per : nt;
+  if ((reads & 64) && warp >= 20) {        // reader warps: the same reads, from warps that store nothing
+    int acc2 = 0;
+    for (size_t t = blockIdx.x * per + (warp - 20); t < t1; t += wpc - 20) {
+      acc2 += sel[t * 32 + lane];
+      const float* r = rowsrc + (t * 32 + (t * 7 & 31)) * 81;
+      acc2 += (int)(r[lane] + r[lane + 32] + (lane < 17 ? r[lane + 64] : 0.f));
+    }
+    if (acc2 == 0x7fffffff) *sink = acc2;
+    return;
+  }
+  for (int i = lane; i < tile_bytes / 4; i += 32) reinterpret_cast<float*>(mine)[i] = (reads & 32) ? __int_as_float(0x3f000000 + i * 2654435 + warp * 977) : 0.f;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (reads & 64) wpc = 20;
   const unsigned src = (unsigned)__cvta_generic_to_shared(mine);
   int acc = 0, pre0 = 0, pre1 = 0;
   float prer0 = 0.f, prer1 = 0.f;
@@ -144,9 +156,9 @@ int main() {
     float* rowsrc; CK(cudaMalloc(&rowsrc, bytes + 4096)); CK(cudaMemset(rowsrc, 0, bytes + 4096));
     int* sink; CK(cudaMalloc(&sink, 4));
     CK(cudaFuncSetAttribute(bulk_fill_reads, cudaFuncAttributeMaxDynamicSharedMemorySize, 20 * 10368));
-    for (int reads : {0, 1, 2, 4, 5, 6, 8, 24}) {
+    for (int reads : {0, 1, 2, 4, 5, 6, 8, 24, 32, 64}) {
       char nm[128]; snprintf(nm, 128, "20 warps x 10368 B bulk stores + reads mode %d", reads);
-      report(nm, timeit([&] { bulk_fill_reads<<<148, 640, 20 * 10368>>>((char*)d, bytes, 10368, sel, rowsrc, reads, sink); }));
+      report(nm, timeit([&] { bulk_fill_reads<<<148, (reads & 64) ? 768 : 640, 20 * 10368>>>((char*)d, bytes, 10368, sel, rowsrc, reads, sink); }));
     }
   }
   CK(cudaFuncSetAttribute(bulk_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
