@@ -103,6 +103,30 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
+// the producer thread of a CTA: requests the CTA's items (blockIdx.x, + gridDim.x, ...) into the ring, in order
+__device__ __forceinline__ void heads_tma_produce(const HeadsTmaPlan& p, unsigned char* ring, uint64_t* full, uint64_t* empty) {
+  const uint64_t pol = l2_evict_first_policy();
+  const long long total = p.item_start[p.num_layers];
+  const int stages = p.stages;
+  int st = 0;
+  uint32_t ph = 0;
+  long long n = 0;
+  for (long long item = blockIdx.x; item < total; item += gridDim.x, ++n) {
+    if (n >= stages) mbar_wait(&empty[st], ph ^ 1u);
+    int k = 0;
+    while (item >= p.item_start[k + 1]) ++k;
+    const long long local = item - p.item_start[k];
+    const int b = (int)(local / p.tiles_hw[k]);
+    const int th = (int)(local - (long long)b * p.tiles_hw[k]);
+    const uint32_t box_bytes = (uint32_t)p.box_rows[k] * 128u;
+    mbar_arrive_expect_tx(&full[st], box_bytes * (uint32_t)p.boxes[k]);
+    unsigned char* dst = ring + (size_t)st * p.stage_bytes;
+    for (int i = 0; i < p.boxes[k]; ++i)
+      tma_load_3d(dst + (size_t)i * box_bytes, &p.map[k], th * kHeadTmaPos, i * p.box_rows[k], b, &full[st], pol);
+    if (++st == stages) { st = 0; ph ^= 1u; }
+  }
+}
+
 // MODE (experiment builds only): 0 = the kernel, 1 = loads without stores, 2 = stores without loads
 template <int MODE, bool ALIGN>
 __global__ void __launch_bounds__((kHeadTmaWarps + 1) * 32, 1)
@@ -125,22 +149,7 @@ heads_tma_kernel(const __grid_constant__ HeadsTmaPlan p, float* __restrict__ out
   uint32_t ph = 0;
   if (warp == kHeadTmaWarps) {
     if (lane != 0 || MODE == 2) return;
-    const uint64_t pol = l2_evict_first_policy();
-    long long n = 0;
-    for (long long item = blockIdx.x; item < total; item += gridDim.x, ++n) {
-      if (n >= stages) mbar_wait(&empty[st], ph ^ 1u);
-      int k = 0;
-      while (item >= p.item_start[k + 1]) ++k;
-      const long long local = item - p.item_start[k];
-      const int b = (int)(local / p.tiles_hw[k]);
-      const int th = (int)(local - (long long)b * p.tiles_hw[k]);
-      const uint32_t box_bytes = (uint32_t)p.box_rows[k] * 128u;
-      mbar_arrive_expect_tx(&full[st], box_bytes * (uint32_t)p.boxes[k]);
-      unsigned char* dst = ring + (size_t)st * p.stage_bytes;
-      for (int i = 0; i < p.boxes[k]; ++i)
-        tma_load_3d(dst + (size_t)i * box_bytes, &p.map[k], th * kHeadTmaPos, i * p.box_rows[k], b, &full[st], pol);
-      if (++st == stages) { st = 0; ph ^= 1u; }
-    }
+    heads_tma_produce(p, ring, full, empty);
     return;
   }
   for (long long item = blockIdx.x; item < total; item += gridDim.x) {
@@ -312,6 +321,7 @@ extern "C" int ssdbox_heads_to_rows(const ssdbox_heads_cfg* cfg, float* out, ssd
     q.stages = stages;
     q.stage_bytes = stage_bytes;
     const size_t smem = (size_t)stages * stage_bytes + 1024;
+    const long long grid = items < dev.sm_count ? items : dev.sm_count;
     void (*kern)(HeadsTmaPlan, float*) = heads_tma_kernel<0, true>;
 #ifdef SSDBOX_EXPERIMENTS
     const bool al = !getenv("SSDBOX_HEADS_ALIGN") || atoi(getenv("SSDBOX_HEADS_ALIGN")) != 0;
@@ -321,7 +331,6 @@ extern "C" int ssdbox_heads_to_rows(const ssdbox_heads_cfg* cfg, float* out, ssd
     if (const char* e = getenv("SSDBOX_HEADS_STAGES")) q.stages = atoi(e) >= 2 && atoi(e) < stages ? atoi(e) : stages;
 #endif
     SSDBOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long grid = items < dev.sm_count ? items : dev.sm_count;
     kern<<<(int)grid, (kHeadTmaWarps + 1) * 32, smem, static_cast<cudaStream_t>(stream)>>>(q, out);
     SSDBOX_LAUNCH_OK("heads_tma_kernel");
   }

@@ -1325,6 +1325,11 @@ mine_only_kernel(const float* __restrict__ keys, const uint8_t* __restrict__ pos
 // backward: d(loss_l)/d(loc) and d(loss_c)/d(conf)   (autograd of multibox_loss.py:87-116)
 // ------------------------------------------------------------------------------------------------
 constexpr int kBwdThreads = 256;
+#ifdef SSDBOX_EXPERIMENTS
+#define SSDBOX_ABLATE(bit) ((a.ablate & (bit)) != 0)
+#else
+#define SSDBOX_ABLATE(bit) false
+#endif
 
 struct BwdArgs {
   int B, P, C;
@@ -1343,7 +1348,8 @@ struct BwdArgs {
   float* grad_conf;
   int conf_aligned;
   RefineArgs rf;           // RefineDet fused: the positives' anchors are decoded from arm_loc
-  int ablate;              // experiment builds only (SSDBOX_BWD_ABLATE): 1 no grad_loc, 2 no gradient rows, 4 no positives, 8 no sel
+  int ablate;              // experiment builds only (SSDBOX_BWD_ABLATE): 1 no grad_loc, 2 no gradient rows, 4 no positives, 8 no sel,
+                           // 16 no phase 0, 32 bulk stores without the evict_first hint, 64 phase 0 keeps the flags only
 };
 
 // (1) grad_conf := 0 at full store bandwidth (only ~4*num_pos rows per image are ever non-zero)
@@ -1466,6 +1472,58 @@ __global__ void __launch_bounds__(kBwdStreamWarps * 32, 1) loss_bwd_stream_kerne
   const double n = a.sums[2];
   const float scale_l = n > 0.0 ? (float)((double)a.grad_out[0] / n) : 0.0f;
   const float scale_c = n > 0.0 ? (float)((double)a.grad_out[1] / n) : 0.0f;
+  // Phase 0, before this CTA writes anything: pull everything the loop below will read -- the selection flags of the
+  // CTA's rows, the logits rows they select, loc / tidx of the positives -- into L2 with evict_last priority (the
+  // bulk stores below go out evict_first, so the 509 MB they write do not push it out again).
+  // Measured (tools/micro/fill_patterns.cu, profiles/r04_micro_fill_patterns.txt): a small DRAM read that arrives
+  // alone inside a saturated write stream costs the stream far more than its bytes (write->read->write
+  // turn-arounds; 49 k flag reads: +6 us, one logits row per tile: +8-14 us, prefetched or not); as L2 hits the
+  // same loads cost +2 us.  The rows are fetched with 4-byte cp.async into the (not yet used) tile: no registers,
+  // every sector touched (prefetch.global.L2 turned out to be dropped: ncu showed the same misses with and without).
+#ifdef SSDBOX_EXPERIMENTS
+  if (!(a.ablate & 16))
+#endif
+  {
+    const long long rbeg = t_begin * kBwdTileRows;
+    const long long rend = t_end * kBwdTileRows < rows ? t_end * kBwdTileRows : rows;
+    const uint64_t keep = l2_evict_last_policy();
+    int slot = 0;
+    for (long long r = rbeg + (long long)warp * 128; r < rend; r += (long long)kBwdStreamWarps * 128) {
+      const long long rl = r + lane * 4;
+      int lb4[4] = {-1, -1, -1, -1};
+      if (rl + 3 < rend) {                     // rbeg is a multiple of 32 and sel is 8-byte aligned
+        const unsigned long long v = ld_u64_l2_keep(a.sel + rl, keep);
+        lb4[0] = (int16_t)(v & 0xffffu); lb4[1] = (int16_t)((v >> 16) & 0xffffu);
+        lb4[2] = (int16_t)((v >> 32) & 0xffffu); lb4[3] = (int16_t)(v >> 48);
+      } else {
+        for (int k = 0; k < 4 && rl + k < rend; ++k) lb4[k] = a.sel[rl + k];
+      }
+#ifdef SSDBOX_EXPERIMENTS
+      if (a.ablate & 64) continue;
+#endif
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t m = __ballot_sync(SSDBOX_FULL_MASK, lb4[k] >= 0);
+        const uint32_t pos = __ballot_sync(SSDBOX_FULL_MASK, lb4[k] > 0);
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const long long row = r + src * 4 + k;
+          const float* x = a.conf + row * C;
+          float* dump = tile + (size_t)(slot & (kBwdTileRows - 1)) * C;
+          for (int c = lane; c < C; c += 32) cp_async_4_hint(dump + c, x + c, keep);
+          if (((pos >> src) & 1u) && lane == 0) {
+            cp_async_4_hint(dump, a.loc + row * 4, keep);
+            cp_async_4_hint(dump + 1, reinterpret_cast<const char*>(a.tidx) + ((row * 2) & ~3ll), keep);
+            if (a.rf.arm_loc) cp_async_4_hint(dump + 2, a.rf.arm_loc + row * 4, keep);
+          }
+          ++slot;
+        }
+      }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+  }
   for (int i = lane; i < kBwdTileRows * C; i += 32) tile[i] = 0.f;
   __syncwarp();
 
@@ -1473,7 +1531,7 @@ __global__ void __launch_bounds__(kBwdStreamWarps * 32, 1) loss_bwd_stream_kerne
   auto load_sel = [&](long long t, int (&lb)[RPL]) {
 #pragma unroll
     for (int k = 0; k < RPL; ++k) lb[k] = -1;
-    if (t < t_end && !(a.ablate & 8)) {
+    if (t < t_end && !SSDBOX_ABLATE(8)) {
       const long long r0 = t * kBwdTileRows + lane * RPL;
       if (RPL == 4 && r0 + 3 < rows) {
         const short4 v = *reinterpret_cast<const short4*>(a.sel + r0);     // 8-byte aligned array, r0 % 4 == 0
@@ -1497,7 +1555,7 @@ __global__ void __launch_bounds__(kBwdStreamWarps * 32, 1) loss_bwd_stream_kerne
 #pragma unroll
     for (int k = 0; k < RPL; ++k) {
       uint32_t m = __ballot_sync(SSDBOX_FULL_MASK, p.lb[k] >= 0);
-      if (a.ablate & 2) m = 0u;
+      if (SSDBOX_ABLATE(2)) m = 0u;
       while (m && nfound < 4) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
@@ -1538,6 +1596,7 @@ __global__ void __launch_bounds__(kBwdStreamWarps * 32, 1) loss_bwd_stream_kerne
     }
   };
 
+  const uint64_t wr_policy = l2_evict_first_policy();     // the 509 MB written here must not evict what phase 0 pulled in
   BwdPre cur, nxt;
   long long t = t_begin + warp;
   load_sel(t, cur.lb);
@@ -1608,7 +1667,12 @@ __global__ void __launch_bounds__(kBwdStreamWarps * 32, 1) loss_bwd_stream_kerne
       if (bytes != 0u && (bytes & 15u) == 0u) {
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) bulk_s2g(dst, part, bytes);
+        if (lane == 0) {
+#ifdef SSDBOX_EXPERIMENTS
+          if (a.ablate & 32) bulk_s2g(dst, part, bytes); else
+#endif
+          bulk_s2g_hint(dst, part, bytes, wr_policy);
+        }
       } else {                                   // ragged last tile: plain stores (and an empty group: one commit per part)
         for (int i = lane; i < nr * C; i += 32) dst[i] = part[i];
         if (lane == 0) bulk_commit();
@@ -1618,9 +1682,9 @@ __global__ void __launch_bounds__(kBwdStreamWarps * 32, 1) loss_bwd_stream_kerne
 #pragma unroll
     for (int k = 0; k < RPL; ++k) {
       const long long row = row0 + lane * RPL + k;
-      if (row >= rows || (a.ablate & 1)) continue;
+      if (row >= rows || SSDBOX_ABLATE(1)) continue;
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (cur.lb[k] > 0 && !(a.ablate & 4)) {
+      if (cur.lb[k] > 0 && !SSDBOX_ABLATE(4)) {
         const int b = (int)((uint32_t)row / (uint32_t)a.P);
         const int pi = (int)((uint32_t)row - (uint32_t)b * (uint32_t)a.P);
         const float4 l = *reinterpret_cast<const float4*>(a.loc + row * 4);
@@ -1643,236 +1707,6 @@ __global__ void __launch_bounds__(kBwdStreamWarps * 32, 1) loss_bwd_stream_kerne
   bulk_wait_all();          // the tile must outlive its last bulk store
 }
 
-
-// ---- backward, reads first: gather the segment's gradient rows, THEN stream ---------------------------------------
-// Measured (tools/micro/fill_patterns.cu, profiles/r04_micro_fill_patterns.txt): a small read that arrives alone in a
-// saturated write stream costs its DRAM channel a write->read->write turn-around -- 49 k 64-byte reads (the selection
-// flags, one request per tile) slow a 509 MB bulk-store fill by 7.5 us, one 324-byte row read per tile by 14.5 us;
-// the same bytes as a few large requests cost nothing.  loss_bwd_stream_kernel above mixes exactly those reads into
-// its stores (ablation: -7 us without the flags, -23 us without the logits rows).  Here every CTA works through its
-// row range in segments and does ALL reads of a segment first, while nothing of it is being written:
-//   1. the segment's selection flags -> shared memory (coalesced), per-tile counts, exclusive scan, slot list
-//   2. all warps: the logits rows of the selected rows (eight rows in flight per warp) -> (softmax - onehot) * grad / N
-//      -> a compact row buffer in shared memory; the positives' smooth-L1' -> a float4 list
-//   3. kBwdGsRing warps stream the tiles: zero tile + the rows copied from the row buffer -> one TMA bulk store,
-//      grad_loc with plain 16-byte stores; no global read is left in this phase
-// A segment ends where the row buffer or the flag slice is full, so any density of selected rows works.
-constexpr int kBwdGsWarps = 16;
-constexpr int kBwdGsRing = 8;            // bulk-store tiles in flight per SM (four already saturate a pure fill)
-constexpr int kBwdGsCapTiles = 352;      // tiles per segment (flag slice 22 KB)
-constexpr int kBwdGsBatch = 8;           // rows gathered together by one warp
-
-struct BwdGsLayout {                     // byte offsets into dynamic shared memory
-  uint32_t tiles, sel, base, cnt, list, rows, gl, total;
-  int cap_sel;
-};
-static BwdGsLayout bwd_gs_layout(int C, size_t budget) {
-  BwdGsLayout l{};
-  uint32_t o = 0;
-  l.tiles = o; o += (uint32_t)kBwdGsRing * kBwdTileRows * C * 4;
-  l.sel = o;   o += (uint32_t)kBwdGsCapTiles * kBwdTileRows * 2;
-  l.base = o;  o += (kBwdGsCapTiles + 1) * 4;
-  l.cnt = o;   o += kBwdGsCapTiles * 4;
-  o = (o + 15u) & ~15u;
-  const size_t per_slot = (size_t)C * 4 + 16 + 4;
-  long long cap = budget > o + 64 ? (long long)((budget - o - 64) / per_slot) : 0;
-  cap &= ~3ll;
-  if (cap > 4096) cap = 4096;
-  l.cap_sel = (int)cap;
-  l.gl = o;    o += (uint32_t)cap * 16;
-  l.rows = o;  o += (uint32_t)cap * C * 4;
-  l.list = o;  o += (uint32_t)cap * 4;
-  l.total = o;
-  return l;
-}
-
-template <int CT>
-__global__ void __launch_bounds__(kBwdGsWarps * 32, 1) loss_bwd_gs_kernel(BwdArgs a, BwdGsLayout L) {
-  extern __shared__ __align__(128) unsigned char smem_bwd[];
-  __shared__ int s_seg_tiles;
-  const int C = CT > 0 ? CT : a.C;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* tile = reinterpret_cast<float*>(smem_bwd + L.tiles) + (size_t)warp * kBwdTileRows * C;     // warps < kBwdGsRing only
-  int16_t* s_sel = reinterpret_cast<int16_t*>(smem_bwd + L.sel);
-  int* s_base = reinterpret_cast<int*>(smem_bwd + L.base);
-  int* s_cnt = reinterpret_cast<int*>(smem_bwd + L.cnt);
-  uint32_t* s_list = reinterpret_cast<uint32_t*>(smem_bwd + L.list);
-  float* s_rows = reinterpret_cast<float*>(smem_bwd + L.rows);
-  float4* s_gl = reinterpret_cast<float4*>(smem_bwd + L.gl);
-  const long long rows = (long long)a.B * a.P;
-  const long long tiles = (rows + kBwdTileRows - 1) / kBwdTileRows;
-  const long long per_cta = (tiles + gridDim.x - 1) / gridDim.x;
-  const long long t_begin = (long long)blockIdx.x * per_cta;
-  const long long t_end = t_begin + per_cta < tiles ? t_begin + per_cta : tiles;
-  const double n = a.sums[2];
-  const float scale_l = n > 0.0 ? (float)((double)a.grad_out[0] / n) : 0.0f;
-  const float scale_c = n > 0.0 ? (float)((double)a.grad_out[1] / n) : 0.0f;
-  if (warp < kBwdGsRing) {
-    for (int i = lane; i < kBwdTileRows * C; i += 32) tile[i] = 0.f;
-    __syncwarp();
-  }
-  uint32_t patched = 0u;                 // rows of my tile that hold non-zero data (bit = row)
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  long long seg0 = t_begin;
-  while (seg0 < t_end) {
-    const int ntile = (int)(t_end - seg0 < kBwdGsCapTiles ? t_end - seg0 : kBwdGsCapTiles);
-    const long long r0 = seg0 * kBwdTileRows;
-    const int nrow = (int)(rows - r0 < (long long)ntile * kBwdTileRows ? rows - r0 : (long long)ntile * kBwdTileRows);
-    // 1. flags of the segment (r0 is a multiple of 32: 8-byte loads of an 8-byte aligned array)
-    for (int i = tid * 4; i < ntile * kBwdTileRows; i += kBwdGsWarps * 32 * 4) {
-      short4 v = make_short4(-1, -1, -1, -1);
-      if (i + 3 < nrow) {
-        v = *reinterpret_cast<const short4*>(a.sel + r0 + i);
-      } else {
-        if (i < nrow) v.x = a.sel[r0 + i];
-        if (i + 1 < nrow) v.y = a.sel[r0 + i + 1];
-        if (i + 2 < nrow) v.z = a.sel[r0 + i + 2];
-      }
-#ifdef SSDBOX_EXPERIMENTS
-      if (a.ablate & 8) v = make_short4(-1, -1, -1, -1);
-#endif
-      *reinterpret_cast<short4*>(s_sel + i) = v;
-    }
-    __syncthreads();
-    for (int t = warp; t < ntile; t += kBwdGsWarps) {
-      const uint32_t m = __ballot_sync(SSDBOX_FULL_MASK, s_sel[t * kBwdTileRows + lane] >= 0);
-      if (lane == 0) s_cnt[t] = __popc(m);
-    }
-    __syncthreads();
-    if (warp == 0) {                     // exclusive scan of the counts; the segment ends where the row buffer is full
-      int running = 0, fit = 0;
-      for (int c = 0; c < ntile; c += 32) {
-        const int v = c + lane < ntile ? s_cnt[c + lane] : 0;
-        const int inc = warp_inclusive_scan(v, lane);
-        if (c + lane < ntile) s_base[c + lane] = running + inc - v;
-        fit += __popc(__ballot_sync(SSDBOX_FULL_MASK, c + lane < ntile && running + inc <= L.cap_sel));
-        running += __shfl_sync(SSDBOX_FULL_MASK, inc, 31);
-      }
-      if (lane == 0) {
-        s_base[ntile] = running;
-        s_seg_tiles = fit > 0 ? fit : 1;       // (a tile holds at most 32 rows <= cap_sel: fit >= 1)
-      }
-    }
-    __syncthreads();
-    const int seg_tiles = s_seg_tiles;
-    const int nsel = s_base[seg_tiles];
-    for (int t = warp; t < seg_tiles; t += kBwdGsWarps) {
-      const int lb = s_sel[t * kBwdTileRows + lane];
-      const uint32_t m = __ballot_sync(SSDBOX_FULL_MASK, lb >= 0);
-      if (lb >= 0) s_list[s_base[t] + __popc(m & lt_mask)] = ((uint32_t)(t * kBwdTileRows + lane) << 16) | (uint32_t)lb;
-    }
-    __syncthreads();
-    // 2a. the positives' smooth-L1' (one thread per slot; issued first, its dependent loads run under the gathers)
-    for (int slot = tid; slot < nsel; slot += kBwdGsWarps * 32) {
-      const uint32_t e = s_list[slot];
-      if ((e & 0xffffu) == 0u) continue;
-      const long long row = r0 + (e >> 16);
-      const int b = (int)((uint32_t)row / (uint32_t)a.P);
-      const int pi = (int)((uint32_t)row - (uint32_t)b * (uint32_t)a.P);
-      const float4 l = *reinterpret_cast<const float4*>(a.loc + row * 4);
-      const float4 pr = refine_center(a.rf, *reinterpret_cast<const float4*>(a.priors + (size_t)b * (size_t)a.prior_stride + (size_t)pi * 4), (size_t)row);
-      const float* tr = a.gt + (size_t)(a.gt_offsets[b] + a.tidx[row]) * 5;
-      Box mbox;
-      mbox.x1 = tr[0]; mbox.y1 = tr[1]; mbox.x2 = tr[2]; mbox.y2 = tr[3];
-      const float4 tt = encode_box(mbox, pr, a.var0, a.var1);
-      float4 g;
-      g.x = scale_l * fminf(fmaxf(l.x - tt.x, -1.f), 1.f);     // smooth-L1': d for |d|<1, sign(d) otherwise
-      g.y = scale_l * fminf(fmaxf(l.y - tt.y, -1.f), 1.f);
-      g.z = scale_l * fminf(fmaxf(l.z - tt.z, -1.f), 1.f);
-      g.w = scale_l * fminf(fmaxf(l.w - tt.w, -1.f), 1.f);
-      s_gl[slot] = g;
-    }
-    // 2b. gradient rows: (softmax - onehot) * grad / N, kBwdGsBatch rows in flight per warp
-    for (int s0 = warp * kBwdGsBatch; s0 < nsel; s0 += kBwdGsWarps * kBwdGsBatch) {
-      float xv[kBwdGsBatch][4];
-      int tl[kBwdGsBatch];
-#pragma unroll
-      for (int j = 0; j < kBwdGsBatch; ++j) {
-        const int slot = s0 + j < nsel ? s0 + j : nsel - 1;
-        const uint32_t e = s_list[slot];
-        tl[j] = (int)(e & 0xffffu);
-        const float* x = a.conf + (r0 + (e >> 16)) * C;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) xv[j][u] = lane + 32 * u < C ? x[lane + 32 * u] : -INFINITY;
-      }
-#pragma unroll
-      for (int j = 0; j < kBwdGsBatch; ++j) {
-        if (s0 + j >= nsel) break;
-        float mx = fmaxf(fmaxf(xv[j][0], xv[j][1]), fmaxf(xv[j][2], xv[j][3]));
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(SSDBOX_FULL_MASK, mx, d));
-        float ev[4], sum = 0.f;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          ev[u] = lane + 32 * u < C ? expf(xv[j][u] - mx) : 0.f;
-          sum += ev[u];
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(SSDBOX_FULL_MASK, sum, d);
-        const float inv = 1.0f / sum;
-        float* g = s_rows + (size_t)(s0 + j) * C;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = lane + 32 * u;
-          if (c < C) g[c] = scale_c * (ev[u] * inv - (c == tl[j] ? 1.0f : 0.0f));
-        }
-      }
-    }
-    __syncthreads();
-    // 3. stream the segment's tiles: nothing is read from global memory any more
-    if (warp < kBwdGsRing) {
-      for (int t = warp; t < seg_tiles; t += kBwdGsRing) {
-        const long long row0 = r0 + (long long)t * kBwdTileRows;
-        const int nrows = (int)(rows - row0 < kBwdTileRows ? rows - row0 : kBwdTileRows);
-        const int lb = s_sel[t * kBwdTileRows + lane];
-        const uint32_t m = __ballot_sync(SSDBOX_FULL_MASK, lb >= 0);
-        const int base = s_base[t];
-        bulk_wait_read_all();          // my previous bulk store has read the tile: clear what it carried
-        __syncwarp();                  // (lane 0 owns the bulk group: nobody touches the tile before its wait returns)
-        uint32_t pm = patched & ~m;    // (rows that are patched again are overwritten in full)
-        while (pm) {
-          const int src = __ffs(pm) - 1;
-          pm &= pm - 1;
-          float* g = tile + (size_t)src * C;
-          for (int c = lane; c < C; c += 32) g[c] = 0.f;
-        }
-        patched = m;
-        uint32_t mm = m;
-        int k = 0;
-        while (mm) {
-          const int src = __ffs(mm) - 1;
-          mm &= mm - 1;
-          const float* gsrc = s_rows + (size_t)(base + k) * C;
-          float* g = tile + (size_t)src * C;
-          for (int c = lane; c < C; c += 32) g[c] = gsrc[c];
-          ++k;
-        }
-        __syncwarp();
-        const uint32_t bytes = (uint32_t)nrows * (uint32_t)C * 4u;
-        float* dst = a.grad_conf + row0 * C;
-        if ((bytes & 15u) == 0u) {
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) bulk_s2g(dst, tile, bytes);
-        } else {                       // ragged last tile: plain stores
-          for (int i = lane; i < nrows * C; i += 32) dst[i] = tile[i];
-        }
-        if (lane < nrows
-#ifdef SSDBOX_EXPERIMENTS
-            && !(a.ablate & 1)
-#endif
-        ) {
-          float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (lb > 0) g = s_gl[base + __popc(m & lt_mask)];
-          __stcs(reinterpret_cast<float4*>(a.grad_loc + (row0 + lane) * 4), g);
-        }
-      }
-    }
-    __syncthreads();                   // the flag slice and the row buffer are free for the next segment
-    seg0 += seg_tiles;
-  }
-  bulk_wait_all();                     // the tile must outlive its last bulk store
-}
 
 }  // namespace ssdbox
 
@@ -2222,22 +2056,10 @@ extern "C" int ssdbox_multibox_loss_bwd_refine(const ssdbox_loss_cfg* cfg, const
   ) {
     long long tiles = (rows + kBwdTileRows - 1) / kBwdTileRows;
     int grid = (int)(tiles < dev.sm_count ? tiles : dev.sm_count);
-    const BwdGsLayout L = bwd_gs_layout(a.C, (size_t)dev.max_smem_optin - 1024);
-    bool reads_first = false;
-#ifdef SSDBOX_EXPERIMENTS
-    if (getenv("SSDBOX_BWD_GS")) reads_first = L.cap_sel >= 64;
-#endif
-    if (reads_first) {
-      void (*kern)(BwdArgs, BwdGsLayout) = a.C == 81 ? loss_bwd_gs_kernel<81> : (a.C == 21 ? loss_bwd_gs_kernel<21> : loss_bwd_gs_kernel<0>);
-      SSDBOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-      TimerScope ts__(KID_LOSS_BWD, st);
-      kern<<<grid, kBwdGsWarps * 32, L.total, st>>>(a, L);
-    } else {
-      void (*kern)(BwdArgs) = a.C == 81 ? loss_bwd_stream_kernel<81> : (a.C == 21 ? loss_bwd_stream_kernel<21> : loss_bwd_stream_kernel<0>);
-      SSDBOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem));
-      TimerScope ts__(KID_LOSS_BWD, st);
-      kern<<<grid, kBwdStreamWarps * 32, stream_smem, st>>>(a);
-    }
+    void (*kern)(BwdArgs) = a.C == 81 ? loss_bwd_stream_kernel<81> : (a.C == 21 ? loss_bwd_stream_kernel<21> : loss_bwd_stream_kernel<0>);
+    SSDBOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem));
+    TimerScope ts__(KID_LOSS_BWD, st);
+    kern<<<grid, kBwdStreamWarps * 32, stream_smem, st>>>(a);
   } else {
     TimerScope ts__(KID_LOSS_BWD, st);
     zero_fill_kernel<<<dev.sm_count * 16, kBwdThreads, 0, st>>>(grad_conf, (size_t)rows * a.C, a.conf_aligned);
