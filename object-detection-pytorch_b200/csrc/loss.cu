@@ -1480,44 +1480,54 @@ __global__ void __launch_bounds__(kBwdStreamWarps * 32, 1) loss_bwd_stream_kerne
   // turn-arounds; 49 k flag reads: +6 us, one logits row per tile: +8-14 us, prefetched or not); as L2 hits the
   // same loads cost +2 us.  The rows are fetched with 4-byte cp.async into the (not yet used) tile: no registers,
   // every sector touched (prefetch.global.L2 turned out to be dropped: ncu showed the same misses with and without).
+  const long long rbeg = t_begin * kBwdTileRows;
+  const long long rend = t_end * kBwdTileRows < rows ? t_end * kBwdTileRows : rows;
 #ifdef SSDBOX_EXPERIMENTS
   if (!(a.ablate & 16))
 #endif
   {
-    const long long rbeg = t_begin * kBwdTileRows;
-    const long long rend = t_end * kBwdTileRows < rows ? t_end * kBwdTileRows : rows;
     const uint64_t keep = l2_evict_last_policy();
     int slot = 0;
-    for (long long r = rbeg + (long long)warp * 128; r < rend; r += (long long)kBwdStreamWarps * 128) {
-      const long long rl = r + lane * 4;
-      int lb4[4] = {-1, -1, -1, -1};
-      if (rl + 3 < rend) {                     // rbeg is a multiple of 32 and sel is 8-byte aligned
-        const unsigned long long v = ld_u64_l2_keep(a.sel + rl, keep);
-        lb4[0] = (int16_t)(v & 0xffffu); lb4[1] = (int16_t)((v >> 16) & 0xffffu);
-        lb4[2] = (int16_t)((v >> 32) & 0xffffu); lb4[3] = (int16_t)(v >> 48);
-      } else {
-        for (int k = 0; k < 4 && rl + k < rend; ++k) lb4[k] = a.sel[rl + k];
+    constexpr int kGroupsAtOnce = 6;       // flag loads of a warp requested together (one round trip for the usual range)
+    for (long long rb = rbeg + (long long)warp * 128; rb < rend; rb += (long long)kBwdStreamWarps * 128 * kGroupsAtOnce) {
+      unsigned long long fl[kGroupsAtOnce];
+#pragma unroll
+      for (int g = 0; g < kGroupsAtOnce; ++g) {
+        const long long rl = rb + (long long)g * kBwdStreamWarps * 128 + lane * 4;
+        fl[g] = ~0ull;                       // four times -1
+        if (rl + 3 < rend) {                 // rbeg is a multiple of 32 and sel is 8-byte aligned
+          fl[g] = ld_u64_l2_keep(a.sel + rl, keep);
+        } else {
+          for (int k = 0; k < 4 && rl + k < rend; ++k)
+            fl[g] = (fl[g] & ~(0xffffull << (16 * k))) | ((unsigned long long)(uint16_t)a.sel[rl + k] << (16 * k));
+        }
       }
 #ifdef SSDBOX_EXPERIMENTS
       if (a.ablate & 64) continue;
 #endif
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint32_t m = __ballot_sync(SSDBOX_FULL_MASK, lb4[k] >= 0);
-        const uint32_t pos = __ballot_sync(SSDBOX_FULL_MASK, lb4[k] > 0);
-        while (m) {
-          const int src = __ffs(m) - 1;
-          m &= m - 1;
-          const long long row = r + src * 4 + k;
-          const float* x = a.conf + row * C;
-          float* dump = tile + (size_t)(slot & (kBwdTileRows - 1)) * C;
-          for (int c = lane; c < C; c += 32) cp_async_4_hint(dump + c, x + c, keep);
-          if (((pos >> src) & 1u) && lane == 0) {
-            cp_async_4_hint(dump, a.loc + row * 4, keep);
-            cp_async_4_hint(dump + 1, reinterpret_cast<const char*>(a.tidx) + ((row * 2) & ~3ll), keep);
-            if (a.rf.arm_loc) cp_async_4_hint(dump + 2, a.rf.arm_loc + row * 4, keep);
+      for (int g = 0; g < kGroupsAtOnce; ++g) {
+        const long long r = rb + (long long)g * kBwdStreamWarps * 128;
+        if (r >= rend) break;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int lbk = (int)(int16_t)((fl[g] >> (16 * k)) & 0xffffull);
+          uint32_t m = __ballot_sync(SSDBOX_FULL_MASK, lbk >= 0);
+          const uint32_t pos = __ballot_sync(SSDBOX_FULL_MASK, lbk > 0);
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const long long row = r + src * 4 + k;
+            const float* x = a.conf + row * C;
+            float* dump = tile + (size_t)(slot & (kBwdTileRows - 1)) * C;
+            for (int c = lane; c < C; c += 32) cp_async_4_hint(dump + c, x + c, keep);
+            if (((pos >> src) & 1u) && lane == 0) {
+              cp_async_4_hint(dump, a.loc + row * 4, keep);
+              cp_async_4_hint(dump + 1, reinterpret_cast<const char*>(a.tidx) + ((row * 2) & ~3ll), keep);
+              if (a.rf.arm_loc) cp_async_4_hint(dump + 2, a.rf.arm_loc + row * 4, keep);
+            }
+            ++slot;
           }
-          ++slot;
         }
       }
     }
