@@ -45,6 +45,7 @@ def test_library_has_sm100a_code_and_tma():
     assert "UBLKCP" in sass                      # cp.async.bulk (TMA bulk copy) in the streaming kernels
     assert "SYNCS" in sass                       # mbarrier
     assert "REDUX" in sass                       # warp reductions in match
+    assert "UTMALDG" in sass                     # cp.async.bulk.tensor (tensor-map TMA) in the head-layout kernel
 
 
 def test_version_and_struct_layouts(lib):

@@ -14,7 +14,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "object-detection-pytorch_b200", "ssdbox", "lib", "libssdbox.so")
 KEY = ["UBLKCP", "SYNCS", "UCGABAR", "REDUX", "MATCH", "VOTE", "SHFL", "ATOMS", "ATOMG", "RED", "MUFU", "LDS", "STS", "LDG",
-       "STG", "BAR", "FFMA", "FFMA2", "FADD", "FADD2", "FMUL", "FMNMX", "FMNMX3", "DADD", "DFMA", "UTMALDG", "UTCHMMA", "UTCQMMA", "HMMA", "LDTM", "QGMMA"]
+       "LDGSTS", "STG", "BAR", "FFMA", "FFMA2", "FADD", "FADD2", "FMUL", "FMNMX", "FMNMX3", "DADD", "DFMA", "UTMALDG", "UTCHMMA", "UTCQMMA", "HMMA", "LDTM", "QGMMA"]
 
 
 def main():
@@ -39,7 +39,8 @@ def main():
     print("# per kernel: total instructions, then the count of each mnemonic of interest (absent = 0)")
     print("# UBLKCP = cp.async.bulk (1-D TMA; .S.G = global->shared load, .G.S = shared->global store), SYNCS = mbarrier,")
     print("# UCGABAR = barrier.cluster, REDUX / MATCH / VOTE = warp reductions / match.any / ballots.")
-    print("# No UTMALDG (tensor-map TMA: the tiles are contiguous 1-D runs), no UTC*MMA / HMMA / LDTM (no contraction on this path).")
+    print("# UTMALDG = cp.async.bulk.tensor (tensor-map TMA: the head-layout kernel's {32 positions x channels} boxes; every other")
+    print("# tile on the path is a contiguous 1-D run), LDGSTS = cp.async; no UTC*MMA / HMMA / LDTM (no contraction on this path).")
     print()
     tot = collections.Counter()
     for name, c in kernels.items():
