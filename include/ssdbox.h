@@ -413,7 +413,9 @@ SSDBOX_API int ssdbox_crop_overlaps(const double* boxes, const int32_t* box_offs
  * and cat(dim 1), i.e. the producer of loc [B,P,4] / conf [B,P,C].
  *   src[k]   [B, channels_k, H_k, W_k] contiguous NCHW, channels_k = anchors_k * (4 | C), hw_k = H_k*W_k
  *   out      [B, sum_k hw_k * channels_k]: per image the layers in order, each in (h, w, channel) order
- * One launch, every element read once and written once. */
+ * Every element read once and written once.  Layers with H*W % 4 == 0, at least 64 positions, 32..576 channels and a
+ * 16-byte aligned pointer go through a tensor-map TMA ring (one launch for all of them), every other layer through a tile
+ * kernel (a second launch); which path a layer takes changes nothing in the result (pure data movement, bit for bit). */
 #define SSDBOX_MAX_HEADS 16
 typedef struct {
   int32_t num_layers, B;
