@@ -464,7 +464,7 @@ def main():
 
         def step():
             with torch.no_grad():
-                if args.serial or world > 1:
+                if args.serial:
                     al, ac = arm_crit.forward_packed_two_step(arm_loc, arm_conf, loc, conf, priors, gt, offs, gmax)
                     ol, oc = odm_crit.forward_packed_two_step(arm_loc, arm_conf, loc, conf, priors, gt, offs, gmax)
                     out = rdet.forward(arm_loc, arm_conf, loc, sc, priors, out=det_out)
@@ -709,6 +709,34 @@ def main():
 
     # ---- N > 1: is the peer-reduced loss the loss of the global batch? (printed in sanity.mgpu) -------------
     mgpu = None
+    if dist is not None and refine:
+        # both losses of the two-step path: the peer-exchanged sums against the rank-ordered fp64 sum of the LOCAL sums
+        with torch.no_grad():
+            step()
+            torch.cuda.synchronize()
+            mgpu = {"reduce": odm_crit.reduce_used, "bit_equal": True, "identical_on_all_ranks": True,
+                    "note": "ARM and ODM loss: peer-exchanged {sum_l, sum_c, N} == rank-ordered fp64 sum of the NCCL-gathered local sums, on every rank"}
+            for name, dcrit, ncls, use_arm in (("arm", arm_crit, 2, False), ("odm", odm_crit, C, True)):
+                lcrit = ssdbox.RefineMultiBoxLoss(ncls, 0.5, True, 0, True, 3, 0.5, False, use_ARM=use_arm, distributed=False)
+                lcrit.forward_packed_two_step(arm_loc, arm_conf, loc, conf, priors, gt, offs, gmax)
+                local_sums = lcrit._last[0].clone()
+                global_sums = dcrit._last[0].clone()
+                gathered = [torch.empty_like(local_sums) for _ in range(world)]
+                dist.all_gather(gathered, local_sums)
+                tot = [0.0, 0.0, 0.0]
+                for r in range(world):
+                    v = gathered[r].cpu().tolist()
+                    for k in range(3):
+                        tot[k] += v[k]
+                mine = global_sums.cpu().tolist()
+                ok = torch.tensor([1 if all(tot[k] == mine[k] for k in range(3)) else 0], dtype=torch.int32, device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                same = [torch.empty_like(global_sums) for _ in range(world)]
+                dist.all_gather(same, global_sums)
+                mgpu["bit_equal"] = mgpu["bit_equal"] and bool(int(ok.item()))
+                mgpu["identical_on_all_ranks"] = mgpu["identical_on_all_ranks"] and all(torch.equal(v, same[0]) for v in same)
+                mgpu[name + "_global_sums"] = mine
+        dist.barrier()
     if dist is not None and not refine:
         with torch.no_grad():
             local_crit = ssdbox.MultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, distributed=False)
@@ -885,7 +913,7 @@ def main():
                    "only": args.only or None, "global_batch": n_gpus * B, "detect_scores": "dense (bkg bias 4)" if args.dense else "sparse/realistic (bkg bias 10)",
                    "l2": "inputs larger than L2 (conf and scores are %.0f MB each vs 126 MB L2)" % (conf.numel() * 4 / 1e6),
                    "launch": ("CUDA graph replay" if graph is not None else "eager launches") +
-                             ("" if (args.serial or args.only or (refine and world > 1)) else
+                             ("" if (args.serial or args.only) else
                               ("; three streams inside the step (RefineDetectOut, ODM loss, ARM loss)" if refine else
                                "; two streams inside the step: DetectOut on a side stream (submitted first), its tail kernels overlap MultiBoxLoss's conf pass")),
                    "parallelism": ("images sharded by rank; {sum_l, sum_c, N_pos} reduced per step: %s" % (
