@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kHeadThreads) heads_to_rows_kernel(HeadsPlan p
 // channels, the swizzle spreads them over the banks) and writes four coalesced 128-byte pieces of four output rows.
 // No register staging of the loads, kHeadTmaStages items in flight per SM, no partial lines inside a run.
 constexpr int kHeadTmaPos = 32;          // positions per item = one 128-byte swizzle row
-constexpr int kHeadTmaWarps = 8;         // consumer warps: one (or two) per 16-byte chunk of a row
+constexpr int kHeadTmaWarps = 8;         // consumer warps = 16-byte chunks per row
 constexpr int kHeadTmaLayers = 8;
 constexpr int kHeadTmaMaxStages = 6;
 constexpr int kHeadTmaMaxRows = 576;     // channel rows of one item (73.7 KB): three stages fit
@@ -128,8 +128,8 @@ __device__ __forceinline__ void heads_tma_produce(const HeadsTmaPlan& p, unsigne
 }
 
 // MODE (experiment builds only): 0 = the kernel, 1 = loads without stores, 2 = stores without loads
-template <int MODE, bool ALIGN, int WARPS>
-__global__ void __launch_bounds__((WARPS + 1) * 32, 1)
+template <int MODE, bool ALIGN>
+__global__ void __launch_bounds__((kHeadTmaWarps + 1) * 32, 1)
 heads_tma_kernel(const __grid_constant__ HeadsTmaPlan p, float* __restrict__ out) {
   extern __shared__ unsigned char smem_heads[];
   __shared__ __align__(8) uint64_t full[kHeadTmaMaxStages], empty[kHeadTmaMaxStages];
@@ -139,7 +139,7 @@ heads_tma_kernel(const __grid_constant__ HeadsTmaPlan p, float* __restrict__ out
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], WARPS);
+      mbar_init(&empty[s], kHeadTmaWarps);
     }
     fence_mbar_init();
   }
@@ -147,9 +147,7 @@ heads_tma_kernel(const __grid_constant__ HeadsTmaPlan p, float* __restrict__ out
   const long long total = p.item_start[p.num_layers];
   int st = 0;
   uint32_t ph = 0;
-  constexpr int NH = WARPS / 8;                     // warps per 16-byte chunk: they split the channel blocks
-  const int q = warp & 7, half = warp >> 3;
-  if (warp == WARPS) {
+  if (warp == kHeadTmaWarps) {
     if (lane != 0 || MODE == 2) return;
     heads_tma_produce(p, ring, full, empty);
     return;
@@ -161,7 +159,7 @@ heads_tma_kernel(const __grid_constant__ HeadsTmaPlan p, float* __restrict__ out
     const int b = (int)(local / p.tiles_hw[k]);
     const int th = (int)(local - (long long)b * p.tiles_hw[k]);
     const int CH = p.channels[k];
-    const int pos0 = th * kHeadTmaPos + q * 4;                     // this warp's four positions
+    const int pos0 = th * kHeadTmaPos + warp * 4;                  // this warp's four positions
     const int npos = p.hw[k] - pos0;                               // how many of them exist
     float* dst = out + (size_t)b * p.row_len + p.out_off[k] + (size_t)pos0 * CH;
     const unsigned char* tile = ring + (size_t)st * p.stage_bytes;
@@ -175,17 +173,12 @@ heads_tma_kernel(const __grid_constant__ HeadsTmaPlan p, float* __restrict__ out
 #pragma unroll
       for (int j = 0; j < 4; ++j) sh[j] = (int)((reinterpret_cast<uintptr_t>(dst + (size_t)j * CH) >> 2) & 31u);
       float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int c0 = half * 128; c0 < CH + 31; c0 += 128 * NH) {
+      for (int c0 = 0; c0 < CH + 31; c0 += 128) {
         float4 v[4];
-        if (NH > 1 && c0 > 0) {            // the channel group before this block belongs to another warp: fetch it again
-          const int ch = c0 - 32 + lane;
-          prev = ch < CH && MODE != 2 ? *reinterpret_cast<const float4*>(tile + (size_t)ch * 128 + ((q ^ (ch & 7)) << 4))
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int ch = c0 + u * 32 + lane;
-          v[u] = ch < CH && MODE != 2 ? *reinterpret_cast<const float4*>(tile + (size_t)ch * 128 + ((q ^ (ch & 7)) << 4))
+          v[u] = ch < CH && MODE != 2 ? *reinterpret_cast<const float4*>(tile + (size_t)ch * 128 + ((warp ^ (ch & 7)) << 4))
                                       : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
@@ -203,12 +196,12 @@ heads_tma_kernel(const __grid_constant__ HeadsTmaPlan p, float* __restrict__ out
         }
       }
     } else {
-    for (int c0 = half * 128; c0 < CH; c0 += 128 * NH) {
+    for (int c0 = 0; c0 < CH; c0 += 128) {
       float4 v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int ch = c0 + u * 32 + lane;
-        v[u] = ch < CH && MODE != 2 ? *reinterpret_cast<const float4*>(tile + (size_t)ch * 128 + ((q ^ (ch & 7)) << 4))
+        v[u] = ch < CH && MODE != 2 ? *reinterpret_cast<const float4*>(tile + (size_t)ch * 128 + ((warp ^ (ch & 7)) << 4))
                                     : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (MODE == 1) {
@@ -329,22 +322,16 @@ extern "C" int ssdbox_heads_to_rows(const ssdbox_heads_cfg* cfg, float* out, ssd
     q.stage_bytes = stage_bytes;
     const size_t smem = (size_t)stages * stage_bytes + 1024;
     const long long grid = items < dev.sm_count ? items : dev.sm_count;
-    void (*kern)(HeadsTmaPlan, float*) = heads_tma_kernel<0, true, kHeadTmaWarps>;
-    int warps = kHeadTmaWarps;
+    void (*kern)(HeadsTmaPlan, float*) = heads_tma_kernel<0, true>;
 #ifdef SSDBOX_EXPERIMENTS
     const bool al = !getenv("SSDBOX_HEADS_ALIGN") || atoi(getenv("SSDBOX_HEADS_ALIGN")) != 0;
-    if (!al) kern = heads_tma_kernel<0, false, kHeadTmaWarps>;
-    if (const char* e = getenv("SSDBOX_HEADS_WARPS")) {
-      warps = atoi(e) == 16 ? 16 : 8;
-      kern = warps == 16 ? heads_tma_kernel<0, true, 16> : heads_tma_kernel<0, true, 8>;
-    }
+    if (!al) kern = heads_tma_kernel<0, false>;
     if (const char* e = getenv("SSDBOX_HEADS_MODE"))
-      kern = atoi(e) == 1 ? heads_tma_kernel<1, true, kHeadTmaWarps>
-                          : (atoi(e) == 2 ? (al ? heads_tma_kernel<2, true, kHeadTmaWarps> : heads_tma_kernel<2, false, kHeadTmaWarps>) : kern);
+      kern = atoi(e) == 1 ? heads_tma_kernel<1, true> : (atoi(e) == 2 ? (al ? heads_tma_kernel<2, true> : heads_tma_kernel<2, false>) : kern);
     if (const char* e = getenv("SSDBOX_HEADS_STAGES")) q.stages = atoi(e) >= 2 && atoi(e) < stages ? atoi(e) : stages;
 #endif
     SSDBOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(int)grid, (warps + 1) * 32, smem, static_cast<cudaStream_t>(stream)>>>(q, out);
+    kern<<<(int)grid, (kHeadTmaWarps + 1) * 32, smem, static_cast<cudaStream_t>(stream)>>>(q, out);
     SSDBOX_LAUNCH_OK("heads_tma_kernel");
   }
   if (tiles > 0) {
