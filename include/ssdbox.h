@@ -284,7 +284,9 @@ SSDBOX_API int ssdbox_multibox_loss_bwd(const ssdbox_loss_cfg* cfg, const float*
 /* ------------------------------------------------------------------------------------------
  * nms -- box_utils.py:279-343.  boxes[n,4] xyxy, scores[n]; keep int64[n] zero padded (indices
  * into boxes, visiting order), count int32[1] (device).  Canonical tie order: equal scores are
- * visited higher index first.  Requires 1 <= top_k <= 1024.  ws: SSDBOX_OP_NMS (P = n).
+ * visited higher index first.  Any top_k >= 1 like the reference (:299-301): up to 1024 the list is sorted and swept in
+ * shared memory; beyond that a slower kernel sorts in the workspace and sweeps without a suppression matrix (at most
+ * 65536 boxes visited).  ws: SSDBOX_OP_NMS (P = n; depends on top_k).
  * ---------------------------------------------------------------------------------------- */
 SSDBOX_API int ssdbox_nms(const float* boxes, const float* scores, int32_t n, float overlap, int32_t top_k,
                int64_t* keep, int32_t* count, void* ws, size_t ws_bytes, ssdbox_stream_t stream);
@@ -300,7 +302,7 @@ SSDBOX_API int ssdbox_nms(const float* boxes, const float* scores, int32_t n, fl
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
   int32_t B, P, C;
-  int32_t top_k;              /* 1..1024 */
+  int32_t top_k;              /* 1..65536; > 1024: the slow any-top_k path (one CTA per list), not with SSDBOX_DETECT_LOGITS */
   float conf_thresh, nms_thresh;
   float var0, var1;
   int64_t prior_batch_stride;

@@ -871,6 +871,210 @@ nms_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, in
   if (tid == 0) *count = cnt;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Any top_k (> kTopKLimit): the reference takes whatever top_k it is given (box_utils.py:299-301).  The fast paths
+// above keep a list's sort keys and its top_k x top_k suppression bits in shared memory; beyond 1024 that does not fit,
+// and nobody runs SSD with such a top_k for speed.  These kernels trade speed for generality: one CTA per list,
+// the keys sorted in GLOBAL memory (same bitonic network), and a greedy sweep that needs no matrix -- 32 boxes at a
+// time, the kept ones of a chunk are tested against every later box that is still alive.  Same visiting order, same
+// suppression test, same results as the fast paths wherever both apply (tests compare them at top_k <= 1024 too).
+// ------------------------------------------------------------------------------------------------
+constexpr int kLargeThreads = 1024;
+
+struct LargeSmem {
+  uint32_t hist[2048];
+  uint32_t removed[kLargeTopKLimit / 32];
+  float4 kbox[32];
+  float karea[32];
+  int iscr[64 + 8];
+  uint32_t kept;
+  int cnt, m;
+};
+
+// box / area: the m boxes in visiting order (global memory).  keep[0..cnt) <- their positions, returns cnt.
+__device__ int nms_sweep_stream(const float4* __restrict__ box, const float* __restrict__ area, int m, float thr,
+                                int32_t* __restrict__ keep, LargeSmem& s) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x;
+  const int W = (m + 31) >> 5;
+  for (int w = tid; w < W; w += T) s.removed[w] = 0u;
+  if (tid == 0) s.cnt = 0;
+  __syncthreads();
+  for (int c = 0; c < W; ++c) {
+    const int base = c << 5;
+    const int nb = m - base < 32 ? m - base : 32;
+    if (warp == 0) {
+      float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
+      float aj = 0.f;
+      if (lane < nb) {
+        bj = box[base + lane];
+        aj = area[base + lane];
+      }
+      Box J;
+      J.x1 = bj.x; J.y1 = bj.y; J.x2 = bj.z; J.y2 = bj.w;
+      uint32_t rem = s.removed[c];                       // warp-uniform from here on
+      if (nb < 32) rem |= ~0u << nb;
+      uint32_t kept = 0u;
+      for (int i = 0; i < nb; ++i) {
+        if ((rem >> i) & 1u) continue;
+        kept |= 1u << i;
+        Box I;
+        I.x1 = __shfl_sync(SSDBOX_FULL_MASK, bj.x, i); I.y1 = __shfl_sync(SSDBOX_FULL_MASK, bj.y, i);
+        I.x2 = __shfl_sync(SSDBOX_FULL_MASK, bj.z, i); I.y2 = __shfl_sync(SSDBOX_FULL_MASK, bj.w, i);
+        const float ai = __shfl_sync(SSDBOX_FULL_MASK, aj, i);
+        const bool bit = lane > i && lane < nb && nms_suppresses(I, ai, J, aj, thr);     // box_utils.py:342 keeps IoU <= overlap
+        rem |= __ballot_sync(SSDBOX_FULL_MASK, bit);
+      }
+      const int cnt = s.cnt;
+      if ((kept >> lane) & 1u) {
+        const int k = __popc(kept & ((1u << lane) - 1u));
+        keep[cnt + k] = base + lane;
+        s.kbox[k] = bj;
+        s.karea[k] = aj;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        s.kept = kept;
+        s.cnt = cnt + __popc(kept);
+      }
+    }
+    __syncthreads();
+    const int nk = __popc(s.kept);
+    for (int j = base + 32 + tid; j < m && nk > 0; j += T) {
+      if ((s.removed[j >> 5] >> (j & 31)) & 1u) continue;
+      const float4 b4 = box[j];
+      Box J;
+      J.x1 = b4.x; J.y1 = b4.y; J.x2 = b4.z; J.y2 = b4.w;
+      const float aj = area[j];
+      bool sup = false;
+      for (int k = 0; k < nk && !sup; ++k) {
+        const float4 bi = s.kbox[k];
+        Box I;
+        I.x1 = bi.x; I.y1 = bi.y; I.x2 = bi.z; I.y2 = bi.w;
+        sup = nms_suppresses(I, s.karea[k], J, aj, thr);
+      }
+      if (sup) atomicOr(&s.removed[j >> 5], 1u << (j & 31));
+    }
+    __syncthreads();
+  }
+  return s.cnt;
+}
+
+// uk[0..n): ordered keys (0 = not a candidate).  Leaves the min(K, candidates) best in keys[0..) sorted in visiting
+// order (key descending, higher index first) and returns their number.
+__device__ int large_select_sort(uint32_t* uk, int n, int K, unsigned long long* keys, LargeSmem& s) {
+  const int tid = threadIdx.x, T = blockDim.x;
+  if (tid == 0) s.m = 0;
+  __syncthreads();
+  const uint32_t Tu = cta_select_threshold<true>(uk, n, K, nullptr, s.hist, s.iscr, s.iscr + 64);
+  __syncthreads();
+  for (int i = tid; i < n; i += T) {
+    const uint32_t u = uk[i];
+    if (u != 0u && u >= Tu) keys[atomicAdd(&s.m, 1)] = ((unsigned long long)u << 32) | (uint32_t)i;
+  }
+  __syncthreads();
+  const int m = s.m;
+  int npad = 32;
+  while (npad < m) npad <<= 1;
+  for (int i = m + tid; i < npad; i += T) keys[i] = 0ull;
+  bitonic_sort_desc(keys, npad);
+  return m < K ? m : K;
+}
+
+// stand-alone nms, any top_k: ws = uk [n] | keys [pow2 >= n] | box [K] | area [K] | pos [K]
+__global__ void __launch_bounds__(kLargeThreads, 1)
+nms_large_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, int n, float thr, int top_k,
+                 int64_t* __restrict__ keep, int32_t* __restrict__ count, uint32_t* uk, unsigned long long* keys,
+                 float4* gbox, float* garea, int32_t* gpos) {
+  __shared__ LargeSmem s;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n; i += kLargeThreads) {
+    uk[i] = f2ord(scores[i]);
+    keep[i] = 0;                                           // box_utils.py:291 zero-initialised keep
+  }
+  __syncthreads();
+  const int K = n < top_k ? n : top_k;                     // :301 idx[-top_k:]
+  const int m = large_select_sort(uk, n, K, keys, s);
+  for (int i = tid; i < m; i += kLargeThreads) {
+    const float* bp = boxes + (size_t)(keys[i] & 0xffffffffull) * 4;
+    Box bx;
+    bx.x1 = bp[0]; bx.y1 = bp[1]; bx.x2 = bp[2]; bx.y2 = bp[3];
+    gbox[i] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
+    garea[i] = box_area(bx);
+  }
+  __syncthreads();
+  const int cnt = nms_sweep_stream(gbox, garea, m, thr, gpos, s);
+  for (int k = tid; k < cnt; k += kLargeThreads) keep[k] = (int64_t)(keys[gpos[k]] & 0xffffffffull);
+  if (tid == 0) *count = cnt;
+}
+
+struct DetLargeArgs {
+  int B, P, C, top_k;
+  float nms_thr, conf_thr, var0, var1;
+  long long prior_stride;
+  const float* loc;
+  const float* scores;
+  const float* priors;
+  const uint8_t* keep;
+  RefineArgs rf;
+  float* out;
+  int32_t* counts;
+  unsigned char* ws;
+  size_t slice_bytes, off_keys, off_box, off_area, off_pos;
+};
+
+// DetectOut, any top_k: persistent CTAs, one (image, class) list at a time, each CTA in its own workspace slice
+__global__ void __launch_bounds__(kLargeThreads, 1) detect_large_kernel(DetLargeArgs a) {
+  __shared__ LargeSmem s;
+  const int tid = threadIdx.x;
+  unsigned char* mine = a.ws + (size_t)blockIdx.x * a.slice_bytes;
+  uint32_t* uk = reinterpret_cast<uint32_t*>(mine);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(mine + a.off_keys);
+  float4* gbox = reinterpret_cast<float4*>(mine + a.off_box);
+  float* garea = reinterpret_cast<float*>(mine + a.off_area);
+  int32_t* gpos = reinterpret_cast<int32_t*>(mine + a.off_pos);
+  for (int seg = blockIdx.x; seg < a.B * a.C; seg += gridDim.x) {
+    const int b = seg / a.C, c = seg - b * a.C;
+    float* o = a.out + (size_t)seg * a.top_k * 5;
+    int cnt = 0;
+    if (c > 0 && a.P > 0) {                                // detection.py:45 for cl in range(1, num_classes)
+      for (int p = tid; p < a.P; p += kLargeThreads) {
+        const size_t row = (size_t)b * a.P + p;
+        const float v = a.scores[row * a.C + c];
+        const bool cand = v > a.conf_thr && refine_member(a.rf, a.keep, row);       // detection.py:47 c_mask = scores.gt(conf_thresh)
+        uk[p] = cand ? f2ord(v) : 0u;
+      }
+      __syncthreads();
+      const int m = large_select_sort(uk, a.P, a.top_k, keys, s);
+      const float* pri = a.priors + (size_t)b * (size_t)a.prior_stride;
+      for (int i = tid; i < m; i += kLargeThreads) {
+        const uint32_t p = (uint32_t)(keys[i] & 0xffffffffull);
+        const Box bx = decode_box(*reinterpret_cast<const float4*>(a.loc + ((size_t)b * a.P + p) * 4),
+                                  refine_center(a.rf, *reinterpret_cast<const float4*>(pri + (size_t)p * 4), (size_t)b * a.P + p),
+                                  a.var0, a.var1);         // detection.py:43
+        gbox[i] = make_float4(bx.x1, bx.y1, bx.x2, bx.y2);
+        garea[i] = box_area(bx);
+      }
+      __syncthreads();
+      cnt = nms_sweep_stream(gbox, garea, m, a.nms_thr, gpos, s);
+    }
+    for (int e = tid; e < a.top_k * 5; e += kLargeThreads) {
+      const int k = e / 5, f = e - k * 5;
+      float v = 0.0f;
+      if (k < cnt) {
+        const int i = gpos[k];
+        if (f == 0) v = ord2f((uint32_t)(keys[i] >> 32));
+        else {
+          const float4 bx = gbox[i];
+          v = f == 1 ? bx.x : (f == 2 ? bx.y : (f == 3 ? bx.z : bx.w));
+        }
+      }
+      o[e] = v;                                            // detection.py:57-59
+    }
+    if (tid == 0 && a.counts) a.counts[seg] = cnt;
+    __syncthreads();
+  }
+}
+
 }  // namespace ssdbox
 
 using namespace ssdbox;
@@ -924,7 +1128,7 @@ static int detect_impl(const ssdbox_detect_cfg* cfg, const float* loc, const flo
   SSDBOX_REQUIRE(cfg->nms_thresh > 0.0f, SSDBOX_EINVAL, "nms_threshold must be non negative.");  // detection.py:19-20
   const int B = cfg->B, P = cfg->P, C = cfg->C, top_k = cfg->top_k;
   SSDBOX_REQUIRE(B >= 0 && P >= 0 && C >= 1, SSDBOX_EINVAL, "detect: negative size");
-  SSDBOX_REQUIRE(top_k >= 1 && top_k <= kTopKLimit, SSDBOX_ESHAPE, "detect: top_k %d outside 1..%d", top_k, kTopKLimit);
+  SSDBOX_REQUIRE(top_k >= 1 && top_k <= kLargeTopKLimit, SSDBOX_ESHAPE, "detect: top_k %d outside 1..%d", top_k, kLargeTopKLimit);
   SSDBOX_REQUIRE((long long)B * P < (1ll << 31) && (long long)B * C < (1ll << 31), SSDBOX_ESHAPE, "detect: B*P and B*C must be < 2^31");
   SSDBOX_REQUIRE(cfg->prior_batch_stride == 0 || cfg->prior_batch_stride == (int64_t)P * 4, SSDBOX_EINVAL,
                  "detect: prior_batch_stride must be 0 or 4*P");
@@ -937,6 +1141,31 @@ static int detect_impl(const ssdbox_detect_cfg* cfg, const float* loc, const flo
   DevInfo dev;
   int rc = get_dev_info(&dev);
   if (rc) return rc;
+  if (top_k > kTopKLimit) {              // the generality path (one CTA per list, no shared-memory suppression matrix)
+    SSDBOX_REQUIRE(!(cfg->flags & SSDBOX_DETECT_LOGITS), SSDBOX_ESHAPE, "detect: top_k > %d needs softmaxed scores (no fused softmax)", kTopKLimit);
+    DetLargeArgs la{};
+    la.B = B; la.P = P; la.C = C; la.top_k = top_k;
+    la.nms_thr = cfg->nms_thresh; la.conf_thr = cfg->conf_thresh; la.var0 = cfg->var0; la.var1 = cfg->var1;
+    la.prior_stride = (long long)cfg->prior_batch_stride;
+    la.loc = loc; la.scores = scores; la.priors = priors; la.keep = score_keep; la.rf = rf;
+    la.out = out; la.counts = counts;
+    la.ws = static_cast<unsigned char*>(ws);
+    const size_t k = (size_t)(top_k < P ? top_k : P);
+    la.slice_bytes = large_list_bytes(P, top_k);
+    la.off_keys = align_up((size_t)P * 4);
+    la.off_box = la.off_keys + align_up(next_pow2((size_t)P) * 8);
+    la.off_area = la.off_box + align_up(k * 16);
+    la.off_pos = la.off_area + align_up(k * 4);
+    int grid = dev.sm_count < kLargeCtas ? dev.sm_count : kLargeCtas;
+    if (grid > B * C) grid = B * C;
+    {
+      TimerScope ts__(KID_DET_SEGMENT_BIG, st);
+      detect_large_kernel<<<grid, kLargeThreads, 0, st>>>(la);
+    }
+    SSDBOX_LAUNCH_OK("detect_large_kernel");
+    if (peers) return ssdbox_multibox_loss_peer_finish(peers, loss_sums, losses, stream);
+    return SSDBOX_OK;
+  }
   const int cap = detect_cand_cap(top_k);
   Carver cv(ws);
   uint32_t* cnt = cv.take<uint32_t>((size_t)B * C + 4);   // [B*C] counters + overflow count / rewritten-list count / tail ticket
@@ -1041,7 +1270,8 @@ static int detect_impl(const ssdbox_detect_cfg* cfg, const float* loc, const flo
 extern "C" int ssdbox_nms(const float* boxes, const float* scores, int32_t n, float overlap, int32_t top_k,
                           int64_t* keep, int32_t* count, void* ws, size_t ws_bytes, ssdbox_stream_t stream) {
   SSDBOX_REQUIRE(n >= 0, SSDBOX_EINVAL, "nms: negative n");
-  SSDBOX_REQUIRE(top_k >= 1 && top_k <= kTopKLimit, SSDBOX_ESHAPE, "nms: top_k %d outside 1..%d", top_k, kTopKLimit);
+  SSDBOX_REQUIRE(top_k >= 1, SSDBOX_ESHAPE, "nms: top_k %d < 1", top_k);
+  SSDBOX_REQUIRE(top_k <= kLargeTopKLimit || n <= kLargeTopKLimit, SSDBOX_ESHAPE, "nms: more than %d boxes to visit", kLargeTopKLimit);
   SSDBOX_REQUIRE(count, SSDBOX_EINVAL, "nms: null count");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n == 0) {                                            // box_utils.py:292-293
@@ -1050,6 +1280,17 @@ extern "C" int ssdbox_nms(const float* boxes, const float* scores, int32_t n, fl
   }
   SSDBOX_REQUIRE(boxes && scores && keep && ws, SSDBOX_EINVAL, "nms: null pointer");
   SSDBOX_REQUIRE(ws_bytes >= nms_ws_bytes(n, top_k), SSDBOX_EWORKSPACE, "nms: workspace too small");
+  if (top_k > kTopKLimit) {              // any top_k (box_utils.py:299-301): keys sorted in global memory, matrix-free sweep
+    unsigned char* w = static_cast<unsigned char*>(ws);
+    const size_t k = (size_t)(top_k < n ? top_k : n);
+    const size_t off_keys = align_up((size_t)n * 4), off_box = off_keys + align_up(next_pow2((size_t)n) * 8);
+    const size_t off_area = off_box + align_up(k * 16), off_pos = off_area + align_up(k * 4);
+    nms_large_kernel<<<1, kLargeThreads, 0, st>>>(boxes, scores, n, overlap, top_k, keep, count, reinterpret_cast<uint32_t*>(w),
+                                                  reinterpret_cast<unsigned long long*>(w + off_keys), reinterpret_cast<float4*>(w + off_box),
+                                                  reinterpret_cast<float*>(w + off_area), reinterpret_cast<int32_t*>(w + off_pos));
+    SSDBOX_LAUNCH_OK("nms_large_kernel");
+    return SSDBOX_OK;
+  }
   size_t smem = 16384 + 288 + nms_smem_bytes(top_k);
   SSDBOX_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   nms_kernel<<<1, kOvfThreads, smem, st>>>(boxes, scores, n, overlap, top_k, keep, count, static_cast<uint32_t*>(ws));

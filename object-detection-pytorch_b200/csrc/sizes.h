@@ -9,7 +9,9 @@ namespace ssdbox {
 
 constexpr int kGmaxLimit = 4096;       // truths per image (smem + int16 truth index)
 constexpr int kHistBins = 2048;        // level-1 mining histogram: mine_bin() of the ordered key (128 bins per octave)
-constexpr int kTopKLimit = 1024;       // NMS sweep keeps one removed-word per lane
+constexpr int kTopKLimit = 1024;       // NMS sweep keeps one removed-word per lane (the fast paths; larger top_k: the *_large kernels)
+constexpr int kLargeTopKLimit = 65536; // removed-bit words of one list in shared memory (8 KB)
+constexpr int kLargeCtas = 160;        // workspace slices of detect_large_kernel (>= SMs of the device that runs it)
 constexpr int kClassLimit = 32766;     // labels travel as int16 (label + 1)
 
 static inline int gt_pad(int gmax) { return gmax < 2 ? 2 : (gmax + 1) / 2 * 2; }
@@ -53,7 +55,18 @@ static inline size_t mine_ws_bytes(int B, int P) { return align_up((size_t)B * P
 // ---- detect --------------------------------------------------------------------------------
 constexpr int kOverflowSlots = 160;    // >= SM count: one ordered-score scratch row per resident CTA
 static inline int detect_cand_cap(int top_k) { return top_k <= 512 ? 1024 : 2048; }
+static inline size_t next_pow2(size_t v) {
+  size_t p = 32;
+  while (p < v) p <<= 1;
+  return p;
+}
+// one list of the any-top_k path: ordered keys [P], sort keys [pow2 >= P], box / area / keep of the top_k
+static inline size_t large_list_bytes(int P, int top_k) {
+  const size_t k = (size_t)(top_k < P ? top_k : P);
+  return align_up((size_t)P * 4) + align_up(next_pow2((size_t)P) * 8) + align_up(k * 16) + 2 * align_up(k * 4);
+}
 static inline size_t detect_ws_bytes(int B, int P, int C, int top_k) {
+  if (top_k > kTopKLimit) return (size_t)kLargeCtas * large_list_bytes(P, top_k);
   return align_up((size_t)B * C * 4 + 16) + 2 * align_up((size_t)B * C * 4) +
          align_up((size_t)B * C * detect_cand_cap(top_k) * 8) +
          align_up((size_t)kOverflowSlots * P * 4) + 2 * align_up((size_t)B * P * 4);   // + softmax row max / sum (logits mode)
@@ -74,7 +87,7 @@ static inline size_t voc_eval_ws_bytes(int rows, int M, int C) {
 
 // ---- nms -----------------------------------------------------------------------------------
 static inline size_t nms_ws_bytes(int n, int top_k) {
-  (void)top_k;
+  if (top_k > kTopKLimit) return large_list_bytes(n, top_k) + 256;
   return align_up((size_t)n * 4) + 256;
 }
 

@@ -43,6 +43,11 @@ class DetectOut(object):
         P = pri.size(-2)
         loc = _abi.as_f32(loc_data).view(num, P, 4)
         scores = _abi.as_f32(conf_data, dev).view(num, P, self.num_classes)      # detection.py:38
+        logits = self.conf_is_logits
+        if logits and int(self.top_k) > 1024:
+            # the any-top_k path of the library has no fused softmax: do what the reference does (ssd_v3.py:123-124)
+            scores = torch.softmax(scores, dim=-1)
+            logits = False
         if out is None:
             out = torch.empty(num, self.num_classes, self.top_k, 5, dtype=torch.float32, device=dev)
         counts = torch.empty(num, self.num_classes, dtype=torch.int32, device=dev)
@@ -51,7 +56,7 @@ class DetectOut(object):
         cfg = _abi.DetectCfg(num, P, self.num_classes, int(self.top_k), float(self.conf_thresh),
                              float(self.nms_thresh), float(self.variance[0]), float(self.variance[1]),
                              4 * P if per_image else 0,
-                             (_abi.DETECT_LOGITS if self.conf_is_logits else 0) | (_abi.DETECT_WS_CLEAN if clean else 0), 0)
+                             (_abi.DETECT_LOGITS if logits else 0) | (_abi.DETECT_WS_CLEAN if clean and int(self.top_k) <= 1024 else 0), 0)
         keep = score_keep.to(dev).to(torch.uint8).contiguous() if score_keep is not None else None
         fin = pending._detect_tail_args() if pending is not None else None
         if refine is not None:        # RefineDet fused (ssdbox_detect_refine): anchors refined / filtered inside the kernels

@@ -81,7 +81,7 @@ def test_argument_validation_without_gpu(lib):
     cfg = _abi.DetectCfg(1, 4, 3, 200, 0.01, 0.0, 0.1, 0.2, 0)
     assert lib.ssdbox_detect(C.byref(cfg), None, None, None, None, None, None, None, 0, None) == _abi.EINVAL
     assert "nms_threshold must be non negative" in _abi.last_error()
-    cfg = _abi.DetectCfg(1, 4, 3, 5000, 0.01, 0.45, 0.1, 0.2, 0)
+    cfg = _abi.DetectCfg(1, 4, 3, 70000, 0.01, 0.45, 0.1, 0.2, 0)      # beyond the any-top_k path (65536)
     assert lib.ssdbox_detect(C.byref(cfg), None, None, None, None, None, None, None, 0, None) == _abi.ESHAPE
     lc = _abi.LossCfg(2, 8, 3, 9999, 0.5, 3, 0.1, 0.2, 0, 1, 0)
     rc = lib.ssdbox_multibox_loss_fwd(C.byref(lc), *([None] * 15), None, 0, None)

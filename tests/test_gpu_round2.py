@@ -562,3 +562,54 @@ def test_head_layout_unaligned_source_falls_back(dev):
     assert o.data_ptr() % 16 != 0
     want = o.permute(0, 2, 3, 1).contiguous().view(2, -1)
     assert torch.equal(H.heads_to_rows([o], 64).view(2, -1), want)
+
+
+# ------------------------------------------------------------------------------------------------
+# any top_k (box_utils.py:299-301 takes whatever it is given): beyond 1024 the slow matrix-free kernels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,k", [(1500, 1025), (3000, 2000), (3000, 5000), (24564, 3000), (70, 4096), (30000, 30000)])
+def test_nms_any_top_k_bit_exact(dev, n, k):
+    g = torch.Generator().manual_seed(n + k)
+    xy = torch.rand(n, 2, generator=g) * 0.8
+    wh = torch.rand(n, 2, generator=g) * 0.12 + 0.01
+    boxes = torch.cat([xy, xy + wh], 1)
+    scores = torch.rand(n, generator=g)
+    if n == 3000:
+        scores = (scores * 50).floor() / 50                 # ties everywhere: equal scores are visited higher index first
+        boxes[::9, 2:] = boxes[::9, :2]                     # zero-area boxes
+    ok, oc = O.greedy_nms(boxes, scores, 0.45, k)
+    keep, cnt = BU.nms(boxes.to(dev), scores.to(dev), 0.45, k)
+    assert cnt == oc and torch.equal(keep.cpu(), ok)
+
+
+@pytest.mark.gpu
+def test_nms_large_path_equals_fast_path(dev):
+    """same input through both kernels: top_k = 1024 (shared-memory matrix) and top_k = 1025 with only 1024 boxes alive"""
+    g = torch.Generator().manual_seed(77)
+    n = 1024
+    xy = torch.rand(n, 2, generator=g) * 0.7
+    boxes = torch.cat([xy, xy + torch.rand(n, 2, generator=g) * 0.2 + 0.01], 1).to(dev)
+    scores = torch.rand(n, generator=g).to(dev)
+    k1, c1 = BU.nms(boxes, scores, 0.45, 1024)
+    k2, c2 = BU.nms(boxes, scores, 0.45, 1025)
+    assert c1 == c2 and torch.equal(k1, k2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,B,seed,bias,top_k", [("ssd300_voc", 2, 3, 4.0, 1500), ("ssd300_voc", 1, 5, 1.0, 2048),
+                                                   ("fssd300_coco", 1, 6, 9.0, 1100)])
+def test_detect_any_top_k(dev, name, B, seed, bias, top_k):
+    x = U.seeded_inputs(name, B, seed, bkg_bias=bias)
+    det = ssdbox.DetectOut(x["C"], 0, top_k, 0.01, 0.45, (0.1, 0.2))
+    out = det(x["loc"].to(dev), x["scores"].to(dev), x["priors"].to(dev))
+    assert out.shape == (B, x["C"], top_k, 5)
+    ref = O.detect(x["loc"], x["scores"], x["priors"], x["C"], top_k=top_k)
+    _compare_detect(out.cpu(), ref, "%s top_k=%d" % (name, top_k))
+    assert torch.equal(det.last_counts.cpu().long(), (ref[..., 0] > 0).sum(-1))
+    # raw logits with such a top_k: the host mirror applies the softmax itself (no fused path beyond 1024)
+    if name == "fssd300_coco":
+        logit = torch.log(x["scores"].clamp_min(1e-30))
+        det2 = ssdbox.DetectOut(x["C"], 0, top_k, 0.01, 0.45, (0.1, 0.2), conf_is_logits=True)
+        out2 = det2(x["loc"].to(dev), logit.to(dev), x["priors"].to(dev)).cpu()
+        assert torch.equal(out2[..., 0] > 0, out.cpu()[..., 0] > 0)
