@@ -119,6 +119,8 @@ SSDBOX_API int ssdbox_decode(const float* loc, const float* priors, int64_t n, i
                   float var1, float* out, float* out_center, ssdbox_stream_t stream);
 /* log_sum_exp :265-273  x[rows,C] -> out[rows]; uses ONE global max over all of x like the
  * reference (two passes).  ws: SSDBOX_OP_LSE. */
+/* out[0] (double, device) = max over x[0..n) -- the x.data.max() of box_utils.py:272; -inf for n = 0.  ws: SSDBOX_OP_LSE. */
+SSDBOX_API int ssdbox_global_max(const float* x, int64_t n, double* out, void* ws, size_t ws_bytes, ssdbox_stream_t stream);
 SSDBOX_API int ssdbox_log_sum_exp(const float* x, int64_t rows, int32_t C, float* out, void* ws, size_t ws_bytes,
                        ssdbox_stream_t stream);
 
@@ -193,6 +195,13 @@ typedef struct {
  * flag nothing is assumed about the workspace contents.  The host mirror (MultiBoxLoss) sets it from the second
  * call on. */
 #define SSDBOX_LOSS_WS_CLEAN 16
+/* The reference's log_sum_exp subtracts ONE maximum -- x.data.max() over the whole batch_conf it sees
+ * (box_utils.py:272-273) -- where this library by default subtracts each row's own maximum (same value up to fp32
+ * rounding, and no underflow for rows far below the batch maximum).  With this flag the value to subtract is taken
+ * from sums[0] ON ENTRY (a double; e.g. written by ssdbox_global_max on the same stream, all-reduced with MAX by the
+ * caller when the batch is sharded over ranks) and the rows are evaluated as logf(sum expf(x - shift)) + shift like the
+ * reference, underflow and all.  Slower (generic streaming kernel); a fidelity mode, not the default. */
+#define SSDBOX_LOSS_LSE_SHIFT 32
 
 /* forward.
  *   loc [B,P,4], conf [B,P,C] raw logits, priors, anchors_xyxy (nullable), gt/gt_offsets

@@ -146,6 +146,11 @@ __global__ void global_max_kernel(const float* __restrict__ x, long long n, uint
   if ((threadIdx.x & 31) == 0) atomicMax(gmax_ord, o);
 }
 
+__global__ void ord_to_double_kernel(const uint32_t* __restrict__ gmax_ord, double* __restrict__ out) {
+  const uint32_t o = *gmax_ord;
+  out[0] = o == 0u ? -(double)INFINITY : (double)ord2f(o);      // key 0 = nothing seen
+}
+
 __global__ void lse_rows_kernel(const float* __restrict__ x, long long rows, int C, const uint32_t* __restrict__ gmax_ord,
                                 float* __restrict__ out) {
   float gm = ord2f(*gmax_ord);
@@ -269,6 +274,23 @@ extern "C" int ssdbox_log_sum_exp(const float* x, int64_t rows, int32_t C, float
   SSDBOX_LAUNCH_OK("global_max_kernel");
   lse_rows_kernel<<<grid_for(rows), 256, 0, st>>>(x, rows, C, g, out);
   SSDBOX_LAUNCH_OK("lse_rows_kernel");
+  return SSDBOX_OK;
+}
+
+extern "C" int ssdbox_global_max(const float* x, int64_t n, double* out, void* ws, size_t ws_bytes, ssdbox_stream_t stream) {
+  SSDBOX_REQUIRE(n >= 0, SSDBOX_EINVAL, "global_max: negative n");
+  SSDBOX_REQUIRE(out && ws && (x || n == 0), SSDBOX_EINVAL, "global_max: null pointer");
+  SSDBOX_REQUIRE(ws_bytes >= 256, SSDBOX_EWORKSPACE, "global_max: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint32_t* g = static_cast<uint32_t*>(ws);
+  int rc = launch_init(nullptr, 0, g, 1, nullptr, 0, nullptr, 0, st);      // ordered key 0 = below every float
+  if (rc) return rc;
+  if (n > 0) {
+    global_max_kernel<<<grid_for(n), 256, 0, st>>>(x, (long long)n, g);
+    SSDBOX_LAUNCH_OK("global_max_kernel");
+  }
+  ord_to_double_kernel<<<1, 1, 0, st>>>(g, out);
+  SSDBOX_LAUNCH_OK("ord_to_double_kernel");
   return SSDBOX_OK;
 }
 

@@ -92,6 +92,7 @@ struct StreamArgs {
   uint32_t* unit_counter;   // next matching work unit (zeroed by init_kernel)
   int unit_bytes;           // one unit buffer in shared memory
   int dbg;                  // SSDBOX_PHASE_TIMING builds: 1 = do not stream conf (matching alone)
+  const double* shift;      // SSDBOX_LOSS_LSE_SHIFT: the value the log-sum-exp subtracts (nullptr: each row's maximum)
 };
 
 // log-sum-exp of one row with the row maximum (box_utils.py:273 uses one global maximum; same value
@@ -134,6 +135,13 @@ __device__ __forceinline__ float row_lse(const float* __restrict__ rp, int C) {
     for (int c = 0; c < C; ++c) s += ex2_approx(fmaf(rp[c], kLog2e, nml));
   }
   return logf(s) + m;
+}
+
+// box_utils.py:272-273 as written: log(sum(exp(x - shift))) + shift with the caller's shift (the batch maximum)
+__device__ __forceinline__ float row_lse_shift(const float* __restrict__ rp, int C, float shift) {
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s = __fadd_rn(s, expf(__fsub_rn(rp[c], shift)));
+  return __fadd_rn(logf(s), shift);
 }
 
 // ---- matching on dedicated warps -----------------------------------------------------------------
@@ -379,7 +387,7 @@ __device__ void match_unit_loop(const StreamArgs& a, unsigned char* mbase, int m
 #endif
 }
 
-template <int CT>
+template <int CT, bool SHIFT = false>
 __global__ void __launch_bounds__(kStreamThreads, 1) loss_stream_kernel(StreamArgs a) {
   extern __shared__ __align__(128) unsigned char smem_ring[];
   const int C = CT > 0 ? CT : a.ring.C;
@@ -416,6 +424,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) loss_stream_kernel(StreamAr
   const int wg = warp / kRingGroupWarps;
   const int rbase = tid % (32 * kRingGroupWarps);
   const int KR = a.ring.KR;
+  const float shift = SHIFT ? (float)*a.shift : 0.f;
   for (int it = wg; it < rc.n_local; it += kRingGroups) {
     const int s = it % NS, j = it % (2 * NS), ph = it / (2 * NS);
     mbar_wait(&rc.full[j], (uint32_t)(ph & 1));
@@ -424,7 +433,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) loss_stream_kernel(StreamAr
       const long long row = (rc.t0 + it * rc.tstep) * R + r;
       if ((r < R) && (row < a.ring.rows)) {
         const float* rp = rc.stages + (size_t)s * rc.stage_floats + (size_t)r * C;
-        const float lse = row_lse<CT>(rp, C);
+        const float lse = SHIFT ? row_lse_shift(rp, C, shift) : row_lse<CT>(rp, C);
         const float k0 = lse - rp[0];                        // multibox_loss.py:94 with conf_t = 0
         a.key0[row] = k0;                                    // (a positive's lse is recovered as key0 + x[0]: no second array)
         if (refine_member(a.rf, a.pool, (size_t)row)) {
@@ -474,6 +483,7 @@ static int launch_stream(const StreamArgs& a, size_t smem, cudaStream_t st) {
   if (C == 81) kern = loss_stream_kernel<81>;
   else if (C == 21) kern = loss_stream_kernel<21>;
   else if (C == 2) kern = loss_stream_kernel<2>;
+  if (a.shift) kern = loss_stream_kernel<0, true>;        // fidelity mode: any C through the generic instantiation
   SSDBOX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   SSDBOX_CARVE(kern);
   {
@@ -1888,6 +1898,7 @@ static int loss_fwd_impl(const ssdbox_loss_cfg* cfg, const float* loc, const flo
   sa.tidx_out = tidx;
   sa.unit_counter = w.ticket + 1;
   sa.dbg = (cfg->flags >> 8) & 0xff;
+  sa.shift = (cfg->flags & SSDBOX_LOSS_LSE_SHIFT) ? sums : nullptr;     // read by the streaming kernel; sums is written by the mining kernel after it
   size_t stream_smem = 0;
   rc = plan_stream(&sa, conf, (long long)B * P, C, dev.sm_count, dev.max_smem_optin,
                    !(cfg->flags & SSDBOX_LOSS_SEPARATE_MATCH), &stream_smem);

@@ -19,6 +19,7 @@ LOSS_GENERIC_MINE = 2
 LOSS_NO_CLUSTER = 4
 LOSS_DEFER_PEER_WAIT = 8
 LOSS_WS_CLEAN = 16
+LOSS_LSE_SHIFT = 32
 OP_MATCH, OP_LOSS_FWD, OP_DETECT, OP_NMS, OP_LSE, OP_MINE, OP_COMPACT, OP_VOC_EVAL = 1, 2, 3, 4, 5, 6, 7, 8
 MAX_LAYERS, MAX_MIN_SIZES, MAX_RATIOS = 16, 4, 6
 
@@ -26,7 +27,7 @@ MAX_LAYERS, MAX_MIN_SIZES, MAX_RATIOS = 16, 4, 6
 SYMBOLS = [
     "ssdbox_abi_version", "ssdbox_last_error", "ssdbox_workspace_bytes", "ssdbox_priorbox_count",
     "ssdbox_priorbox", "ssdbox_point_form", "ssdbox_center_form", "ssdbox_jaccard", "ssdbox_encode",
-    "ssdbox_decode", "ssdbox_log_sum_exp", "ssdbox_match_encode", "ssdbox_hard_negative_mine",
+    "ssdbox_decode", "ssdbox_log_sum_exp", "ssdbox_global_max", "ssdbox_match_encode", "ssdbox_hard_negative_mine",
     "ssdbox_multibox_loss_fwd", "ssdbox_multibox_loss_fwd_peers", "ssdbox_multibox_loss_peer_finish",
     "ssdbox_peer_buffer_bytes",
     "ssdbox_multibox_loss_finalize", "ssdbox_multibox_loss_bwd",
@@ -125,6 +126,7 @@ def _declare(lib):
         "ssdbox_encode": [P_, P_, i64, f32, f32, P_, P_],
         "ssdbox_decode": [P_, P_, i64, i64, f32, f32, P_, P_, P_],
         "ssdbox_log_sum_exp": [P_, i64, i32, P_, P_, sz, P_],
+        "ssdbox_global_max": [P_, i64, P_, P_, sz, P_],
         "ssdbox_match_encode": [P_, P_, i32, P_, i64, P_, i32, i32, f32, f32, f32, i32, P_, P_, P_, P_, P_, sz, P_],
         "ssdbox_hard_negative_mine": [P_, P_, P_, i32, i32, i32, P_, P_, sz, P_],
         "ssdbox_multibox_loss_fwd": [C.POINTER(LossCfg)] + [P_] * 15 + [P_, sz, P_],

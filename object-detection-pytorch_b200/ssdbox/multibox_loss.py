@@ -51,6 +51,7 @@ class _State(object):
     def __init__(self):
         self.ws = _abi.Workspace()
         self.slots = {}
+        self.scratch = None
         self.sel = self.tidx = self.sums = self.losses = None
 
     def ensure(self, B, P, device):
@@ -76,7 +77,7 @@ def make_refine(refine):
 
 def loss_forward_raw(state, loc, conf, priors, gt, offsets, gmax, num_classes, threshold, negpos_ratio,
                      variance, anchors_xyxy=None, pool=None, binarize=False, finalize=True, debug=None,
-                     fresh=False, flags=0, peers=None, refine=None):
+                     fresh=False, flags=0, peers=None, refine=None, lse_group=False):
     """One call of ssdbox_multibox_loss_fwd on validated CUDA tensors.  Returns
     (cfg, sums[3] f64, losses[2] f32, sel[B,P] i16, tidx[B,P] i16).  With fresh=False the outputs are
     the module's persistent buffers (overwritten by the next call); fresh=True allocates new ones
@@ -107,6 +108,15 @@ def loss_forward_raw(state, loc, conf, priors, gt, offsets, gmax, num_classes, t
     gmax = gq if gmax > 0 else 0
     ws, n, clean = state.ws.acquire(_abi.workspace_bytes(_abi.OP_LOSS_FWD, B, P, num_classes, gmax), dev,
                                     ("loss", B, P, int(num_classes), gmax))
+    if int(flags) & _abi.LOSS_LSE_SHIFT:
+        # fidelity mode (box_utils.py:272-273): the log-sum-exp subtracts the maximum of the whole batch_conf -- of the
+        # GLOBAL batch when it is sharded over ranks -- handed to the kernels in sums[0]
+        if state.scratch is None or state.scratch.device != dev:
+            state.scratch = torch.empty(256, dtype=torch.uint8, device=dev)
+        _abi.check(_abi.lib().ssdbox_global_max(_abi.ptr(conf, torch.float32, "conf_data"), conf.numel(), _abi.ptr(sums),
+                                                _abi.ptr(state.scratch), 256, _abi.stream_ptr(dev)))
+        if lse_group is not False and torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(sums[:1], op=torch.distributed.ReduceOp.MAX, group=lse_group)
     cfg = _abi.LossCfg(B, P, int(num_classes), gmax, float(threshold), int(negpos_ratio),
                        float(variance[0]), float(variance[1]), 1 if binarize else 0, 1 if finalize else 0,
                        4 * P if per_image else 0, int(flags) | (_abi.LOSS_WS_CLEAN if clean else 0), 0)
@@ -153,7 +163,8 @@ class _MultiBoxLossFn(torch.autograd.Function):
         cfg, sums, losses, sel, tidx = loss_forward_raw(
             st, loc, conf, priors, gt, offsets, gmax, mod.num_classes, mod.threshold, mod.negpos_ratio,
             mod.variance, anchors_xyxy, pool, mod.binarize_labels, finalize=(not distributed) or peers is not None,
-            debug=mod._debug, fresh=need_grad, flags=mod.abi_flags, peers=peers, refine=refine)
+            debug=mod._debug, fresh=need_grad, flags=mod.abi_flags | (_abi.LOSS_LSE_SHIFT if mod.lse_global_max else 0), peers=peers,
+            refine=refine, lse_group=(mod.process_group if distributed else False))
         if distributed and peers is None:
             import torch.distributed as dist
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=mod.process_group)
@@ -269,6 +280,10 @@ class MultiBoxLoss(nn.Module):
         self._pending_unwaited = False
         self._peers = None
         self.abi_flags = 0          # _abi.LOSS_SEPARATE_MATCH: matching as its own kernel
+        # fidelity switch (default off): log_sum_exp with ONE maximum over the whole (global) batch like box_utils.py:272-273
+        # instead of each row's own maximum -- same values up to fp32 rounding, but also the reference's underflow for rows
+        # far below the batch maximum; costs a pass over conf and the generic streaming kernel
+        self.lse_global_max = False
         self._state = _State()
         self._debug = None
         self._last = None
@@ -360,7 +375,8 @@ class MultiBoxLoss(nn.Module):
             cfg, sums, losses, sel, tidx = loss_forward_raw(
                 self._state, loc, conf, priors, gt, offsets, gmax, self.num_classes, self.threshold,
                 self.negpos_ratio, self.variance, None, None, self.binarize_labels, finalize=True,
-                debug=None, fresh=False, flags=self.abi_flags | _abi.LOSS_DEFER_PEER_WAIT, peers=peers)
+                debug=None, fresh=False, flags=self.abi_flags | _abi.LOSS_DEFER_PEER_WAIT | (_abi.LOSS_LSE_SHIFT if self.lse_global_max else 0),
+                peers=peers, lse_group=self.process_group)
             self._last = (sums, sel, tidx)
             self._pending_unwaited = True
             return PendingLoss(peers, sums, losses, None, owner=self)

@@ -613,3 +613,60 @@ def test_detect_any_top_k(dev, name, B, seed, bias, top_k):
         det2 = ssdbox.DetectOut(x["C"], 0, top_k, 0.01, 0.45, (0.1, 0.2), conf_is_logits=True)
         out2 = det2(x["loc"].to(dev), logit.to(dev), x["priors"].to(dev)).cpu()
         assert torch.equal(out2[..., 0] > 0, out.cpu()[..., 0] > 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# log_sum_exp with ONE maximum over the batch (box_utils.py:272-273) as a fidelity switch
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_global_max_entry_point(dev):
+    from ssdbox import _abi
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(5, 777, 21, generator=g) * 7).to(dev)
+    out = torch.zeros(1, dtype=torch.float64, device=dev)
+    ws = torch.empty(256, dtype=torch.uint8, device=dev)
+    _abi.check(_abi.lib().ssdbox_global_max(_abi.ptr(x), x.numel(), _abi.ptr(out), _abi.ptr(ws), 256, _abi.stream_ptr(dev)))
+    assert float(out) == float(x.max())
+    _abi.check(_abi.lib().ssdbox_global_max(None, 0, _abi.ptr(out), _abi.ptr(ws), 256, _abi.stream_ptr(dev)))
+    assert float(out) == float("-inf")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,B,seed,offset", [("ssd300_voc", 3, 0, 0.0), ("ssd300_voc", 2, 1, 40.0), ("fssd300_coco", 2, 2, 60.0)])
+def test_loss_lse_global_max_mode(dev, name, B, seed, offset):
+    """lse_global_max=True evaluates log(sum(exp(x - M))) + M with M = the batch maximum, like the reference: against the
+    oracle (which does exactly that) the mining keys agree at least as tightly as in the default per-row mode, the mined
+    sets agree up to keys tied within that tolerance, the losses to 1e-5."""
+    x = U.seeded_inputs(name, B, seed)
+    conf = x["conf"].clone()
+    conf[0, :50] += offset                     # one image far above the others: its maximum is everybody's shift
+    ref = O.multibox_loss(x["loc"], conf, x["priors"], x["targets"], x["C"], detail=True)
+    crit = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False)
+    crit.lse_global_max = True
+    pred = (x["loc"].to(dev), conf.to(dev), x["priors"].to(dev))
+    tg = [t.to(dev) for t in x["targets"]]
+    d = crit.intermediates(pred, tg)
+    assert torch.equal(d["conf_t"].cpu(), ref["conf_t"])
+    keys = d["keys"].cpu().clone()
+    keys[ref["pos"]] = 0                       # (the oracle's mining keys are zeroed at the positives, multibox_loss.py:96)
+    # absolute agreement relative to the magnitude the arithmetic ran at (the shift), as in the reference
+    scale = max(1.0, float(conf.max()))
+    assert float((keys - ref["mining_keys"]).abs().max()) <= 4e-6 * scale
+    diff = d["neg"].cpu().bool() != ref["neg"]            # mined sets: identical except at keys tied with the cut within the tolerance
+    for b in diff.any(1).nonzero().flatten().tolist():
+        k = int(ref["neg"][b].sum())
+        kth = ref["mining_keys"][b].sort(descending=True).values[k - 1]
+        assert float((ref["mining_keys"][b][diff[b]] - kth).abs().max()) <= 8e-6 * scale, "non-tie mining mismatch in image %d" % b
+    U.assert_close_rel(d["loss_l"].cpu(), ref["loss_l"], 1e-5, 1e-7, "loss_l")
+    U.assert_close_rel(d["loss_c"].cpu(), ref["loss_c"], 2e-5 * scale, 1e-6, "loss_c")
+    # the default mode on the same inputs: same targets, same losses to the same tolerance
+    crit2 = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False)
+    ll2, lc2 = crit2(pred, tg)
+    U.assert_close_rel(lc2.cpu(), ref["loss_c"], 2e-5 * scale, 1e-6, "loss_c (row max)")
+    # and the flag survives backward (the gradient is the same softmax either way)
+    loc_g = pred[0].clone().requires_grad_(True)
+    conf_g = pred[1].clone().requires_grad_(True)
+    ll, lc = crit((loc_g, conf_g, pred[2]), tg)
+    (ll + lc).backward()
+    gl, gc = O.multibox_loss_grads(x["loc"], conf, x["priors"], x["targets"], x["C"])
+    U.assert_close_rel(conf_g.grad.cpu(), gc, 1e-4, 1e-6, "grad_conf")
