@@ -670,3 +670,45 @@ def test_loss_lse_global_max_mode(dev, name, B, seed, offset):
     (ll + lc).backward()
     gl, gc = O.multibox_loss_grads(x["loc"], conf, x["priors"], x["targets"], x["C"])
     U.assert_close_rel(conf_g.grad.cpu(), gc, 1e-4, 1e-6, "grad_conf")
+
+
+@pytest.mark.gpu
+def test_any_top_k_edge_cases(dev):
+    # nms: nothing / one box / top_k far beyond n
+    keep = BU.nms(torch.zeros(0, 4, device=dev), torch.zeros(0, device=dev), 0.45, 5000)
+    assert isinstance(keep, torch.Tensor) and keep.numel() == 0
+    k, c = BU.nms(torch.tensor([[0.1, 0.1, 0.4, 0.5]], device=dev), torch.tensor([0.7], device=dev), 0.45, 60000)
+    assert c == 1 and int(k[0]) == 0
+    # DetectOut: fewer priors than top_k, an image without any candidate, B = 0
+    g = torch.Generator().manual_seed(21)
+    P, C, top_k = 300, 4, 1200
+    cxcy = torch.rand(P, 2, generator=g)
+    pri = torch.cat([cxcy, torch.rand(P, 2, generator=g) * 0.3 + 0.05], 1)
+    loc = torch.randn(2, P, 4, generator=g) * 0.3
+    sc = torch.softmax(torch.randn(2, P, C, generator=g) * 2, -1)
+    sc[1] = 0.0                                                   # image 1: nothing above conf_thresh
+    det = ssdbox.DetectOut(C, 0, top_k, 0.01, 0.45, (0.1, 0.2))
+    out = det(loc.to(dev), sc.to(dev), pri.to(dev)).cpu()
+    ref = O.detect(loc, sc, pri, C, top_k=top_k)
+    _compare_detect(out, ref, "P < top_k")
+    assert float(out[1].abs().sum()) == 0.0
+    out0 = det(loc[:0].to(dev), sc[:0].to(dev), pri.to(dev))
+    assert out0.shape == (0, C, top_k, 5)
+
+
+@pytest.mark.gpu
+def test_head_layout_edge_cases(dev):
+    from ssdbox import heads as H
+    g = torch.Generator().manual_seed(31)
+    # exactly at the limits of the TMA path (64 positions, 32 channels), next to layers just outside it, and B = 0
+    shapes = [(32, 8, 8), (31, 8, 8), (32, 7, 9), (576, 8, 8), (64, 2, 32)]
+    outs = [torch.randn(3, ch, h, w, generator=g).to(dev) for ch, h, w in shapes]
+    want = torch.cat([o.permute(0, 2, 3, 1).contiguous().view(3, -1) for o in outs], 1)
+    assert torch.equal(H.heads_to_rows(outs, 1).view(3, -1), want)
+    # channels-last / sliced inputs are made contiguous by the host mirror
+    big = torch.randn(3, 80, 8, 8, generator=g).to(dev)
+    view = big[:, 8:72]                                            # non-contiguous NCHW slice
+    want = view.permute(0, 2, 3, 1).contiguous().view(3, -1)
+    assert torch.equal(H.heads_to_rows([view], 64).view(3, -1), want)
+    empty = [torch.zeros(0, 64, 8, 8, device=dev)]
+    assert H.heads_to_rows(empty, 64).shape[0] == 0
