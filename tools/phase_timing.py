@@ -8,9 +8,10 @@ _abi.LIB_PATH = os.path.join(ROOT, "tools", "libssdbox_dbg.so")
 import ssdbox
 from ssdbox import configs, synth
 dev = torch.device("cuda:0")
-cfg, c = configs.get("ssd512_coco"); Cn = 81; B = 64
+NAME = sys.argv[1] if len(sys.argv) > 1 else "ssd512_coco"
+cfg, c = configs.get(NAME); Cn = cfg.MODEL.NUM_CLASSES; B = int(sys.argv[2]) if len(sys.argv) > 2 else c["batch"]
 pri = ssdbox.PriorBoxSSD(cfg).forward(c["layer_dims"], keep_on_device=True); P = pri.size(0)
-tg = [t.to(dev) for t in synth.gen_targets(B, Cn, 32, 0)]
+tg = [t.to(dev) for t in synth.gen_targets(B, Cn, c["gt_max"], 0)]
 loc = torch.randn(B, P, 4, device=dev) * 0.5
 conf = torch.randn(B, P, Cn, device=dev); conf[..., 0] += 4
 crit = ssdbox.MultiBoxLoss(Cn, 0.5, True, 0, True, 3, 0.5, False)
