@@ -202,6 +202,10 @@ typedef struct {
  * caller when the batch is sharded over ranks) and the rows are evaluated as logf(sum expf(x - shift)) + shift like the
  * reference, underflow and all.  Slower (generic streaming kernel); a fidelity mode, not the default. */
 #define SSDBOX_LOSS_LSE_SHIFT 32
+/* mining with two 512-thread CTAs per SM instead of one 1024-thread CTA (chosen automatically when the batch has more
+ * images than the device has SMs and the image fits: P <= 12288; this flag forces it wherever it fits -- tests).  The
+ * selected sets are the same; the fp64 partial sums are added in a different (still fixed) order. */
+#define SSDBOX_LOSS_MINE_HALF_CTA 64
 
 /* forward.
  *   loc [B,P,4], conf [B,P,C] raw logits, priors, anchors_xyxy (nullable), gt/gt_offsets

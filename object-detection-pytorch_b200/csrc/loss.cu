@@ -840,9 +840,12 @@ __device__ __forceinline__ int reg_find(const uint32_t* s_hist, int nbins, int K
   return s_res[0];
 }
 
-template <int CL>
-__global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineArgs a) {
+// T = threads per CTA: 1024 (one CTA per SM), or 512 with two CTAs per SM for batches of more images than SMs -- the
+// 256 images of RFB300-VOC then mine in ONE wave of 256 resident CTAs instead of two waves of 148.
+template <int CL, int T = kMineThreads>
+__global__ void __launch_bounds__(T, kMineThreads / T) mine_reduce_reg_kernel(MineArgs a) {
   constexpr int Q = kMineQ / CL;     // quads (4 priors) per thread
+  constexpr int HB = kHistBins / T;  // histogram bins per thread
   extern __shared__ __align__(16) unsigned char smem_mine[];
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_mine);                        // 2048
   double* s_dscr = reinterpret_cast<double*>(smem_mine + 8192);                     // 100
@@ -876,7 +879,9 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   PHASE_MARK(0);
   // (1) everything this CTA needs from memory, requested together.  The loads that do not depend on the image's
   // truth count go first: a warp issues in order, and the truth offsets take a round trip of their own.
-  uint32_t h0 = a.hist[(size_t)b * kHistBins + tid], h1 = a.hist[(size_t)b * kHistBins + 1024 + tid];
+  uint32_t hreg[HB];
+#pragma unroll
+  for (int i = 0; i < HB; ++i) hreg[i] = a.hist[(size_t)b * kHistBins + i * T + tid];
   uint32_t uk[Q][4];     // ordered mining keys (0 = outside the ranking)
   short4 ll[Q];
   uint32_t poolmask = 0u;     // bit j*4+e: prior is ranked (inside P and inside the caller's pool)
@@ -885,7 +890,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   const uchar4* p4 = a.pool ? reinterpret_cast<const uchar4*>(a.pool + off) : nullptr;
 #pragma unroll
   for (int j = 0; j < Q; ++j) {
-    const int ql = tid + j * kMineThreads, q = q0 + ql;
+    const int ql = tid + j * T, q = q0 + ql;
     float4 kv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ql < n4h && q < n4) {
       kv = k4[q];
@@ -910,12 +915,13 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   unsigned long long my_best = 0ull;
   if (small_g && tid < G) my_best = __ldcg(&a.gt_best[(size_t)b * a.gpad + tid]);
   const bool gt_cached = G <= kForceListMax;
-  float my_gt = 0.f;
+  float my_gt = 0.f, my_gt2 = 0.f;      // 5 * G <= 640 floats: one per thread, a second one for the 512-thread CTA
   if (gt_cached && tid < 5 * G) my_gt = a.gt[(size_t)g0 * 5 + tid];
+  if (T < 5 * kForceListMax && gt_cached && tid + T < 5 * G) my_gt2 = a.gt[(size_t)g0 * 5 + tid + T];
   if (a.fuse && !small_g) {
     // many truths: replay the forced assignment through global memory first (box_utils.py:123-130)
     const unsigned long long* best = a.gt_best + (size_t)b * a.gpad;
-    for (int j = tid; j < G && rank == 0; j += kMineThreads) {
+    for (int j = tid; j < G && rank == 0; j += T) {
       const uint32_t pj = ~(uint32_t)(__ldcg(&best[j]) & 0xffffffffull);
       bool winner = pj < (uint32_t)P;
       for (int j2 = j + 1; winner && j2 < G; ++j2)
@@ -930,29 +936,30 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   }
 #pragma unroll
   for (int j = 0; j < Q; ++j) {
-    const int ql = tid + j * kMineThreads, q = q0 + ql;
+    const int ql = tid + j * T, q = q0 + ql;
     ll[j] = make_short4(0, 0, 0, 0);
     if (ql < n4h && q < n4) ll[j] = l4[q];
   }
-  s_hist[tid] = h0;
-  s_hist[1024 + tid] = h1;
+#pragma unroll
+  for (int i = 0; i < HB; ++i) s_hist[i * T + tid] = hreg[i];
   if (small_g) {
 #pragma unroll
     for (int j = 0; j < Q; ++j) {
-      const int ql = tid + j * kMineThreads;
+      const int ql = tid + j * T;
       if (ql < n4h) *reinterpret_cast<short4*>(s_ovr + ql * 4) = make_short4(-1, -1, -1, -1);
     }
   }
   if (small_g && tid < G) s_best[tid] = my_best;
   if (gt_cached && tid < 5 * G) s_gt[tid] = my_gt;
+  if (T < 5 * kForceListMax && gt_cached && tid + T < 5 * G) s_gt[tid + T] = my_gt2;
   sync_all();          // cluster: the peer's histogram copy is in place before it receives remote updates
   // every CTA of the image has read its streamed histogram and best-prior keys: hand them back initialised
   // (the workspace state is clean again after the call, SSDBOX_LOSS_WS_CLEAN)
   if (rank == 0) {
-    a.hist[(size_t)b * kHistBins + tid] = 0u;
-    a.hist[(size_t)b * kHistBins + 1024 + tid] = 0u;
+#pragma unroll
+    for (int i = 0; i < HB; ++i) a.hist[(size_t)b * kHistBins + i * T + tid] = 0u;
     if (a.fuse)
-      for (int j = tid; j < G; j += kMineThreads) a.gt_best_w[(size_t)b * a.gpad + j] = kBestInit;
+      for (int j = tid; j < G; j += T) a.gt_best_w[(size_t)b * a.gpad + j] = kBestInit;
   }
 
   PHASE_MARK(1);
@@ -982,7 +989,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < Q; ++j) {
-      const int ql = tid + j * kMineThreads;
+      const int ql = tid + j * T;
       if (ql < n4h) {
         const short4 o = *reinterpret_cast<const short4*>(s_ovr + ql * 4);
         if (o.x >= 0) ll[j].x = o.x;
@@ -1001,7 +1008,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   const uint32_t rhist = CL > 1 ? peer_smem(s_hist, (uint32_t)(rank ^ 1)) : 0u;
 #pragma unroll
   for (int j = 0; j < Q; ++j) {
-    const int ql = tid + j * kMineThreads, q = q0 + ql;
+    const int ql = tid + j * T, q = q0 + ql;
     if (a.dbg_keys && ql < n4h && q < n4)
       *reinterpret_cast<float4*>(a.dbg_keys + off + (size_t)q * 4) =
           make_float4(ord2f(uk[j][0]), ord2f(uk[j][1]), ord2f(uk[j][2]), ord2f(uk[j][3]));
@@ -1034,7 +1041,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
 #pragma unroll
       for (int e = 0; e < 4; ++e)
         if (((poolmask >> (4 * j + e)) & 1u) && lb[e] > 0)
-          s_list[slot++] = (uint32_t)((q0 + tid + j * kMineThreads) * 4 + e) | ((uint32_t)lb[e] << 16);
+          s_list[slot++] = (uint32_t)((q0 + tid + j * T) * 4 + e) | ((uint32_t)lb[e] << 16);
     }
   }
   if (CL > 1 && tid == 0) {       // positives of this CTA -> both CTAs of the cluster
@@ -1102,14 +1109,14 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
           for (int e = 0; e < 4; ++e) {
             const uint32_t u = uk[j][e];
             if (u && (int)mine_bin(u) == d1) {
-              const uint32_t p = (uint32_t)((q0 + tid + j * kMineThreads) * 4 + e);
+              const uint32_t p = (uint32_t)((q0 + tid + j * T) * 4 + e);
               const unsigned long long v = ((unsigned long long)u << 32) | (unsigned long long)(uint32_t)(~p);
               s_cand[atomicAdd(s_ncand, 1u)] = v;
               if (CL > 1) peer_st_u64(rcand + peer_atom_add(rcnt, 1u) * 8u, v);
             }
           }
         sync_all();
-        for (int t = tid; t < n1; t += kMineThreads) {     // distinct values: exactly one has `need - 1` larger ones
+        for (int t = tid; t < n1; t += T) {     // distinct values: exactly one has `need - 1` larger ones
           const unsigned long long x = s_cand[t];
           int larger = 0;
           for (int i = 0; i < n1; ++i) larger += s_cand[i] > x ? 1 : 0;
@@ -1120,8 +1127,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
       } else {
         // crowded bin: exact radix select, level 1 rebuilt from the registers (top 11 bits of the ordered key)
         uint32_t Tu;
-        s_hist[tid] = 0u;
-        s_hist[1024 + tid] = 0u;
+        for (int i = tid; i < kHistBins; i += T) s_hist[i] = 0u;
         sync_all();
 #pragma unroll
         for (int j = 0; j < Q; ++j)
@@ -1141,8 +1147,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
         if (K2 == n1r) {
           Tu = ((uint32_t)r1 << 21) ? ((uint32_t)r1 << 21) : 1u;
         } else {
-          s_hist[tid] = 0u;
-          s_hist[1024 + tid] = 0u;
+          for (int i = tid; i < kHistBins; i += T) s_hist[i] = 0u;
           sync_all();
 #pragma unroll
           for (int j = 0; j < Q; ++j)
@@ -1163,7 +1168,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
           if (K3 == n2) {
             Tu = (pre2 << 10) ? (pre2 << 10) : 1u;
           } else {
-            s_hist[tid] = 0u;
+            for (int i = tid; i < 1024; i += T) s_hist[i] = 0u;
             sync_all();
 #pragma unroll
             for (int j = 0; j < Q; ++j)
@@ -1237,7 +1242,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
     l1 += (double)(smooth_l1(l.x, tt.x) + smooth_l1(l.y, tt.y) + smooth_l1(l.z, tt.z) + smooth_l1(l.w, tt.w));
   };
   if (havepos) positive(off + p_p, p_p, p_lse, p_xt, p_t, p_l, p_pr);
-  for (int sidx = tid + kMineThreads; sidx < npos_blk; sidx += kMineThreads) {
+  for (int sidx = tid + T; sidx < npos_blk; sidx += T) {
     const uint32_t ent = s_list[sidx];
     const int p = (int)(ent & 0xffffu), lb = (int)(ent >> 16);
     const size_t i = off + p;
@@ -1249,7 +1254,7 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_reduce_reg_kernel(MineAr
   double ce_neg = 0.0;
 #pragma unroll
   for (int j = 0; j < Q; ++j) {
-    const int ql = tid + j * kMineThreads, q = q0 + ql;
+    const int ql = tid + j * T, q = q0 + ql;
     const int lb[4] = {ll[j].x, ll[j].y, ll[j].z, ll[j].w};
     int16_t so[4];
     unsigned char ng[4];
@@ -1942,12 +1947,17 @@ static int loss_fwd_impl(const ssdbox_loss_cfg* cfg, const float* loc, const flo
                     (!dbg_neg || (reinterpret_cast<uintptr_t>(dbg_neg) & 3u) == 0) && (!dbg_keys || aligned16(dbg_keys));
   void (*mkern)(MineArgs) = vec4 ? mine_reduce_kernel<4> : mine_reduce_kernel<1>;
   bool launched = false;
+  int mine_threads = kMineThreads;
   if (vec4 && P <= 4 * kMineQ * kMineThreads && !(cfg->flags & SSDBOX_LOSS_GENERIC_MINE)) {
     // keys and class targets stay in registers; images with many priors are split over a cluster of
     // two CTAs (two SMs pull the image's keys, histograms merged through distributed shared memory)
     // (only while the 2*B CTAs still fit in one wave: one 1024-thread CTA per SM)
     const bool pair = P >= 8192 && 2 * B <= dev.sm_count && !(cfg->flags & SSDBOX_LOSS_NO_CLUSTER);
-    mkern = pair ? mine_reduce_reg_kernel<2> : mine_reduce_reg_kernel<1>;
+    // more images than SMs (RFB300-VOC B = 256): 512-thread CTAs, two per SM, so that the batch mines in one wave
+    const bool half = !pair && P <= 4 * kMineQ * (kMineThreads / 2) &&
+                      (B > dev.sm_count || (cfg->flags & SSDBOX_LOSS_MINE_HALF_CTA));
+    mine_threads = half ? kMineThreads / 2 : kMineThreads;
+    mkern = pair ? mine_reduce_reg_kernel<2> : (half ? mine_reduce_reg_kernel<1, kMineThreads / 2> : mine_reduce_reg_kernel<1>);
     smem = kMineFixedSmem + (size_t)kForceListMax * 16 + (size_t)(5 * kForceListMax + 8) * 4 + (size_t)P * 4 + 16 +
            (size_t)P * 2 + 16;      // ... + positives list + forced-label override array
     if (pair) {
@@ -1976,7 +1986,7 @@ static int loss_fwd_impl(const ssdbox_loss_cfg* cfg, const float* loc, const flo
     SSDBOX_CUDA(cudaFuncSetAttribute(mkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SSDBOX_CARVE(mkern);
     TimerScope ts__(KID_MINE, st);
-    mkern<<<B, kMineThreads, smem, st>>>(m);
+    mkern<<<B, mine_threads, smem, st>>>(m);
   }
   SSDBOX_LAUNCH_OK("mine_reduce_kernel");
 

@@ -20,6 +20,7 @@ LOSS_NO_CLUSTER = 4
 LOSS_DEFER_PEER_WAIT = 8
 LOSS_WS_CLEAN = 16
 LOSS_LSE_SHIFT = 32
+LOSS_MINE_HALF_CTA = 64
 OP_MATCH, OP_LOSS_FWD, OP_DETECT, OP_NMS, OP_LSE, OP_MINE, OP_COMPACT, OP_VOC_EVAL = 1, 2, 3, 4, 5, 6, 7, 8
 MAX_LAYERS, MAX_MIN_SIZES, MAX_RATIOS = 16, 4, 6
 

@@ -712,3 +712,53 @@ def test_head_layout_edge_cases(dev):
     assert torch.equal(H.heads_to_rows([view], 64).view(3, -1), want)
     empty = [torch.zeros(0, 64, 8, 8, device=dev)]
     assert H.heads_to_rows(empty, 64).shape[0] == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# mining with two 512-thread CTAs per SM (batches of more images than SMs): same selection as the 1024-thread kernel
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,B,seed", [("ssd300_voc", 5, 0), ("rfb300_voc", 3, 1), ("refinedet320_voc", 4, 2)])
+def test_mining_half_cta_equals_full_cta(dev, name, B, seed):
+    from ssdbox import _abi
+    x = U.seeded_inputs(name, B, seed)
+    pred = (x["loc"].to(dev), x["conf"].to(dev), x["priors"].to(dev))
+    tg = [t.to(dev) for t in x["targets"]]
+    res = {}
+    for flags in (0, _abi.LOSS_MINE_HALF_CTA):
+        crit = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False)
+        crit.abi_flags = flags
+        res[flags] = crit.intermediates(pred, tg)
+    a, b = res[0], res[_abi.LOSS_MINE_HALF_CTA]
+    for k in ("conf_t", "neg", "sel", "tidx", "keys"):
+        assert torch.equal(a[k], b[k]), k
+    assert float(a["sums"][2]) == float(b["sums"][2])
+    assert float(((a["sums"] - b["sums"]).abs() / a["sums"].abs().clamp_min(1e-30)).max()) <= 1e-12      # fp64 sums, another fixed order
+    U.assert_close_rel(b["loss_l"].cpu(), a["loss_l"].cpu(), 2e-7, 0, "loss_l")
+    U.assert_close_rel(b["loss_c"].cpu(), a["loss_c"].cpu(), 2e-7, 0, "loss_c")
+
+
+@pytest.mark.gpu
+def test_mining_more_images_than_sms(dev):
+    """B = 150 > 148 SMs: the 512-thread kernel is picked by itself; the generic kernel (any shape) selects the same rows"""
+    from ssdbox import _abi
+    cfg, c = configs.get("ssd300_voc")
+    x = U.seeded_inputs("ssd300_voc", 2, 7)
+    B = 150
+    g = torch.Generator().manual_seed(9)
+    loc = torch.randn(B, x["P"], 4, generator=g).to(dev) * 0.5
+    conf = torch.randn(B, x["P"], x["C"], generator=g).to(dev)
+    conf[..., 0] += 3.0
+    tg = [t.to(dev) for t in synth.gen_targets(B, x["C"], 8, 11)]
+    pri = x["priors"].to(dev)
+    out = {}
+    for flags in (0, _abi.LOSS_GENERIC_MINE):
+        crit = ssdbox.MultiBoxLoss(x["C"], 0.5, True, 0, True, 3, 0.5, False)
+        crit.abi_flags = flags
+        ll, lc = crit((loc, conf, pri), tg)
+        out[flags] = (ll.cpu(), lc.cpu(), crit._last[1].clone(), crit._last[0].clone())
+    a, b = out[0], out[_abi.LOSS_GENERIC_MINE]
+    assert torch.equal(a[2], b[2])                                   # the selection flags of all 150 images
+    assert float(a[3][2]) == float(b[3][2])
+    U.assert_close_rel(a[0], b[0], 2e-7, 0, "loss_l")
+    U.assert_close_rel(a[1], b[1], 2e-7, 0, "loss_c")
