@@ -57,11 +57,13 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 #define SMARK(k) do { } while (0)
 #endif
 
-constexpr int kMatchWarpsMax = 8;                                  // the kernel is launched with 6 or 8 match warps:
-// 8 when the matching is the longer half of the kernel (narrow conf rows, C = 21: RFB300-VOC B=256 87 us against
-// 102 us with 6), 6 when the conf stream is (C = 81: 16 warps = 4 per scheduler, 90 us against 93 us with 8;
-// 4 / 5 / 7 warps measured 91.4 / - / 95.0 us).  One work unit = match_warps * 128 priors.
-static inline int match_warps_for(int C) { return C >= 48 ? 6 : 8; }
+constexpr int kMatchWarpsMax = 10;                                 // the kernel is launched with 6 or 10 match warps:
+// 10 when the matching is the longer half of the kernel (narrow conf rows, C = 21: RFB300-VOC B=256 102 us with 6,
+// 87 us with 8, 84 us with 10 -- 640 threads x 96 registers still fit the register file; 12 warps under a 704-thread
+// launch bound: 78.5 us there but slower on the small batches, not kept), 6 when the conf stream is (C = 81: 16 warps
+// = 4 per scheduler, 90 us against 93 us with 8; 4 / 5 / 7 warps measured 91.4 / - / 95.0 us).
+// One work unit = match_warps * 128 priors.
+static inline int match_warps_for(int C) { return C >= 48 ? 6 : 10; }
 constexpr int kSchedWarp = kRingConsumerWarps + 1;                 // warp 8 = conf producer, 9 = unit scheduler
 constexpr int kFirstMatchWarp = kRingConsumerWarps + 2;
 constexpr int kStreamThreads = (kRingConsumerWarps + 2 + kMatchWarpsMax) * 32;      // launch bound; launched with match_warps
