@@ -75,6 +75,16 @@ def test_workspace_query(lib):
     assert _abi.workspace_bytes(_abi.OP_LOSS_FWD, 64, 24564, 81, 32) > 64 * 24564 * 10
     assert _abi.workspace_bytes(_abi.OP_DETECT, 64, 24564, 81, 0, 200) >= 64 * 81 * 1024 * 8
     assert _abi.workspace_bytes(99) == 0
+    # any top_k: beyond 1024 the lists are sorted in the workspace (keys of every prior / box, a slice per CTA)
+    assert _abi.workspace_bytes(_abi.OP_NMS, 0, 30000, 0, 0, 200) < 30000 * 4 + 1024
+    assert _abi.workspace_bytes(_abi.OP_NMS, 0, 30000, 0, 0, 5000) >= 30000 * 4 + 32768 * 8 + 5000 * 24
+    assert _abi.workspace_bytes(_abi.OP_DETECT, 2, 8732, 21, 0, 1500) >= 148 * (8732 * 4 + 16384 * 8 + 1500 * 24)
+    # flags of the C ABI and of the host mirror agree
+    hdr = open(os.path.join(ROOT, "include", "ssdbox.h")).read()
+    for name in ("LOSS_SEPARATE_MATCH", "LOSS_GENERIC_MINE", "LOSS_NO_CLUSTER", "LOSS_DEFER_PEER_WAIT", "LOSS_WS_CLEAN", "LOSS_LSE_SHIFT",
+                 "LOSS_MINE_HALF_CTA"):
+        m = re.search(r"#define SSDBOX_%s (\d+)" % name, hdr)
+        assert m and int(m.group(1)) == getattr(_abi, name), name
 
 
 def test_argument_validation_without_gpu(lib):
